@@ -1,0 +1,227 @@
+// conv2 of the subsampling stack (reference: conv_transformer.py:203-214, i=1) as an
+// implicit GEMM on tcgen05:  out[(b,t,f), co] = sum_{kh,kw,ci} x[b, 2t-1+kh, 2f-1+kw, ci] * w[co,ci,kh,kw]
+//
+// No im2col buffer: for each of the 9 taps the A tile (R output rows x F2 output columns x 64
+// input channels) is ONE TMA box over the channels-last conv1 output with element strides
+// {1,2,2,1}; the box's start coordinate (kw-1, 2*t0+kh-1) goes out of bounds at the borders and
+// TMA's zero fill is exactly the conv's zero padding.  K loop = 9 taps x (C/64) channel chunks.
+// Epilogue: +bias -> ReLU -> BatchNorm(eval) affine -> bf16, written channels-last, which is the
+// (t, f*C + c) operand layout of the fc3 GEMM (its weight columns are permuted to match).
+//
+// Same warp roles as gemm_tcgen05.cu (TMA / MMA / TMEM alloc / 4 epilogue warps), persistent.
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace fbkst {
+
+struct Conv2Params {
+  const float* bias;
+  const float* scale;
+  const float* shift;
+  __nv_bfloat16* out;
+  int B, T2, F2, R, tiles_per_utt;
+};
+
+template <int C, int STAGES>
+__global__ void __launch_bounds__(256, 1)
+    conv2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                 Conv2Params p) {
+  constexpr int A_BYTES = 128 * 64 * 2;
+  constexpr int B_BYTES = C * 64 * 2;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int KCH = C / 64;
+  constexpr int NUM_KB = 9 * KCH;
+  constexpr uint32_t TMEM_COLS = 2 * C;
+  constexpr uint32_t IDESC = idesc_bf16_f32(128, C, 0, 0);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.B * p.tiles_per_utt;
+  const uint32_t a_tx = (uint32_t)(p.R * p.F2) * 128u;  // bytes TMA writes for one A box
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int b = tile / p.tiles_per_utt;
+        const int t0 = (tile - b * p.tiles_per_utt) * p.R;
+        for (int kb = 0; kb < NUM_KB; ++kb) {
+          const int tap = kb / KCH, kc = kb - tap * KCH;
+          const int kh = tap / 3, kw = tap - kh * 3;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], a_tx + B_BYTES);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          tma_load_4d(sa, &tmX, &full_bar[stage], kc * 64, kw - 1, 2 * t0 + kh - 1, b);
+          tma_load_2d(sa + A_BYTES, &tmW, &full_bar[stage], kc * 64, tap * C);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * C;
+        for (int kb = 0; kb < NUM_KB; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t adesc = desc_kmajor_sw128(sa);
+          const uint64_t bdesc = desc_kmajor_sw128(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int b = tile / p.tiles_per_utt;
+      const int t0 = (tile - b * p.tiles_per_utt) * p.R;
+      const int valid_rows = min(p.R, p.T2 - t0) * p.F2;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int r = ew * 32 + lane;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * C;
+      __nv_bfloat16* orow = p.out + ((size_t)((size_t)b * p.T2 + t0) * p.F2 + r) * C;
+#pragma unroll 1
+      for (int c = 0; c < C / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c * 32, v);
+        tmem_ld_wait();
+        if (r < valid_rows) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int ch = c * 32 + j;
+            const float a = fmaxf(__uint_as_float(v[j]) + __ldg(p.bias + ch), 0.0f);
+            f[j] = fmaf(a, __ldg(p.scale + ch), __ldg(p.shift + ch));
+          }
+          uint4* o4 = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            o4[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]),
+                               pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                               pack_bf16x2(f[8 * j + 4], f[8 * j + 5]),
+                               pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int C, int STAGES>
+static int launch_conv2(const void* x, const void* w_taps, const Conv2Params& p, int T1, int F1,
+                        cudaStream_t stream) {
+  constexpr int SMEM = STAGES * (128 * 64 * 2 + C * 64 * 2) + 1024 + 256;
+  auto kern = conv2_kernel<C, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    FBKST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    configured = true;
+  }
+  CUtensorMap tmX, tmW;
+  uint64_t dims[4] = {(uint64_t)C, (uint64_t)F1, (uint64_t)T1, (uint64_t)p.B};
+  uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)F1 * C * 2, (uint64_t)T1 * F1 * C * 2};
+  uint32_t box[4] = {64, (uint32_t)(2 * p.F2), (uint32_t)(2 * p.R), 1};
+  uint32_t es[4] = {1, 2, 2, 1};
+  int rc = make_tensor_map(&tmX, x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 4, dims, strides, box, es);
+  if (rc) return rc;
+  rc = make_tensor_map_2d_bf16(&tmW, w_taps, (uint64_t)9 * C, (uint64_t)C, (uint64_t)C, C, 64);
+  if (rc) return rc;
+  const int tiles = p.B * p.tiles_per_utt;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, 256, SMEM, stream>>>(tmX, tmW, p);
+  FBKST_CHECK_CUDA(cudaGetLastError());
+  return FBKST_OK;
+}
+
+}  // namespace fbkst
+
+extern "C" int fbkst_conv2_relu_bn(const void* x, const void* w_taps, const float* bias,
+                                   const float* bn_scale, const float* bn_shift, void* y, int B,
+                                   int T1, int F1, int C, fbkst_stream_t stream) {
+  using namespace fbkst;
+  FBKST_REQUIRE(x && w_taps && bias && bn_scale && bn_shift && y, "fbkst_conv2_relu_bn: null pointer");
+  FBKST_REQUIRE(C == 64 || C == 128, "fbkst_conv2_relu_bn: C must be 64 or 128 (got %d)", C);
+  FBKST_REQUIRE(B > 0 && T1 > 0 && F1 > 0, "fbkst_conv2_relu_bn: bad shape");
+  Conv2Params p;
+  p.bias = bias;
+  p.scale = bn_scale;
+  p.shift = bn_shift;
+  p.out = reinterpret_cast<__nv_bfloat16*>(y);
+  p.B = B;
+  p.T2 = (T1 + 1) / 2;
+  p.F2 = (F1 + 1) / 2;
+  FBKST_REQUIRE(p.F2 <= 128, "fbkst_conv2_relu_bn: F2=%d exceeds one 128-row tile", p.F2);
+  p.R = 128 / p.F2;
+  if (p.R > p.T2) p.R = p.T2;
+  p.tiles_per_utt = (p.T2 + p.R - 1) / p.R;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (C == 64) return launch_conv2<64, 6>(x, w_taps, p, T1, F1, st);
+  return launch_conv2<128, 6>(x, w_taps, p, T1, F1, st);
+}

@@ -1,0 +1,370 @@
+// HBM-bound kernels of the path: fbank CMVN, conv1 (Cin=1, K=9: no tensor cores), LayerNorm,
+// sinusoidal table, padding mask, and the weight-format preparation kernels.
+#include <math.h>
+
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace fbkst {
+
+// ------------------------------------------------------------------ CMVN (a1)
+// Pass 1: per (utterance, feature) sum and sum of squares in fp64 (unbiased variance needs
+// sumsq - sum^2/n; fp64 keeps the cancellation harmless).  grid = (chunks, B).
+__global__ void cmvn_stats_kernel(const float* __restrict__ x, const int* __restrict__ lengths,
+                                  double* __restrict__ ws, int T, int F, int rows_per_block) {
+  extern __shared__ double sred[];  // [2][blockDim.x]
+  const int b = blockIdx.y;
+  const int len = min(lengths[b], T);
+  const int t0 = blockIdx.x * rows_per_block;
+  const int t1 = min(t0 + rows_per_block, len);
+  const int groups = blockDim.x / F;  // row groups handled concurrently
+  const int f = threadIdx.x % F, g = threadIdx.x / F;
+  double s = 0.0, ss = 0.0;
+  if (g < groups) {
+    const float* xp = x + ((size_t)b * T) * F + f;
+    for (int t = t0 + g; t < t1; t += groups) {
+      const double v = (double)__ldg(xp + (size_t)t * F);
+      s += v;
+      ss += v * v;
+    }
+  }
+  sred[threadIdx.x] = s;
+  sred[blockDim.x + threadIdx.x] = ss;
+  __syncthreads();
+  if (threadIdx.x < F) {
+    double a = 0.0, c = 0.0;
+    for (int k = 0; k < groups; ++k) {
+      a += sred[k * F + threadIdx.x];
+      c += sred[blockDim.x + k * F + threadIdx.x];
+    }
+    if (t0 < t1) {
+      atomicAdd(&ws[((size_t)b * F + threadIdx.x) * 2 + 0], a);
+      atomicAdd(&ws[((size_t)b * F + threadIdx.x) * 2 + 1], c);
+    }
+  }
+}
+
+// Pass 2: y = (x - mean) * inv with the reference's eps rule (data_utils.py:15-19): if ANY
+// feature of the utterance has var < 1e-8, inv = 1/(sqrt(var)+1e-8) for all features.
+__global__ void cmvn_apply_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                  const int* __restrict__ lengths, const double* __restrict__ ws,
+                                  int T, int F, int rows_per_block) {
+  extern __shared__ float sstat[];  // mean[F], inv[F]
+  const int b = blockIdx.y;
+  const int len = min(lengths[b], T);
+  int small = 0;
+  float mean = 0.f, var = 0.f;
+  if (threadIdx.x < F) {
+    const double n = (double)len;
+    const double s = ws[((size_t)b * F + threadIdx.x) * 2 + 0];
+    const double ss = ws[((size_t)b * F + threadIdx.x) * 2 + 1];
+    const double m = s / n;
+    double v = (ss - s * m) / (n - 1.0);
+    if (v < 0.0) v = 0.0;
+    mean = (float)m;
+    var = (float)v;
+    small = var < 1e-8f;
+  }
+  const int any_small = __syncthreads_or(small);
+  if (threadIdx.x < F) {
+    sstat[threadIdx.x] = mean;
+    sstat[F + threadIdx.x] = any_small ? 1.0f / (sqrtf(var) + 1e-8f) : 1.0f / sqrtf(var);
+  }
+  __syncthreads();
+  const int t0 = blockIdx.x * rows_per_block;
+  const int t1 = min(t0 + rows_per_block, T);
+  const size_t base = ((size_t)b * T + t0) * F;
+  const int n = (t1 - t0) * F;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int t = t0 + i / F, f = i % F;
+    y[base + i] = (t < len) ? (__ldg(x + base + i) - sstat[f]) * sstat[F + f] : 0.0f;
+  }
+}
+
+// ----------------------------------------------------------------- conv1 (a2)
+// One thread = one output pixel x 8 channels (one 16-byte store); weights in smem.
+template <int C>
+__global__ void __launch_bounds__(256)
+    conv1_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                 const float* __restrict__ bias, const float* __restrict__ scale,
+                 const float* __restrict__ shift, uint4* __restrict__ y, int B, int T, int F, int T1,
+                 int F1) {
+  __shared__ float sw[C * 9];
+  __shared__ float sb[3 * C];
+  for (int i = threadIdx.x; i < C * 9; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    sb[i] = bias[i];
+    sb[C + i] = scale[i];
+    sb[2 * C + i] = shift[i];
+  }
+  __syncthreads();
+  constexpr int G = C / 8;
+  const long long total = (long long)B * T1 * F1 * G;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % G);
+    long long p = idx / G;
+    const int f1 = (int)(p % F1);
+    p /= F1;
+    const int t1 = (int)(p % T1);
+    const int b = (int)(p / T1);
+    float in[9];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int t = 2 * t1 - 1 + kh;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int f = 2 * f1 - 1 + kw;
+        in[kh * 3 + kw] =
+            (t >= 0 && t < T && f >= 0 && f < F) ? __ldg(x + ((size_t)b * T + t) * F + f) : 0.0f;
+      }
+    }
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = g * 8 + j;
+      float a = sb[c];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) a = fmaf(sw[c * 9 + k], in[k], a);
+      a = fmaxf(a, 0.0f);
+      o[j] = fmaf(a, sb[C + c], sb[2 * C + c]);
+    }
+    y[idx] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
+                        pack_bf16x2(o[6], o[7]));
+  }
+}
+
+// ------------------------------------------------------------- LayerNorm (a8)
+// One warp per row, the row held in registers (NV float4 per lane), two-pass variance.
+template <int NV>
+__global__ void __launch_bounds__(256)
+    layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, void* __restrict__ y, int out_f32, int M,
+                     float eps) {
+  constexpr int D = NV * 128;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  const float4* xp = reinterpret_cast<const float4*>(x + (size_t)row * D);
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i] = xp[i * 32 + lane];
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+  const float4* gp = reinterpret_cast<const float4*>(gamma);
+  const float4* bp = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 g = __ldg(gp + i * 32 + lane), b = __ldg(bp + i * 32 + lane);
+    float4 o;
+    o.x = (v[i].x - mean) * rstd * g.x + b.x;
+    o.y = (v[i].y - mean) * rstd * g.y + b.y;
+    o.z = (v[i].z - mean) * rstd * g.z + b.z;
+    o.w = (v[i].w - mean) * rstd * g.w + b.w;
+    if (out_f32) {
+      reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + (size_t)row * D)[i * 32 + lane] = o;
+    } else {
+      reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(y) + (size_t)row * D)[i * 32 + lane] =
+          make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+    }
+  }
+}
+
+// ------------------------------------------------------ sinusoidal table (a4)
+__global__ void sinusoidal_table_kernel(float* __restrict__ table, int rows, int D) {
+  const int half = D / 2;
+  const float step = -(logf(10000.0f) / (float)(half - 1));
+  const long long total = (long long)rows * D;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(i / D), c = (int)(i % D);
+    float val = 0.0f;
+    if (p > 0 && c < 2 * half) {
+      const int k = c < half ? c : c - half;
+      const float ang = (float)p * expf((float)k * step);
+      val = c < half ? sinf(ang) : cosf(ang);
+    }
+    table[i] = val;
+  }
+}
+
+// ----------------------------------------------------------- padding mask (a5)
+__global__ void lengths_to_mask_kernel(const int* __restrict__ lengths, uint8_t* __restrict__ mask,
+                                       int* __restrict__ any_pad, int B, int L) {
+  const int total = B * L;
+  int pad_seen = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = i / L, t = i - b * L;
+    const uint8_t m = t >= lengths[b];
+    mask[i] = m;
+    pad_seen |= m;
+  }
+  if (__syncthreads_or(pad_seen) && threadIdx.x == 0) atomicOr(any_pad, 1);
+}
+
+// ----------------------------------------------------------- weight preparation
+__global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                 long long n, float scale) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    dst[i] = __float2bfloat16_rn(src[i] * scale);
+}
+__global__ void prep_conv2_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ o,
+                                         int C) {
+  const int total = 9 * C * C;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int ci = i % C, co = (i / C) % C, tap = i / (C * C);
+    o[i] = __float2bfloat16_rn(w[((size_t)co * C + ci) * 9 + tap]);
+  }
+}
+__global__ void prep_fc3_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ o,
+                                       int D, int C, int F2) {
+  const long long total = (long long)D * C * F2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C), f = (int)((i / C) % F2), d = (int)(i / ((long long)C * F2));
+    o[i] = __float2bfloat16_rn(w[((size_t)d * C + c) * F2 + f]);
+  }
+}
+__global__ void prep_bn_affine_kernel(const float* gamma, const float* beta, const float* mean,
+                                      const float* var, float eps, float* scale, float* shift,
+                                      int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    const float s = gamma[c] / sqrtf(var[c] + eps);
+    scale[c] = s;
+    shift[c] = beta[c] - mean[c] * s;
+  }
+}
+
+static inline int grid_for(long long n, int block, int cap_mult = 8) {
+  long long g = (n + block - 1) / block;
+  const long long cap = (long long)num_sms() * cap_mult;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace fbkst
+
+using namespace fbkst;
+
+extern "C" int fbkst_cmvn_f32(const float* x, float* y, const int32_t* lengths, int B, int T, int F,
+                              double* workspace, fbkst_stream_t stream) {
+  FBKST_REQUIRE(x && y && lengths && workspace, "fbkst_cmvn_f32: null pointer");
+  FBKST_REQUIRE(B > 0 && T > 0 && F > 0 && F <= 256, "fbkst_cmvn_f32: bad shape B=%d T=%d F=%d", B,
+                T, F);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  FBKST_CHECK_CUDA(cudaMemsetAsync(workspace, 0, sizeof(double) * 2 * B * F, st));
+  const int rows = 128;
+  dim3 grid((T + rows - 1) / rows, B);
+  cmvn_stats_kernel<<<grid, 256, 2 * 256 * sizeof(double), st>>>(x, lengths, workspace, T, F, rows);
+  cmvn_apply_kernel<<<grid, 256, 2 * F * sizeof(float), st>>>(x, y, lengths, workspace, T, F, rows);
+  FBKST_CHECK_CUDA(cudaGetLastError());
+  return FBKST_OK;
+}
+
+extern "C" int fbkst_conv1_relu_bn(const float* x, const float* w, const float* bias,
+                                   const float* bn_scale, const float* bn_shift, void* y, int B,
+                                   int T, int F, int C, fbkst_stream_t stream) {
+  FBKST_REQUIRE(x && w && bias && bn_scale && bn_shift && y, "fbkst_conv1_relu_bn: null pointer");
+  FBKST_REQUIRE(C == 64 || C == 128, "fbkst_conv1_relu_bn: C must be 64 or 128 (got %d)", C);
+  FBKST_REQUIRE(B > 0 && T > 0 && F > 0, "fbkst_conv1_relu_bn: bad shape");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int T1 = (T + 1) / 2, F1 = (F + 1) / 2;
+  const long long total = (long long)B * T1 * F1 * (C / 8);
+  const int grid = grid_for(total, 256, 16);
+  if (C == 64)
+    conv1_kernel<64><<<grid, 256, 0, st>>>(x, w, bias, bn_scale, bn_shift, (uint4*)y, B, T, F, T1, F1);
+  else
+    conv1_kernel<128><<<grid, 256, 0, st>>>(x, w, bias, bn_scale, bn_shift, (uint4*)y, B, T, F, T1, F1);
+  FBKST_CHECK_CUDA(cudaGetLastError());
+  return FBKST_OK;
+}
+
+extern "C" int fbkst_layernorm(const float* x, const float* gamma, const float* beta, void* y,
+                               int out_dtype, int M, int D, float eps, fbkst_stream_t stream) {
+  FBKST_REQUIRE(x && gamma && beta && y, "fbkst_layernorm: null pointer");
+  FBKST_REQUIRE(M > 0, "fbkst_layernorm: M must be positive");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int f32 = out_dtype == FBKST_F32;
+  const int grid = (M + 7) / 8;
+  switch (D) {
+    case 128: layernorm_kernel<1><<<grid, 256, 0, st>>>(x, gamma, beta, y, f32, M, eps); break;
+    case 256: layernorm_kernel<2><<<grid, 256, 0, st>>>(x, gamma, beta, y, f32, M, eps); break;
+    case 384: layernorm_kernel<3><<<grid, 256, 0, st>>>(x, gamma, beta, y, f32, M, eps); break;
+    case 512: layernorm_kernel<4><<<grid, 256, 0, st>>>(x, gamma, beta, y, f32, M, eps); break;
+    case 768: layernorm_kernel<6><<<grid, 256, 0, st>>>(x, gamma, beta, y, f32, M, eps); break;
+    case 1024: layernorm_kernel<8><<<grid, 256, 0, st>>>(x, gamma, beta, y, f32, M, eps); break;
+    default:
+      return set_error(FBKST_ERR_ARG, "fbkst_layernorm: unsupported D=%d (128..1024, multiple of 128)", D);
+  }
+  FBKST_CHECK_CUDA(cudaGetLastError());
+  return FBKST_OK;
+}
+
+extern "C" int fbkst_sinusoidal_table(float* table, int rows, int D, fbkst_stream_t stream) {
+  FBKST_REQUIRE(table && rows > 0 && D >= 4, "fbkst_sinusoidal_table: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  sinusoidal_table_kernel<<<grid_for((long long)rows * D, 256), 256, 0, st>>>(table, rows, D);
+  FBKST_CHECK_CUDA(cudaGetLastError());
+  return FBKST_OK;
+}
+
+extern "C" int fbkst_lengths_to_mask(const int32_t* lengths, uint8_t* mask, int32_t* any_pad, int B,
+                                     int L, fbkst_stream_t stream) {
+  FBKST_REQUIRE(lengths && mask && any_pad && B > 0 && L > 0, "fbkst_lengths_to_mask: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  FBKST_CHECK_CUDA(cudaMemsetAsync(any_pad, 0, sizeof(int32_t), st));
+  lengths_to_mask_kernel<<<grid_for((long long)B * L, 256), 256, 0, st>>>(lengths, mask, any_pad, B, L);
+  FBKST_CHECK_CUDA(cudaGetLastError());
+  return FBKST_OK;
+}
+
+extern "C" int fbkst_cast_bf16(const float* src, void* dst, int64_t n, float scale,
+                               fbkst_stream_t stream) {
+  FBKST_REQUIRE(src && dst && n > 0, "fbkst_cast_bf16: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cast_bf16_kernel<<<grid_for(n, 256), 256, 0, st>>>(src, (__nv_bfloat16*)dst, n, scale);
+  FBKST_CHECK_CUDA(cudaGetLastError());
+  return FBKST_OK;
+}
+
+extern "C" int fbkst_prep_conv2_weight(const float* w, void* w_taps, int C, fbkst_stream_t stream) {
+  FBKST_REQUIRE(w && w_taps && C > 0, "fbkst_prep_conv2_weight: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  prep_conv2_weight_kernel<<<grid_for(9LL * C * C, 256), 256, 0, st>>>(w, (__nv_bfloat16*)w_taps, C);
+  FBKST_CHECK_CUDA(cudaGetLastError());
+  return FBKST_OK;
+}
+
+extern "C" int fbkst_prep_fc3_weight(const float* w, void* w_perm, int D, int C, int F2,
+                                     fbkst_stream_t stream) {
+  FBKST_REQUIRE(w && w_perm && D > 0 && C > 0 && F2 > 0, "fbkst_prep_fc3_weight: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  prep_fc3_weight_kernel<<<grid_for((long long)D * C * F2, 256), 256, 0, st>>>(
+      w, (__nv_bfloat16*)w_perm, D, C, F2);
+  FBKST_CHECK_CUDA(cudaGetLastError());
+  return FBKST_OK;
+}
+
+extern "C" int fbkst_prep_bn_affine(const float* gamma, const float* beta, const float* mean,
+                                    const float* var, float eps, float* scale, float* shift, int C,
+                                    fbkst_stream_t stream) {
+  FBKST_REQUIRE(gamma && beta && mean && var && scale && shift && C > 0,
+                "fbkst_prep_bn_affine: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  prep_bn_affine_kernel<<<(C + 127) / 128, 128, 0, st>>>(gamma, beta, mean, var, eps, scale, shift, C);
+  FBKST_CHECK_CUDA(cudaGetLastError());
+  return FBKST_OK;
+}

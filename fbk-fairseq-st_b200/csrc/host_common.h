@@ -1,0 +1,45 @@
+// Host-side helpers shared by the C-ABI entry points: error reporting (no exceptions
+// cross the ABI) and TMA tensor-map construction through the driver entry point
+// (no link-time dependency on libcuda: the symbol is resolved with
+// cudaGetDriverEntryPoint at first use).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/fbkst_b200.h"
+
+namespace fbkst {
+
+// Records `msg` (thread-local) and returns `code`.
+int set_error(int code, const char* fmt, ...);
+
+#define FBKST_CHECK_CUDA(expr)                                                              \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess)                                                                  \
+      return ::fbkst::set_error(                                                            \
+          _e == cudaErrorMemoryAllocation ? FBKST_ERR_OOM : FBKST_ERR_CUDA,                 \
+          "%s failed: %s%s", #expr, cudaGetErrorString(_e),                                 \
+          _e == cudaErrorMemoryAllocation ? " (CUDA out of memory)" : "");                  \
+  } while (0)
+
+#define FBKST_REQUIRE(cond, ...)                                                            \
+  do {                                                                                      \
+    if (!(cond)) return ::fbkst::set_error(FBKST_ERR_ARG, __VA_ARGS__);                     \
+  } while (0)
+
+// rank-N bf16/fp32 tiled tensor map, 128B swizzle.  dims/strides innermost first;
+// strides_bytes[i] is the byte stride of dim i+1 (dim 0 is contiguous).
+int make_tensor_map(CUtensorMap* out, const void* base, CUtensorMapDataType dtype, int elem_bytes,
+                    int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, const uint32_t* elem_strides,
+                    CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B);
+
+// 2-D row-major [rows, cols] bf16 matrix with row pitch `ld` elements; box = {box_cols, box_rows}.
+int make_tensor_map_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+                            uint64_t ld, uint32_t box_rows, uint32_t box_cols);
+
+int num_sms();
+
+}  // namespace fbkst

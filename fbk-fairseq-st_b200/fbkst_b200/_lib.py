@@ -1,0 +1,83 @@
+"""ctypes binding of ``libfbkst_b200.so`` (declared in ``include/fbkst_b200.h``)."""
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfbkst_b200.so")
+
+ERR_ARG, ERR_CUDA, ERR_OOM = -1, -2, -3
+BF16, F32 = 0, 1
+CTC_STRATEGY = {"avg": 0, "weighted": 1, "softmax": 2}
+EPI_RELU, EPI_OUT_F32, EPI_ROW_REMAP, EPI_POSEMB = 1, 2, 4, 8
+
+P, I, I64, F = c_void_p, c_int, c_int64, c_float
+
+# name -> argtypes; every entry point returns int (0 = ok) unless listed in _RESTYPES
+SIGNATURES = {
+    "fbkst_abi_version": [],
+    "fbkst_device_ok": [],
+    "fbkst_cmvn_f32": [P, P, P, I, I, I, P, P],
+    "fbkst_conv1_relu_bn": [P, P, P, P, P, P, I, I, I, I, P],
+    "fbkst_conv2_relu_bn": [P, P, P, P, P, P, I, I, I, I, P],
+    "fbkst_linear_bf16": [P, I64, P, I64, P, P, I64, P, I64, I, I, I, I, I, I, P, P],
+    "fbkst_layernorm": [P, P, P, P, I, I, I, F, P],
+    "fbkst_attention_fwd": [P, P, P, I, I, I, I, P],
+    "fbkst_sinusoidal_table": [P, I, I, P],
+    "fbkst_lengths_to_mask": [P, P, P, I, I, P],
+    "fbkst_ctc_argmax": [P, I, I64, P, P, P, I, I, I, P],
+    "fbkst_ctc_segment": [P, P, P, I, P, P, P, P, P, I, I, P],
+    "fbkst_ctc_compress": [P, P, P, P, P, P, P, I, I, I, P],
+    "fbkst_cast_bf16": [P, P, I64, F, P],
+    "fbkst_prep_conv2_weight": [P, P, I, P],
+    "fbkst_prep_fc3_weight": [P, P, I, I, I, P],
+    "fbkst_prep_bn_affine": [P, P, P, P, F, P, P, I, P],
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (no GPU needed); raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "fbkst_b200: %s is missing -- build it with `python fbk-fairseq-st_b200/build.py` "
+            "(there is no CPU / PyTorch fallback)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.fbkst_last_error.restype = c_char_p
+    lib.fbkst_last_error.argtypes = []
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = c_int
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc == 0:
+        return
+    msg = load().fbkst_last_error().decode("utf-8", "replace")
+    if rc == ERR_OOM:
+        raise RuntimeError("CUDA out of memory in fbkst_b200: " + msg)
+    if rc == ERR_ARG:
+        raise ValueError("fbkst_b200: " + msg)
+    raise RuntimeError("fbkst_b200: " + msg)
+
+
+_device_checked = False
+
+
+def require_device():
+    """The product path needs the library AND a compute-capability-10.x device."""
+    global _device_checked
+    lib = load()
+    if not _device_checked:
+        if not lib.fbkst_device_ok():
+            raise RuntimeError("fbkst_b200: no sm_100 (B200) CUDA device visible; this package has "
+                               "no CPU fallback")
+        _device_checked = True
+    return lib

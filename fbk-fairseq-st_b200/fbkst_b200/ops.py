@@ -1,0 +1,237 @@
+"""Tensor-level wrappers over the C ABI.  PyTorch is plumbing here: it owns device memory and the
+current stream; all arithmetic happens in ``libfbkst_b200.so``.  Every wrapper raises if the
+library or the GPU is missing (no fallback)."""
+import torch
+
+from . import _lib
+from ._lib import BF16, CTC_STRATEGY, EPI_OUT_F32, EPI_POSEMB, EPI_RELU, EPI_ROW_REMAP, F32, check
+
+LAUNCHES = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
+
+
+def _count(n=1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _req(t, dtype, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise ValueError("fbkst_b200.%s: expected a CUDA tensor" % name)
+    if t.dtype != dtype:
+        raise ValueError("fbkst_b200.%s: expected %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError("fbkst_b200.%s: tensor must be contiguous" % name)
+    return t
+
+
+def cmvn(x, lengths, out=None):
+    """apply_mv_norm on a padded batch: x [B,T,F] fp32, lengths [B] int32."""
+    lib = _lib.require_device()
+    _req(x, torch.float32, "cmvn.x"); _req(lengths, torch.int32, "cmvn.lengths")
+    B, T, Fd = x.shape
+    out = torch.empty_like(x) if out is None else out
+    ws = torch.empty(B * Fd * 2, dtype=torch.float64, device=x.device)
+    check(lib.fbkst_cmvn_f32(x.data_ptr(), out.data_ptr(), lengths.data_ptr(), B, T, Fd,
+                             ws.data_ptr(), _stream()))
+    _count(2)
+    return out
+
+
+def conv1_relu_bn(x, w, bias, scale, shift):
+    lib = _lib.require_device()
+    _req(x, torch.float32, "conv1.x")
+    B, T, Fd = x.shape
+    C = w.shape[0]
+    y = torch.empty(B, (T + 1) // 2, (Fd + 1) // 2, C, dtype=torch.bfloat16, device=x.device)
+    check(lib.fbkst_conv1_relu_bn(x.data_ptr(), _req(w, torch.float32, "conv1.w").data_ptr(),
+                                  bias.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+                                  y.data_ptr(), B, T, Fd, C, _stream()))
+    _count()
+    return y
+
+
+def conv2_relu_bn(x, w_taps, bias, scale, shift):
+    lib = _lib.require_device()
+    _req(x, torch.bfloat16, "conv2.x"); _req(w_taps, torch.bfloat16, "conv2.w_taps")
+    B, T1, F1, C = x.shape
+    y = torch.empty(B, (T1 + 1) // 2, (F1 + 1) // 2, C, dtype=torch.bfloat16, device=x.device)
+    check(lib.fbkst_conv2_relu_bn(x.data_ptr(), w_taps.data_ptr(), bias.data_ptr(),
+                                  scale.data_ptr(), shift.data_ptr(), y.data_ptr(), B, T1, F1, C,
+                                  _stream()))
+    _count()
+    return y
+
+
+def linear(a, w, bias=None, relu=False, residual=None, out_dtype=torch.bfloat16, out=None,
+           remap=None, posemb=None):
+    """out = epi(a @ w.T).  a [M,K] bf16, w [N,K] bf16, bias [N] fp32, residual [M,N] fp32.
+    remap=(inner, outer): out row = (m % inner)*outer + m // inner.
+    posemb=(table [P,N] fp32, lengths [outer] int32): adds table[pos(m)] (needs remap dims)."""
+    lib = _lib.require_device()
+    _req(a, torch.bfloat16, "linear.a"); _req(w, torch.bfloat16, "linear.w")
+    M, K = a.shape
+    N = w.shape[0]
+    if w.shape[1] != K:
+        raise ValueError("fbkst_b200.linear: K mismatch %s vs %s" % (tuple(a.shape), tuple(w.shape)))
+    flags = (EPI_RELU if relu else 0) | (EPI_OUT_F32 if out_dtype == torch.float32 else 0)
+    inner = outer = 0
+    lengths = None
+    res, ldr = residual, 0
+    if remap is not None:
+        inner, outer = remap
+        flags |= EPI_ROW_REMAP
+    if posemb is not None:
+        res, lengths = posemb
+        flags |= EPI_POSEMB
+    if res is not None:
+        _req(res, torch.float32, "linear.residual")
+        ldr = res.stride(0)
+    if out is None:
+        ldo = (N + 7) // 8 * 8
+        out = torch.empty(M, ldo, dtype=out_dtype, device=a.device)
+        if ldo != N:
+            out = out[:, :N]
+    if out.dtype != out_dtype or out.stride(-1) != 1:
+        raise ValueError("fbkst_b200.linear: bad out tensor")
+    check(lib.fbkst_linear_bf16(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _ptr(bias),
+                                _ptr(res), ldr, out.data_ptr(), out.stride(0), M, N, K, flags,
+                                inner, outer, _ptr(lengths), _stream()))
+    _count()
+    return out
+
+
+def layernorm(x, gamma, beta, out_dtype=torch.bfloat16, eps=1e-5):
+    lib = _lib.require_device()
+    _req(x, torch.float32, "layernorm.x")
+    M, D = x.shape
+    y = torch.empty(M, D, dtype=out_dtype, device=x.device)
+    check(lib.fbkst_layernorm(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(),
+                              F32 if out_dtype == torch.float32 else BF16, M, D, eps, _stream()))
+    _count()
+    return y
+
+
+def attention(qkv, lengths, L, B, H, log_penalty=True):
+    """qkv [L*B, 3*H*64] bf16 (row t*B+b) -> [L*B, H*64] bf16."""
+    lib = _lib.require_device()
+    _req(qkv, torch.bfloat16, "attention.qkv"); _req(lengths, torch.int32, "attention.lengths")
+    if qkv.shape != (L * B, 3 * H * 64):
+        raise ValueError("fbkst_b200.attention: qkv shape %s != (%d, %d)" %
+                         (tuple(qkv.shape), L * B, 3 * H * 64))
+    out = torch.empty(L * B, H * 64, dtype=torch.bfloat16, device=qkv.device)
+    check(lib.fbkst_attention_fwd(qkv.data_ptr(), out.data_ptr(), lengths.data_ptr(), L, B, H,
+                                  1 if log_penalty else 0, _stream()))
+    _count()
+    return out
+
+
+def sinusoidal_table(rows, D, device):
+    lib = _lib.require_device()
+    t = torch.empty(rows, D, dtype=torch.float32, device=device)
+    check(lib.fbkst_sinusoidal_table(t.data_ptr(), rows, D, _stream()))
+    _count()
+    return t
+
+
+def lengths_to_mask(lengths, L):
+    """-> (mask [B,L] bool, any_pad [1] int32 device tensor)."""
+    lib = _lib.require_device()
+    _req(lengths, torch.int32, "lengths_to_mask.lengths")
+    B = lengths.numel()
+    mask = torch.empty(B, L, dtype=torch.uint8, device=lengths.device)
+    any_pad = torch.empty(1, dtype=torch.int32, device=lengths.device)
+    check(lib.fbkst_lengths_to_mask(lengths.data_ptr(), mask.data_ptr(), any_pad.data_ptr(), B, L,
+                                    _stream()))
+    _count()
+    return mask.view(torch.bool), any_pad
+
+
+def ctc_argmax(logits, lengths, L, B, V, want_prob=True):
+    """logits [L*B, >=V] bf16/fp32 (possibly a column-narrowed view) -> labels, top_prob."""
+    lib = _lib.require_device()
+    if logits.dtype not in (torch.bfloat16, torch.float32) or logits.stride(-1) != 1:
+        raise ValueError("fbkst_b200.ctc_argmax: logits must be bf16/fp32 with unit column stride")
+    labels = torch.empty(L * B, dtype=torch.int32, device=logits.device)
+    prob = torch.empty(L * B, dtype=torch.float32, device=logits.device) if want_prob else None
+    check(lib.fbkst_ctc_argmax(logits.data_ptr(), BF16 if logits.dtype == torch.bfloat16 else F32,
+                               logits.stride(0), lengths.data_ptr(), labels.data_ptr(), _ptr(prob),
+                               L, B, V, _stream()))
+    _count()
+    return labels, prob
+
+
+def ctc_segment(labels, top_prob, lengths, strategy, L, B):
+    lib = _lib.require_device()
+    dev = labels.device
+    seg_id = torch.empty(L * B, dtype=torch.int32, device=dev)
+    seg_start = torch.empty(L * B, dtype=torch.int32, device=dev)
+    weight = torch.empty(L * B, dtype=torch.float32, device=dev)
+    new_len = torch.empty(B, dtype=torch.int32, device=dev)
+    max_new = torch.empty(1, dtype=torch.int32, device=dev)
+    check(lib.fbkst_ctc_segment(labels.data_ptr(), _ptr(top_prob), lengths.data_ptr(),
+                                CTC_STRATEGY[strategy], seg_id.data_ptr(), seg_start.data_ptr(),
+                                weight.data_ptr(), new_len.data_ptr(), max_new.data_ptr(), L, B,
+                                _stream()))
+    _count()
+    return seg_id, seg_start, weight, new_len, max_new
+
+
+def ctc_compress(x, seg_start, weight, lengths, new_len, max_new, L, B):
+    lib = _lib.require_device()
+    _req(x, torch.float32, "ctc_compress.x")
+    D = x.shape[-1]
+    out = torch.empty(L * B, D, dtype=torch.float32, device=x.device)
+    check(lib.fbkst_ctc_compress(x.data_ptr(), seg_start.data_ptr(), weight.data_ptr(),
+                                 lengths.data_ptr(), new_len.data_ptr(), max_new.data_ptr(),
+                                 out.data_ptr(), L, B, D, _stream()))
+    _count()
+    return out
+
+
+def cast_bf16(src, scale=1.0):
+    lib = _lib.require_device()
+    src = _req(src.contiguous(), torch.float32, "cast_bf16.src")
+    dst = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    check(lib.fbkst_cast_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), float(scale), _stream()))
+    _count()
+    return dst
+
+
+def prep_conv2_weight(w):
+    lib = _lib.require_device()
+    w = _req(w.contiguous(), torch.float32, "prep_conv2_weight.w")
+    C = w.shape[0]
+    out = torch.empty(9, C, C, dtype=torch.bfloat16, device=w.device)
+    check(lib.fbkst_prep_conv2_weight(w.data_ptr(), out.data_ptr(), C, _stream()))
+    _count()
+    return out
+
+
+def prep_fc3_weight(w, C, F2):
+    lib = _lib.require_device()
+    w = _req(w.contiguous(), torch.float32, "prep_fc3_weight.w")
+    D = w.shape[0]
+    out = torch.empty(D, F2 * C, dtype=torch.bfloat16, device=w.device)
+    check(lib.fbkst_prep_fc3_weight(w.data_ptr(), out.data_ptr(), D, C, F2, _stream()))
+    _count()
+    return out
+
+
+def prep_bn_affine(gamma, beta, mean, var, eps=1e-5):
+    lib = _lib.require_device()
+    C = gamma.numel()
+    scale = torch.empty(C, dtype=torch.float32, device=gamma.device)
+    shift = torch.empty(C, dtype=torch.float32, device=gamma.device)
+    check(lib.fbkst_prep_bn_affine(gamma.data_ptr(), beta.data_ptr(), mean.data_ptr(),
+                                   var.data_ptr(), eps, scale.data_ptr(), shift.data_ptr(), C,
+                                   _stream()))
+    _count()
+    return scale, shift

@@ -1,0 +1,163 @@
+/*
+ * fbkst_b200 -- C ABI of the B200-native (sm_100a) speech-translation encoder hot path.
+ *
+ * Drop-in boundary for the forward of FBK-fairseq-ST's ConvolutionalTransformerEncoder
+ * (reference: examples/speech_recognition/models/conv_transformer.py:195-291 and the
+ * modules it calls).  The reference has no native code on this path (every op is a
+ * PyTorch call), so each entry point below names the reference *Python* call site it
+ * replaces; INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless named h_*;
+ *   - every function launches on `stream` and returns immediately (no host sync unless stated);
+ *   - return 0 on success, a negative FBKST_ERR_* otherwise; fbkst_last_error() returns the
+ *     message of the last failure on the calling thread.  Allocation failures contain the
+ *     substring "out of memory" (fairseq/trainer.py:394-405 greps for it);
+ *   - the library never allocates device memory for results: callers own every buffer;
+ *   - time-major activations: row m = t * B + b  (the reference's T x B x C layout);
+ *   - bf16 = __nv_bfloat16 storage, fp32 accumulation everywhere.
+ */
+#ifndef FBKST_B200_H_
+#define FBKST_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* fbkst_stream_t;
+
+enum {
+  FBKST_OK = 0,
+  FBKST_ERR_ARG = -1,  /* bad argument / unsupported shape */
+  FBKST_ERR_CUDA = -2, /* CUDA runtime / driver error */
+  FBKST_ERR_OOM = -3   /* CUDA out of memory */
+};
+
+enum { FBKST_BF16 = 0, FBKST_F32 = 1 };
+
+enum { FBKST_CTC_AVG = 0, FBKST_CTC_WEIGHTED = 1, FBKST_CTC_SOFTMAX = 2 };
+
+/* epilogue flags of fbkst_linear_bf16 */
+enum {
+  FBKST_EPI_RELU = 1,      /* y = max(y, 0) after the bias                                  */
+  FBKST_EPI_OUT_F32 = 2,   /* out is fp32 (default bf16)                                    */
+  FBKST_EPI_ROW_REMAP = 4, /* out row = (m % remap_inner) * remap_outer + m / remap_inner    */
+  FBKST_EPI_POSEMB = 8     /* residual is a [*, N] table indexed by position (see fc3)      */
+};
+
+const char* fbkst_last_error(void);
+int fbkst_abi_version(void);
+/* 1 when a CUDA device of compute capability 10.x is present, else 0 (never a CPU fallback) */
+int fbkst_device_ok(void);
+
+/* ---- a1: per-utterance fbank mean/variance normalisation ------------------------------
+ * replaces examples/speech_recognition/data/data_utils.py:9-24 (apply_mv_norm), called at
+ * data/fbank_dataset.py:44-45.  x, y: [B, T, F] fp32 (y may alias x); lengths[B] int32.
+ * Rows t >= lengths[b] are written as 0.  workspace: B*F*2 doubles. */
+int fbkst_cmvn_f32(const float* x, float* y, const int32_t* lengths, int B, int T, int F,
+                   double* workspace, fbkst_stream_t stream);
+
+/* ---- a2 (conv 1): Conv2d(1->C,k3,s2,p1)+bias -> ReLU -> BatchNorm(eval affine) -----------
+ * replaces conv_transformer.py:203-214 for i=0.  x [B,T,F] fp32; w [C,9] fp32; bias,
+ * bn_scale, bn_shift [C] fp32 (scale = gamma/sqrt(var+eps), shift = beta - mean*scale);
+ * y [B,T1,F1,C] bf16 channels-last, T1=ceil(T/2), F1=ceil(F/2).  C must be 64 or 128. */
+int fbkst_conv1_relu_bn(const float* x, const float* w, const float* bias, const float* bn_scale,
+                        const float* bn_shift, void* y, int B, int T, int F, int C,
+                        fbkst_stream_t stream);
+
+/* ---- a2 (conv 2): Conv2d(C->C,k3,s2,p1)+bias -> ReLU -> BatchNorm(eval affine) -----------
+ * replaces conv_transformer.py:203-214 for i=1 as a TMA-fed implicit GEMM on tcgen05.
+ * x [B,T1,F1,C] bf16 channels-last; w_taps [9][C][C] bf16 (tap = kh*3+kw, then out-ch,
+ * in-ch); y [B,T2,F2,C] bf16 channels-last (T2=ceil(T1/2), F2=ceil(F1/2)), i.e. row
+ * (b,t) of the fc3 operand with the flatten order (f, c). */
+int fbkst_conv2_relu_bn(const void* x, const void* w_taps, const float* bias,
+                        const float* bn_scale, const float* bn_shift, void* y, int B, int T1,
+                        int F1, int C, fbkst_stream_t stream);
+
+/* ---- generic fused linear: out = epi(A @ W^T) on tcgen05 --------------------------------
+ * replaces every F.linear / nn.Linear on the path (conv_transformer.py:227,279;
+ * local_attention.py:178,141; fairseq/modules/transformer_layer.py:131-133).
+ * A [M,K] bf16 (row pitch lda), W [N,K] bf16 (row pitch ldw), bias [N] fp32 or NULL.
+ * y = A W^T + bias; ReLU if FBKST_EPI_RELU; then, if residual != NULL:
+ *   default            : y += residual[m, n]            (fp32, row pitch ldr)
+ *   FBKST_EPI_POSEMB   : y += residual[pos(m), n]  with m = b*remap_inner + t,
+ *                        pos = t < lengths[b] ? t+1 : 0   (sinusoidal table, row 0 = 0)
+ * out row is m, or the remapped row if FBKST_EPI_ROW_REMAP; out pitch ldo; dtype by flag.
+ * K % 8 == 0; lda, ldw % 8 == 0; all bases 16-byte aligned. */
+int fbkst_linear_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                      const float* residual, int64_t ldr, void* out, int64_t ldo, int M, int N,
+                      int K, int flags, int remap_inner, int remap_outer,
+                      const int32_t* lengths, fbkst_stream_t stream);
+
+/* ---- a8: LayerNorm over the last dim (eps 1e-5, affine) ----------------------------------
+ * replaces fairseq/modules/layer_norm.py:29-32 call sites (transformer_layer.py:108,126;
+ * conv_transformer.py:253-254).  x [M,D] fp32 -> y [M,D] bf16 or fp32.  D % 128 == 0, D<=2048 */
+int fbkst_layernorm(const float* x, const float* gamma, const float* beta, void* y, int out_dtype,
+                    int M, int D, float eps, fbkst_stream_t stream);
+
+/* ---- a7: self-attention core with key-padding mask and log distance penalty --------------
+ * replaces local_attention.py:115-139 (and the math of F.multi_head_attention_forward when
+ * log_penalty = 0).  qkv [L*B, 3D] bf16, row m = t*B+b, columns [q | k | v], q pre-scaled by
+ * head_dim^-0.5 (folded into the projection weights); heads of 64 channels.
+ * out [L*B, D] bf16.  lengths[B] int32: keys t >= lengths[b] are masked; query rows in tiles
+ * entirely beyond lengths[b] are written as 0.  scores - ln(max(1,|i-j|)) if log_penalty. */
+int fbkst_attention_fwd(const void* qkv, void* out, const int32_t* lengths, int L, int B, int H,
+                        int log_penalty, fbkst_stream_t stream);
+
+/* ---- a4: sinusoidal position table (row 0 = zeros) ---------------------------------------
+ * replaces fairseq/modules/sinusoidal_positional_embedding.py:36-58.  table [rows, D] fp32. */
+int fbkst_sinusoidal_table(float* table, int rows, int D, fbkst_stream_t stream);
+
+/* ---- a5: padding mask -----------------------------------------------------------------
+ * replaces conv_transformer.py:293-300.  mask [B, L] uint8 (1 = pad); any_pad[1] int32 is
+ * set non-zero if some element is padding (the reference returns None otherwise). */
+int fbkst_lengths_to_mask(const int32_t* lengths, uint8_t* mask, int32_t* any_pad, int B, int L,
+                          fbkst_stream_t stream);
+
+/* ---- a10 step 1: CTC argmax (+ probability of the arg-max label) --------------------------
+ * replaces conv_transformer.py:282-284 (softmax + per-utterance argmax().tolist()).
+ * logits [L*B, ldv] bf16 or fp32 (row m = t*B+b, V valid columns); labels[L*B] int32
+ * (-1 for t >= lengths[b]); top_prob[L*B] fp32 = softmax(logits)[label] (0 for padding), or
+ * NULL to skip the log-sum-exp (avg strategy).  Ties resolve to the lowest index. */
+int fbkst_ctc_argmax(const void* logits, int logits_dtype, int64_t ldv, const int32_t* lengths,
+                     int32_t* labels, float* top_prob, int L, int B, int V, fbkst_stream_t stream);
+
+/* ---- a10 step 2 + a11: run-length segmentation and per-frame pooling weights ----------------
+ * replaces conv_transformer.py:285-288 (groupby) and :385-426 (CTCCompressStrategy.*).
+ * seg_id[L*B] int32: index of the run frame (t,b) belongs to (-1 for padding);
+ * seg_start[L*B] int32: seg_start[s*B+b] = first frame of run s of utterance b (s < new length);
+ * weight[L*B] fp32: W[b,t,seg_id] (0 for padding); new_lengths[B] int32; max_new_len[1] int32.
+ * top_prob may be NULL for FBKST_CTC_AVG. */
+int fbkst_ctc_segment(const int32_t* labels, const float* top_prob, const int32_t* lengths,
+                      int strategy, int32_t* seg_id, int32_t* seg_start, float* weight,
+                      int32_t* new_lengths, int32_t* max_new_len, int L, int B,
+                      fbkst_stream_t stream);
+
+/* ---- a10 step 3: segmented weighted reduction (the reference's dense bmm) ------------------
+ * replaces conv_transformer.py:290-291.  x [L*B, D] fp32 -> out [L*B, D] fp32 (rows
+ * s*B+b; rows with new_lengths[b] <= s < max_new_len are written as 0; rows >= max_new_len
+ * are untouched).  D % 4 == 0. */
+int fbkst_ctc_compress(const float* x, const int32_t* seg_start, const float* weight,
+                       const int32_t* lengths, const int32_t* new_lengths,
+                       const int32_t* max_new_len, float* out, int L, int B, int D,
+                       fbkst_stream_t stream);
+
+/* ---- weight preparation (fp32 master parameters -> kernel operand formats) ----------------- */
+/* dst[i] = bf16(src[i] * scale) */
+int fbkst_cast_bf16(const float* src, void* dst, int64_t n, float scale, fbkst_stream_t stream);
+/* conv2 weight [C,C,3,3] fp32 -> [9][C][C] bf16 (tap, out, in) */
+int fbkst_prep_conv2_weight(const float* w, void* w_taps, int C, fbkst_stream_t stream);
+/* fc3 weight [D, C*F2] (flatten c*F2+f) fp32 -> [D, F2*C] (flatten f*C+c) bf16 */
+int fbkst_prep_fc3_weight(const float* w, void* w_perm, int D, int C, int F2,
+                          fbkst_stream_t stream);
+/* BatchNorm eval affine: scale = gamma / sqrt(var + eps), shift = beta - mean * scale */
+int fbkst_prep_bn_affine(const float* gamma, const float* beta, const float* mean,
+                         const float* var, float eps, float* scale, float* shift, int C,
+                         fbkst_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FBKST_B200_H_ */

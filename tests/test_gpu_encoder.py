@@ -1,0 +1,113 @@
+"""End-to-end parity of the drop-in encoder against golden outputs of the LIVE reference
+(tests/golden/*.pt, made by oracle/make_golden.py) and against the CPU oracle at larger sizes.
+bf16 path: encoder outputs within 2e-2 (relative to max |ref|); lengths / masks bit-exact."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from helpers import build_encoder, rel_err  # noqa: E402
+from oracle import encoder_oracle as O  # noqa: E402  (checker only)
+
+TOL = 2e-2
+
+
+def check_against(out, ref, lens_in, tol=TOL):
+    assert out.src_lengths.cpu().tolist() == ref["src_lengths"].tolist()
+    if ref["encoder_padding_mask"] is None:
+        assert out.encoder_padding_mask is None
+    else:
+        assert torch.equal(out.encoder_padding_mask.cpu(), ref["encoder_padding_mask"])
+    assert out.encoder_out.shape == ref["encoder_out"].shape
+    nl = ref["src_lengths"].tolist()
+    worst = 0.0
+    for b, n in enumerate(nl):  # valid positions
+        worst = max(worst, rel_err(out.encoder_out[:n, b], ref["encoder_out"][:n, b]))
+    assert worst < tol, worst
+    assert torch.isfinite(out.encoder_out).all()
+    return worst
+
+
+@pytest.mark.parametrize("name", ["enc_tiny_log.pt", "enc_tiny_nopen.pt"])
+def test_encoder_golden(golden_dir, name):
+    fx = torch.load(os.path.join(golden_dir, name), weights_only=False)
+    cfg = fx["cfg"]
+    for strategy, ref in fx["outputs"].items():
+        enc = build_encoder(dict(cfg, ctc_strategy=strategy), fx["state_dict"])
+        if "bump_labels" in fx:
+            hook = O.bump_hook(fx["bump_labels"], fx["bump_margin"])
+            enc.ctc_fc.register_forward_hook(lambda m, i, o: hook(o))
+        out = enc(fx["src_tokens"].cuda(), fx["src_lengths"].cuda(), return_all_hiddens=True)
+        check_against(out, ref, fx["src_lengths"])
+        assert len(out.encoder_states) == len(ref["encoder_states"])
+        for a, r in zip(out.encoder_states, ref["encoder_states"]):
+            assert a.shape == r.shape
+        if cfg.get("ctc_layer", 0) > 0:
+            assert out.ctc_out.shape == ref["ctc_out"].shape
+            n0 = int(fx["src_lengths"][0] + 3) // 4
+            assert torch.equal(out.ctc_padding_mask.cpu(), ref["ctc_padding_mask"])
+
+
+def test_state_dict_layout_matches_reference(golden_dir):
+    """Reference checkpoints load strict=True and our keys/shapes equal the reference's."""
+    for name in ["enc_tiny_log.pt", "enc_tiny_nopen.pt"]:
+        fx = torch.load(os.path.join(golden_dir, name), weights_only=False)
+        enc = build_encoder(fx["cfg"], fx["state_dict"])
+        ours = enc.state_dict()
+        assert set(ours.keys()) == set(fx["state_dict"].keys())
+        for k, v in fx["state_dict"].items():
+            assert tuple(ours[k].shape) == tuple(v.shape), k
+
+
+def test_encoder_cfg1_vs_oracle():
+    """BASELINE configs[0]: 6L d256 h4 ffn768, avg@4, batch 8 x 1000 x 40 (no penalty)."""
+    cfg = dict(embed_dim=256, ffn_dim=768, heads=4, layers=6, conv_channels=64, feat_dim=40,
+               vocab=105, distance_penalty=None, ctc_layer=4, ctc_strategy="avg")
+    sd = O.init_state_dict(cfg, seed=0)
+    x, lens = O.synthetic_batch([1000, 950, 900, 800, 700, 600, 500, 400], 40, seed=1234)
+    labels = O.synthetic_ctc_bump(250, 8, 105, seed=7)
+    hook = O.bump_hook(labels, 30.0)
+    ref = O.encoder_forward(sd, cfg, x, lens, ctc_logits_hook=hook)
+    enc = build_encoder(cfg, sd)
+    enc.ctc_fc.register_forward_hook(lambda m, i, o: hook(o))
+    out = enc(x.cuda(), lens.cuda())
+    check_against(out, ref, lens)
+
+
+@pytest.mark.parametrize("strategy", ["avg", "weighted", "softmax"])
+def test_encoder_big2_ragged_vs_oracle(strategy):
+    """EACL'21 model shape (d512 h8 ffn2048, log penalty) at reduced depth/batch, ragged batch with
+    odd conv lengths, all three strategies."""
+    cfg = dict(embed_dim=512, ffn_dim=2048, heads=8, layers=3, conv_channels=64, feat_dim=40,
+               vocab=1005, distance_penalty="log", ctc_layer=2, ctc_strategy=strategy)
+    sd = O.init_state_dict(cfg, seed=1)
+    x, lens = O.synthetic_batch([601, 598, 411, 203], 40, seed=77)
+    labels = O.synthetic_ctc_bump(151, 4, 1005, seed=9)
+    hook = O.bump_hook(labels, 30.0)
+    ref = O.encoder_forward(sd, cfg, x, lens, ctc_logits_hook=hook)
+    enc = build_encoder(cfg, sd)
+    enc.ctc_fc.register_forward_hook(lambda m, i, o: hook(o))
+    out = enc(x.cuda(), lens.cuda())
+    check_against(out, ref, lens)
+
+
+def test_reorder_and_non_torchscript(golden_dir):
+    fx = torch.load(os.path.join(golden_dir, "enc_tiny_log.pt"), weights_only=False)
+    enc = build_encoder(fx["cfg"], fx["state_dict"])
+    net_input = dict(src_tokens=fx["src_tokens"].cuda(), src_lengths=fx["src_lengths"].cuda(),
+                     prev_output_tokens=torch.zeros(3, 5), transcript_prev_output_tokens=None)
+    out = enc.forward_non_torchscript(net_input)
+    order = torch.tensor([2, 0, 0, 1], device="cuda")
+    re = enc.reorder_encoder_out(out, order)
+    assert re.encoder_out.shape[1] == 4
+    assert torch.equal(re.encoder_out[:, 0], out.encoder_out[:, 2])
+    assert enc.output_batch_first is False
+
+
+def test_training_mode_raises(golden_dir):
+    fx = torch.load(os.path.join(golden_dir, "enc_tiny_log.pt"), weights_only=False)
+    enc = build_encoder(fx["cfg"], fx["state_dict"]).train()
+    with pytest.raises(NotImplementedError):
+        enc(fx["src_tokens"].cuda(), fx["src_lengths"].cuda())

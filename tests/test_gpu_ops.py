@@ -1,0 +1,264 @@
+"""GPU parity of every kernel, called through the C ABI (fbkst_b200.ops -> ctypes), against the
+CPU oracle / golden vectors made from the live reference, or a plain fp32 PyTorch formula.
+
+Tolerances (BASELINE.json north_star): integer outputs bit-exact; bf16-path floats 2e-2
+relative to the tensor's max magnitude; fp32 kernels 1e-3 or tighter."""
+import math
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import encoder_oracle as O  # noqa: E402  (checker only)
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def rel_err(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+
+
+def bf(x):
+    return x.to(torch.bfloat16)
+
+
+# ------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 128), (300, 512, 512), (1000, 1536, 512),
+                                   (77, 200, 640), (513, 2048, 512), (640, 512, 2048), (130, 1005, 256)])
+def test_linear_plain(M, N, K):
+    from fbkst_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    a = bf(torch.randn(M, K, generator=g)).to(dev())
+    w = bf(torch.randn(N, K, generator=g) / math.sqrt(K)).to(dev())
+    bias = torch.randn(N, generator=g).to(dev())
+    ref = a.float() @ w.float().t() + bias
+    out = ops.linear(a, w, bias, out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    assert out.shape == (M, N)
+    e = rel_err(out, ref)
+    assert e < 1e-4, (M, N, K, e)
+    out = ops.linear(a, w, bias, relu=True)
+    e = rel_err(out.float(), torch.relu(ref))
+    assert e < 1e-2, (M, N, K, e)
+
+
+def test_linear_residual_remap_posemb():
+    from fbkst_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    B, L, K, N = 3, 50, 640, 256
+    a = bf(torch.randn(B * L, K, generator=g)).to(dev())
+    w = bf(torch.randn(N, K, generator=g) / math.sqrt(K)).to(dev())
+    bias = torch.randn(N, generator=g).to(dev())
+    res = torch.randn(B * L, N, generator=g).to(dev())
+    ref = a.float() @ w.float().t() + bias
+    out = ops.linear(a, w, bias, residual=res, out_dtype=torch.float32)
+    assert rel_err(out, ref + res) < 1e-4
+    # fc3 mode: rows (b, t) -> (t, b), ReLU, + sinusoidal position
+    lengths = torch.tensor([50, 33, 7], dtype=torch.int32, device=dev())
+    table = ops.sinusoidal_table(L + 1, N, dev())
+    assert rel_err(table, O.sinusoidal_table(L + 1, N)) < 1e-5
+    out = ops.linear(a, w, bias, relu=True, out_dtype=torch.float32, remap=(L, B),
+                     posemb=(table, lengths))
+    pe = O.positional_embedding(lengths.cpu().long(), N).to(dev())  # B x L x N
+    exp = (torch.relu(ref).view(B, L, N) + pe).transpose(0, 1).reshape(L * B, N)
+    assert rel_err(out, exp) < 1e-4
+
+
+# ------------------------------------------------------------------------------- LayerNorm
+@pytest.mark.parametrize("D", [128, 256, 512, 1024])
+def test_layernorm(D):
+    from fbkst_b200 import ops
+    g = torch.Generator().manual_seed(D)
+    x = (torch.randn(333, D, generator=g) * 2 + 0.5).to(dev())
+    gamma, beta = torch.randn(D, generator=g).to(dev()), torch.randn(D, generator=g).to(dev())
+    ref = torch.nn.functional.layer_norm(x, (D,), gamma, beta, 1e-5)
+    assert rel_err(ops.layernorm(x, gamma, beta, out_dtype=torch.float32), ref) < 1e-5
+    assert rel_err(ops.layernorm(x, gamma, beta).float(), ref) < 1e-2
+
+
+# ------------------------------------------------------------------------------------ CMVN
+def test_cmvn_golden(golden_dir):
+    from fbkst_b200 import ops
+    cases = torch.load(os.path.join(golden_dir, "cmvn.pt"), weights_only=False)
+    for c in cases:
+        x = c["x"]
+        T, Fd = x.shape
+        xb = torch.zeros(2, T + 5, Fd)
+        xb[0, :T] = x
+        xb[1, : T // 2 + 1] = x[: T // 2 + 1]
+        lengths = torch.tensor([T, T // 2 + 1], dtype=torch.int32)
+        y = ops.cmvn(xb.to(dev()), lengths.to(dev())).cpu()
+        assert rel_err(y[0, :T], c["y"]) < 1e-4
+        assert y[0, T:].abs().max() == 0 and y[1, T // 2 + 1:].abs().max() == 0
+        if T // 2 + 1 >= 2:
+            assert rel_err(y[1, : T // 2 + 1], O.cmvn(x[: T // 2 + 1])) < 1e-4
+
+
+# ----------------------------------------------------------------------------------- convs
+def conv_ref(x, w, b, gamma, beta, mean, var):
+    y = torch.nn.functional.conv2d(x, w, b, stride=2, padding=1)
+    return torch.nn.functional.batch_norm(torch.relu(y), mean, var, gamma, beta, False, 0.0, 1e-5)
+
+
+@pytest.mark.parametrize("B,T,Fd,C", [(2, 61, 40, 64), (3, 100, 40, 64), (2, 37, 80, 64), (2, 45, 80, 128)])
+def test_conv_stack(B, T, Fd, C):
+    """conv1 (SIMT) then conv2 (TMA implicit GEMM, tcgen05) vs F.conv2d+ReLU+BN (eval)."""
+    from fbkst_b200 import ops
+    g = torch.Generator().manual_seed(B * T + Fd)
+    x = torch.randn(B, T, Fd, generator=g)
+    w1 = torch.randn(C, 1, 3, 3, generator=g) * 0.6
+    w2 = torch.randn(C, C, 3, 3, generator=g) * (1.0 / math.sqrt(9 * C))
+    b1, b2 = torch.randn(C, generator=g) * 0.1, torch.randn(C, generator=g) * 0.1
+    bn = [(1 + 0.1 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g),
+           0.1 * torch.randn(C, generator=g), torch.rand(C, generator=g) + 0.5) for _ in range(2)]
+    r1 = conv_ref(x.unsqueeze(1), w1, b1, *bn[0])
+    d = dev()
+    s0 = ops.prep_bn_affine(*[t.to(d) for t in bn[0]])
+    s1 = ops.prep_bn_affine(*[t.to(d) for t in bn[1]])
+    y1 = ops.conv1_relu_bn(x.to(d), w1.reshape(C, 9).contiguous().to(d), b1.to(d), *s0)
+    assert y1.shape == (B, (T + 1) // 2, (Fd + 1) // 2, C)
+    e1 = rel_err(y1.float().permute(0, 3, 1, 2), r1)
+    assert e1 < 1e-2, e1
+    # conv2 reference consumes OUR bf16 conv1 output so the test isolates conv2
+    r2 = conv_ref(y1.float().permute(0, 3, 1, 2).cpu(), w2.bfloat16().float(), b2, *bn[1])
+    y2 = ops.conv2_relu_bn(y1, ops.prep_conv2_weight(w2.to(d)), b2.to(d), *s1)
+    torch.cuda.synchronize()
+    assert y2.shape == (B, r2.shape[2], r2.shape[3], C)
+    e2 = rel_err(y2.float().permute(0, 3, 1, 2), r2)
+    assert e2 < 1e-2, e2
+
+
+def test_fc3_weight_permutation():
+    from fbkst_b200 import ops
+    D, C, F2 = 128, 64, 10
+    w = torch.randn(D, C * F2)
+    p = ops.prep_fc3_weight(w.to(dev()), C, F2).float().cpu()
+    exp = w.view(D, C, F2).permute(0, 2, 1).reshape(D, F2 * C).bfloat16().float()
+    assert torch.equal(p, exp)
+
+
+# ------------------------------------------------------------------------------- attention
+def attn_ref(qkv, lengths, L, B, H, log_penalty):
+    """local_attention.py:115-139 in fp32 on (already scaled) q."""
+    D = H * 64
+    q, k, v = qkv.float().view(L, B, 3, H, 64).permute(2, 1, 3, 0, 4)  # [3] B H L 64
+    s = q @ k.transpose(-1, -2)
+    key_pad = torch.arange(L, device=qkv.device)[None, :] >= lengths[:, None]
+    s = s.masked_fill(key_pad[:, None, None, :], float("-inf"))
+    if log_penalty:
+        i = torch.arange(L, device=qkv.device)
+        s = s - torch.clamp(torch.log((i[:, None] - i[None, :]).abs().float()), min=0)
+    o = torch.softmax(s, -1) @ v  # B H L 64
+    return o.permute(2, 0, 1, 3).reshape(L * B, D)
+
+
+@pytest.mark.parametrize("L,B,H,lens,pen", [
+    (128, 2, 2, [128, 128], True), (100, 3, 2, [100, 64, 5], True), (375, 2, 8, [375, 201], True),
+    (300, 2, 4, [300, 129], False), (700, 1, 2, [700], True)])
+def test_attention(L, B, H, lens, pen):
+    from fbkst_b200 import ops
+    g = torch.Generator().manual_seed(L + B)
+    qkv = bf(torch.randn(L * B, 3 * H * 64, generator=g) * 0.7).to(dev())
+    lengths = torch.tensor(lens, dtype=torch.int32, device=dev())
+    out = ops.attention(qkv, lengths, L, B, H, pen).float().view(L, B, H * 64)
+    torch.cuda.synchronize()
+    ref = attn_ref(qkv, lengths, L, B, H, pen).view(L, B, H * 64)
+    for b, n in enumerate(lens):  # only valid query rows are defined by the reference
+        e = rel_err(out[:n, b], ref[:n, b])
+        assert e < 2e-2, (b, n, e)
+    assert torch.isfinite(out).all()
+
+
+# ------------------------------------------------------------------------------------- CTC
+def run_ctc(x, logits, lengths, strategy):
+    from fbkst_b200 import ops
+    L, B, V = logits.shape
+    D = x.shape[-1]
+    d = dev()
+    lg = logits.to(d).reshape(L * B, V)
+    ln = lengths.to(torch.int32).to(d)
+    labels, prob = ops.ctc_argmax(lg, ln, L, B, V, want_prob=strategy != "avg")
+    seg_id, seg_start, weight, new_len, max_new = ops.ctc_segment(labels, prob, ln, strategy, L, B)
+    out = ops.ctc_compress(x.to(d).reshape(L * B, D).contiguous(), seg_start, weight, ln, new_len,
+                           max_new, L, B)
+    nl = new_len.cpu()
+    L2 = int(max_new.item())
+    return out[: L2 * B].view(L2, B, D).cpu(), nl.long(), labels.view(L, B).cpu(), seg_id.view(L, B).cpu()
+
+
+def test_ctc_compress_golden(golden_dir):
+    cases = torch.load(os.path.join(golden_dir, "ctc_compress.pt"), weights_only=False)
+    for c in cases:
+        out, nl, labels, seg_id = run_ctc(c["x"], c["logits"], c["lengths"], c["strategy"])
+        assert torch.equal(nl, c["new_lengths"].long()), c["name"]
+        segs = O.ctc_segments(c["logits"], c["lengths"])
+        for b, sg in enumerate(segs):  # labels and segment boundaries bit-exact
+            exp_lab = [lab for lab, run in sg for _ in range(run)]
+            exp_seg = [s for s, (lab, run) in enumerate(sg) for _ in range(run)]
+            n = int(c["lengths"][b])
+            assert labels[:n, b].tolist() == exp_lab, c["name"]
+            assert seg_id[:n, b].tolist() == exp_seg, c["name"]
+            assert (labels[n:, b] == -1).all() and (seg_id[n:, b] == -1).all()
+        assert out.shape == c["out"].shape, c["name"]
+        assert rel_err(out, c["out"]) < 1e-5, c["name"]
+
+
+def test_ctc_argmax_bf16_unaligned_and_ties():
+    """bf16 logits with an odd V (rows not 16-byte aligned) and exact ties -> lowest index."""
+    from fbkst_b200 import ops
+    L, B, V = 9, 3, 1005
+    g = torch.Generator().manual_seed(0)
+    logits = bf(torch.randn(L, B, V, generator=g))
+    logits[0, 0, 17] = logits[0, 0, 900] = 9.0      # tie -> 17
+    logits[1, 1, 1004] = 11.0                       # last column
+    logits[2, 2, 0] = 12.0                          # first column
+    lengths = torch.tensor([9, 9, 4], dtype=torch.int32)
+    labels, prob = ops.ctc_argmax(logits.to(dev()).view(L * B, V), lengths.to(dev()), L, B, V)
+    labels = labels.view(L, B).cpu()
+    ref = logits.float().argmax(-1)
+    for b in range(B):
+        n = int(lengths[b])
+        assert labels[:n, b].tolist() == ref[:n, b].tolist()
+        assert (labels[n:, b] == -1).all()
+    assert labels[0, 0] == 17 and labels[1, 1] == 1004 and labels[2, 2] == 0
+    p_ref = torch.softmax(logits.float(), -1).max(-1).values
+    p = prob.view(L, B).cpu()
+    assert rel_err(p[:4], p_ref[:4]) < 1e-4
+
+
+def test_ctc_full_size_properties():
+    """cfg2-sized compression (L=375, B=64, V=8005): size-independent properties --
+    new lengths == number of label changes, every column of W sums to 1 (out of a constant
+    input is that constant), padding rows are exactly 0."""
+    from fbkst_b200 import ops
+    L, B, V, D = 375, 64, 8005, 512
+    d = dev()
+    labels_plan = O.synthetic_ctc_bump(L, B, V, seed=3)
+    g = torch.Generator().manual_seed(1)
+    lens = torch.randint(200, L + 1, (B,), generator=g).sort(descending=True).values
+    lens[0] = L
+    logits = torch.randn(L, B, V, generator=g, dtype=torch.float32).bfloat16()
+    logits = O.bump_hook(labels_plan, 8.0)(logits.float()).bfloat16()
+    x = torch.ones(L * B, D, device=d) * 1.5
+    ln = lens.to(torch.int32).to(d)
+    for strategy in ("avg", "weighted", "softmax"):
+        lab, prob = ops.ctc_argmax(logits.to(d).view(L * B, V), ln, L, B, V, want_prob=strategy != "avg")
+        seg_id, seg_start, weight, new_len, max_new = ops.ctc_segment(lab, prob, ln, strategy, L, B)
+        out = ops.ctc_compress(x, seg_start, weight, ln, new_len, max_new, L, B)
+        lab = lab.view(L, B).cpu()
+        nl = new_len.cpu()
+        L2 = int(max_new.item())
+        out = out[: L2 * B].view(L2, B, D).cpu()
+        for b in range(0, B, 7):
+            n = int(lens[b])
+            assert lab[:n, b].tolist() == labels_plan[:n, b].tolist()
+            changes = 1 + int((lab[1:n, b] != lab[: n - 1, b]).sum())
+            assert int(nl[b]) == changes
+            assert torch.allclose(out[: changes, b], torch.full((changes, D), 1.5), atol=1e-5)
+            assert out[changes:, b].abs().max() == 0
+        assert L2 == int(nl.max())
