@@ -1,51 +1,5 @@
 """Shared helpers for the GPU parity tests (test infrastructure)."""
-import argparse
-
-import torch
-
-
-class DictStub:
-    """len()-only stand-in for fairseq's Dictionary (the encoder reads only ``len(dictionary)``)."""
-
-    def __init__(self, n):
-        self.n = n
-
-    def __len__(self):
-        return self.n
-
-
-def make_args(cfg):
-    """Namespace with the fields the reference ctor reads (conv_transformer.py:134-193)."""
-    a = argparse.Namespace()
-    a.encoder_embed_dim = cfg["embed_dim"]
-    a.encoder_ffn_embed_dim = cfg["ffn_dim"]
-    a.encoder_attention_heads = cfg["heads"]
-    a.encoder_layers = cfg["layers"]
-    a.encoder_convolutions = "[(%d, 3, 3)] * 2" % cfg.get("conv_channels", 64)
-    a.input_feat_per_channel = cfg["feat_dim"]
-    a.distance_penalty = "log" if cfg.get("distance_penalty", "log") == "log" else False
-    a.attn_2d = False
-    a.ctc_compress_out = cfg.get("ctc_layer", 0) > 0
-    a.ctc_compress_strategy = cfg.get("ctc_strategy", "avg")
-    a.ctc_encoder_layer = cfg.get("ctc_layer", 0)
-    a.criterion = "ctc_multi_loss"
-    a.max_source_positions = 100000
-    a.encoder_layerdrop = 0.0
-    a.dropout = cfg.get("dropout", 0.1)
-    a.encoder_normalize_before = True
-    a.encoder_learned_pos = False
-    a.no_token_positional_embeddings = False
-    a.layernorm_embedding = False
-    return a
-
-
-def build_encoder(cfg, state_dict=None, device="cuda:0"):
-    from fbkst_b200.encoder import ConvolutionalTransformerEncoder
-    enc = ConvolutionalTransformerEncoder(make_args(cfg), DictStub(cfg["vocab"]),
-                                          audio_features=cfg["feat_dim"])
-    if state_dict is not None:
-        enc.load_state_dict(state_dict, strict=True)
-    return enc.to(device).eval()
+from fbkst_b200.config import DictStub, build_encoder, make_args  # noqa: F401
 
 
 def rel_err(a, b):
