@@ -1,12 +1,17 @@
 // Fused self-attention core for the ST encoder (reference: local_attention.py:115-139 with
-// LogPenalty conv_transformer_layer.py:22-27): flash-style streaming softmax with
-//   S = Q K^T      tcgen05.mma, both operands K-major in smem (TMA, 128B swizzle), S in TMEM
-//   P = softmax    128 threads, one query row each: key-padding mask from lengths, the
-//                  log-distance penalty as a 255-entry per-tile LUT in log2 domain, fp32 exp2
-//   O += P V       tcgen05.mma, P written to smem as bf16 (K-major), V consumed MN-major
-// One CTA = one (128-query tile, utterance, head); 2 CTAs per SM interleave MMA and softmax.
+// LogPenalty conv_transformer_layer.py:22-27): flash-style streaming softmax on tcgen05.
 //
-//   warp 0     TMA producer (Q once, K double-buffered, V single-buffered)
+//   S_j = Q K_j^T   tcgen05.mma (M128 x N64 x K64), operands K-major in smem (TMA, 128B swizzle),
+//                   S double-buffered in TMEM so QK of tile j+1/j+2 runs under the softmax of tile j
+//   P_j = softmax   128 threads, one query row each, the 64 scores of the row held in registers:
+//                   key-padding mask (last tile only), log-distance penalty from a per-tile LUT in
+//                   log2 domain (4 shifted copies -> aligned LDS.128), lazy max (O is rescaled only
+//                   when the running max grows by more than 2^8), exp2 in fp32
+//   O  += P_j V_j   tcgen05.mma (M128 x N64 x K64), P as bf16 in swizzled smem (double-buffered),
+//                   V consumed MN-major straight from its TMA tile
+// One CTA = one (128-query tile, utterance, head); 2 CTAs per SM.
+//
+//   warp 0     TMA producer (Q once; K 3-stage, V 2-stage rings)
 //   warp 1     TMEM allocator + MMA issuer
 //   warps 2-5  softmax / correction / output (TMEM lane quarter = warp % 4)
 #include <math.h>
@@ -16,22 +21,44 @@
 
 namespace fbkst {
 
-constexpr int AT_BM = 128;   // queries per CTA
-constexpr int AT_BN = 128;   // keys per tile
-constexpr int AT_HD = 64;    // head dim (all reference archs: embed_dim / heads = 64)
-constexpr int AT_TILE = AT_BM * AT_HD * 2;  // 16 KB
-constexpr int AT_SMEM = AT_TILE /*Q*/ + 2 * AT_TILE /*K*/ + AT_TILE /*V*/ + 2 * AT_TILE /*P*/ +
-                        2 * 256 * 4 /*LUT*/ + 128 /*barriers*/ + 1024 /*align*/;
+constexpr int AT_BM = 128;  // queries per CTA
+constexpr int AT_BN = 64;   // keys per tile
+constexpr int AT_HD = 64;   // head dim (all reference archs: embed_dim / heads = 64)
+constexpr int AT_QB = AT_BM * AT_HD * 2;  // 16 KB
+constexpr int AT_KB = AT_BN * AT_HD * 2;  // 8 KB
+constexpr int AT_KST = 3, AT_VST = 2;
+constexpr int AT_LCP = 200;      // floats per LUT copy (192 used; 200 keeps the 4 copies on distinct banks)
+constexpr int AT_LUT = 4 * AT_LCP;  // floats per LUT buffer (4 shifted copies)
+constexpr int AT_SMEM = AT_QB + AT_KST * AT_KB + AT_VST * AT_KB + 2 * AT_QB /*P x2*/ +
+                        2 * AT_LUT * 4 + 256 /*barriers*/ + 1024 /*align*/;
 constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
+}
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 template <int LOGPEN>
 __global__ void __launch_bounds__(192, 2)
-    attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ out,
-                         const int* __restrict__ lengths, int L, int B, int H) {
+    attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                         __nv_bfloat16* __restrict__ out, const int* __restrict__ lengths, int L, int B,
+                         int H) {
   const int D = H * AT_HD;
   const int q0 = blockIdx.x * AT_BM;
   const int b = blockIdx.y / H, h = blockIdx.y - b * H;
@@ -53,38 +80,41 @@ __global__ void __launch_bounds__(192, 2)
   }
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  // 1024-byte alignment by pointer arithmetic (keeps the shared address space visible to ptxas)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;
-  uint8_t* sK = sQ + AT_TILE;      // 2 stages
-  uint8_t* sV = sK + 2 * AT_TILE;  // 1 stage
-  uint8_t* sP = sV + AT_TILE;      // 128 x 128 bf16 as two K-major 64-column halves
-  float* sLut = reinterpret_cast<float*>(sP + 2 * AT_TILE);  // 2 x 256
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sLut + 512);
+  uint8_t* sK = sQ + AT_QB;            // AT_KST stages
+  uint8_t* sV = sK + AT_KST * AT_KB;   // AT_VST stages
+  uint8_t* sP = sV + AT_VST * AT_KB;   // 2 x [128 rows x 128 B]
+  float* sLut = reinterpret_cast<float*>(sP + 2 * AT_QB);  // 2 x AT_LUT
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sLut + 2 * AT_LUT);
   uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;   // [2]
-  uint64_t* k_empty = bars + 3;  // [2]
-  uint64_t* v_full = bars + 5;
-  uint64_t* v_empty = bars + 6;
-  uint64_t* s_full = bars + 7;
-  uint64_t* p_full = bars + 8;
-  uint64_t* pv_done = bars + 9;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* k_full = bars + 1;    // [3]
+  uint64_t* k_empty = bars + 4;   // [3]
+  uint64_t* v_full = bars + 7;    // [2]
+  uint64_t* v_empty = bars + 9;   // [2]
+  uint64_t* s_full = bars + 11;   // [2]
+  uint64_t* p_full = bars + 13;   // [2]
+  uint64_t* pv_done = bars + 15;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
   const int n_kv = (len + AT_BN - 1) / AT_BN;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
     mbar_init(q_full, 1);
-    mbar_init(&k_full[0], 1);
-    mbar_init(&k_full[1], 1);
-    mbar_init(&k_empty[0], 1);
-    mbar_init(&k_empty[1], 1);
-    mbar_init(v_full, 1);
-    mbar_init(v_empty, 1);
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
-    mbar_init(pv_done, 1);
+    for (int s = 0; s < AT_KST; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+      mbar_init(&s_full[s], 1);
+      mbar_init(&p_full[s], 128);
+      mbar_init(&pv_done[s], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -95,22 +125,21 @@ __global__ void __launch_bounds__(192, 2)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base;        // 128 columns
-  const uint32_t tmem_O = tmem_base + 128;  // 64 columns
+  const uint32_t tmem_O = tmem_base + 128;  // S[0] = +0, S[1] = +64, O = +128 (64 columns each)
 
   if (warp == 0) {
     if (lane == 0) {
       const int cq = h * AT_HD, ck = D + h * AT_HD, cv = 2 * D + h * AT_HD;
-      mbar_arrive_expect_tx(q_full, AT_TILE);
-      tma_load_3d(sQ, &tmQKV, q_full, cq, b, q0);
+      mbar_arrive_expect_tx(q_full, AT_QB);
+      tma_load_3d(sQ, &tmQ, q_full, cq, b, q0);
       for (int j = 0; j < n_kv; ++j) {
-        const int ks = j & 1;
-        mbar_wait(&k_empty[ks], ((j >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&k_full[ks], AT_TILE);
-        tma_load_3d(sK + ks * AT_TILE, &tmQKV, &k_full[ks], ck, b, j * AT_BN);
-        mbar_wait(v_empty, (j & 1) ^ 1);
-        mbar_arrive_expect_tx(v_full, AT_TILE);
-        tma_load_3d(sV, &tmQKV, v_full, cv, b, j * AT_BN);
+        const int ks = j % AT_KST, vs = j & 1;
+        mbar_wait(&k_empty[ks], ((j / AT_KST) & 1) ^ 1);
+        mbar_arrive_expect_tx(&k_full[ks], AT_KB);
+        tma_load_3d(sK + ks * AT_KB, &tmKV, &k_full[ks], ck, b, j * AT_BN);
+        mbar_wait(&v_empty[vs], ((j >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&v_full[vs], AT_KB);
+        tma_load_3d(sV + vs * AT_KB, &tmKV, &v_full[vs], cv, b, j * AT_BN);
       }
     }
   } else if (warp == 1) {
@@ -120,136 +149,156 @@ __global__ void __launch_bounds__(192, 2)
       const uint64_t qdesc = desc_kmajor_sw128(smem_u32(sQ));
       mbar_wait(q_full, 0);
       auto issue_qk = [&](int j) {
-        const int ks = j & 1;
-        mbar_wait(&k_full[ks], (j >> 1) & 1);
+        const int ks = j % AT_KST;
+        mbar_wait(&k_full[ks], (j / AT_KST) & 1);
         tc_fence_after();
-        const uint64_t kdesc = desc_kmajor_sw128(smem_u32(sK + ks * AT_TILE));
+        const uint64_t kdesc = desc_kmajor_sw128(smem_u32(sK + ks * AT_KB));
+        const uint32_t d_tmem = tmem_base + (j & 1) * AT_BN;
 #pragma unroll
         for (int k = 0; k < AT_HD / 16; ++k)
-          umma_bf16_ss(tmem_S, qdesc + 2 * k, kdesc + 2 * k, IDESC_QK, k != 0);
-        umma_commit(s_full);
+          umma_bf16_ss(d_tmem, qdesc + 2 * k, kdesc + 2 * k, IDESC_QK, k != 0);
+        umma_commit(&s_full[j & 1]);
         umma_commit(&k_empty[ks]);
       };
       issue_qk(0);
+      if (n_kv > 1) issue_qk(1);
       for (int j = 0; j < n_kv; ++j) {
-        mbar_wait(p_full, j & 1);  // S_j consumed, P_j in smem, O rescaled
-        mbar_wait(v_full, j & 1);
+        const int pb = j & 1;
+        mbar_wait(&p_full[pb], (j >> 1) & 1);  // S_j consumed, P_j in smem, O rescaled if needed
+        mbar_wait(&v_full[pb], (j >> 1) & 1);
         tc_fence_after();
+        const uint32_t pa = smem_u32(sP + pb * AT_QB), va = smem_u32(sV + pb * AT_KB);
 #pragma unroll
-        for (int kk = 0; kk < AT_BN / 16; ++kk) {
-          const uint64_t pdesc =
-              desc_kmajor_sw128(smem_u32(sP + (kk >> 2) * AT_TILE)) + 2 * (kk & 3);
-          const uint64_t vdesc = desc_mnmajor_sw128(smem_u32(sV + kk * 2048), AT_TILE);
-          umma_bf16_ss(tmem_O, pdesc, vdesc, IDESC_PV, (j | kk) != 0);
-        }
-        umma_commit(pv_done);
-        umma_commit(v_empty);
-        if (j + 1 < n_kv) issue_qk(j + 1);
+        for (int kk = 0; kk < AT_BN / 16; ++kk)
+          umma_bf16_ss(tmem_O, desc_kmajor_sw128(pa) + 2 * kk, desc_mnmajor_sw128(va + kk * 2048, AT_KB),
+                       IDESC_PV, (j | kk) != 0);
+        umma_commit(&pv_done[pb]);
+        umma_commit(&v_empty[pb]);
+        if (j + 2 < n_kv) issue_qk(j + 2);
       }
     }
   } else {
     // ---- softmax / correction / output: thread <-> query row
     const int q = (warp & 3) * 32 + lane;  // row in the tile == TMEM lane
-    const int st = threadIdx.x - 64;       // 0..127, LUT writer index
+    const int st = threadIdx.x - 64;       // 0..127
     const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    float m = -INFINITY, l = 0.0f;
+    const uint32_t lut_base = smem_u32(sLut);
+    const uint32_t p_base = smem_u32(sP) + q * 128;
+    const int swz = q & 7;
+    // LUT copy s holds entry (idx + s); thread reads copy (127-q)&3 at aligned offset (127-q)&~3
+    const int lsh = (127 - q) & 3;
+    const uint32_t lut_off = (uint32_t)(lsh * AT_LCP + ((127 - q) & ~3)) * 4;
+    float m_used = -INFINITY, l = 0.0f;
     for (int j = 0; j < n_kv; ++j) {
+      const int sb = j & 1;
       const int k0 = j * AT_BN;
       const int nvalid = min(AT_BN, len - k0);
-      float* lut = sLut + (j & 1) * 256;
-      if (LOGPEN) {
+      if (LOGPEN) {  // penalty LUT of this tile: entry e <-> key-minus-query offset (e - 127)
         const int delta = k0 - q0;
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          const int idx = st + r * 128;
+        float* lut = sLut + sb * AT_LUT;
+        for (int e = st; e < AT_LUT; e += 128) {
+          const int s = e / AT_LCP, idx = e - s * AT_LCP + s;
           const int d = abs(delta + idx - 127);
-          lut[idx] = (d > 1) ? __log2f((float)d) : 0.0f;
+          lut[e] = (d > 1) ? __log2f((float)d) : 0.0f;
         }
       }
-      mbar_wait(s_full, j & 1);
+      mbar_wait(&s_full[sb], (j >> 1) & 1);
       tc_fence_after();
-      // pass 1: row max of the raw scores over the valid keys
+      uint32_t s0[32], s1[32];
+      tmem_ld32(tmem_base + lane_addr + sb * AT_BN, s0);
+      tmem_ld32(tmem_base + lane_addr + sb * AT_BN + 32, s1);
+      tmem_ld_wait();
       float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem_S + lane_addr + c * 32, v);
-        tmem_ld_wait();
+      if (nvalid == AT_BN) {
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj)
-          if (c * 32 + jj < nvalid) mx = fmaxf(mx, __uint_as_float(v[jj]));
+        for (int c = 0; c < 32; ++c)
+          mx = fmaxf(mx, fmaxf(__uint_as_float(s0[c]), __uint_as_float(s1[c])));
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          if (c < nvalid) mx = fmaxf(mx, __uint_as_float(s0[c]));
+          if (c + 32 < nvalid) mx = fmaxf(mx, __uint_as_float(s1[c]));
+        }
       }
-      const float m_new = fmaxf(m, mx * kLog2e);
-      const float alpha = exp2f(m - m_new);
-      if (j > 0) {
-        mbar_wait(pv_done, (j - 1) & 1);  // O_{j-1} final, P smem free
-        tc_fence_after();
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          uint32_t v[32];
-          tmem_ld32(tmem_O + lane_addr + c * 32, v);
+      const float m_new = fmaxf(m_used, mx * kLog2e);
+      // lazy rescale: only when some row of the warp grew by more than 2^8 (always at j == 0)
+      const bool grow = m_new > m_used + kRescaleThreshold;
+      if (__any_sync(0xffffffffu, grow)) {
+        const float m_next = grow ? m_new : m_used;
+        if (j > 0) {
+          const float alpha = ex2(m_used - m_next);
+          mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);  // O_{j-1} final
+          tc_fence_after();
+          uint32_t o0[32], o1[32];
+          tmem_ld32(tmem_O + lane_addr, o0);
+          tmem_ld32(tmem_O + lane_addr + 32, o1);
           tmem_ld_wait();
 #pragma unroll
-          for (int jj = 0; jj < 32; ++jj) v[jj] = __float_as_uint(__uint_as_float(v[jj]) * alpha);
-          tmem_st32(tmem_O + lane_addr + c * 32, v);
-        }
-        tmem_st_wait();
-      }
-      if (LOGPEN) named_bar_sync(1, 128);  // LUT_j complete
-      // pass 2: p = exp2(s*log2e - pen2 - m_new), P -> smem (bf16, swizzled K-major)
-      float sum = 0.0f;
-      const float* lrow = lut + (127 - q);
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem_S + lane_addr + c * 32, v);
-        tmem_ld_wait();
-        uint32_t pk[16];
-#pragma unroll
-        for (int jj = 0; jj < 32; jj += 2) {
-          float t0 = fmaf(__uint_as_float(v[jj]), kLog2e, -m_new);
-          float t1 = fmaf(__uint_as_float(v[jj + 1]), kLog2e, -m_new);
-          if (LOGPEN) {
-            t0 -= lrow[c * 32 + jj];
-            t1 -= lrow[c * 32 + jj + 1];
+          for (int c = 0; c < 32; ++c) {
+            o0[c] = __float_as_uint(__uint_as_float(o0[c]) * alpha);
+            o1[c] = __float_as_uint(__uint_as_float(o1[c]) * alpha);
           }
-          const float p0 = (c * 32 + jj < nvalid) ? exp2f(t0) : 0.0f;
-          const float p1 = (c * 32 + jj + 1 < nvalid) ? exp2f(t1) : 0.0f;
-          sum += p0 + p1;
-          pk[jj >> 1] = pack_bf16x2(p0, p1);
+          tmem_st32(tmem_O + lane_addr, o0);
+          tmem_st32(tmem_O + lane_addr + 32, o1);
+          tmem_st_wait();
+          l *= alpha;
         }
-        uint8_t* prow = sP + (c >> 1) * AT_TILE + q * 128;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int ch = ((c & 1) * 4 + g) ^ (q & 7);
-          *reinterpret_cast<uint4*>(prow + ch * 16) =
-              make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-        }
+        m_used = m_next;
       }
-      l = l * alpha + sum;
-      m = m_new;
+      if (j >= 2) mbar_wait(&pv_done[sb], ((j >> 1) & 1) ^ 1);  // P buffer sb free (PV_{j-2} done)
+      if (LOGPEN) named_bar_sync(1, 128);                        // LUT_j complete
+      const uint32_t la = lut_base + sb * (AT_LUT * 4) + lut_off;
+      const uint32_t pa = p_base + sb * AT_QB;
+      const float negm = -m_used;
+      float sum = 0.0f;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {  // 8 keys -> one 16-byte chunk of the P row
+        const uint32_t* sv = (g < 4) ? s0 : s1;
+        const int o = (g & 3) * 8;
+        float t[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) t[e] = fmaf(__uint_as_float(sv[o + e]), kLog2e, negm);
+        if (LOGPEN) {
+          const float4 pa4 = lds128(la + g * 32), pb4 = lds128(la + g * 32 + 16);
+          t[0] -= pa4.x; t[1] -= pa4.y; t[2] -= pa4.z; t[3] -= pa4.w;
+          t[4] -= pb4.x; t[5] -= pb4.y; t[6] -= pb4.z; t[7] -= pb4.w;
+        }
+        float p[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) p[e] = ex2(t[e]);
+        if (nvalid != AT_BN) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (g * 8 + e >= nvalid) p[e] = 0.0f;
+        }
+        sum += ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
+        sts128(pa + ((g ^ swz) << 4), pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]),
+               pack_bf16x2(p[4], p[5]), pack_bf16x2(p[6], p[7]));
+      }
+      l += sum;
       tc_fence_before();
       fence_proxy_async_smem();
-      mbar_arrive(p_full);
+      mbar_arrive(&p_full[sb]);
     }
-    mbar_wait(pv_done, (n_kv - 1) & 1);
+    mbar_wait(&pv_done[(n_kv - 1) & 1], ((n_kv - 1) >> 1) & 1);
     tc_fence_after();
     const int i = q0 + q;
     const float inv = 1.0f / l;
-    uint4* op = reinterpret_cast<uint4*>(out + ((size_t)i * B + b) * D + h * AT_HD);
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
-      uint32_t v[32];
-      tmem_ld32(tmem_O + lane_addr + c * 32, v);
-      tmem_ld_wait();
-      if (i < L) {
+    uint32_t o0[32], o1[32];
+    tmem_ld32(tmem_O + lane_addr, o0);
+    tmem_ld32(tmem_O + lane_addr + 32, o1);
+    tmem_ld_wait();
+    if (i < L) {
+      uint4* op = reinterpret_cast<uint4*>(out + ((size_t)i * B + b) * D + h * AT_HD);
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
-          op[c * 4 + g] = make_uint4(
-              pack_bf16x2(__uint_as_float(v[8 * g]) * inv, __uint_as_float(v[8 * g + 1]) * inv),
-              pack_bf16x2(__uint_as_float(v[8 * g + 2]) * inv, __uint_as_float(v[8 * g + 3]) * inv),
-              pack_bf16x2(__uint_as_float(v[8 * g + 4]) * inv, __uint_as_float(v[8 * g + 5]) * inv),
-              pack_bf16x2(__uint_as_float(v[8 * g + 6]) * inv, __uint_as_float(v[8 * g + 7]) * inv));
+      for (int g = 0; g < 8; ++g) {
+        const uint32_t* v = (g < 4) ? o0 : o1;
+        const int o = (g & 3) * 8;
+        op[g] = make_uint4(
+            pack_bf16x2(__uint_as_float(v[o]) * inv, __uint_as_float(v[o + 1]) * inv),
+            pack_bf16x2(__uint_as_float(v[o + 2]) * inv, __uint_as_float(v[o + 3]) * inv),
+            pack_bf16x2(__uint_as_float(v[o + 4]) * inv, __uint_as_float(v[o + 5]) * inv),
+            pack_bf16x2(__uint_as_float(v[o + 6]) * inv, __uint_as_float(v[o + 7]) * inv));
       }
     }
   }
@@ -272,12 +321,15 @@ extern "C" int fbkst_attention_fwd(const void* qkv, void* out, const int32_t* le
   FBKST_REQUIRE((long long)B * H <= 65535, "fbkst_attention_fwd: B*H=%d exceeds the grid limit", B * H);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int D = H * AT_HD;
-  CUtensorMap tm;
+  CUtensorMap tmQ, tmKV;
   uint64_t dims[3] = {(uint64_t)3 * D, (uint64_t)B, (uint64_t)L};
   uint64_t strides[2] = {(uint64_t)3 * D * 2, (uint64_t)B * 3 * D * 2};
-  uint32_t box[3] = {AT_HD, 1, AT_BM};
-  int rc = make_tensor_map(&tm, qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3, dims, strides, box,
+  uint32_t boxq[3] = {AT_HD, 1, AT_BM};
+  uint32_t boxk[3] = {AT_HD, 1, AT_BN};
+  int rc = make_tensor_map(&tmQ, qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3, dims, strides, boxq,
                            nullptr);
+  if (rc) return rc;
+  rc = make_tensor_map(&tmKV, qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3, dims, strides, boxk, nullptr);
   if (rc) return rc;
   static bool configured = false;
   if (!configured) {
@@ -289,9 +341,9 @@ extern "C" int fbkst_attention_fwd(const void* qkv, void* out, const int32_t* le
   }
   dim3 grid((L + AT_BM - 1) / AT_BM, B * H);
   if (log_penalty)
-    attention_fwd_kernel<1><<<grid, 192, AT_SMEM, st>>>(tm, (__nv_bfloat16*)out, lengths, L, B, H);
+    attention_fwd_kernel<1><<<grid, 192, AT_SMEM, st>>>(tmQ, tmKV, (__nv_bfloat16*)out, lengths, L, B, H);
   else
-    attention_fwd_kernel<0><<<grid, 192, AT_SMEM, st>>>(tm, (__nv_bfloat16*)out, lengths, L, B, H);
+    attention_fwd_kernel<0><<<grid, 192, AT_SMEM, st>>>(tmQ, tmKV, (__nv_bfloat16*)out, lengths, L, B, H);
   FBKST_CHECK_CUDA(cudaGetLastError());
   return FBKST_OK;
 }

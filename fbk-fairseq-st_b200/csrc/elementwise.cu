@@ -82,55 +82,65 @@ __global__ void cmvn_apply_kernel(const float* __restrict__ x, float* __restrict
 }
 
 // ----------------------------------------------------------------- conv1 (a2)
-// One thread = one output pixel x 8 channels (one 16-byte store); weights in smem.
+// Thread = (output row (b,t1), 8-channel group g): the 72 weights + 24 epilogue constants of the
+// group live in registers; the thread slides along the F1 output columns of its row (stride-2
+// window: 6 new inputs per pixel, no index division in the loop).  The 8 threads of a pixel write
+// its 128 contiguous bytes of channels-last bf16 output.
 template <int C>
 __global__ void __launch_bounds__(256)
     conv1_kernel(const float* __restrict__ x, const float* __restrict__ w,
                  const float* __restrict__ bias, const float* __restrict__ scale,
                  const float* __restrict__ shift, uint4* __restrict__ y, int B, int T, int F, int T1,
                  int F1) {
-  __shared__ float sw[C * 9];
-  __shared__ float sb[3 * C];
-  for (int i = threadIdx.x; i < C * 9; i += blockDim.x) sw[i] = w[i];
-  for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    sb[i] = bias[i];
-    sb[C + i] = scale[i];
-    sb[2 * C + i] = shift[i];
-  }
-  __syncthreads();
   constexpr int G = C / 8;
-  const long long total = (long long)B * T1 * F1 * G;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(idx % G);
-    long long p = idx / G;
-    const int f1 = (int)(p % F1);
-    p /= F1;
-    const int t1 = (int)(p % T1);
-    const int b = (int)(p / T1);
-    float in[9];
+  const int g = threadIdx.x % G;
+  float wr[8][9], br[8], sr[8], hr[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = g * 8 + j;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) wr[j][k] = __ldg(w + c * 9 + k);
+    br[j] = __ldg(bias + c);
+    sr[j] = __ldg(scale + c);
+    hr[j] = __ldg(shift + c);
+  }
+  const int rows_per_block = blockDim.x / G;
+  const int total_rows = B * T1;
+  for (int row = blockIdx.x * rows_per_block + threadIdx.x / G; row < total_rows;
+       row += gridDim.x * rows_per_block) {
+    const int t1 = row % T1, b = row / T1;
+    const float* xr[3];
+    bool ok[3];
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
       const int t = 2 * t1 - 1 + kh;
+      ok[kh] = (t >= 0 && t < T);
+      xr[kh] = x + ((size_t)b * T + (ok[kh] ? t : 0)) * F;
+    }
+    float in[9];
 #pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const int f = 2 * f1 - 1 + kw;
-        in[kh * 3 + kw] =
-            (t >= 0 && t < T && f >= 0 && f < F) ? __ldg(x + ((size_t)b * T + t) * F + f) : 0.0f;
+    for (int kh = 0; kh < 3; ++kh) in[kh * 3 + 2] = 0.0f;  // column -1 (left zero padding)
+    uint4* yp = y + (size_t)row * F1 * G + g;
+    for (int f1 = 0; f1 < F1; ++f1) {
+      const int f = 2 * f1;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        in[kh * 3 + 0] = in[kh * 3 + 2];
+        in[kh * 3 + 1] = (ok[kh] && f < F) ? __ldg(xr[kh] + f) : 0.0f;
+        in[kh * 3 + 2] = (ok[kh] && f + 1 < F) ? __ldg(xr[kh] + f + 1) : 0.0f;
       }
-    }
-    float o[8];
+      float o[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = g * 8 + j;
-      float a = sb[c];
+      for (int j = 0; j < 8; ++j) {
+        float a = br[j];
 #pragma unroll
-      for (int k = 0; k < 9; ++k) a = fmaf(sw[c * 9 + k], in[k], a);
-      a = fmaxf(a, 0.0f);
-      o[j] = fmaf(a, sb[C + c], sb[2 * C + c]);
+        for (int k = 0; k < 9; ++k) a = fmaf(wr[j][k], in[k], a);
+        a = fmaxf(a, 0.0f);
+        o[j] = fmaf(a, sr[j], hr[j]);
+      }
+      yp[(size_t)f1 * G] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+                                      pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
     }
-    y[idx] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
-                        pack_bf16x2(o[6], o[7]));
   }
 }
 
@@ -282,8 +292,9 @@ extern "C" int fbkst_conv1_relu_bn(const float* x, const float* w, const float* 
   FBKST_REQUIRE(B > 0 && T > 0 && F > 0, "fbkst_conv1_relu_bn: bad shape");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int T1 = (T + 1) / 2, F1 = (F + 1) / 2;
-  const long long total = (long long)B * T1 * F1 * (C / 8);
-  const int grid = grid_for(total, 256, 16);
+  FBKST_REQUIRE((long long)B * T1 * F1 < (1ll << 31), "fbkst_conv1_relu_bn: too many pixels");
+  const long long total = (long long)B * T1 * (C / 8);
+  const int grid = grid_for(total, 256, 8);
   if (C == 64)
     conv1_kernel<64><<<grid, 256, 0, st>>>(x, w, bias, bn_scale, bn_shift, (uint4*)y, B, T, F, T1, F1);
   else

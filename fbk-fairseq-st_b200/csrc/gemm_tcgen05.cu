@@ -123,8 +123,7 @@ __global__ void __launch_bounds__(256, 1)
   constexpr uint32_t IDESC = idesc_bf16_f32(BM, BN, 0, 0);
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps .shared
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
@@ -271,8 +270,7 @@ __global__ void __launch_bounds__(384, 1)
   constexpr uint32_t IDESC = idesc_bf16_f32(BM, BN, 0, 0);
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps .shared
   uint8_t* smem_epi = smem + STAGES * STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_epi + EPI_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
