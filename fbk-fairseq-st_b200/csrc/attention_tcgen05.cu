@@ -4,9 +4,9 @@
 //   S_j = Q K_j^T   tcgen05.mma (M128 x N64 x K64), operands K-major in smem (TMA, 128B swizzle),
 //                   S double-buffered in TMEM so QK of tile j+1/j+2 runs under the softmax of tile j
 //   P_j = softmax   128 threads, one query row each, the 64 scores of the row held in registers:
-//                   key-padding mask (last tile only), log-distance penalty from a per-tile LUT in
-//                   log2 domain (4 shifted copies -> aligned LDS.128), lazy max (O is rescaled only
-//                   when the running max grows by more than 2^8), exp2 in fp32
+//                   key-padding mask (last tile only), log-distance penalty from a per-CTA LUT in
+//                   log2 domain indexed by (key - query), lazy max (O is rescaled only when the
+//                   running max grows by more than 2^8), exp2 in fp32
 //   O  += P_j V_j   tcgen05.mma (M128 x N64 x K64), P as bf16 in swizzled smem (double-buffered),
 //                   V consumed MN-major straight from its TMA tile
 // One CTA = one (128-query tile, utterance, head); 2 CTAs per SM.
@@ -27,10 +27,11 @@ constexpr int AT_HD = 64;   // head dim (all reference archs: embed_dim / heads 
 constexpr int AT_QB = AT_BM * AT_HD * 2;  // 16 KB
 constexpr int AT_KB = AT_BN * AT_HD * 2;  // 8 KB
 constexpr int AT_KST = 3, AT_VST = 2;
-constexpr int AT_LCP = 200;      // floats per LUT copy (192 used; 200 keeps the 4 copies on distinct banks)
-constexpr int AT_LUT = 4 * AT_LCP;  // floats per LUT buffer (4 shifted copies)
-constexpr int AT_SMEM = AT_QB + AT_KST * AT_KB + AT_VST * AT_KB + 2 * AT_QB /*P x2*/ +
-                        2 * AT_LUT * 4 + 256 /*barriers*/ + 1024 /*align*/;
+// shared memory without the penalty LUT (its size depends on L: see attention_smem_bytes)
+constexpr int AT_SMEM_FIXED = AT_QB + AT_KST * AT_KB + AT_VST * AT_KB + 2 * AT_QB /*P x2*/ +
+                              256 /*barriers*/ + 1024 /*align*/;
+static inline int attention_lut_floats(int L) { return ((L + AT_BN - 1) / AT_BN) * AT_BN + 128; }
+static inline int attention_smem_bytes(int L) { return AT_SMEM_FIXED + 4 * attention_lut_floats(L); }
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
@@ -44,6 +45,11 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
                : "r"(addr));
   return v;
 }
+__device__ __forceinline__ float lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d)
                : "memory");
@@ -53,6 +59,13 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+
+// Optional per-CTA timeline (debug only; null in production): 16 x int64 per CTA.
+__device__ long long* g_attn_trace = nullptr;
+#define AT_TRACE(slot)                                                                  \
+  do {                                                                                  \
+    if (trace != nullptr && threadIdx.x == 64) trace[slot] = clock64();                 \
+  } while (0)
 
 template <int LOGPEN>
 __global__ void __launch_bounds__(192, 2)
@@ -65,6 +78,17 @@ __global__ void __launch_bounds__(192, 2)
   const int len = min(__ldg(lengths + b), L);
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
+  long long* trace = g_attn_trace;
+  if (trace != nullptr) {
+    const int cta = blockIdx.y * gridDim.x + blockIdx.x;
+    trace = (cta < 4096) ? trace + (size_t)cta * 16 : nullptr;
+    if (trace != nullptr && threadIdx.x == 64) {
+      uint32_t smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      trace[15] = smid;
+    }
+  }
+  AT_TRACE(0);
 
   if (q0 >= len) {  // tile of padded queries: defined output, no work (CTA-uniform exit)
     const int tid = threadIdx.x;
@@ -86,8 +110,8 @@ __global__ void __launch_bounds__(192, 2)
   uint8_t* sK = sQ + AT_QB;            // AT_KST stages
   uint8_t* sV = sK + AT_KST * AT_KB;   // AT_VST stages
   uint8_t* sP = sV + AT_VST * AT_KB;   // 2 x [128 rows x 128 B]
-  float* sLut = reinterpret_cast<float*>(sP + 2 * AT_QB);  // 2 x AT_LUT
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sLut + 2 * AT_LUT);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * AT_QB);
+  float* sLut = reinterpret_cast<float*>(bars + 32);  // [n_kv*64 + 128]
   uint64_t* q_full = bars + 0;
   uint64_t* k_full = bars + 1;    // [3]
   uint64_t* k_empty = bars + 4;   // [3]
@@ -125,6 +149,7 @@ __global__ void __launch_bounds__(192, 2)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  AT_TRACE(1);
   const uint32_t tmem_O = tmem_base + 128;  // S[0] = +0, S[1] = +64, O = +128 (64 columns each)
 
   if (warp == 0) {
@@ -182,37 +207,39 @@ __global__ void __launch_bounds__(192, 2)
     const int q = (warp & 3) * 32 + lane;  // row in the tile == TMEM lane
     const int st = threadIdx.x - 64;       // 0..127
     const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const uint32_t lut_base = smem_u32(sLut);
-    const uint32_t p_base = smem_u32(sP) + q * 128;
     const int swz = q & 7;
-    // LUT copy s holds entry (idx + s); thread reads copy (127-q)&3 at aligned offset (127-q)&~3
-    const int lsh = (127 - q) & 3;
-    const uint32_t lut_off = (uint32_t)(lsh * AT_LCP + ((127 - q) & ~3)) * 4;
+    // Penalty LUT, once per CTA: entry o <-> (key - query) = o - 127 - q0, i.e. key k and tile row r
+    // read entry k - r + 127.  pen2 = log2(max(1, |key - query|)).
+    if (LOGPEN) {
+      const int n_lut = n_kv * AT_BN + 128;
+      for (int o = st; o < n_lut; o += 128) {
+        const int d = abs(o - 127 - q0);
+        sLut[o] = (d > 1) ? __log2f((float)d) : 0.0f;
+      }
+      named_bar_sync(1, 128);
+    }
+    AT_TRACE(2);
     float m_used = -INFINITY, l = 0.0f;
     for (int j = 0; j < n_kv; ++j) {
       const int sb = j & 1;
       const int k0 = j * AT_BN;
       const int nvalid = min(AT_BN, len - k0);
-      if (LOGPEN) {  // penalty LUT of this tile: entry e <-> key-minus-query offset (e - 127)
-        const int delta = k0 - q0;
-        float* lut = sLut + sb * AT_LUT;
-        for (int e = st; e < AT_LUT; e += 128) {
-          const int s = e / AT_LCP, idx = e - s * AT_LCP + s;
-          const int d = abs(delta + idx - 127);
-          lut[e] = (d > 1) ? __log2f((float)d) : 0.0f;
-        }
-      }
       mbar_wait(&s_full[sb], (j >> 1) & 1);
+      if (j == 0) AT_TRACE(3);
+      if (j == 2) AT_TRACE(12);
       tc_fence_after();
       uint32_t s0[32], s1[32];
       tmem_ld32(tmem_base + lane_addr + sb * AT_BN, s0);
       tmem_ld32(tmem_base + lane_addr + sb * AT_BN + 32, s1);
       tmem_ld_wait();
+      if (j == 2) AT_TRACE(13);
       float mx = -INFINITY;
       if (nvalid == AT_BN) {
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // 4 independent chains
 #pragma unroll
         for (int c = 0; c < 32; ++c)
-          mx = fmaxf(mx, fmaxf(__uint_as_float(s0[c]), __uint_as_float(s1[c])));
+          m4[c & 3] = fmaxf(m4[c & 3], fmaxf(__uint_as_float(s0[c]), __uint_as_float(s1[c])));
+        mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
       } else {
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
@@ -246,41 +273,60 @@ __global__ void __launch_bounds__(192, 2)
         m_used = m_next;
       }
       if (j >= 2) mbar_wait(&pv_done[sb], ((j >> 1) & 1) ^ 1);  // P buffer sb free (PV_{j-2} done)
-      if (LOGPEN) named_bar_sync(1, 128);                        // LUT_j complete
-      const uint32_t la = lut_base + sb * (AT_LUT * 4) + lut_off;
-      const uint32_t pa = p_base + sb * AT_QB;
+      if (j == 2) AT_TRACE(14);
+      const float* lrow = sLut + (127 - q) + k0;  // penalty of key k0+c for this row: lrow[c]
+      uint4* prow = reinterpret_cast<uint4*>(sP + sb * AT_QB + q * 128);
       const float negm = -m_used;
-      float sum = 0.0f;
+      // stage A (in place): t = s*log2e - m - pen2   (all 64 LDS independent -> full ILP)
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {  // 8 keys -> one 16-byte chunk of the P row
+      for (int c = 0; c < 32; ++c) {
+        float t0 = fmaf(__uint_as_float(s0[c]), kLog2e, negm);
+        float t1 = fmaf(__uint_as_float(s1[c]), kLog2e, negm);
+        if (LOGPEN) {
+          t0 -= lrow[c];
+          t1 -= lrow[c + 32];
+        }
+        s0[c] = __float_as_uint(t0);
+        s1[c] = __float_as_uint(t1);
+      }
+      // stage B (in place): p = 2^t, masked keys -> 0
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        s0[c] = __float_as_uint(ex2(__uint_as_float(s0[c])));
+        s1[c] = __float_as_uint(ex2(__uint_as_float(s1[c])));
+      }
+      if (nvalid != AT_BN) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          if (c >= nvalid) s0[c] = 0u;
+          if (c + 32 >= nvalid) s1[c] = 0u;
+        }
+      }
+      if (j == 2) AT_TRACE(8);
+      // stage C: row sum (4 chains) + bf16 pack -> swizzled K-major P row
+      float sm4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < 32; ++c) sm4[c & 3] += __uint_as_float(s0[c]) + __uint_as_float(s1[c]);
+      const float sum = (sm4[0] + sm4[1]) + (sm4[2] + sm4[3]);
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
         const uint32_t* sv = (g < 4) ? s0 : s1;
         const int o = (g & 3) * 8;
-        float t[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) t[e] = fmaf(__uint_as_float(sv[o + e]), kLog2e, negm);
-        if (LOGPEN) {
-          const float4 pa4 = lds128(la + g * 32), pb4 = lds128(la + g * 32 + 16);
-          t[0] -= pa4.x; t[1] -= pa4.y; t[2] -= pa4.z; t[3] -= pa4.w;
-          t[4] -= pb4.x; t[5] -= pb4.y; t[6] -= pb4.z; t[7] -= pb4.w;
-        }
-        float p[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) p[e] = ex2(t[e]);
-        if (nvalid != AT_BN) {
-#pragma unroll
-          for (int e = 0; e < 8; ++e)
-            if (g * 8 + e >= nvalid) p[e] = 0.0f;
-        }
-        sum += ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
-        sts128(pa + ((g ^ swz) << 4), pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]),
-               pack_bf16x2(p[4], p[5]), pack_bf16x2(p[6], p[7]));
+        prow[g ^ swz] = make_uint4(
+            pack_bf16x2(__uint_as_float(sv[o]), __uint_as_float(sv[o + 1])),
+            pack_bf16x2(__uint_as_float(sv[o + 2]), __uint_as_float(sv[o + 3])),
+            pack_bf16x2(__uint_as_float(sv[o + 4]), __uint_as_float(sv[o + 5])),
+            pack_bf16x2(__uint_as_float(sv[o + 6]), __uint_as_float(sv[o + 7])));
       }
       l += sum;
       tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(&p_full[sb]);
+      if (j < 4) AT_TRACE(4 + j);
+      if (j == 5) AT_TRACE(9);
     }
     mbar_wait(&pv_done[(n_kv - 1) & 1], ((n_kv - 1) >> 1) & 1);
+    AT_TRACE(10);
     tc_fence_after();
     const int i = q0 + q;
     const float inv = 1.0f / l;
@@ -302,6 +348,7 @@ __global__ void __launch_bounds__(192, 2)
       }
     }
   }
+  AT_TRACE(11);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -311,6 +358,12 @@ __global__ void __launch_bounds__(192, 2)
 }
 
 }  // namespace fbkst
+
+// debug hook (not part of the public ABI): buffer of 4096*16 int64, or NULL to disable
+extern "C" int fbkst_debug_set_attention_trace(long long* buf) {
+  cudaError_t e = cudaMemcpyToSymbol(fbkst::g_attn_trace, &buf, sizeof(buf));
+  return e == cudaSuccess ? 0 : -2;
+}
 
 using namespace fbkst;
 
@@ -334,16 +387,18 @@ extern "C" int fbkst_attention_fwd(const void* qkv, void* out, const int32_t* le
   static bool configured = false;
   if (!configured) {
     FBKST_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<0>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     FBKST_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<1>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
+  const int smem = attention_smem_bytes(L);
+  FBKST_REQUIRE(smem <= 227 * 1024, "fbkst_attention_fwd: L=%d needs %d B of shared memory", L, smem);
   dim3 grid((L + AT_BM - 1) / AT_BM, B * H);
   if (log_penalty)
-    attention_fwd_kernel<1><<<grid, 192, AT_SMEM, st>>>(tmQ, tmKV, (__nv_bfloat16*)out, lengths, L, B, H);
+    attention_fwd_kernel<1><<<grid, 192, smem, st>>>(tmQ, tmKV, (__nv_bfloat16*)out, lengths, L, B, H);
   else
-    attention_fwd_kernel<0><<<grid, 192, AT_SMEM, st>>>(tmQ, tmKV, (__nv_bfloat16*)out, lengths, L, B, H);
+    attention_fwd_kernel<0><<<grid, 192, smem, st>>>(tmQ, tmKV, (__nv_bfloat16*)out, lengths, L, B, H);
   FBKST_CHECK_CUDA(cudaGetLastError());
   return FBKST_OK;
 }

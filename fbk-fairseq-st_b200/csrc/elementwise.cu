@@ -87,7 +87,7 @@ __global__ void cmvn_apply_kernel(const float* __restrict__ x, float* __restrict
 // window: 6 new inputs per pixel, no index division in the loop).  The 8 threads of a pixel write
 // its 128 contiguous bytes of channels-last bf16 output.
 template <int C>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
     conv1_kernel(const float* __restrict__ x, const float* __restrict__ w,
                  const float* __restrict__ bias, const float* __restrict__ scale,
                  const float* __restrict__ shift, uint4* __restrict__ y, int B, int T, int F, int T1,
