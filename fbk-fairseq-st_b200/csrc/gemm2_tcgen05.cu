@@ -1,0 +1,430 @@
+// out = epilogue(A @ W^T) with CTA-PAIR tensor-core tiles (tcgen05 cta_group::2).
+//
+// The single-CTA kernel (gemm_tcgen05.cu) moves 48 KB of operands from L2 per 128x256x64 MMA
+// block, i.e. 94 B/clk/SM at full tensor rate -- more than twice what L2 can deliver to 148 SMs
+// (measured: the kernel saturates at ~11.5 TB/s of L2->SM traffic, ~50% tensor-pipe utilisation).
+// Here two CTAs of a cluster (one TPC) compute ONE 256x256 tile: each CTA stages its own 128 rows
+// of A and HALF of the W tile (128 of the 256 columns); the leader CTA issues
+// tcgen05.mma.cta_group::2 (M=256, N=256), which reads both halves of W from both CTAs' shared
+// memory and writes each CTA's 128 accumulator rows into that CTA's TMEM.  Operand traffic per
+// FLOP drops by 1.5x, the smem ring gets 5 stages of 32 KB, and the epilogue staging buffers are
+// double-buffered.
+//
+// Per CTA: warp 0 TMA producer (loads signal the LEADER's full barrier), warp 1 MMA issuer
+// (leader only; commits are multicast to both CTAs), warp 2 TMEM allocator, warps 4-11 epilogue
+// (TMEM -> registers -> bias/ReLU/residual -> swizzled smem -> per-warp TMA store).
+#include <stdlib.h>
+
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace fbkst {
+
+constexpr int G2_BM = 128;      // rows per CTA (256 per pair)
+constexpr int G2_BN = 256;      // tile columns (each CTA stages 128 of them)
+constexpr int G2_BK = 64;
+constexpr int G2_STAGES = 5;
+constexpr int G2_A_BYTES = G2_BM * G2_BK * 2;        // 16 KB
+constexpr int G2_B_BYTES = (G2_BN / 2) * G2_BK * 2;  // 16 KB
+constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
+constexpr int G2_EPI_BYTES = 8 * 2 * 4096;
+constexpr int G2_SMEM = G2_STAGES * G2_STAGE_BYTES + G2_EPI_BYTES + 512 + 1024;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_addr` (a shared::cta address) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(smem_result)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_cg2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+// TMA load whose completion bytes are credited to an mbarrier given as a shared::cluster address
+// (the leader CTA's full barrier), as both CTAs of the pair feed one MMA.
+__device__ __forceinline__ void tma_load_2d_cg2(void* smem_dst, const void* tmap, uint32_t mbar_cluster,
+                                                int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(tmap), "r"(mbar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ss_cg2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                                 uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (count 1) on the barrier at the same smem offset in every CTA of `cta_mask` once all
+// tcgen05.mma issued so far by this thread have completed
+__device__ __forceinline__ void umma_commit_cg2_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::
+          "r"(smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ float4 bcast4_g2(const float4& v, int src_lane) {
+  return make_float4(__shfl_sync(0xffffffffu, v.x, src_lane), __shfl_sync(0xffffffffu, v.y, src_lane),
+                     __shfl_sync(0xffffffffu, v.z, src_lane), __shfl_sync(0xffffffffu, v.w, src_lane));
+}
+
+template <bool OUT_F32, bool RESID>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+    gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, int M,
+                 int N, int K, const float* __restrict__ bias, int relu, int dbg) {
+  constexpr uint32_t TMEM_COLS = 512;  // two 256-column accumulator stages
+  constexpr uint32_t IDESC = idesc_bf16_f32(256, G2_BN, 0, 0);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* smem_epi = smem + G2_STAGES * G2_STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_epi + G2_EPI_BYTES);  // used in the leader
+  uint64_t* empty_bar = full_bar + G2_STAGES;                                 // per CTA
+  uint64_t* tfull_bar = empty_bar + G2_STAGES;                                // per CTA
+  uint64_t* tempty_bar = tfull_bar + 2;                                       // used in the leader
+  uint64_t* res_bar = tempty_bar + 2;                                         // [8][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 16);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int num_n = (N + G2_BN - 1) / G2_BN;
+  const int num_m = (M + 2 * G2_BM - 1) / (2 * G2_BM);
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (K + G2_BK - 1) / G2_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmO);
+    if (RESID) tma_prefetch_desc(&tmR);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < G2_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 16);  // 8 epilogue warps x 2 CTAs
+    }
+    for (int s = 0; s < 16; ++s) mbar_init(&res_bar[s], 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_cg2(tmem_slot, TMEM_COLS);
+    tmem_relinquish_cg2();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
+        const int row_a = m_blk * 2 * G2_BM + (int)rank * G2_BM;
+        const int row_b = n_blk * G2_BN + (int)rank * (G2_BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);
+          const uint32_t leader_full = map_to_cta(smem_u32(&full_bar[stage]), 0);
+          uint8_t* sa = smem + stage * G2_STAGE_BYTES;
+          tma_load_2d_cg2(sa, &tmA, leader_full, kb * G2_BK, row_a);
+          tma_load_2d_cg2(sa + G2_A_BYTES, &tmB, leader_full, kb * G2_BK, row_b);
+          if (++stage == G2_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * G2_BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * G2_STAGE_BYTES);
+          const uint64_t adesc = desc_kmajor_sw128(sa);
+          const uint64_t bdesc = desc_kmajor_sw128(sa + G2_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < G2_BK / 16; ++k)
+            umma_bf16_ss_cg2(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
+          umma_commit_cg2_mc(&empty_bar[stage], 0x3);
+          if (++stage == G2_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_cg2_mc(&tfull_bar[acc], 0x3);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4;
+    const int q = ew & 3;      // TMEM lane quarter == row block of 32
+    const int half = ew >> 2;  // column half of the tile
+    uint8_t* stg = smem_epi + ew * 2 * 4096;
+    uint64_t* rbar = res_bar + ew * 2;
+    uint32_t rphase[2] = {0, 0};
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int swz = lane & 7;
+    int sbuf = 0;  // staging buffer toggle (non-residual path)
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
+      const int m0 = m_blk * 2 * G2_BM + (int)rank * G2_BM + q * 32;
+      const int n0 = n_blk * G2_BN + half * 128;
+      const uint32_t tempty_leader = map_to_cta(smem_u32(&tempty_bar[acc]), 0);
+      if (n0 >= N || m0 >= M) {  // nothing to write for this warp (warp-uniform)
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_before();
+        if (lane == 0) mbar_arrive_cluster(tempty_leader);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+        continue;
+      }
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (bias != nullptr) {
+        const int c = n0 + lane * 4;
+        if (c + 3 < N) {
+          b4 = __ldg(reinterpret_cast<const float4*>(bias + c));
+        } else {
+          if (c + 0 < N) b4.x = __ldg(bias + c + 0);
+          if (c + 1 < N) b4.y = __ldg(bias + c + 1);
+          if (c + 2 < N) b4.z = __ldg(bias + c + 2);
+        }
+      }
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * G2_BN + half * 128;
+      if (RESID) {  // fp32 out, 4 units of 32 columns, residual prefetched one unit ahead
+        if (lane == 0) {
+          tma_store_wait_read<0>();
+          mbar_arrive_expect_tx(&rbar[0], 4096);
+          tma_load_2d(stg, &tmR, &rbar[0], n0, m0);
+        }
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        uint32_t v[32];
+        tmem_ld32(taddr, v);
+#pragma unroll 1
+        for (int u = 0; u < 4; ++u) {
+          const int col0 = n0 + u * 32;
+          if (col0 >= N) break;
+          const int bsel = u & 1;
+          if (u + 1 < 4 && col0 + 32 < N && lane == 0) {  // prefetch the next residual unit
+            tma_store_wait_read<0>();                    // its buffer was read by store(u-1)
+            mbar_arrive_expect_tx(&rbar[bsel ^ 1], 4096);
+            tma_load_2d(stg + (bsel ^ 1) * 4096, &tmR, &rbar[bsel ^ 1], col0 + 32, m0);
+          }
+          tmem_ld_wait();
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (u + 1 < 4) tmem_ld32(taddr + (u + 1) * 32, v);
+          mbar_wait(&rbar[bsel], rphase[bsel]);
+          rphase[bsel] ^= 1;
+          uint8_t* rowp = stg + bsel * 4096 + lane * 128;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 bb = bcast4_g2(b4, u * 8 + g);
+            float4* sp = reinterpret_cast<float4*>(rowp + ((g ^ swz) << 4));
+            float4 r = *sp;
+            float a0 = f[4 * g] + bb.x, a1 = f[4 * g + 1] + bb.y, a2 = f[4 * g + 2] + bb.z,
+                  a3 = f[4 * g + 3] + bb.w;
+            if (relu) {
+              a0 = fmaxf(a0, 0.f);
+              a1 = fmaxf(a1, 0.f);
+              a2 = fmaxf(a2, 0.f);
+              a3 = fmaxf(a3, 0.f);
+            }
+            r.x += a0;
+            r.y += a1;
+            r.z += a2;
+            r.w += a3;
+            *sp = r;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmO, stg + bsel * 4096, col0, m0);
+            tma_store_commit();
+          }
+        }
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tempty_leader);
+      } else {
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        constexpr int UNITS = OUT_F32 ? 4 : 2;  // staging rows are 128 B: 32 fp32 or 64 bf16 columns
+        constexpr int UCOLS = OUT_F32 ? 32 : 64;
+#pragma unroll 1
+        for (int u = 0; u < UNITS; ++u) {
+          const int col0 = n0 + u * UCOLS;
+          if (col0 >= N) break;
+          uint32_t v0[32], v1[32];
+          tmem_ld32(taddr + u * UCOLS, v0);
+          if (!OUT_F32) tmem_ld32(taddr + u * UCOLS + 32, v1);
+          if (lane == 0) tma_store_wait_read<1>();  // the buffer used two units ago is free again
+          tmem_ld_wait();
+          if (u == UNITS - 1 || col0 + UCOLS >= N) {  // all TMEM reads of this tile done: release it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tempty_leader);
+          }
+          __syncwarp();
+          uint8_t* rowp = stg + sbuf * 4096 + lane * 128;
+          if (dbg & 2) continue;
+          if (OUT_F32) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const float4 bb = bcast4_g2(b4, u * 8 + g);
+              float a0 = __uint_as_float(v0[4 * g]) + bb.x, a1 = __uint_as_float(v0[4 * g + 1]) + bb.y,
+                    a2 = __uint_as_float(v0[4 * g + 2]) + bb.z, a3 = __uint_as_float(v0[4 * g + 3]) + bb.w;
+              if (relu) {
+                a0 = fmaxf(a0, 0.f);
+                a1 = fmaxf(a1, 0.f);
+                a2 = fmaxf(a2, 0.f);
+                a3 = fmaxf(a3, 0.f);
+              }
+              *reinterpret_cast<float4*>(rowp + ((g ^ swz) << 4)) = make_float4(a0, a1, a2, a3);
+            }
+          } else {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const uint32_t* src = (g < 4) ? v0 : v1;
+              const int o = (g & 3) * 8;
+              const float4 b0 = bcast4_g2(b4, u * 16 + 2 * g);
+              const float4 b1 = bcast4_g2(b4, u * 16 + 2 * g + 1);
+              float a[8] = {__uint_as_float(src[o]) + b0.x,     __uint_as_float(src[o + 1]) + b0.y,
+                            __uint_as_float(src[o + 2]) + b0.z, __uint_as_float(src[o + 3]) + b0.w,
+                            __uint_as_float(src[o + 4]) + b1.x, __uint_as_float(src[o + 5]) + b1.y,
+                            __uint_as_float(src[o + 6]) + b1.z, __uint_as_float(src[o + 7]) + b1.w};
+              if (relu) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a[j] = fmaxf(a[j], 0.f);
+              }
+              *reinterpret_cast<uint4*>(rowp + ((g ^ swz) << 4)) =
+                  make_uint4(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]), pack_bf16x2(a[4], a[5]),
+                             pack_bf16x2(a[6], a[7]));
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && !(dbg & 1)) {
+            tma_store_2d(&tmO, stg + sbuf * 4096, col0, m0);
+            tma_store_commit();
+          }
+          sbuf ^= 1;
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (lane == 0) tma_store_wait<0>();
+  }
+  tc_fence_before();
+  cluster_sync_all();  // the peer's smem / TMEM must stay alive until every multicast landed
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_cg2(tmem_base, TMEM_COLS);
+  }
+}
+
+template <bool OUT_F32, bool RESID>
+static int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                        const float* resid, int64_t ldr, void* out, int64_t ldo, int M, int N, int K,
+                        int relu, cudaStream_t stream) {
+  static_assert(G2_SMEM <= 232448, "shared memory budget exceeded");
+  auto kern = gemm2_kernel<OUT_F32, RESID>;
+  static bool configured = false;
+  if (!configured) {
+    FBKST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM));
+    configured = true;
+  }
+  CUtensorMap tmA, tmB, tmO, tmR;
+  int rc = make_tensor_map_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, G2_BM, G2_BK);
+  if (rc) return rc;
+  rc = make_tensor_map_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, G2_BN / 2, G2_BK);
+  if (rc) return rc;
+  {
+    uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
+    uint64_t strides[1] = {(uint64_t)ldo * (OUT_F32 ? 4 : 2)};
+    uint32_t box[2] = {OUT_F32 ? 32u : 64u, 32u};
+    rc = make_tensor_map(&tmO, out,
+                         OUT_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                         OUT_F32 ? 4 : 2, 2, dims, strides, box, nullptr);
+    if (rc) return rc;
+  }
+  if (RESID) {
+    uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
+    uint64_t strides[1] = {(uint64_t)ldr * 4};
+    uint32_t box[2] = {32u, 32u};
+    rc = make_tensor_map(&tmR, resid, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, 2, dims, strides, box, nullptr);
+    if (rc) return rc;
+  } else {
+    tmR = tmO;
+  }
+  const int tiles = ((M + 2 * G2_BM - 1) / (2 * G2_BM)) * ((N + G2_BN - 1) / G2_BN);
+  const int max_clusters = num_sms() / 2;
+  const int clusters = tiles < max_clusters ? tiles : max_clusters;
+  static const int dbg = getenv("FBKST_GEMM_DBG") ? atoi(getenv("FBKST_GEMM_DBG")) : 0;
+  kern<<<2 * clusters, 384, G2_SMEM, stream>>>(tmA, tmB, tmO, tmR, M, N, K, bias, relu, dbg);
+  FBKST_CHECK_CUDA(cudaGetLastError());
+  return FBKST_OK;
+}
+
+// Entry used by fbkst_linear_bf16 (gemm_tcgen05.cu) for the plain / residual epilogues.
+int linear_pair_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                         const float* resid, int64_t ldr, void* out, int64_t ldo, int M, int N, int K,
+                         int relu, int out_f32, cudaStream_t stream) {
+  if (resid != nullptr)
+    return launch_gemm2<true, true>(A, lda, W, ldw, bias, resid, ldr, out, ldo, M, N, K, relu, stream);
+  if (out_f32)
+    return launch_gemm2<true, false>(A, lda, W, ldw, bias, nullptr, 0, out, ldo, M, N, K, relu, stream);
+  return launch_gemm2<false, false>(A, lda, W, ldw, bias, nullptr, 0, out, ldo, M, N, K, relu, stream);
+}
+
+}  // namespace fbkst

@@ -11,7 +11,14 @@
 #include "host_common.h"
 #include "ptx.cuh"
 
+#include <stdlib.h>
+
 namespace fbkst {
+
+// gemm2_tcgen05.cu: CTA-pair (cta_group::2) kernel for the plain / residual epilogues
+int linear_pair_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                         const float* resid, int64_t ldr, void* out, int64_t ldo, int M, int N, int K,
+                         int relu, int out_f32, cudaStream_t stream);
 
 struct EpiParams {
   const float* bias;
@@ -631,8 +638,13 @@ extern "C" int fbkst_linear_bf16(const void* A, int64_t lda, const void* W, int6
     return launch_gemm<128, 6>(A, lda, W, ldw, M, N, K, ep, st);
   }
   const int relu = (flags & FBKST_EPI_RELU) ? 1 : 0;
-  if (residual != nullptr) {
+  if (residual != nullptr)
     FBKST_REQUIRE(flags & FBKST_EPI_OUT_F32, "fbkst_linear_bf16: a residual requires fp32 output");
+  static const bool single_cta = getenv("FBKST_GEMM_1CTA") != nullptr;  // A/B switch for profiling
+  if (!single_cta)
+    return linear_pair_dispatch(A, lda, W, ldw, bias, residual, ldr, out, ldo, M, N, K, relu,
+                                (flags & FBKST_EPI_OUT_F32) ? 1 : 0, st);
+  if (residual != nullptr) {
     return launch_gemm_tma<true, true, 3>(A, lda, W, ldw, bias, residual, ldr, out, ldo, M, N, K, relu, st);
   }
   if (flags & FBKST_EPI_OUT_F32)
