@@ -158,244 +158,254 @@ class CtcProjection(nn.Linear):
         return self._prep
 
 
-class ConvolutionalTransformerEncoder(_Base):
-    def __init__(self, args, dictionary, audio_features=40):
-        super().__init__(dictionary)
-        convs = eval(args.encoder_convolutions) if args.encoder_convolutions is not None \
-            else ((512, 3),) * 2
-        if len(convs) != 2:
-            raise NotImplementedError("fbkst_b200: exactly two subsampling convolutions are supported")
-        self.dropout = args.dropout
-        if getattr(args, "activation_fn", "relu") != "relu":
-            raise NotImplementedError("fbkst_b200: only activation_fn=relu is supported")
-        if getattr(args, "attn_2d", False):
-            raise NotImplementedError(
-                "fbkst_b200: ConvAttention2D is outside the accelerated path; pass --no-attn-2d")
-        penalty = getattr(args, "distance_penalty", False)
-        if penalty is True:
-            penalty = "log"
-        if penalty not in (False, None, "log"):
-            raise NotImplementedError("fbkst_b200: distance penalty %r is not supported (the "
-                                      "reference's 'gauss' penalty crashes on construction)" % penalty)
-        self.log_penalty = penalty == "log"
-        if not getattr(args, "encoder_normalize_before", True):
-            raise NotImplementedError("fbkst_b200: only pre-LayerNorm encoders (all reference archs)")
-        if getattr(args, "encoder_learned_pos", False):
-            raise NotImplementedError("fbkst_b200: learned positional embeddings are not supported")
+def make_encoder_class(base):
+    """The encoder class on top of ``base`` (fairseq's ``FairseqEncoder`` inside fairseq, a small
+    ``nn.Module`` shim standalone).  ``fairseq_model.py:247`` asserts ``isinstance(encoder,
+    FairseqEncoder)``, so the plugin instantiates this with the real base class."""
 
-        self.convolutions = nn.ModuleList()
-        cin = 1
-        for spec in convs:
-            cout, k = spec[0], spec[1]
-            if k != 3 or (len(spec) > 2 and spec[2] != 3):
-                raise NotImplementedError("fbkst_b200: only 3x3 convolutions are supported")
-            self.convolutions.append(_conv2d(cin, cout, k, self.dropout))
-            cin = cout
-        self.conv_channels = cin
-        if convs[0][0] != convs[1][0] or cin not in (64, 128):
-            raise NotImplementedError("fbkst_b200: conv channels must be equal and 64 or 128")
-        self.bn = nn.ModuleList([nn.BatchNorm2d(cin) for _ in range(2)])
+    class ConvolutionalTransformerEncoder(base):
+        def __init__(self, args, dictionary, audio_features=40):
+            super().__init__(dictionary)
+            convs = eval(args.encoder_convolutions) if args.encoder_convolutions is not None \
+                else ((512, 3),) * 2
+            if len(convs) != 2:
+                raise NotImplementedError("fbkst_b200: exactly two subsampling convolutions are supported")
+            self.dropout = args.dropout
+            if getattr(args, "activation_fn", "relu") != "relu":
+                raise NotImplementedError("fbkst_b200: only activation_fn=relu is supported")
+            if getattr(args, "attn_2d", False):
+                raise NotImplementedError(
+                    "fbkst_b200: ConvAttention2D is outside the accelerated path; pass --no-attn-2d")
+            penalty = getattr(args, "distance_penalty", False)
+            if penalty is True:
+                penalty = "log"
+            if penalty not in (False, None, "log"):
+                raise NotImplementedError("fbkst_b200: distance penalty %r is not supported (the "
+                                          "reference's 'gauss' penalty crashes on construction)" % penalty)
+            self.log_penalty = penalty == "log"
+            if not getattr(args, "encoder_normalize_before", True):
+                raise NotImplementedError("fbkst_b200: only pre-LayerNorm encoders (all reference archs)")
+            if getattr(args, "encoder_learned_pos", False):
+                raise NotImplementedError("fbkst_b200: learned positional embeddings are not supported")
 
-        D = args.encoder_embed_dim
-        self.embed_dim = D
-        self.heads = args.encoder_attention_heads
-        if D != 64 * self.heads:
-            raise NotImplementedError("fbkst_b200: head_dim must be 64 (all reference archs)")
-        flat = audio_features
-        for _ in range(2):
-            flat = math.ceil(flat / 2)
-        self.feat_out = flat
-        self.fc3 = _linear(flat * cin, D)
-        self.embed_positions = None if getattr(args, "no_token_positional_embeddings", False) \
-            else _PositionalParams()
-        self.encoder_layerdrop = getattr(args, "encoder_layerdrop", 0.0)
-        self.layers = nn.ModuleList(
-            [_EncoderLayerParams(D, args.encoder_ffn_embed_dim, self.log_penalty)
-             for _ in range(args.encoder_layers)])
-        self.num_layers = len(self.layers)
-        self.layer_norm = nn.LayerNorm(D)
-        self.layernorm_embedding = nn.LayerNorm(D) if getattr(args, "layernorm_embedding", False) \
-            else None
-        self.ctc_compress_out = getattr(args, "ctc_compress_out", False)
-        if self.ctc_compress_out:
-            self.ctc_fc = CtcProjection(D, len(dictionary))
-            assert args.criterion == "ctc_multi_loss"
-            self.ctc_layer = args.ctc_encoder_layer
-            self.ctc_compress_strategy = args.ctc_compress_strategy
-            if self.ctc_compress_strategy not in ("avg", "weighted", "softmax"):
-                raise ValueError("unknown --ctc-compress-strategy %r" % self.ctc_compress_strategy)
-        self._prep = None
-        self._prep_key = None
-        self._pos_table = None
+            self.convolutions = nn.ModuleList()
+            cin = 1
+            for spec in convs:
+                cout, k = spec[0], spec[1]
+                if k != 3 or (len(spec) > 2 and spec[2] != 3):
+                    raise NotImplementedError("fbkst_b200: only 3x3 convolutions are supported")
+                self.convolutions.append(_conv2d(cin, cout, k, self.dropout))
+                cin = cout
+            self.conv_channels = cin
+            if convs[0][0] != convs[1][0] or cin not in (64, 128):
+                raise NotImplementedError("fbkst_b200: conv channels must be equal and 64 or 128")
+            self.bn = nn.ModuleList([nn.BatchNorm2d(cin) for _ in range(2)])
 
-    # ------------------------------------------------------------------ derived operand formats
-    def _prepared(self):
-        params = list(self.parameters()) + list(self.buffers())
-        key = tuple((p._version, p.data_ptr()) for p in params)
-        if self._prep_key == key:
-            return self._prep
-        with torch.no_grad():
-            P = {}
-            C = self.conv_channels
-            P["w1"] = self.convolutions[0].weight.detach().reshape(C, 9).float().contiguous()
-            P["b1"] = self.convolutions[0].bias.detach().float().contiguous()
-            P["w2"] = ops.prep_conv2_weight(self.convolutions[1].weight.detach().float())
-            P["b2"] = self.convolutions[1].bias.detach().float().contiguous()
-            for i in range(2):
-                bn = self.bn[i]
-                P["bn%d" % i] = ops.prep_bn_affine(bn.weight.detach().float(), bn.bias.detach().float(),
-                                                   bn.running_mean.float(), bn.running_var.float(),
-                                                   bn.eps)
-            P["w3"] = ops.prep_fc3_weight(self.fc3.weight.detach().float(), C, self.feat_out)
-            P["b3"] = self.fc3.bias.detach().float().contiguous()
-            D = self.embed_dim
-            scale = 64 ** -0.5  # head_dim ** -0.5, folded into the q projection (exact: 2^-3)
-            layers = []
-            for lyr in self.layers:
-                w, b = lyr.self_attn.qkv()
-                w = w.detach().float().clone()
-                b = b.detach().float().clone()
-                w[:D] *= scale
-                b[:D] *= scale
-                layers.append(dict(
-                    ln1=(lyr.self_attn_layer_norm.weight.detach().float().contiguous(),
-                         lyr.self_attn_layer_norm.bias.detach().float().contiguous()),
-                    wqkv=ops.cast_bf16(w), bqkv=b.contiguous(),
-                    wo=ops.cast_bf16(lyr.self_attn.out_proj.weight.detach().float()),
-                    bo=lyr.self_attn.out_proj.bias.detach().float().contiguous(),
-                    ln2=(lyr.final_layer_norm.weight.detach().float().contiguous(),
-                         lyr.final_layer_norm.bias.detach().float().contiguous()),
-                    w1=ops.cast_bf16(lyr.fc1.weight.detach().float()),
-                    b1=lyr.fc1.bias.detach().float().contiguous(),
-                    w2=ops.cast_bf16(lyr.fc2.weight.detach().float()),
-                    b2=lyr.fc2.bias.detach().float().contiguous()))
-            P["layers"] = layers
-            P["lnf"] = (self.layer_norm.weight.detach().float().contiguous(),
-                        self.layer_norm.bias.detach().float().contiguous())
+            D = args.encoder_embed_dim
+            self.embed_dim = D
+            self.heads = args.encoder_attention_heads
+            if D != 64 * self.heads:
+                raise NotImplementedError("fbkst_b200: head_dim must be 64 (all reference archs)")
+            flat = audio_features
+            for _ in range(2):
+                flat = math.ceil(flat / 2)
+            self.feat_out = flat
+            self.fc3 = _linear(flat * cin, D)
+            self.embed_positions = None if getattr(args, "no_token_positional_embeddings", False) \
+                else _PositionalParams()
+            self.encoder_layerdrop = getattr(args, "encoder_layerdrop", 0.0)
+            self.layers = nn.ModuleList(
+                [_EncoderLayerParams(D, args.encoder_ffn_embed_dim, self.log_penalty)
+                 for _ in range(args.encoder_layers)])
+            self.num_layers = len(self.layers)
+            self.layer_norm = nn.LayerNorm(D)
+            self.layernorm_embedding = nn.LayerNorm(D) if getattr(args, "layernorm_embedding", False) \
+                else None
+            self.ctc_compress_out = getattr(args, "ctc_compress_out", False)
+            if self.ctc_compress_out:
+                self.ctc_fc = CtcProjection(D, len(dictionary))
+                assert args.criterion == "ctc_multi_loss"
+                self.ctc_layer = args.ctc_encoder_layer
+                self.ctc_compress_strategy = args.ctc_compress_strategy
+                if self.ctc_compress_strategy not in ("avg", "weighted", "softmax"):
+                    raise ValueError("unknown --ctc-compress-strategy %r" % self.ctc_compress_strategy)
+            self._prep = None
+            self._prep_key = None
+            self._pos_table = None
+
+        # ------------------------------------------------------------------ derived operand formats
+        def _prepared(self):
+            params = list(self.parameters()) + list(self.buffers())
+            key = tuple((p._version, p.data_ptr()) for p in params)
+            if self._prep_key == key:
+                return self._prep
+            with torch.no_grad():
+                P = {}
+                C = self.conv_channels
+                P["w1"] = self.convolutions[0].weight.detach().reshape(C, 9).float().contiguous()
+                P["b1"] = self.convolutions[0].bias.detach().float().contiguous()
+                P["w2"] = ops.prep_conv2_weight(self.convolutions[1].weight.detach().float())
+                P["b2"] = self.convolutions[1].bias.detach().float().contiguous()
+                for i in range(2):
+                    bn = self.bn[i]
+                    P["bn%d" % i] = ops.prep_bn_affine(bn.weight.detach().float(), bn.bias.detach().float(),
+                                                       bn.running_mean.float(), bn.running_var.float(),
+                                                       bn.eps)
+                P["w3"] = ops.prep_fc3_weight(self.fc3.weight.detach().float(), C, self.feat_out)
+                P["b3"] = self.fc3.bias.detach().float().contiguous()
+                D = self.embed_dim
+                scale = 64 ** -0.5  # head_dim ** -0.5, folded into the q projection (exact: 2^-3)
+                layers = []
+                for lyr in self.layers:
+                    w, b = lyr.self_attn.qkv()
+                    w = w.detach().float().clone()
+                    b = b.detach().float().clone()
+                    w[:D] *= scale
+                    b[:D] *= scale
+                    layers.append(dict(
+                        ln1=(lyr.self_attn_layer_norm.weight.detach().float().contiguous(),
+                             lyr.self_attn_layer_norm.bias.detach().float().contiguous()),
+                        wqkv=ops.cast_bf16(w), bqkv=b.contiguous(),
+                        wo=ops.cast_bf16(lyr.self_attn.out_proj.weight.detach().float()),
+                        bo=lyr.self_attn.out_proj.bias.detach().float().contiguous(),
+                        ln2=(lyr.final_layer_norm.weight.detach().float().contiguous(),
+                             lyr.final_layer_norm.bias.detach().float().contiguous()),
+                        w1=ops.cast_bf16(lyr.fc1.weight.detach().float()),
+                        b1=lyr.fc1.bias.detach().float().contiguous(),
+                        w2=ops.cast_bf16(lyr.fc2.weight.detach().float()),
+                        b2=lyr.fc2.bias.detach().float().contiguous()))
+                P["layers"] = layers
+                P["lnf"] = (self.layer_norm.weight.detach().float().contiguous(),
+                            self.layer_norm.bias.detach().float().contiguous())
+                if self.layernorm_embedding is not None:
+                    P["lne"] = (self.layernorm_embedding.weight.detach().float().contiguous(),
+                                self.layernorm_embedding.bias.detach().float().contiguous())
+            self._prep, self._prep_key = P, key
+            return P
+
+        def _positions(self, rows, device):
+            t = self._pos_table
+            if t is None or t.shape[0] < rows or t.device != device:
+                t = ops.sinusoidal_table(max(rows, 1024), self.embed_dim, device)
+                self._pos_table = t
+            return t
+
+        # ------------------------------------------------------------------------------- forward
+        def forward(self, src_tokens, src_lengths, cls_input: Optional[Tensor] = None,
+                    return_all_hiddens: bool = False, **unused):
+            if self.training and torch.is_grad_enabled():
+                raise NotImplementedError(
+                    "fbkst_b200: the training backward of the encoder is not implemented yet; call "
+                    "eval() / torch.no_grad() (there is no PyTorch fallback)")
+            if not src_tokens.is_cuda:
+                raise RuntimeError("fbkst_b200: src_tokens must be a CUDA tensor (no CPU fallback)")
+            with torch.no_grad():
+                return self._forward(src_tokens, src_lengths, return_all_hiddens)
+
+        def _forward(self, src_tokens, src_lengths, return_all_hiddens):
+            dev = src_tokens.device
+            P = self._prepared()
+            B, T, Fd = src_tokens.shape
+            x_in = src_tokens if src_tokens.dtype == torch.float32 else src_tokens.float()
+            x_in = x_in.contiguous()
+            # lengths: one host copy drives all shape logic (the reference syncs per utterance)
+            len_host = src_lengths.tolist() if not src_lengths.is_cuda else src_lengths.cpu().tolist()
+            len_host = [((n + 1) // 2 + 1) // 2 for n in len_host]  # ceil(ceil(n/2)/2), :213
+            T1, T2 = (T + 1) // 2, ((T + 1) // 2 + 1) // 2
+            D, H = self.embed_dim, self.heads
+            y = ops.conv1_relu_bn(x_in, P["w1"], P["b1"], *P["bn0"])
+            y = ops.conv2_relu_bn(y, P["w2"], P["b2"], *P["bn1"])  # [B, T2, F2, C]
+            L = T2
+            lengths = torch.tensor(len_host, dtype=torch.int32).to(dev, non_blocking=True)
+            a = y.view(B * L, -1)
+            if self.embed_positions is not None:
+                table = self._positions(L + 1, dev)
+                x = ops.linear(a, P["w3"], P["b3"], relu=True, out_dtype=torch.float32,
+                               remap=(L, B), posemb=(table, lengths))
+            else:
+                x = ops.linear(a, P["w3"], P["b3"], relu=True, out_dtype=torch.float32, remap=(L, B))
             if self.layernorm_embedding is not None:
-                P["lne"] = (self.layernorm_embedding.weight.detach().float().contiguous(),
-                            self.layernorm_embedding.bias.detach().float().contiguous())
-        self._prep, self._prep_key = P, key
-        return P
-
-    def _positions(self, rows, device):
-        t = self._pos_table
-        if t is None or t.shape[0] < rows or t.device != device:
-            t = ops.sinusoidal_table(max(rows, 1024), self.embed_dim, device)
-            self._pos_table = t
-        return t
-
-    # ------------------------------------------------------------------------------- forward
-    def forward(self, src_tokens, src_lengths, cls_input: Optional[Tensor] = None,
-                return_all_hiddens: bool = False, **unused):
-        if self.training and torch.is_grad_enabled():
-            raise NotImplementedError(
-                "fbkst_b200: the training backward of the encoder is not implemented yet; call "
-                "eval() / torch.no_grad() (there is no PyTorch fallback)")
-        if not src_tokens.is_cuda:
-            raise RuntimeError("fbkst_b200: src_tokens must be a CUDA tensor (no CPU fallback)")
-        with torch.no_grad():
-            return self._forward(src_tokens, src_lengths, return_all_hiddens)
-
-    def _forward(self, src_tokens, src_lengths, return_all_hiddens):
-        dev = src_tokens.device
-        P = self._prepared()
-        B, T, Fd = src_tokens.shape
-        x_in = src_tokens if src_tokens.dtype == torch.float32 else src_tokens.float()
-        x_in = x_in.contiguous()
-        # lengths: one host copy drives all shape logic (the reference syncs per utterance)
-        len_host = src_lengths.tolist() if not src_lengths.is_cuda else src_lengths.cpu().tolist()
-        len_host = [((n + 1) // 2 + 1) // 2 for n in len_host]  # ceil(ceil(n/2)/2), :213
-        T1, T2 = (T + 1) // 2, ((T + 1) // 2 + 1) // 2
-        D, H = self.embed_dim, self.heads
-        y = ops.conv1_relu_bn(x_in, P["w1"], P["b1"], *P["bn0"])
-        y = ops.conv2_relu_bn(y, P["w2"], P["b2"], *P["bn1"])  # [B, T2, F2, C]
-        L = T2
-        lengths = torch.tensor(len_host, dtype=torch.int32).to(dev, non_blocking=True)
-        a = y.view(B * L, -1)
-        if self.embed_positions is not None:
-            table = self._positions(L + 1, dev)
-            x = ops.linear(a, P["w3"], P["b3"], relu=True, out_dtype=torch.float32,
-                           remap=(L, B), posemb=(table, lengths))
-        else:
-            x = ops.linear(a, P["w3"], P["b3"], relu=True, out_dtype=torch.float32, remap=(L, B))
-        if self.layernorm_embedding is not None:
-            x = ops.layernorm(x, *P["lne"], out_dtype=torch.float32)
-        mask = self._mask(lengths, len_host, L)
-        states = [] if return_all_hiddens else None
-        x_ctc, ctc_mask = None, None
-        for li, W in enumerate(P["layers"]):
-            torch.empty(1).uniform_()  # LayerDrop draw: keeps the CPU RNG stream of the reference
-            h = ops.layernorm(x, *W["ln1"])
-            qkv = ops.linear(h, W["wqkv"], W["bqkv"])
-            att = ops.attention(qkv, lengths, L, B, H, self.log_penalty)
-            x = ops.linear(att, W["wo"], W["bo"], residual=x, out_dtype=torch.float32)
-            h = ops.layernorm(x, *W["ln2"])
-            f = ops.linear(h, W["w1"], W["b1"], relu=True)
-            x = ops.linear(f, W["w2"], W["b2"], residual=x, out_dtype=torch.float32)
-            if self.ctc_compress_out and self.ctc_layer == li + 1:
-                ctc_mask = mask
-                x_ctc, x, lengths, len_host, L = self._ctc_compress(x, lengths, L, B)
-                mask = self._mask(lengths, len_host, L)
+                x = ops.layernorm(x, *P["lne"], out_dtype=torch.float32)
+            mask = self._mask(lengths, len_host, L)
+            states = [] if return_all_hiddens else None
+            x_ctc, ctc_mask = None, None
+            for li, W in enumerate(P["layers"]):
+                torch.empty(1).uniform_()  # LayerDrop draw: keeps the CPU RNG stream of the reference
+                h = ops.layernorm(x, *W["ln1"])
+                qkv = ops.linear(h, W["wqkv"], W["bqkv"])
+                att = ops.attention(qkv, lengths, L, B, H, self.log_penalty)
+                x = ops.linear(att, W["wo"], W["bo"], residual=x, out_dtype=torch.float32)
+                h = ops.layernorm(x, *W["ln2"])
+                f = ops.linear(h, W["w1"], W["b1"], relu=True)
+                x = ops.linear(f, W["w2"], W["b2"], residual=x, out_dtype=torch.float32)
+                if self.ctc_compress_out and self.ctc_layer == li + 1:
+                    ctc_mask = mask
+                    x_ctc, x, lengths, len_host, L = self._ctc_compress(x, lengths, L, B)
+                    mask = self._mask(lengths, len_host, L)
+                if return_all_hiddens:
+                    states.append(x.view(L, B, D))
+            x = ops.layernorm(x, *P["lnf"], out_dtype=torch.float32).view(L, B, D)
             if return_all_hiddens:
-                states.append(x.view(L, B, D))
-        x = ops.layernorm(x, *P["lnf"], out_dtype=torch.float32).view(L, B, D)
-        if return_all_hiddens:
-            states[-1] = x
-        out_lengths = torch.tensor(len_host, dtype=src_lengths.dtype).to(dev, non_blocking=True)
-        if self.ctc_compress_out:
-            return CTCAwareEncoderOut(x, mask, None, states, src_tokens, out_lengths, x_ctc, ctc_mask)
-        return EncoderOut(x, mask, None, states, src_tokens, out_lengths)
+                states[-1] = x
+            out_lengths = torch.tensor(len_host, dtype=src_lengths.dtype).to(dev, non_blocking=True)
+            if self.ctc_compress_out:
+                return CTCAwareEncoderOut(x, mask, None, states, src_tokens, out_lengths, x_ctc, ctc_mask)
+            return EncoderOut(x, mask, None, states, src_tokens, out_lengths)
 
-    def _mask(self, lengths, len_host, L):
-        """conv_transformer.py:293-300: B x L bool (True = pad) or None when nothing is padded."""
-        if min(len_host) >= L:
-            return None
-        return ops.lengths_to_mask(lengths, L)[0]
+        def _mask(self, lengths, len_host, L):
+            """conv_transformer.py:293-300: B x L bool (True = pad) or None when nothing is padded."""
+            if min(len_host) >= L:
+                return None
+            return ops.lengths_to_mask(lengths, L)[0]
 
-    def _ctc_compress(self, x, lengths, L, B):
-        """conv_transformer.py:278-291 on device; one D2H copy (the new lengths)."""
-        D = self.embed_dim
-        logits = self.ctc_fc(x.view(L, B, D))  # module call: forward hooks apply
-        V = logits.shape[-1]
-        try:
-            lg = logits.view(L * B, V)
-        except RuntimeError:
-            lg = logits.contiguous().view(L * B, V)
-        if lg.stride(-1) != 1:
-            lg = lg.contiguous()
-        want_prob = self.ctc_compress_strategy != "avg"
-        labels, prob = ops.ctc_argmax(lg, lengths, L, B, V, want_prob)
-        seg_id, seg_start, weight, new_len, max_new = ops.ctc_segment(
-            labels, prob, lengths, self.ctc_compress_strategy, L, B)
-        out = ops.ctc_compress(x, seg_start, weight, lengths, new_len, max_new, L, B)
-        new_host = new_len.cpu().tolist()  # the single host sync of the forward
-        L2 = max(new_host)
-        return logits, out[: L2 * B], new_len, new_host, L2
+        def _ctc_compress(self, x, lengths, L, B):
+            """conv_transformer.py:278-291 on device; one D2H copy (the new lengths)."""
+            D = self.embed_dim
+            logits = self.ctc_fc(x.view(L, B, D))  # module call: forward hooks apply
+            V = logits.shape[-1]
+            try:
+                lg = logits.view(L * B, V)
+            except RuntimeError:
+                lg = logits.contiguous().view(L * B, V)
+            if lg.stride(-1) != 1:
+                lg = lg.contiguous()
+            want_prob = self.ctc_compress_strategy != "avg"
+            labels, prob = ops.ctc_argmax(lg, lengths, L, B, V, want_prob)
+            seg_id, seg_start, weight, new_len, max_new = ops.ctc_segment(
+                labels, prob, lengths, self.ctc_compress_strategy, L, B)
+            out = ops.ctc_compress(x, seg_start, weight, lengths, new_len, max_new, L, B)
+            new_host = new_len.cpu().tolist()  # the single host sync of the forward
+            L2 = max(new_host)
+            return logits, out[: L2 * B], new_len, new_host, L2
 
-    # ----------------------------------------------------------------- reference interface
-    @property
-    def output_batch_first(self):
-        return False
+        # ----------------------------------------------------------------- reference interface
+        @property
+        def output_batch_first(self):
+            return False
 
-    @torch.jit.unused
-    def forward_non_torchscript(self, net_input: Dict[str, Tensor]):
-        encoder_input = {k: v for k, v in net_input.items()
-                         if k not in ("prev_output_tokens", "transcript_prev_output_tokens")}
-        return self.forward(**encoder_input)
+        @torch.jit.unused
+        def forward_non_torchscript(self, net_input: Dict[str, Tensor]):
+            encoder_input = {k: v for k, v in net_input.items()
+                             if k not in ("prev_output_tokens", "transcript_prev_output_tokens")}
+            return self.forward(**encoder_input)
 
-    def reorder_encoder_out(self, encoder_out, new_order):
-        """conv_transformer.py:315-345: index_select batch dim by ``new_order`` (beam search)."""
-        if encoder_out.encoder_out is not None:
-            encoder_out = encoder_out._replace(
-                encoder_out=encoder_out.encoder_out.index_select(1, new_order))
-        if encoder_out.encoder_padding_mask is not None:
-            encoder_out = encoder_out._replace(
-                encoder_padding_mask=encoder_out.encoder_padding_mask.index_select(0, new_order))
-        if encoder_out.encoder_embedding is not None:
-            encoder_out = encoder_out._replace(
-                encoder_embedding=encoder_out.encoder_embedding.index_select(0, new_order))
-        if encoder_out.encoder_states is not None:
-            for idx, state in enumerate(encoder_out.encoder_states):
-                encoder_out.encoder_states[idx] = state.index_select(1, new_order)
-        return encoder_out
+        def reorder_encoder_out(self, encoder_out, new_order):
+            """conv_transformer.py:315-345: index_select batch dim by ``new_order`` (beam search)."""
+            if encoder_out.encoder_out is not None:
+                encoder_out = encoder_out._replace(
+                    encoder_out=encoder_out.encoder_out.index_select(1, new_order))
+            if encoder_out.encoder_padding_mask is not None:
+                encoder_out = encoder_out._replace(
+                    encoder_padding_mask=encoder_out.encoder_padding_mask.index_select(0, new_order))
+            if encoder_out.encoder_embedding is not None:
+                encoder_out = encoder_out._replace(
+                    encoder_embedding=encoder_out.encoder_embedding.index_select(0, new_order))
+            if encoder_out.encoder_states is not None:
+                for idx, state in enumerate(encoder_out.encoder_states):
+                    encoder_out.encoder_states[idx] = state.index_select(1, new_order)
+            return encoder_out
+
+    return ConvolutionalTransformerEncoder
+
+
+ConvolutionalTransformerEncoder = make_encoder_class(_Base)

@@ -1,0 +1,63 @@
+"""fairseq ``--user-dir`` plugin: registers ``conv_transformer_b200`` and its four architectures.
+
+    python train.py DATA --user-dir /path/to/fbk-fairseq-st_b200/fbkst_b200/plugin \\
+        --arch conv_transformer_big2_b200 --task speech_translation_with_transcription \\
+        --criterion ctc_multi_loss ... --no-attn-2d --distance-penalty log --ctc-compress-out
+
+fairseq imports the user dir before parsing arguments (fairseq/options.py:119-122,
+fairseq/utils.py:344-359).  The plugin first imports the reference's own
+``examples.speech_recognition`` package (tasks, criterions, the reference model), then registers a
+model whose ``build_model`` is the reference's (examples/speech_recognition/models/
+conv_transformer.py:74-103) with the encoder swapped for the sm_100a one; decoder, task, criterion,
+trainer and checkpoints are fairseq's.  Architectures reuse the reference's arch functions, so every
+default (``:429-586``) is inherited.
+"""
+import os
+import sys
+
+_PKG_PARENT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+if _PKG_PARENT not in sys.path:
+    sys.path.insert(0, _PKG_PARENT)
+
+from fairseq.models import FairseqEncoder, register_model, register_model_architecture  # noqa: E402
+from fairseq.models.transformer import TransformerDecoder  # noqa: E402
+
+import examples.speech_recognition  # noqa: E402,F401  (registers the reference task/criterion/model)
+from examples.speech_recognition.models import conv_transformer as _ref  # noqa: E402
+
+from fbkst_b200 import encoder as _enc  # noqa: E402
+
+B200ConvolutionalTransformerEncoder = _enc.make_encoder_class(FairseqEncoder)
+# hand fairseq's own NamedTuple types to downstream isinstance checks
+_enc.EncoderOut = _ref.EncoderOut
+_enc.CTCAwareEncoderOut = _ref.CTCAwareEncoderOut
+
+
+@register_model("conv_transformer_b200")
+class B200ConvolutionalTransformerModel(_ref.ConvolutionalTransformerModel):
+    """Reference model class (args, state-dict upgrade hooks, freeze logic) with our encoder."""
+
+    @classmethod
+    def build_model(cls, args, task):
+        _ref.base_architecture(args)
+        if not hasattr(args, "max_source_positions"):
+            args.max_source_positions = 100000
+        if not hasattr(args, "max_target_positions"):
+            args.max_target_positions = 100000
+        src_dict, tgt_dict = task.source_dictionary, task.target_dictionary
+        emb = _ref.Embedding(len(tgt_dict), args.decoder_embed_dim, tgt_dict.pad())
+        if args.decoder_embed_path:
+            from fairseq import utils
+            utils.load_embedding(utils.parse_embedding(args.decoder_embed_path), tgt_dict, emb)
+        encoder = B200ConvolutionalTransformerEncoder(
+            args, src_dict if src_dict is not None else tgt_dict,
+            audio_features=args.input_feat_per_channel)
+        decoder = TransformerDecoder(args, tgt_dict, emb)
+        return cls(encoder, decoder)
+
+
+for _name, _fn in (("conv_transformer_b200", _ref.base_architecture),
+                   ("conv_transformer_big_b200", _ref.speechtransformer_big),
+                   ("conv_transformer_big2_b200", _ref.speechtransformer_big2),
+                   ("conv_transformer_giant_b200", _ref.speechtransformer_giant)):
+    register_model_architecture("conv_transformer_b200", _name)(_fn)
