@@ -108,7 +108,7 @@ class ClockSampler:
         try:
             self.p = subprocess.Popen(
                 ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS,
-                 "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL)
+                 "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
@@ -273,15 +273,16 @@ def run_ours(args, rank, world, local_rank):
         xn = ops.cmvn(x, len32)
         return enc(xn, l)  # lengths stay on the host: no D2H sync for shape logic
 
-    def step_e2e(i):
-        xh, l = host[i % n_batches]
-        x = xh.to(dev, non_blocking=True)
-        xn = ops.cmvn(x, len32)
-        out = enc(xn, l)
-        res = out.encoder_out.to("cpu", non_blocking=True)
-        nl = out.src_lengths.to("cpu", non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return res, nl
+    from fbkst_b200.pipeline import EncoderPipeline
+    pipe = EncoderPipeline(enc, normalize=True, device=dev)
+
+    def run_e2e(n):
+        """n steps through the public host-buffer API: pinned host batch -> H2D -> CMVN -> encoder
+        -> D2H of encoder_out + lengths (copies overlap the kernels of the neighbouring steps)."""
+        last = None
+        for res, nl in pipe.run(host[i % n_batches] for i in range(n)):
+            last = (res, nl)
+        return last
 
     def barrier():
         if world > 1:
@@ -290,7 +291,7 @@ def run_ours(args, rank, world, local_rank):
 
     for i in range(args.warmup):
         step_resident(i)
-        step_e2e(i)
+    run_e2e(args.warmup)
     barrier()
 
     # ---- timed region 1: inputs resident in HBM; L2 flushed (untimed) between steps
@@ -315,8 +316,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- timed region 2: end to end from pinned host buffers (H2D + D2H inside)
     barrier()
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        res, nl = step_e2e(i)
+    res, nl = run_e2e(args.steps)
     barrier()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop() if sampler else None

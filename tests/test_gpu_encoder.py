@@ -111,3 +111,26 @@ def test_training_mode_raises(golden_dir):
     enc = build_encoder(fx["cfg"], fx["state_dict"]).train()
     with pytest.raises(NotImplementedError):
         enc(fx["src_tokens"].cuda(), fx["src_lengths"].cuda())
+
+
+def test_pipeline_matches_direct_calls(golden_dir):
+    """The host-buffer serving loop (3 streams) returns exactly what direct calls return."""
+    from fbkst_b200 import ops
+    from fbkst_b200.pipeline import EncoderPipeline
+    fx = torch.load(os.path.join(golden_dir, "enc_tiny_log.pt"), weights_only=False)
+    enc = build_encoder(fx["cfg"], fx["state_dict"])
+    batches = []
+    for i, lens in enumerate([[61, 47, 30], [90, 90], [33, 20, 20, 7], [61, 47, 30]]):
+        x, l = O.synthetic_batch(lens, 40, seed=50 + i)
+        batches.append(((x * 2 + 1).pin_memory(), l))
+    direct = []
+    for x, l in batches:
+        xn = ops.cmvn(x.cuda(), l.to(torch.int32).cuda())
+        o = enc(xn, l)
+        direct.append((o.encoder_out.cpu(), o.src_lengths.cpu()))
+    pipe = EncoderPipeline(enc)
+    got = [(h.clone(), l.clone()) for h, l in pipe.run(iter(batches))]
+    assert len(got) == len(direct)
+    for (a, la), (b, lb) in zip(got, direct):
+        assert torch.equal(la, lb)
+        assert torch.equal(a, b)
