@@ -150,8 +150,9 @@ template <int NV>
 __global__ void __launch_bounds__(256)
     layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ beta, void* __restrict__ y, int out_f32, int M,
-                     float eps) {
+                     float eps, const int* __restrict__ m_limit, int m_limit_mult) {
   constexpr int D = NV * 128;
+  if (m_limit != nullptr) M = min(M, __ldg(m_limit) * m_limit_mult);
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
@@ -304,19 +305,20 @@ extern "C" int fbkst_conv1_relu_bn(const float* x, const float* w, const float* 
 }
 
 extern "C" int fbkst_layernorm(const float* x, const float* gamma, const float* beta, void* y,
-                               int out_dtype, int M, int D, float eps, fbkst_stream_t stream) {
+                               int out_dtype, int M, int D, float eps, const int32_t* m_limit,
+                               int m_limit_mult, fbkst_stream_t stream) {
   FBKST_REQUIRE(x && gamma && beta && y, "fbkst_layernorm: null pointer");
   FBKST_REQUIRE(M > 0, "fbkst_layernorm: M must be positive");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int f32 = out_dtype == FBKST_F32;
   const int grid = (M + 7) / 8;
   switch (D) {
-    case 128: layernorm_kernel<1><<<grid, 256, 0, st>>>(x, gamma, beta, y, f32, M, eps); break;
-    case 256: layernorm_kernel<2><<<grid, 256, 0, st>>>(x, gamma, beta, y, f32, M, eps); break;
-    case 384: layernorm_kernel<3><<<grid, 256, 0, st>>>(x, gamma, beta, y, f32, M, eps); break;
-    case 512: layernorm_kernel<4><<<grid, 256, 0, st>>>(x, gamma, beta, y, f32, M, eps); break;
-    case 768: layernorm_kernel<6><<<grid, 256, 0, st>>>(x, gamma, beta, y, f32, M, eps); break;
-    case 1024: layernorm_kernel<8><<<grid, 256, 0, st>>>(x, gamma, beta, y, f32, M, eps); break;
+    case 128: layernorm_kernel<1><<<grid, 256, 0, st>>>(x, gamma, beta, y, f32, M, eps, m_limit, m_limit_mult); break;
+    case 256: layernorm_kernel<2><<<grid, 256, 0, st>>>(x, gamma, beta, y, f32, M, eps, m_limit, m_limit_mult); break;
+    case 384: layernorm_kernel<3><<<grid, 256, 0, st>>>(x, gamma, beta, y, f32, M, eps, m_limit, m_limit_mult); break;
+    case 512: layernorm_kernel<4><<<grid, 256, 0, st>>>(x, gamma, beta, y, f32, M, eps, m_limit, m_limit_mult); break;
+    case 768: layernorm_kernel<6><<<grid, 256, 0, st>>>(x, gamma, beta, y, f32, M, eps, m_limit, m_limit_mult); break;
+    case 1024: layernorm_kernel<8><<<grid, 256, 0, st>>>(x, gamma, beta, y, f32, M, eps, m_limit, m_limit_mult); break;
     default:
       return set_error(FBKST_ERR_ARG, "fbkst_layernorm: unsupported D=%d (128..1024, multiple of 128)", D);
   }

@@ -98,7 +98,8 @@ template <bool OUT_F32, bool RESID>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
     gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, int M,
-                 int N, int K, const float* __restrict__ bias, int relu, int dbg) {
+                 int N, int K, const float* __restrict__ bias, int relu, int dbg,
+                 const int* __restrict__ m_limit, int m_limit_mult) {
   constexpr uint32_t TMEM_COLS = 512;  // two 256-column accumulator stages
   constexpr uint32_t IDESC = idesc_bf16_f32(256, G2_BN, 0, 0);
 
@@ -117,6 +118,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
   const uint32_t rank = cluster_ctarank();
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
+  // device-side row limit (rows valid after CTC compression): tiles beyond it are skipped
+  if (m_limit != nullptr) M = min(M, __ldg(m_limit) * m_limit_mult);
   const int num_n = (N + G2_BN - 1) / G2_BN;
   const int num_m = (M + 2 * G2_BM - 1) / (2 * G2_BM);
   const int num_tiles = num_m * num_n;
@@ -376,7 +379,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 template <bool OUT_F32, bool RESID>
 static int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
                         const float* resid, int64_t ldr, void* out, int64_t ldo, int M, int N, int K,
-                        int relu, cudaStream_t stream) {
+                        int relu, const int* m_limit, int m_limit_mult, cudaStream_t stream) {
   static_assert(G2_SMEM <= 232448, "shared memory budget exceeded");
   auto kern = gemm2_kernel<OUT_F32, RESID>;
   static bool configured = false;
@@ -411,7 +414,8 @@ static int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, 
   const int max_clusters = num_sms() / 2;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
   static const int dbg = getenv("FBKST_GEMM_DBG") ? atoi(getenv("FBKST_GEMM_DBG")) : 0;
-  kern<<<2 * clusters, 384, G2_SMEM, stream>>>(tmA, tmB, tmO, tmR, M, N, K, bias, relu, dbg);
+  kern<<<2 * clusters, 384, G2_SMEM, stream>>>(tmA, tmB, tmO, tmR, M, N, K, bias, relu, dbg, m_limit,
+                                               m_limit_mult);
   FBKST_CHECK_CUDA(cudaGetLastError());
   return FBKST_OK;
 }
@@ -419,12 +423,15 @@ static int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, 
 // Entry used by fbkst_linear_bf16 (gemm_tcgen05.cu) for the plain / residual epilogues.
 int linear_pair_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
                          const float* resid, int64_t ldr, void* out, int64_t ldo, int M, int N, int K,
-                         int relu, int out_f32, cudaStream_t stream) {
+                         int relu, int out_f32, const int* m_limit, int m_limit_mult, cudaStream_t stream) {
   if (resid != nullptr)
-    return launch_gemm2<true, true>(A, lda, W, ldw, bias, resid, ldr, out, ldo, M, N, K, relu, stream);
+    return launch_gemm2<true, true>(A, lda, W, ldw, bias, resid, ldr, out, ldo, M, N, K, relu, m_limit,
+                                    m_limit_mult, stream);
   if (out_f32)
-    return launch_gemm2<true, false>(A, lda, W, ldw, bias, nullptr, 0, out, ldo, M, N, K, relu, stream);
-  return launch_gemm2<false, false>(A, lda, W, ldw, bias, nullptr, 0, out, ldo, M, N, K, relu, stream);
+    return launch_gemm2<true, false>(A, lda, W, ldw, bias, nullptr, 0, out, ldo, M, N, K, relu, m_limit,
+                                     m_limit_mult, stream);
+  return launch_gemm2<false, false>(A, lda, W, ldw, bias, nullptr, 0, out, ldo, M, N, K, relu, m_limit,
+                                    m_limit_mult, stream);
 }
 
 }  // namespace fbkst

@@ -18,7 +18,7 @@ namespace fbkst {
 // gemm2_tcgen05.cu: CTA-pair (cta_group::2) kernel for the plain / residual epilogues
 int linear_pair_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
                          const float* resid, int64_t ldr, void* out, int64_t ldo, int M, int N, int K,
-                         int relu, int out_f32, cudaStream_t stream);
+                         int relu, int out_f32, const int* m_limit, int m_limit_mult, cudaStream_t stream);
 
 struct EpiParams {
   const float* bias;
@@ -607,7 +607,8 @@ static int launch_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, i
 extern "C" int fbkst_linear_bf16(const void* A, int64_t lda, const void* W, int64_t ldw,
                                  const float* bias, const float* residual, int64_t ldr, void* out,
                                  int64_t ldo, int M, int N, int K, int flags, int remap_inner,
-                                 int remap_outer, const int32_t* lengths, fbkst_stream_t stream) {
+                                 int remap_outer, const int32_t* lengths, const int32_t* m_limit,
+                                 int m_limit_mult, fbkst_stream_t stream) {
   using namespace fbkst;
   FBKST_REQUIRE(A && W && out, "fbkst_linear_bf16: null operand");
   FBKST_REQUIRE(M > 0 && N > 0 && K > 0, "fbkst_linear_bf16: empty problem M=%d N=%d K=%d", M, N, K);
@@ -643,7 +644,7 @@ extern "C" int fbkst_linear_bf16(const void* A, int64_t lda, const void* W, int6
   static const bool single_cta = getenv("FBKST_GEMM_1CTA") != nullptr;  // A/B switch for profiling
   if (!single_cta)
     return linear_pair_dispatch(A, lda, W, ldw, bias, residual, ldr, out, ldo, M, N, K, relu,
-                                (flags & FBKST_EPI_OUT_F32) ? 1 : 0, st);
+                                (flags & FBKST_EPI_OUT_F32) ? 1 : 0, m_limit, m_limit_mult, st);
   if (residual != nullptr) {
     return launch_gemm_tma<true, true, 3>(A, lda, W, ldw, bias, residual, ldr, out, ldo, M, N, K, relu, st);
   }

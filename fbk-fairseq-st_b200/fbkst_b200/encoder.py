@@ -232,6 +232,8 @@ def make_encoder_class(base):
             self._prep = None
             self._prep_key = None
             self._pos_table = None
+            self._ws = None
+            self._ws_key = None
 
         # ------------------------------------------------------------------ derived operand formats
         def _prepared(self):
@@ -311,11 +313,10 @@ def make_encoder_class(base):
             # lengths: one host copy drives all shape logic (the reference syncs per utterance)
             len_host = src_lengths.tolist() if not src_lengths.is_cuda else src_lengths.cpu().tolist()
             len_host = [((n + 1) // 2 + 1) // 2 for n in len_host]  # ceil(ceil(n/2)/2), :213
-            T1, T2 = (T + 1) // 2, ((T + 1) // 2 + 1) // 2
             D, H = self.embed_dim, self.heads
             y = ops.conv1_relu_bn(x_in, P["w1"], P["b1"], *P["bn0"])
             y = ops.conv2_relu_bn(y, P["w2"], P["b2"], *P["bn1"])  # [B, T2, F2, C]
-            L = T2
+            L = y.shape[1]
             lengths = torch.tensor(len_host, dtype=torch.int32).to(dev, non_blocking=True)
             a = y.view(B * L, -1)
             if self.embed_positions is not None:
@@ -329,28 +330,72 @@ def make_encoder_class(base):
             mask = self._mask(lengths, len_host, L)
             states = [] if return_all_hiddens else None
             x_ctc, ctc_mask = None, None
+            # After CTC compression the number of valid rows is known only on the device.  Unless the
+            # caller wants every hidden state (exact shapes per layer), the remaining layers are
+            # launched for the worst case with a device-side row limit and persistent, finite
+            # workspaces; the single host sync of the forward is the final read of the new lengths.
+            limit, ws, new_len = None, None, None
             for li, W in enumerate(P["layers"]):
                 torch.empty(1).uniform_()  # LayerDrop draw: keeps the CPU RNG stream of the reference
-                h = ops.layernorm(x, *W["ln1"])
-                qkv = ops.linear(h, W["wqkv"], W["bqkv"])
-                att = ops.attention(qkv, lengths, L, B, H, self.log_penalty)
-                x = ops.linear(att, W["wo"], W["bo"], residual=x, out_dtype=torch.float32)
-                h = ops.layernorm(x, *W["ln2"])
-                f = ops.linear(h, W["w1"], W["b1"], relu=True)
-                x = ops.linear(f, W["w2"], W["b2"], residual=x, out_dtype=torch.float32)
+                if limit is None:
+                    h = ops.layernorm(x, *W["ln1"])
+                    qkv = ops.linear(h, W["wqkv"], W["bqkv"])
+                    att = ops.attention(qkv, lengths, L, B, H, self.log_penalty)
+                    x = ops.linear(att, W["wo"], W["bo"], residual=x, out_dtype=torch.float32)
+                    h = ops.layernorm(x, *W["ln2"])
+                    f = ops.linear(h, W["w1"], W["b1"], relu=True)
+                    x = ops.linear(f, W["w2"], W["b2"], residual=x, out_dtype=torch.float32)
+                else:
+                    h = ops.layernorm(x, *W["ln1"], out=ws["h"], rows_limit=limit)
+                    qkv = ops.linear(h, W["wqkv"], W["bqkv"], out=ws["qkv"], rows_limit=limit)
+                    att = ops.attention(qkv, lengths, L, B, H, self.log_penalty, out=ws["att"])
+                    x1 = ops.linear(att, W["wo"], W["bo"], residual=x, out_dtype=torch.float32,
+                                    out=ws["x1"], rows_limit=limit)
+                    h = ops.layernorm(x1, *W["ln2"], out=ws["h"], rows_limit=limit)
+                    f = ops.linear(h, W["w1"], W["b1"], relu=True, out=ws["f"], rows_limit=limit)
+                    x = ops.linear(f, W["w2"], W["b2"], residual=x1, out_dtype=torch.float32,
+                                   out=ws["x0"], rows_limit=limit)
                 if self.ctc_compress_out and self.ctc_layer == li + 1:
                     ctc_mask = mask
-                    x_ctc, x, lengths, len_host, L = self._ctc_compress(x, lengths, L, B)
-                    mask = self._mask(lengths, len_host, L)
+                    if return_all_hiddens:
+                        x_ctc, x, lengths, len_host, L = self._ctc_compress(x, lengths, L, B)
+                        mask = self._mask(lengths, len_host, L)
+                    else:
+                        ws = self._workspace(L * B, dev)
+                        x_ctc, x, lengths, max_new = self._ctc_compress(x, lengths, L, B, out=ws["x0"])
+                        new_len = lengths
+                        limit = (max_new, B)
                 if return_all_hiddens:
                     states.append(x.view(L, B, D))
-            x = ops.layernorm(x, *P["lnf"], out_dtype=torch.float32).view(L, B, D)
+            xf = ops.layernorm(x, *P["lnf"], out_dtype=torch.float32, rows_limit=limit)
+            if limit is not None:
+                mask_full = ops.lengths_to_mask(new_len, L)[0]
+                len_host = new_len.cpu().tolist()  # the single host sync of the forward
+                L2 = max(len_host)
+                xf = xf[: L2 * B]
+                mask = None if min(len_host) >= L2 else mask_full[:, :L2].contiguous()
+                L = L2
+            xf = xf.view(L, B, D)
             if return_all_hiddens:
-                states[-1] = x
+                states[-1] = xf
             out_lengths = torch.tensor(len_host, dtype=src_lengths.dtype).to(dev, non_blocking=True)
             if self.ctc_compress_out:
-                return CTCAwareEncoderOut(x, mask, None, states, src_tokens, out_lengths, x_ctc, ctc_mask)
-            return EncoderOut(x, mask, None, states, src_tokens, out_lengths)
+                return CTCAwareEncoderOut(xf, mask, None, states, src_tokens, out_lengths, x_ctc, ctc_mask)
+            return EncoderOut(xf, mask, None, states, src_tokens, out_lengths)
+
+        def _workspace(self, M, dev):
+            """Persistent zero-initialised buffers for the layers after compression (rows beyond the
+            device-side limit are never written, so they must hold finite values: 0 * NaN would
+            poison the P.V product of a partially valid key tile)."""
+            key = (M, str(dev))
+            if self._ws_key != key:
+                D, Dff = self.embed_dim, self.layers[0].fc1.out_features
+                z = lambda n, dt: torch.zeros(M, n, dtype=dt, device=dev)
+                self._ws = dict(h=z(D, torch.bfloat16), qkv=z(3 * D, torch.bfloat16),
+                                att=z(D, torch.bfloat16), f=z(Dff, torch.bfloat16),
+                                x0=z(D, torch.float32), x1=z(D, torch.float32))
+                self._ws_key = key
+            return self._ws
 
         def _mask(self, lengths, len_host, L):
             """conv_transformer.py:293-300: B x L bool (True = pad) or None when nothing is padded."""
@@ -358,8 +403,10 @@ def make_encoder_class(base):
                 return None
             return ops.lengths_to_mask(lengths, L)[0]
 
-        def _ctc_compress(self, x, lengths, L, B):
-            """conv_transformer.py:278-291 on device; one D2H copy (the new lengths)."""
+        def _ctc_compress(self, x, lengths, L, B, out=None):
+            """conv_transformer.py:278-291 on device.  With ``out`` (workspace mode) nothing is read
+            back: returns (logits, out, new_len, max_new) as device tensors.  Otherwise one D2H copy
+            (the new lengths) gives the exact output shape."""
             D = self.embed_dim
             logits = self.ctc_fc(x.view(L, B, D))  # module call: forward hooks apply
             V = logits.shape[-1]
@@ -373,10 +420,12 @@ def make_encoder_class(base):
             labels, prob = ops.ctc_argmax(lg, lengths, L, B, V, want_prob)
             seg_id, seg_start, weight, new_len, max_new = ops.ctc_segment(
                 labels, prob, lengths, self.ctc_compress_strategy, L, B)
-            out = ops.ctc_compress(x, seg_start, weight, lengths, new_len, max_new, L, B)
-            new_host = new_len.cpu().tolist()  # the single host sync of the forward
+            res = ops.ctc_compress(x, seg_start, weight, lengths, new_len, max_new, L, B, out=out)
+            if out is not None:
+                return logits, res, new_len, max_new
+            new_host = new_len.cpu().tolist()  # host sync: exact shapes for encoder_states
             L2 = max(new_host)
-            return logits, out[: L2 * B], new_len, new_host, L2
+            return logits, res[: L2 * B], new_len, new_host, L2
 
         # ----------------------------------------------------------------- reference interface
         @property

@@ -71,10 +71,11 @@ def conv2_relu_bn(x, w_taps, bias, scale, shift):
 
 
 def linear(a, w, bias=None, relu=False, residual=None, out_dtype=torch.bfloat16, out=None,
-           remap=None, posemb=None):
+           remap=None, posemb=None, rows_limit=None):
     """out = epi(a @ w.T).  a [M,K] bf16, w [N,K] bf16, bias [N] fp32, residual [M,N] fp32.
     remap=(inner, outer): out row = (m % inner)*outer + m // inner.
-    posemb=(table [P,N] fp32, lengths [outer] int32): adds table[pos(m)] (needs remap dims)."""
+    posemb=(table [P,N] fp32, lengths [outer] int32): adds table[pos(m)] (needs remap dims).
+    rows_limit=(count [1] int32 device tensor, mult): only rows < count*mult are computed."""
     lib = _lib.require_device()
     _req(a, torch.bfloat16, "linear.a"); _req(w, torch.bfloat16, "linear.w")
     M, K = a.shape
@@ -103,30 +104,35 @@ def linear(a, w, bias=None, relu=False, residual=None, out_dtype=torch.bfloat16,
         raise ValueError("fbkst_b200.linear: bad out tensor")
     check(lib.fbkst_linear_bf16(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _ptr(bias),
                                 _ptr(res), ldr, out.data_ptr(), out.stride(0), M, N, K, flags,
-                                inner, outer, _ptr(lengths), _stream()))
+                                inner, outer, _ptr(lengths),
+                                _ptr(rows_limit[0]) if rows_limit else 0,
+                                rows_limit[1] if rows_limit else 0, _stream()))
     _count()
     return out
 
 
-def layernorm(x, gamma, beta, out_dtype=torch.bfloat16, eps=1e-5):
+def layernorm(x, gamma, beta, out_dtype=torch.bfloat16, eps=1e-5, out=None, rows_limit=None):
     lib = _lib.require_device()
     _req(x, torch.float32, "layernorm.x")
     M, D = x.shape
-    y = torch.empty(M, D, dtype=out_dtype, device=x.device)
+    y = torch.empty(M, D, dtype=out_dtype, device=x.device) if out is None else out
     check(lib.fbkst_layernorm(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(),
-                              F32 if out_dtype == torch.float32 else BF16, M, D, eps, _stream()))
+                              F32 if out_dtype == torch.float32 else BF16, M, D, eps,
+                              _ptr(rows_limit[0]) if rows_limit else 0,
+                              rows_limit[1] if rows_limit else 0, _stream()))
     _count()
     return y
 
 
-def attention(qkv, lengths, L, B, H, log_penalty=True):
+def attention(qkv, lengths, L, B, H, log_penalty=True, out=None):
     """qkv [L*B, 3*H*64] bf16 (row t*B+b) -> [L*B, H*64] bf16."""
     lib = _lib.require_device()
     _req(qkv, torch.bfloat16, "attention.qkv"); _req(lengths, torch.int32, "attention.lengths")
     if qkv.shape != (L * B, 3 * H * 64):
         raise ValueError("fbkst_b200.attention: qkv shape %s != (%d, %d)" %
                          (tuple(qkv.shape), L * B, 3 * H * 64))
-    out = torch.empty(L * B, H * 64, dtype=torch.bfloat16, device=qkv.device)
+    if out is None:
+        out = torch.empty(L * B, H * 64, dtype=torch.bfloat16, device=qkv.device)
     check(lib.fbkst_attention_fwd(qkv.data_ptr(), out.data_ptr(), lengths.data_ptr(), L, B, H,
                                   1 if log_penalty else 0, _stream()))
     _count()
@@ -184,11 +190,12 @@ def ctc_segment(labels, top_prob, lengths, strategy, L, B):
     return seg_id, seg_start, weight, new_len, max_new
 
 
-def ctc_compress(x, seg_start, weight, lengths, new_len, max_new, L, B):
+def ctc_compress(x, seg_start, weight, lengths, new_len, max_new, L, B, out=None):
     lib = _lib.require_device()
     _req(x, torch.float32, "ctc_compress.x")
     D = x.shape[-1]
-    out = torch.empty(L * B, D, dtype=torch.float32, device=x.device)
+    if out is None:
+        out = torch.empty(L * B, D, dtype=torch.float32, device=x.device)
     check(lib.fbkst_ctc_compress(x.data_ptr(), seg_start.data_ptr(), weight.data_ptr(),
                                  lengths.data_ptr(), new_len.data_ptr(), max_new.data_ptr(),
                                  out.data_ptr(), L, B, D, _stream()))

@@ -85,17 +85,24 @@ int fbkst_conv2_relu_bn(const void* x, const void* w_taps, const float* bias,
  *   FBKST_EPI_POSEMB   : y += residual[pos(m), n]  with m = b*remap_inner + t,
  *                        pos = t < lengths[b] ? t+1 : 0   (sinusoidal table, row 0 = 0)
  * out row is m, or the remapped row if FBKST_EPI_ROW_REMAP; out pitch ldo; dtype by flag.
+ * m_limit (device, may be NULL): only rows m < m_limit[0] * m_limit_mult are computed -- the
+ * number of rows that are valid after CTC compression is known only on the device, so the
+ * layers after it are launched for the worst case and skip the tiles beyond the limit
+ * (no host synchronisation in the middle of the forward).
  * K % 8 == 0; lda, ldw % 8 == 0; all bases 16-byte aligned. */
 int fbkst_linear_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
                       const float* residual, int64_t ldr, void* out, int64_t ldo, int M, int N,
                       int K, int flags, int remap_inner, int remap_outer,
-                      const int32_t* lengths, fbkst_stream_t stream);
+                      const int32_t* lengths, const int32_t* m_limit, int m_limit_mult,
+                      fbkst_stream_t stream);
 
 /* ---- a8: LayerNorm over the last dim (eps 1e-5, affine) ----------------------------------
  * replaces fairseq/modules/layer_norm.py:29-32 call sites (transformer_layer.py:108,126;
- * conv_transformer.py:253-254).  x [M,D] fp32 -> y [M,D] bf16 or fp32.  D % 128 == 0, D<=2048 */
+ * conv_transformer.py:253-254).  x [M,D] fp32 -> y [M,D] bf16 or fp32.  D in {128,256,384,512,
+ * 768,1024}.  m_limit as in fbkst_linear_bf16. */
 int fbkst_layernorm(const float* x, const float* gamma, const float* beta, void* y, int out_dtype,
-                    int M, int D, float eps, fbkst_stream_t stream);
+                    int M, int D, float eps, const int32_t* m_limit, int m_limit_mult,
+                    fbkst_stream_t stream);
 
 /* ---- a7: self-attention core with key-padding mask and log distance penalty --------------
  * replaces local_attention.py:115-139 (and the math of F.multi_head_attention_forward when
