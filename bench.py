@@ -46,6 +46,12 @@ CONFIGS = {
                  name="6L d256 h4 ffn768, ctc-compress avg @4, batch 8x1000x40"),
 }
 CTC_MARGIN = 30.0
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
+# captures (profiles/r01a_ncu_gemm2.txt: mean over the captured launches of each kernel)
+NCU_TRAFFIC = {
+    "gemm2_kernel<bf16 out> (qkv, fc1, ctc_fc)": int((26.21 + 17.19 + 26.78 + 40.57) / 2 * 1e6),
+    "gemm2_kernel<f32 out + residual> (out_proj, fc2)": int((74.30 + 9.23 + 151.59 + 23.07) / 2 * 1e6),
+}
 
 
 def peaks():
@@ -180,7 +186,14 @@ class KernelProfile:
             by = (M * K + N * K) * 2 + M * N * (4 if out.dtype == torch.float32 else 2)
             if k.get("residual") is not None:
                 by += M * N * 4
-            return dict(flops=2.0 * M * N * K, bytes=by)
+            # which kernel serves this launch (csrc/gemm2_tcgen05.cu, csrc/gemm_tcgen05.cu)
+            if k.get("remap") is not None:
+                sub = "gemm_bf16_kernel (fc3: row remap + pos-emb epilogue)"
+            elif k.get("residual") is not None:
+                sub = "gemm2_kernel<f32 out + residual> (out_proj, fc2)"
+            else:
+                sub = "gemm2_kernel<bf16 out> (qkv, fc1, ctc_fc)"
+            return dict(flops=2.0 * M * N * K, bytes=by, sub=sub)
 
         def att(a, k, out):
             qkv, lengths, L, B, H = a[:5]
@@ -228,11 +241,14 @@ class KernelProfile:
         torch.cuda.synchronize()
         agg = {}
         for name, s, e, w in self.records:
-            d = agg.setdefault(name, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
-            d["ms"] += s.elapsed_time(e)
-            d["flops"] += w["flops"]
-            d["bytes"] += w["bytes"]
-            d["launches"] += 1
+            for key in (name, w.get("sub")):
+                if key is None:
+                    continue
+                d = agg.setdefault(key, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
+                d["ms"] += s.elapsed_time(e)
+                d["flops"] += w["flops"]
+                d["bytes"] += w["bytes"]
+                d["launches"] += 1
         out = {}
         for name, d in agg.items():
             sec = d["ms"] * 1e-3
@@ -255,6 +271,7 @@ def run_ours(args, rank, world, local_rank):
     enc = build_encoder(model, None, device="cpu")
     randomise_norm_stats(enc, 1)
     enc = enc.to(dev).eval()
+    enc.use_cuda_graph = not args.no_graph  # one captured graph per input shape (see encoder._replay)
     L = ((T + 1) // 2 + 1) // 2
     plan = label_plan(L, B, model["vocab"], seed=7 + rank).to(dev)
 
@@ -333,11 +350,17 @@ def run_ours(args, rank, world, local_rank):
     # ---- per-kernel attribution (separate, untimed pass; same stream, CUDA events)
     kern = None
     if rank == 0:
+        enc.use_cuda_graph = False  # the attribution pass needs the individual launches
         with KernelProfile(ops) as kp:
             kp.att_lengths = [((n + 1) // 2 + 1) // 2 for n in lengths]
             kp.new_lengths = out.src_lengths.tolist()
             kp.L_pre = L
             prof_steps = 3
+            step_resident(0)  # eager warm-up (allocations, workspaces) before the events
+            torch.cuda.synchronize()
+            kp.records.clear()
+            # keep the GPU behind the CPU so that no launch gap leaks into an event interval
+            torch.cuda._sleep(int(0.06 * 1.9e9))
             for i in range(prof_steps):
                 step_resident(i)
             kern = kp.summary(prof_steps)
@@ -347,11 +370,19 @@ def run_ours(args, rank, world, local_rank):
     pk = peaks()
     ms_per_step = dev_ms / args.steps
     value = world * frames / (ms_per_step * 1e-3)
-    lin = kern["linear"]
-    roofline = dict(kernel="gemm_bf16_kernel (tcgen05 linear, all %d launches/step)" % lin["launches_per_step"],
+    # dominant kernel = the kernel with the largest share of the step
+    dom = max((k for k in kern if k.startswith("gemm")), key=lambda k: kern[k]["ms_per_step"])
+    lin = kern[dom]
+    roofline = dict(kernel="%s, %d launches/step, %.1f%% of the step" % (
+                        dom, lin["launches_per_step"], 100 * lin["ms_per_step"] / sum(
+                            v["ms_per_step"] for k, v in kern.items() if not k.startswith("gemm"))),
                     bound="tensor", achieved=lin["tflops"], peak=pk["tf_sust"], unit="TFLOP/s",
-                    frac=round(lin["tflops"] / pk["tf_sust"], 4), traffic=None,
-                    peak_source=pk["src"] + " (sustained bf16: kernel timed inside a long step)")
+                    frac=round(lin["tflops"] / pk["tf_sust"], 4), traffic=NCU_TRAFFIC.get(dom),
+                    traffic_unit="bytes/launch (dram read+write, ncu --set full, profiles/)",
+                    algorithmic="flops of the valid rows of every launch / CUDA-event time of the "
+                                "launches (separate attribution pass, same stream)",
+                    peak_source=pk["src"] + " (sustained bf16: kernel timed inside a long step)",
+                    all_linear_tflops=kern["linear"]["tflops"])
     h2d = host[0][0].numel() * 4
     d2h = res.numel() * res.element_size() + nl.numel() * nl.element_size()
     result = dict(
@@ -363,6 +394,7 @@ def run_ours(args, rank, world, local_rank):
                     ctc_logit_injection="run-structured labels (geometric mean 3, 50%% blank), margin %g" % CTC_MARGIN,
                     compression_ratio=round(new_frames / sum(((n + 1) // 2 + 1) // 2 for n in lengths), 3),
                     cache="L2 flushed (256 MB write) between timed steps; 4 rotating input batches",
+                    launch="eager" if args.no_graph else "CUDA graph replay of the encoder body",
                     parallelism="utterance-batch sharded x%d, no forward collective" % world),
         e2e=dict(value=round(world * frames / (e2e_ms * 1e-3 / args.steps), 1), unit="frames/s",
                  h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
@@ -429,6 +461,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch kernel by kernel instead of graph replay")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

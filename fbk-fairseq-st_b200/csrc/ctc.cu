@@ -42,6 +42,12 @@ __device__ __forceinline__ void argmax_merge(ArgMax& a, float v, int i, float s,
   }
 }
 
+constexpr float kLog2eCtc = 1.4426950408889634f;
+__device__ __forceinline__ float exp2f_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 
@@ -119,6 +125,154 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Fast path (rows 16-byte aligned: base and pitch multiples of 16 B -- the layout fbkst_linear_bf16
+// produces).  One warp per row; every lane issues UNROLL independent 16-byte loads before touching
+// any of them (the generic kernel above interleaves load and use: one load in flight per lane).
+// The streaming loop only tracks, per lane, the running maximum and the index of the 16-byte
+// VECTOR that holds it (bf16: packed HMNMX2, ~1 instruction per element instead of 4); the element
+// index is recovered once per row by re-reading that one vector.  The optional sum of exponentials
+// is rescaled once per vector.  Ties resolve to the lowest index at every level (strict '>' in
+// index order inside a lane, (value, index) merge across lanes).
+__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+
+template <int IS_BF16, int WANT_SUM>
+__global__ void __launch_bounds__(256)
+    ctc_argmax_vec_kernel(const uint4* __restrict__ logits, long long row_vecs,
+                          const int* __restrict__ lengths, int* __restrict__ labels,
+                          float* __restrict__ top_prob, int rows, int B, int V) {
+  constexpr int EPV = IS_BF16 ? 8 : 4;  // elements per 16-byte vector
+  constexpr int UNROLL = 8;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int t = row / B, b = row - t * B;
+  if (t >= __ldg(lengths + b)) {
+    if (lane == 0) {
+      labels[row] = -1;
+      if (WANT_SUM) top_prob[row] = 0.0f;
+    }
+    return;
+  }
+  const uint4* vp = logits + (size_t)row * row_vecs;
+  const int nvec = (V + EPV - 1) / EPV;  // the last vector may hold columns >= V (masked below)
+  const int tail = V - (nvec - 1) * EPV;  // valid elements of the last vector (1..EPV)
+  float bv = -INFINITY, bs = 0.0f;  // running max / sum of exp(x - bv) of this lane
+  int bvec = -1;                    // vector that holds the running max
+  // columns >= V of the last vector -> -inf
+  auto mask_tail = [&](uint4& u) {
+    uint32_t* w = reinterpret_cast<uint32_t*>(&u);
+    if (IS_BF16) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k >= tail) w[k >> 1] = (k & 1) ? ((w[k >> 1] & 0x0000ffffu) | 0xff800000u)
+                                           : ((w[k >> 1] & 0xffff0000u) | 0x0000ff80u);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (k >= tail) w[k] = 0xff800000u;
+    }
+  };
+  int bi0 = 0x7fffffff;  // WANT_SUM == 0: element index tracked directly (memory-bound already)
+  auto consume = [&](uint4 u, int vi) {
+    if (vi == nvec - 1 && tail != EPV) mask_tail(u);
+    if (!WANT_SUM) {
+      float x[EPV];
+      if (IS_BF16) {
+        x[0] = bf16_lo(u.x); x[1] = bf16_hi(u.x); x[2] = bf16_lo(u.y); x[3] = bf16_hi(u.y);
+        x[4 % EPV] = bf16_lo(u.z); x[5 % EPV] = bf16_hi(u.z);
+        x[6 % EPV] = bf16_lo(u.w); x[7 % EPV] = bf16_hi(u.w);
+      } else {
+        x[0] = __uint_as_float(u.x); x[1] = __uint_as_float(u.y);
+        x[2] = __uint_as_float(u.z); x[3] = __uint_as_float(u.w);
+      }
+#pragma unroll
+      for (int k = 0; k < EPV; ++k) {  // strict '>' keeps the lowest index of equal values
+        const bool g2 = x[k] > bv;
+        bv = g2 ? x[k] : bv;
+        bi0 = g2 ? vi * EPV + k : bi0;
+      }
+      return;
+    }
+    float m;
+    if (IS_BF16) {
+      const uint32_t p = bf16x2_max(bf16x2_max(u.x, u.y), bf16x2_max(u.z, u.w));
+      m = fmaxf(bf16_lo(p), bf16_hi(p));
+    } else {
+      m = fmaxf(fmaxf(__uint_as_float(u.x), __uint_as_float(u.y)),
+                fmaxf(__uint_as_float(u.z), __uint_as_float(u.w)));
+    }
+    const bool gt = m > bv;  // strict: an earlier vector keeps equal values
+    const float mn = gt ? m : bv;
+    if (WANT_SUM) {
+      if (mn != -INFINITY) {
+        const float nb = -mn * kLog2eCtc;
+        float x[EPV];
+        if (IS_BF16) {
+          x[0] = bf16_lo(u.x); x[1] = bf16_hi(u.x); x[2] = bf16_lo(u.y); x[3] = bf16_hi(u.y);
+          x[4 % EPV] = bf16_lo(u.z); x[5 % EPV] = bf16_hi(u.z);
+          x[6 % EPV] = bf16_lo(u.w); x[7 % EPV] = bf16_hi(u.w);
+        } else {
+          x[0] = __uint_as_float(u.x); x[1] = __uint_as_float(u.y);
+          x[2] = __uint_as_float(u.z); x[3] = __uint_as_float(u.w);
+        }
+        float add0 = 0.0f, add1 = 0.0f;
+#pragma unroll
+        for (int k = 0; k < EPV; k += 2) {
+          add0 += exp2f_approx(fmaf(x[k], kLog2eCtc, nb));
+          add1 += exp2f_approx(fmaf(x[k + 1], kLog2eCtc, nb));
+        }
+        bs = fmaf(bs, exp2f_approx(fmaf(bv, kLog2eCtc, nb)), add0 + add1);
+      }
+    }
+    bv = mn;
+    bvec = gt ? vi : bvec;
+  };
+  int i = lane;
+  for (; i + 32 * (UNROLL - 1) < nvec; i += 32 * UNROLL) {
+    uint4 u[UNROLL];
+#pragma unroll
+    for (int k = 0; k < UNROLL; ++k) u[k] = ld_nc_na(vp + i + 32 * k);
+#pragma unroll
+    for (int k = 0; k < UNROLL; ++k) consume(u[k], i + 32 * k);
+  }
+  {
+    uint4 u[UNROLL];
+#pragma unroll
+    for (int k = 0; k < UNROLL; ++k)
+      if (i + 32 * k < nvec) u[k] = ld_nc_na(vp + i + 32 * k);
+#pragma unroll
+    for (int k = 0; k < UNROLL; ++k)
+      if (i + 32 * k < nvec) consume(u[k], i + 32 * k);
+  }
+  // element index of the lane's maximum: first element of vector bvec equal to bv
+  int bi = bi0;
+  if (WANT_SUM && bvec >= 0) {
+    uint4 u = __ldg(vp + bvec);
+    if (bvec == nvec - 1 && tail != EPV) mask_tail(u);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(&u);
+#pragma unroll
+    for (int k = EPV - 1; k >= 0; --k) {
+      const float x = IS_BF16 ? ((k & 1) ? bf16_hi(w[k >> 1]) : bf16_lo(w[k >> 1])) : __uint_as_float(w[k]);
+      if (x == bv) bi = bvec * EPV + k;
+    }
+  }
+  ArgMax a{bv, bi, bs};
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float v = __shfl_xor_sync(0xffffffffu, a.v, o);
+    const int ii = __shfl_xor_sync(0xffffffffu, a.i, o);
+    const float ss = __shfl_xor_sync(0xffffffffu, a.s, o);
+    argmax_merge(a, v, ii, ss, WANT_SUM);
+  }
+  if (lane == 0) {
+    labels[row] = a.i;
+    if (WANT_SUM) top_prob[row] = 1.0f / a.s;
+  }
+}
+
 // One CTA per utterance.  smem: lab[L] | start[L+1] ints.
 __global__ void __launch_bounds__(512)
     ctc_segment_kernel(const int* __restrict__ labels, const float* __restrict__ top_prob,
@@ -191,25 +345,22 @@ __global__ void __launch_bounds__(512)
   }
 }
 
-// out[s*B+b, :] = sum_{t in segment s of b} weight[t,b] * x[t*B+b, :]; one CTA row-loop,
-// threads over D as float4.  Grid covers the worst case (L*B rows); rows >= max_new_len exit.
+// Generic D (any multiple of 4; small test shapes): one CTA per output row, threads over D.
 __global__ void __launch_bounds__(128)
-    ctc_compress_kernel(const float* __restrict__ x, const int* __restrict__ seg_start,
-                        const float* __restrict__ weight, const int* __restrict__ lengths,
-                        const int* __restrict__ new_lengths, const int* __restrict__ max_new_len,
-                        float* __restrict__ out, int L, int B, int D) {
+    ctc_compress_generic_kernel(const float* __restrict__ x, const int* __restrict__ seg_start,
+                                const float* __restrict__ weight, const int* __restrict__ lengths,
+                                const int* __restrict__ new_lengths,
+                                const int* __restrict__ max_new_len, float* __restrict__ out, int L,
+                                int B, int D) {
   const int rows = min(__ldg(max_new_len), L) * B;
   const int nvec = D >> 2;
   for (int row = blockIdx.x; row < rows; row += gridDim.x) {
     const int s = row / B, b = row - s * B;
     const int nl = __ldg(new_lengths + b);
     float4* op = reinterpret_cast<float4*>(out + (size_t)row * D);
-    if (s >= nl) {
-      for (int j = threadIdx.x; j < nvec; j += blockDim.x) op[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      continue;
-    }
-    const int a = __ldg(seg_start + (size_t)s * B + b);
-    const int e = (s + 1 < nl) ? __ldg(seg_start + (size_t)(s + 1) * B + b) : min(__ldg(lengths + b), L);
+    const bool pad = s >= nl;
+    const int a = pad ? 0 : __ldg(seg_start + (size_t)s * B + b);
+    const int e = pad ? 0 : ((s + 1 < nl) ? __ldg(seg_start + (size_t)(s + 1) * B + b) : min(__ldg(lengths + b), L));
     for (int j = threadIdx.x; j < nvec; j += blockDim.x) {
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int t = a; t < e; ++t) {
@@ -223,6 +374,98 @@ __global__ void __launch_bounds__(128)
       op[j] = acc;
     }
   }
+}
+
+// out[s*B+b, :] = sum_{t in segment s of b} weight[t,b] * x[t*B+b, :].
+// INPUT-stationary: a warp task is (chunk of FR consecutive frames, utterance b, 128-column group);
+// a lane owns one float4 column, so a frame is one coalesced 512-byte warp load and all FR loads
+// of a task are issued up front -- their addresses depend on nothing but the task index, so they
+// fly in parallel with the per-frame metadata (run id, pooling weight) that lanes 0..FR-1 fetch.
+// The frames are then folded in time order; a run is written by the task in whose chunk it STARTS
+// (that task keeps reading past its chunk until the run ends), so every output row has exactly one
+// writer and a fixed summation order: no atomics, run-to-run identical results.
+// Why not one task per output row (rounds r01a/r01b in profiles/): run lengths are skewed (mean 4,
+// merged blank runs reach 60-80 frames), so per-run tasks either leave most of their load
+// registers idle or serialise on the longest run; 20-25 % of HBM peak both ways.
+// The task of chunk c also zero-fills the padding rows new_len[b] <= s < max_new_len, s in chunk c.
+template <int FR>
+__global__ void __launch_bounds__(256)
+    ctc_compress_kernel(const float* __restrict__ x, const int* __restrict__ seg_id,
+                        const float* __restrict__ weight, const int* __restrict__ /*lengths*/,
+                        const int* __restrict__ new_lengths, const int* __restrict__ max_new_len,
+                        float* __restrict__ out, int L, int B, int D, int tasks) {
+  static_assert(FR <= 16, "metadata is fetched by lanes 0..FR-1, lane 16 looks one frame back");
+  const int ncg = D >> 7;  // 128-column groups per row
+  const int lane = threadIdx.x & 31;
+  const int task = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (task >= tasks) return;
+  const int cg = task % ncg, b = (task / ncg) % B, c = task / (ncg * B);
+  const int t0 = c * FR;
+  const size_t fstride = (size_t)B * (D >> 2);  // float4 elements between consecutive frames
+  const float4* xcol = reinterpret_cast<const float4*>(x + (size_t)b * D) + cg * 32 + lane;
+  float4* ocol = reinterpret_cast<float4*>(out + (size_t)b * D) + cg * 32 + lane;
+  // Nothing below waits for lengths[b]: fbkst_ctc_segment wrote seg_id = -1 and weight = 0 for every
+  // padding frame t < L, so the frame loads, the metadata loads and the bounds all go out together
+  // (one memory round trip per task).  Padding frames are loaded but never folded.
+  float4 v[FR];
+#pragma unroll
+  for (int k = 0; k < FR; ++k)
+    v[k] = (t0 + k < L) ? __ldg(xcol + (size_t)(t0 + k) * fstride) : make_float4(0.f, 0.f, 0.f, 0.f);
+  // metadata: lane k < FR <-> frame t0 + k; lane 16 <-> frame t0 - 1
+  const int tm = (lane == 16) ? t0 - 1 : t0 + lane;
+  const bool has = (lane < FR || lane == 16) && tm >= 0 && tm < L;
+  int sid = has ? __ldg(seg_id + (size_t)tm * B + b) : -1;
+  float wt = (has && lane < FR) ? __ldg(weight + (size_t)tm * B + b) : 0.0f;
+  const int nl = __ldg(new_lengths + b);
+  const int mx = min(__ldg(max_new_len), L);
+  const int len = L;  // run extension stops at the first frame with another run id (-1 = padding)
+  const int prev = __shfl_sync(0xffffffffu, sid, 16);  // run id of frame t0 - 1 (-1: none)
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int cur = -1;       // run being accumulated (warp-uniform)
+  bool owned = false; // it started inside this chunk
+#pragma unroll
+  for (int k = 0; k < FR; ++k) {
+    const int sk = __shfl_sync(0xffffffffu, sid, k);
+    const float wk = __shfl_sync(0xffffffffu, wt, k);
+    if (sk != cur) {
+      if (cur >= 0 && owned) ocol[(size_t)cur * fstride] = acc;
+      acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      cur = sk;
+      owned = sk != prev;
+    }
+    if (sk >= 0) {  // warp-uniform; padding frames may hold anything
+      acc.x = fmaf(wk, v[k].x, acc.x);
+      acc.y = fmaf(wk, v[k].y, acc.y);
+      acc.z = fmaf(wk, v[k].z, acc.z);
+      acc.w = fmaf(wk, v[k].w, acc.w);
+    }
+  }
+  if (cur >= 0 && owned) {
+    // the last run of the chunk may continue beyond it: keep folding until it ends
+    for (int t = t0 + FR; t < len; t += FR) {
+      const bool h2 = lane < FR && t + lane < len;
+      sid = h2 ? __ldg(seg_id + (size_t)(t + lane) * B + b) : -1;
+      wt = h2 ? __ldg(weight + (size_t)(t + lane) * B + b) : 0.0f;
+      const unsigned same = __ballot_sync(0xffffffffu, sid == cur) | ~((1u << FR) - 1u);
+      const int n = __ffs(~same) ? __ffs(~same) - 1 : FR;  // leading frames still in the run
+      if (n == 0) break;
+#pragma unroll
+      for (int k = 0; k < FR; ++k)
+        v[k] = (k < n) ? __ldg(xcol + (size_t)(t + k) * fstride) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < FR; ++k) {
+        const float wk = (k < n) ? __shfl_sync(0xffffffffu, wt, k) : 0.0f;
+        acc.x = fmaf(wk, v[k].x, acc.x);
+        acc.y = fmaf(wk, v[k].y, acc.y);
+        acc.z = fmaf(wk, v[k].z, acc.z);
+        acc.w = fmaf(wk, v[k].w, acc.w);
+      }
+      if (n < FR) break;
+    }
+    ocol[(size_t)cur * fstride] = acc;
+  }
+  // padding rows of the compressed output that fall into this chunk's index range
+  for (int s = max(t0, nl); s < min(t0 + FR, mx); ++s) ocol[(size_t)s * fstride] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 }  // namespace fbkst
@@ -239,6 +482,23 @@ extern "C" int fbkst_ctc_argmax(const void* logits, int logits_dtype, int64_t ld
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int rows = L * B;
   int grid = (rows + 7) / 8;
+  const size_t esz = logits_dtype == FBKST_BF16 ? 2 : 4;
+  const bool aligned = (reinterpret_cast<uintptr_t>(logits) & 15u) == 0 && ((size_t)ldv * esz) % 16 == 0 &&
+                       (size_t)((V + 16 / esz - 1) / (16 / esz)) * 16 <= (size_t)ldv * esz;
+  if (aligned) {
+    const uint4* lp = reinterpret_cast<const uint4*>(logits);
+    const long long rv = (long long)((size_t)ldv * esz / 16);
+    if (logits_dtype == FBKST_BF16 && top_prob)
+      ctc_argmax_vec_kernel<1, 1><<<grid, 256, 0, st>>>(lp, rv, lengths, labels, top_prob, rows, B, V);
+    else if (logits_dtype == FBKST_BF16)
+      ctc_argmax_vec_kernel<1, 0><<<grid, 256, 0, st>>>(lp, rv, lengths, labels, top_prob, rows, B, V);
+    else if (top_prob)
+      ctc_argmax_vec_kernel<0, 1><<<grid, 256, 0, st>>>(lp, rv, lengths, labels, top_prob, rows, B, V);
+    else
+      ctc_argmax_vec_kernel<0, 0><<<grid, 256, 0, st>>>(lp, rv, lengths, labels, top_prob, rows, B, V);
+    FBKST_CHECK_CUDA(cudaGetLastError());
+    return FBKST_OK;
+  }
   const int cap = num_sms() * 8;
   if (grid > cap) grid = cap;
   if (logits_dtype == FBKST_BF16)
@@ -274,19 +534,28 @@ extern "C" int fbkst_ctc_segment(const int32_t* labels, const float* top_prob,
   return FBKST_OK;
 }
 
-extern "C" int fbkst_ctc_compress(const float* x, const int32_t* seg_start, const float* weight,
-                                  const int32_t* lengths, const int32_t* new_lengths,
-                                  const int32_t* max_new_len, float* out, int L, int B, int D,
-                                  fbkst_stream_t stream) {
-  FBKST_REQUIRE(x && seg_start && weight && lengths && new_lengths && max_new_len && out,
+extern "C" int fbkst_ctc_compress(const float* x, const int32_t* seg_id, const int32_t* seg_start,
+                                  const float* weight, const int32_t* lengths,
+                                  const int32_t* new_lengths, const int32_t* max_new_len, float* out,
+                                  int L, int B, int D, fbkst_stream_t stream) {
+  FBKST_REQUIRE(x && seg_id && seg_start && weight && lengths && new_lengths && max_new_len && out,
                 "fbkst_ctc_compress: null pointer");
   FBKST_REQUIRE(L > 0 && B > 0 && D > 0 && D % 4 == 0, "fbkst_ctc_compress: bad shape (D %% 4)");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  int grid = L * B;
-  const int cap = num_sms() * 16;
-  if (grid > cap) grid = cap;
-  ctc_compress_kernel<<<grid, 128, 0, st>>>(x, seg_start, weight, lengths, new_lengths, max_new_len,
-                                            out, L, B, D);
+  if (D % 128 != 0 || D > 1024) {
+    int g = L * B;
+    const int gcap = num_sms() * 16;
+    if (g > gcap) g = gcap;
+    ctc_compress_generic_kernel<<<g, 128, 0, st>>>(x, seg_start, weight, lengths, new_lengths,
+                                                   max_new_len, out, L, B, D);
+    FBKST_CHECK_CUDA(cudaGetLastError());
+    return FBKST_OK;
+  }
+  constexpr int FR = 16;
+  const long long tasks = (long long)((L + FR - 1) / FR) * B * (D / 128);
+  FBKST_REQUIRE(tasks < (1ll << 31), "fbkst_ctc_compress: too many tasks");
+  ctc_compress_kernel<FR><<<(int)((tasks + 7) / 8), 256, 0, st>>>(
+      x, seg_id, weight, lengths, new_lengths, max_new_len, out, L, B, D, (int)tasks);
   FBKST_CHECK_CUDA(cudaGetLastError());
   return FBKST_OK;
 }

@@ -27,7 +27,7 @@ SIGNATURES = {
     "fbkst_lengths_to_mask": [P, P, P, I, I, P],
     "fbkst_ctc_argmax": [P, I, I64, P, P, P, I, I, I, P],
     "fbkst_ctc_segment": [P, P, P, I, P, P, P, P, P, I, I, P],
-    "fbkst_ctc_compress": [P, P, P, P, P, P, P, I, I, I, P],
+    "fbkst_ctc_compress": [P, P, P, P, P, P, P, P, I, I, I, P],
     "fbkst_cast_bf16": [P, P, I64, F, P],
     "fbkst_prep_conv2_weight": [P, P, I, P],
     "fbkst_prep_fc3_weight": [P, P, I, I, I, P],

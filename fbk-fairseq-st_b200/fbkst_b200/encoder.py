@@ -234,6 +234,9 @@ def make_encoder_class(base):
             self._pos_table = None
             self._ws = None
             self._ws_key = None
+            # opt-in: replay one captured CUDA graph per input shape instead of ~90 launches
+            self.use_cuda_graph = False
+            self._graphs = {}
 
         # ------------------------------------------------------------------ derived operand formats
         def _prepared(self):
@@ -306,18 +309,59 @@ def make_encoder_class(base):
 
         def _forward(self, src_tokens, src_lengths, return_all_hiddens):
             dev = src_tokens.device
-            P = self._prepared()
             B, T, Fd = src_tokens.shape
             x_in = src_tokens if src_tokens.dtype == torch.float32 else src_tokens.float()
             x_in = x_in.contiguous()
             # lengths: one host copy drives all shape logic (the reference syncs per utterance)
             len_host = src_lengths.tolist() if not src_lengths.is_cuda else src_lengths.cpu().tolist()
             len_host = [((n + 1) // 2 + 1) // 2 for n in len_host]  # ceil(ceil(n/2)/2), :213
+            D = self.embed_dim
+            L = ((T + 1) // 2 + 1) // 2
+            for _ in range(self.num_layers):
+                torch.empty(1).uniform_()  # LayerDrop draws: keep the CPU RNG stream of the reference
+            compress = self.ctc_compress_out and 0 < self.ctc_layer <= self.num_layers
+            if self.use_cuda_graph and not return_all_hiddens:
+                r = self._replay(x_in, len_host, B, T, Fd, L)
+            else:
+                lengths = torch.tensor(len_host, dtype=torch.int32).to(dev, non_blocking=True)
+                r = self._body(self._prepared(), x_in, lengths, len_host, L, B, return_all_hiddens,
+                               self._workspace(L * B, dev) if compress and not return_all_hiddens else None)
+            x, limit, new_len, states = r["x"], r["limit"], r["new_len"], r["states"]
+            mask = r["mask"] if min(len_host) < L else None  # :298-299: None when nothing is padded
+            if mask is not None and self.use_cuda_graph:
+                mask = mask.clone()  # do not hand out a buffer the next replay overwrites
+            ctc_mask = mask
+            if return_all_hiddens and compress:
+                len_host, L = r["len_host"], r["L"]
+                mask = r["mask2"] if min(len_host) < L else None
+            xf = ops.layernorm(x, *self._prepared()["lnf"], out_dtype=torch.float32, rows_limit=limit)
+            if limit is not None:
+                mask_full = ops.lengths_to_mask(new_len, L)[0]
+                len_host = new_len.cpu().tolist()  # the single host sync of the forward
+                L2 = max(len_host)
+                xf = xf[: L2 * B]
+                mask = None if min(len_host) >= L2 else mask_full[:, :L2].contiguous()
+                L = L2
+            xf = xf.view(L, B, D)
+            if return_all_hiddens:
+                states[-1] = xf
+            out_lengths = torch.tensor(len_host, dtype=src_lengths.dtype).to(dev, non_blocking=True)
+            if self.ctc_compress_out:
+                return CTCAwareEncoderOut(xf, mask, None, states, src_tokens, out_lengths, r["x_ctc"],
+                                          ctc_mask)
+            return EncoderOut(xf, mask, None, states, src_tokens, out_lengths)
+
+        def _body(self, P, x_in, lengths, len_host, L, B, want_states, ws):
+            """Everything between the input batch and the final LayerNorm.  Shape-static when
+            ``want_states`` is False (no host synchronisation, every launch sized for the worst case
+            with device-side row limits after CTC compression), so it can be captured in a CUDA graph.
+            ``lengths``: subsampled lengths, int32 on the device; ``len_host``: the same on the host
+            (only needed when ``want_states``)."""
+            dev = x_in.device
             D, H = self.embed_dim, self.heads
             y = ops.conv1_relu_bn(x_in, P["w1"], P["b1"], *P["bn0"])
             y = ops.conv2_relu_bn(y, P["w2"], P["b2"], *P["bn1"])  # [B, T2, F2, C]
-            L = y.shape[1]
-            lengths = torch.tensor(len_host, dtype=torch.int32).to(dev, non_blocking=True)
+            assert y.shape[1] == L
             a = y.view(B * L, -1)
             if self.embed_positions is not None:
                 table = self._positions(L + 1, dev)
@@ -327,16 +371,16 @@ def make_encoder_class(base):
                 x = ops.linear(a, P["w3"], P["b3"], relu=True, out_dtype=torch.float32, remap=(L, B))
             if self.layernorm_embedding is not None:
                 x = ops.layernorm(x, *P["lne"], out_dtype=torch.float32)
-            mask = self._mask(lengths, len_host, L)
-            states = [] if return_all_hiddens else None
-            x_ctc, ctc_mask = None, None
+            mask = ops.lengths_to_mask(lengths, L)[0]
+            r = dict(mask=mask, mask2=None, x_ctc=None, len_host=len_host, L=L, tables=table
+                     if self.embed_positions is not None else None)
+            states = [] if want_states else None
             # After CTC compression the number of valid rows is known only on the device.  Unless the
             # caller wants every hidden state (exact shapes per layer), the remaining layers are
             # launched for the worst case with a device-side row limit and persistent, finite
             # workspaces; the single host sync of the forward is the final read of the new lengths.
-            limit, ws, new_len = None, None, None
+            limit, new_len = None, None
             for li, W in enumerate(P["layers"]):
-                torch.empty(1).uniform_()  # LayerDrop draw: keeps the CPU RNG stream of the reference
                 if limit is None:
                     h = ops.layernorm(x, *W["ln1"])
                     qkv = ops.linear(h, W["wqkv"], W["bqkv"])
@@ -356,52 +400,82 @@ def make_encoder_class(base):
                     x = ops.linear(f, W["w2"], W["b2"], residual=x1, out_dtype=torch.float32,
                                    out=ws["x0"], rows_limit=limit)
                 if self.ctc_compress_out and self.ctc_layer == li + 1:
-                    ctc_mask = mask
-                    if return_all_hiddens:
-                        x_ctc, x, lengths, len_host, L = self._ctc_compress(x, lengths, L, B)
-                        mask = self._mask(lengths, len_host, L)
+                    if want_states:
+                        r["x_ctc"], x, lengths, len_host, L = self._ctc_compress(x, lengths, L, B)
+                        r["mask2"] = ops.lengths_to_mask(lengths, L)[0]
+                        r["len_host"], r["L"] = len_host, L
                     else:
-                        ws = self._workspace(L * B, dev)
-                        x_ctc, x, lengths, max_new = self._ctc_compress(x, lengths, L, B, out=ws["x0"])
+                        r["x_ctc"], x, lengths, max_new = self._ctc_compress(x, lengths, L, B, out=ws["x0"])
                         new_len = lengths
                         limit = (max_new, B)
-                if return_all_hiddens:
+                if want_states:
                     states.append(x.view(L, B, D))
-            xf = ops.layernorm(x, *P["lnf"], out_dtype=torch.float32, rows_limit=limit)
-            if limit is not None:
-                mask_full = ops.lengths_to_mask(new_len, L)[0]
-                len_host = new_len.cpu().tolist()  # the single host sync of the forward
-                L2 = max(len_host)
-                xf = xf[: L2 * B]
-                mask = None if min(len_host) >= L2 else mask_full[:, :L2].contiguous()
-                L = L2
-            xf = xf.view(L, B, D)
-            if return_all_hiddens:
-                states[-1] = xf
-            out_lengths = torch.tensor(len_host, dtype=src_lengths.dtype).to(dev, non_blocking=True)
-            if self.ctc_compress_out:
-                return CTCAwareEncoderOut(xf, mask, None, states, src_tokens, out_lengths, x_ctc, ctc_mask)
-            return EncoderOut(xf, mask, None, states, src_tokens, out_lengths)
+            r.update(x=x, limit=limit, new_len=new_len, states=states)
+            return r
+
+        # ------------------------------------------------------------------------- CUDA graphs
+        def _graph_key(self, B, T, Fd, dev):
+            hooks = tuple(sorted(self.ctc_fc._forward_hooks)) if self.ctc_compress_out else ()
+            return (B, T, Fd, str(dev), self._prep_key, hooks)
+
+        def _replay(self, x_in, len_host, B, T, Fd, L):
+            """Graph mode (``use_cuda_graph``): the ~90 launches of ``_body`` for one input shape are
+            captured once and replayed with one ``cudaGraphLaunch``; the batch is copied into the
+            graph's static input buffer (device-to-device) and the subsampled lengths into its static
+            length vector.  ``ctc_out`` then aliases a buffer owned by the graph: it is valid until
+            the next forward with the same input shape."""
+            dev = x_in.device
+            P = self._prepared()
+            key = self._graph_key(B, T, Fd, dev)
+            G = self._graphs.get(key)
+            if G is None:
+                if len(self._graphs) >= 16:  # bounded: every graph pins its activations
+                    self._graphs.pop(next(iter(self._graphs)))
+                G = self._capture(P, B, T, Fd, L, dev)
+                self._graphs[key] = G
+            G["len_pin"].copy_(torch.tensor(len_host, dtype=torch.int32))
+            G["lengths"].copy_(G["len_pin"], non_blocking=True)
+            G["x"].copy_(x_in, non_blocking=True)
+            G["graph"].replay()
+            ops._count(G["launches"])
+            return G["out"]
+
+        def _capture(self, P, B, T, Fd, L, dev):
+            compress = self.ctc_compress_out and 0 < self.ctc_layer <= self.num_layers
+            G = dict(x=torch.zeros(B, T, Fd, dtype=torch.float32, device=dev),
+                     lengths=torch.full((B,), L, dtype=torch.int32, device=dev),
+                     len_pin=torch.empty(B, dtype=torch.int32).pin_memory(), P=P,
+                     ws=self._make_workspace(L * B, dev) if compress else None)
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):  # warm-up outside capture: lazy one-time initialisation
+                self._body(P, G["x"], G["lengths"], None, L, B, False, G["ws"])
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            n0 = ops.LAUNCHES
+            with torch.cuda.graph(graph):
+                G["out"] = self._body(P, G["x"], G["lengths"], None, L, B, False, G["ws"])
+            G["launches"] = ops.LAUNCHES - n0
+            G["graph"] = graph
+            return G
+
+        def _make_workspace(self, M, dev):
+            """Zero-initialised buffers for the layers after compression (rows beyond the device-side
+            limit are never written, so they must hold finite values: 0 * NaN would poison the P.V
+            product of a partially valid key tile)."""
+            D, Dff = self.embed_dim, self.layers[0].fc1.out_features
+            z = lambda n, dt: torch.zeros(M, n, dtype=dt, device=dev)
+            return dict(h=z(D, torch.bfloat16), qkv=z(3 * D, torch.bfloat16), att=z(D, torch.bfloat16),
+                        f=z(Dff, torch.bfloat16), x0=z(D, torch.float32), x1=z(D, torch.float32))
 
         def _workspace(self, M, dev):
-            """Persistent zero-initialised buffers for the layers after compression (rows beyond the
-            device-side limit are never written, so they must hold finite values: 0 * NaN would
-            poison the P.V product of a partially valid key tile)."""
+            """The eager path keeps one workspace (for the last shape seen)."""
             key = (M, str(dev))
             if self._ws_key != key:
-                D, Dff = self.embed_dim, self.layers[0].fc1.out_features
-                z = lambda n, dt: torch.zeros(M, n, dtype=dt, device=dev)
-                self._ws = dict(h=z(D, torch.bfloat16), qkv=z(3 * D, torch.bfloat16),
-                                att=z(D, torch.bfloat16), f=z(Dff, torch.bfloat16),
-                                x0=z(D, torch.float32), x1=z(D, torch.float32))
+                self._ws = self._make_workspace(M, dev)
                 self._ws_key = key
             return self._ws
-
-        def _mask(self, lengths, len_host, L):
-            """conv_transformer.py:293-300: B x L bool (True = pad) or None when nothing is padded."""
-            if min(len_host) >= L:
-                return None
-            return ops.lengths_to_mask(lengths, L)[0]
 
         def _ctc_compress(self, x, lengths, L, B, out=None):
             """conv_transformer.py:278-291 on device.  With ``out`` (workspace mode) nothing is read
@@ -420,7 +494,7 @@ def make_encoder_class(base):
             labels, prob = ops.ctc_argmax(lg, lengths, L, B, V, want_prob)
             seg_id, seg_start, weight, new_len, max_new = ops.ctc_segment(
                 labels, prob, lengths, self.ctc_compress_strategy, L, B)
-            res = ops.ctc_compress(x, seg_start, weight, lengths, new_len, max_new, L, B, out=out)
+            res = ops.ctc_compress(x, seg_id, seg_start, weight, lengths, new_len, max_new, L, B, out=out)
             if out is not None:
                 return logits, res, new_len, max_new
             new_host = new_len.cpu().tolist()  # host sync: exact shapes for encoder_states

@@ -190,13 +190,13 @@ def ctc_segment(labels, top_prob, lengths, strategy, L, B):
     return seg_id, seg_start, weight, new_len, max_new
 
 
-def ctc_compress(x, seg_start, weight, lengths, new_len, max_new, L, B, out=None):
+def ctc_compress(x, seg_id, seg_start, weight, lengths, new_len, max_new, L, B, out=None):
     lib = _lib.require_device()
     _req(x, torch.float32, "ctc_compress.x")
     D = x.shape[-1]
     if out is None:
         out = torch.empty(L * B, D, dtype=torch.float32, device=x.device)
-    check(lib.fbkst_ctc_compress(x.data_ptr(), seg_start.data_ptr(), weight.data_ptr(),
+    check(lib.fbkst_ctc_compress(x.data_ptr(), seg_id.data_ptr(), seg_start.data_ptr(), weight.data_ptr(),
                                  lengths.data_ptr(), new_len.data_ptr(), max_new.data_ptr(),
                                  out.data_ptr(), L, B, D, _stream()))
     _count()

@@ -145,9 +145,11 @@ int fbkst_ctc_segment(const int32_t* labels, const float* top_prob, const int32_
 /* ---- a10 step 3: segmented weighted reduction (the reference's dense bmm) ------------------
  * replaces conv_transformer.py:290-291.  x [L*B, D] fp32 -> out [L*B, D] fp32 (rows
  * s*B+b; rows with new_lengths[b] <= s < max_new_len are written as 0; rows >= max_new_len
- * are untouched).  D % 4 == 0. */
-int fbkst_ctc_compress(const float* x, const int32_t* seg_start, const float* weight,
-                       const int32_t* lengths, const int32_t* new_lengths,
+ * are untouched).  seg_id, seg_start, weight as produced by fbkst_ctc_segment.  D % 4 == 0
+ * (D % 128 == 0 takes the input-stationary streaming kernel).  Every output row has one writer
+ * and a fixed summation order (ascending t): results are run-to-run identical. */
+int fbkst_ctc_compress(const float* x, const int32_t* seg_id, const int32_t* seg_start,
+                       const float* weight, const int32_t* lengths, const int32_t* new_lengths,
                        const int32_t* max_new_len, float* out, int L, int B, int D,
                        fbkst_stream_t stream);
 

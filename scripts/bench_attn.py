@@ -19,6 +19,7 @@ for name, L, B, H, lens in [("pre  L=375", 375, 64, 8, [375] * 64),
     ts = []
     for i in range(reps + 2):
         flush.fill_(i)
+        flush.view(torch.int32).sum()  # read pass: leaves CLEAN lines in L2 (no write-back under the kernel)
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         out = ops.attention(qkv, lengths, L, B, H, True)

@@ -31,6 +31,7 @@ for name, M, N, K, relu, resid, odt in SHAPES:
     ts = []
     for i in range(reps + 2):
         flush.fill_(i)
+        flush.view(torch.int32).sum()  # read pass: leaves CLEAN lines in L2 (no write-back under the kernel)
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         out = ops.linear(a, w, bias, relu=relu, residual=res, out_dtype=odt)

@@ -134,3 +134,39 @@ def test_pipeline_matches_direct_calls(golden_dir):
     for (a, la), (b, lb) in zip(got, direct):
         assert torch.equal(la, lb)
         assert torch.equal(a, b)
+
+
+def test_cuda_graph_mode_is_bit_identical():
+    """use_cuda_graph replays the same kernels: outputs equal the eager path bit for bit, across
+    batches of one shape with different lengths/content and across a second shape."""
+    cfg = dict(embed_dim=256, ffn_dim=512, heads=4, layers=4, conv_channels=64, feat_dim=40,
+               vocab=205, distance_penalty="log", ctc_layer=2, ctc_strategy="weighted")
+    sd = O.init_state_dict(cfg, seed=3)
+    enc = build_encoder(cfg, sd)
+    labels = O.synthetic_ctc_bump(80, 4, 205, seed=5).cuda()
+
+    def bump(m, i, o):  # device-resident plan (capturable); the second shape is left as it is
+        if tuple(o.shape[:2]) != tuple(labels.shape):
+            return o
+        return o.scatter_add(2, labels.unsqueeze(-1), torch.full_like(o[..., :1], 30.0))
+    enc.ctc_fc.register_forward_hook(bump)
+    batches = [O.synthetic_batch(l, 40, seed=s) for s, l in
+               enumerate([[320, 301, 222, 95], [320, 320, 320, 320], [317, 200, 100, 64], [200, 111]])]
+    eager = []
+    for x, l in batches:
+        o = enc(x.cuda(), l.cuda())
+        eager.append((o.encoder_out.clone(), o.src_lengths.clone(),
+                      None if o.encoder_padding_mask is None else o.encoder_padding_mask.clone(),
+                      o.ctc_out.float().clone()))
+    enc.use_cuda_graph = True
+    for rep in range(2):  # second round replays the cached graphs
+        for (x, l), (eo, sl, pm, co) in zip(batches, eager):
+            o = enc(x.cuda(), l.cuda())
+            assert torch.equal(o.src_lengths, sl)
+            assert torch.equal(o.encoder_out, eo)
+            assert (o.encoder_padding_mask is None) == (pm is None)
+            if pm is not None:
+                assert torch.equal(o.encoder_padding_mask, pm)
+            n = int(l[0] + 3) // 4
+            assert torch.equal(o.ctc_out.float()[:n], co[:n])
+    assert len(enc._graphs) == 3  # T = 320, 317, 200

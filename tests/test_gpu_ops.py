@@ -159,7 +159,11 @@ def attn_ref(qkv, lengths, L, B, H, log_penalty):
 
 @pytest.mark.parametrize("L,B,H,lens,pen", [
     (128, 2, 2, [128, 128], True), (100, 3, 2, [100, 64, 5], True), (375, 2, 8, [375, 201], True),
-    (300, 2, 4, [300, 129], False), (700, 1, 2, [700], True)])
+    (300, 2, 4, [300, 129], False), (700, 1, 2, [700], True),
+    # more work items than persistent CTAs (several items per CTA, item boundaries inside the
+    # flattened key-tile stream), ragged lengths incl. tiles of padded queries
+    (375, 24, 8, [375] * 6 + [300] * 6 + [190] * 6 + [64, 65, 127, 128, 129, 1], True),
+    (200, 48, 4, [200 - 3 * i for i in range(48)], False)])
 def test_attention(L, B, H, lens, pen):
     from fbkst_b200 import ops
     g = torch.Generator().manual_seed(L + B)
@@ -184,7 +188,7 @@ def run_ctc(x, logits, lengths, strategy):
     ln = lengths.to(torch.int32).to(d)
     labels, prob = ops.ctc_argmax(lg, ln, L, B, V, want_prob=strategy != "avg")
     seg_id, seg_start, weight, new_len, max_new = ops.ctc_segment(labels, prob, ln, strategy, L, B)
-    out = ops.ctc_compress(x.to(d).reshape(L * B, D).contiguous(), seg_start, weight, ln, new_len,
+    out = ops.ctc_compress(x.to(d).reshape(L * B, D).contiguous(), seg_id, seg_start, weight, ln, new_len,
                            max_new, L, B)
     nl = new_len.cpu()
     L2 = int(max_new.item())
@@ -249,7 +253,7 @@ def test_ctc_full_size_properties():
     for strategy in ("avg", "weighted", "softmax"):
         lab, prob = ops.ctc_argmax(logits.to(d).view(L * B, V), ln, L, B, V, want_prob=strategy != "avg")
         seg_id, seg_start, weight, new_len, max_new = ops.ctc_segment(lab, prob, ln, strategy, L, B)
-        out = ops.ctc_compress(x, seg_start, weight, ln, new_len, max_new, L, B)
+        out = ops.ctc_compress(x, seg_id, seg_start, weight, ln, new_len, max_new, L, B)
         lab = lab.view(L, B).cpu()
         nl = new_len.cpu()
         L2 = int(max_new.item())
