@@ -16,9 +16,18 @@
 // one-CTA-per-item version spent ~45 % of its life in those prologues: profiles/r01a).  The K/V
 // rings, the S/P double buffers and all mbarrier phases simply keep counting across items.
 //
+// Split-KV inside the CTA: the key tiles of an item alternate between two softmax warpgroups, each
+// with its own running (max, sum) and its own O accumulator in TMEM (even tiles -> S[0]/P[0]/O[0],
+// odd tiles -> S[1]/P[1]/O[1]); the two partial results are merged once per item.  With 2 CTAs per
+// SM this puts 16 softmax warps on an SM (4 per scheduler) instead of 8: the one-group version ran
+// at 0.4 IPC per scheduler, stalled on fixed-latency dependencies it had too few warps to hide
+// (profiles/r01a_ncu_attention.txt).  Registers are capped at 102/thread (2 x 320 threads), so S is
+// read from TMEM twice (max pass, exp pass) instead of being held across the O rescale.
+//
 //   warp 0     TMA producer (Q single-buffered; K 3-stage, V 2-stage rings)
 //   warp 1     TMEM allocator + MMA issuer (QK runs two key tiles ahead of PV, across items)
-//   warps 2-5  softmax / correction / output (TMEM lane quarter = warp % 4)
+//   warps 2-5  softmax group 0 (even tiles of the CTA's tile stream), TMEM lane quarter = warp % 4
+//   warps 6-9  softmax group 1 (odd tiles)
 #include <math.h>
 
 #include "host_common.h"
@@ -33,9 +42,14 @@ constexpr int AT_QB = AT_BM * AT_HD * 2;  // 16 KB
 constexpr int AT_KB = AT_BN * AT_HD * 2;  // 8 KB
 constexpr int AT_KST = 3, AT_VST = 2;
 // shared memory without the penalty LUT (its size depends on L: see attention_smem_bytes)
+constexpr int AT_THREADS = 320;
 constexpr int AT_SMEM_FIXED = AT_QB + AT_KST * AT_KB + AT_VST * AT_KB + 2 * AT_QB /*P x2*/ +
-                              256 /*barriers*/ + 1024 /*align*/;
-// penalty LUT: entry o <-> (key - query) = o - lut_off, lut_off = nq*128; keys < nkv*64
+                              256 /*barriers*/ + 2 * 2 * AT_BM * 4 /*(m, l) exchange*/ +
+                              64 * 16 /*item table*/ + 1024 /*align*/;
+// penalty LUT (stored negated): entry o <-> (key - query) = o - lut_off, lut_off = nq*128; keys <
+// nkv*64.  One copy, read with scalar LDS in explicit batches of 16: four shifted copies would allow
+// LDS.128 but cost 32*L bytes (1 CTA/SM beyond L ~ 700) and bought nothing -- the exp pass is bound
+// by the MUFU pipe and the MMA round trip, not by shared-memory issue (profiles/r01c).
 static inline int attention_lut_floats(int L) {
   return ((L + AT_BM - 1) / AT_BM) * AT_BM + ((L + AT_BN - 1) / AT_BN) * AT_BN;
 }
@@ -68,34 +82,65 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+// Optional timeline of CTA 0 (debug only; null in production): rows of 8 x int64 per key tile of
+// the CTA's stream: [0] MMA: p_full seen  [1] MMA: PV issued  [2] MMA: QK(+2) issued
+// [3] softmax: s_full seen  [4] pass 1 done  [5] P/O free  [6] p_full arrive  [7] item epilogue done (last tile row)
+// Compiled in only with -DFBKST_ATTN_TRACE (scripts/trace_attn.py); the hooks cost a few percent.
+__device__ long long* g_attn_trace = nullptr;
+#ifdef FBKST_ATTN_TRACE
+#define AT_TRACE(tile, slot)                                                         \
+  do {                                                                               \
+    if (trace != nullptr && (tile) < 64) trace[(tile) * 8 + (slot)] = clock64();    \
+  } while (0)
+#else
+#define AT_TRACE(tile, slot) \
+  do {                       \
+  } while (0)
+#endif
+
 // Static work list of a CTA: items w = blockIdx.x, blockIdx.x + gridDim.x, ...; item index
 // w = (b*H + h)*nq + q_tile, so CTAs running side by side share K/V of one (b, h) through L2.
+// The first AT_TABLE items of the CTA are decoded once, cooperatively, into shared memory: the
+// integer divisions and the lengths[] load (a global-memory round trip) would otherwise sit on the
+// critical path of all three roles at every item boundary.
+constexpr int AT_TABLE = 64;
 struct AttnItem {
   int w, q0, b, h, len, n_kv;  // n_kv == 0: tile of padded queries (zero fill, no pipeline work)
 };
-__device__ __forceinline__ void attn_decode(AttnItem& it, const int* __restrict__ lengths, int L,
-                                            int H, int nq, int n_items) {
-  if (it.w >= n_items) return;
-  const int qt = it.w % nq, bh = it.w / nq;
-  it.b = bh / H;
-  it.h = bh - it.b * H;
-  it.q0 = qt * AT_BM;
-  it.len = min(__ldg(lengths + it.b), L);
-  it.n_kv = (it.q0 < it.len) ? (it.len + AT_BN - 1) / AT_BN : 0;
+__device__ __forceinline__ int4 attn_decode_raw(int w, const int* __restrict__ lengths, int L, int H,
+                                                int nq) {
+  const int qt = w % nq, bh = w / nq;
+  const int b = bh / H, h = bh - b * H;
+  const int q0 = qt * AT_BM;
+  const int len = min(__ldg(lengths + b), L);
+  const int n_kv = (q0 < len) ? (len + AT_BN - 1) / AT_BN : 0;
+  return make_int4(q0, b, h, (len << 8) | n_kv);
 }
-// advance to the next item that has pipeline work (n_kv > 0)
-__device__ __forceinline__ void attn_next_work(AttnItem& it, const int* __restrict__ lengths, int L,
-                                               int H, int nq, int n_items, bool first) {
-  if (!first) it.w += gridDim.x;
-  for (;;) {
-    attn_decode(it, lengths, L, H, nq, n_items);
-    if (it.w >= n_items || it.n_kv > 0) return;
-    it.w += gridDim.x;
+struct AttnList {
+  const int4* table;  // shared memory
+  const int* lengths;
+  int L, H, nq, n_items;
+  __device__ __forceinline__ void get(AttnItem& it, int k) const {  // k-th item of this CTA
+    it.w = blockIdx.x + k * gridDim.x;
+    if (it.w >= n_items) return;
+    const int4 r = (k < AT_TABLE) ? table[k] : attn_decode_raw(it.w, lengths, L, H, nq);
+    it.q0 = r.x;
+    it.b = r.y;
+    it.h = r.z;
+    it.len = r.w >> 8;
+    it.n_kv = r.w & 255;
   }
-}
+  // next item at or after index k that has pipeline work (n_kv > 0); returns its index
+  __device__ __forceinline__ int next_work(AttnItem& it, int k) const {
+    for (;; ++k) {
+      get(it, k);
+      if (it.w >= n_items || it.n_kv > 0) return k;
+    }
+  }
+};
 
 template <int LOGPEN>
-__global__ void __launch_bounds__(192, 2)
+__global__ void __launch_bounds__(AT_THREADS, 2)
     attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                          __nv_bfloat16* __restrict__ out, const int* __restrict__ lengths, int L, int B,
                          int H) {
@@ -104,6 +149,9 @@ __global__ void __launch_bounds__(192, 2)
   const int n_items = nq * B * H;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
+#ifdef FBKST_ATTN_TRACE
+  long long* trace = (blockIdx.x == 0 && (lane == 0)) ? g_attn_trace : nullptr;
+#endif
 
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment by pointer arithmetic (keeps the shared address space visible to ptxas)
@@ -113,7 +161,9 @@ __global__ void __launch_bounds__(192, 2)
   uint8_t* sV = sK + AT_KST * AT_KB;   // AT_VST stages
   uint8_t* sP = sV + AT_VST * AT_KB;   // 2 x [128 rows x 128 B]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * AT_QB);
-  float* sLut = reinterpret_cast<float*>(bars + 32);
+  float* sXch = reinterpret_cast<float*>(bars + 32);  // [group][m | l][128 rows]
+  int4* sItems = reinterpret_cast<int4*>(sXch + 2 * 2 * AT_BM);
+  float* sLut = reinterpret_cast<float*>(sItems + AT_TABLE);
   uint64_t* q_full = bars + 0;
   uint64_t* k_full = bars + 1;    // [3]
   uint64_t* k_empty = bars + 4;   // [3]
@@ -147,32 +197,57 @@ __global__ void __launch_bounds__(192, 2)
     tmem_alloc(tmem_slot, 256);
     tmem_relinquish();
   }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + AT_TABLE) {
+    const int w = blockIdx.x + (threadIdx.x - 64) * gridDim.x;
+    if (w < n_items) sItems[threadIdx.x - 64] = attn_decode_raw(w, lengths, L, H, nq);
+  }
+  const AttnList items{sItems, lengths, L, H, nq, n_items};
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_O = tmem_base + 128;  // S[0] = +0, S[1] = +64, O = +128 (64 columns each)
+  const uint32_t tmem_O = tmem_base + 128;  // S[0] +0, S[1] +64, O[0] +128, O[1] +192 (64 columns each)
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      AttnItem it;
-      it.w = blockIdx.x;
-      uint32_t g = 0, n = 0;  // g: key tiles loaded so far, n: items loaded so far
-      for (attn_next_work(it, lengths, L, H, nq, n_items, true); it.w < n_items;
-           attn_next_work(it, lengths, L, H, nq, n_items, false), ++n) {
-        const int cq = it.h * AT_HD, ck = D + cq, cv = 2 * D + cq;
-        mbar_wait(q_empty, (n & 1) ^ 1);  // every QK of the previous item has completed
-        mbar_arrive_expect_tx(q_full, AT_QB);
-        tma_load_3d(sQ, &tmQ, q_full, cq, it.b, it.q0);
-        for (int j = 0; j < it.n_kv; ++j, ++g) {
-          const uint32_t ks = g % AT_KST, vs = g & 1;
-          mbar_wait(&k_empty[ks], ((g / AT_KST) & 1) ^ 1);
+      // Two cursors over the flattened key-tile stream: K runs two tiles ahead of V.  QK(t+2) is
+      // issued while tile t is being soft-maxed, so K(t+2) must not queue behind V(t+1), whose
+      // buffer frees only when PV(t-1) has completed (one producer thread, blocking waits).
+      AttnItem ki, vi;
+      int kk_ = items.next_work(ki, 0), vk_ = items.next_work(vi, 0);
+      int kj = 0, vj = 0;
+      uint32_t gk = 0, gv = 0, n = 0;  // K / V tiles loaded so far, items whose Q has been loaded
+      while (ki.w < n_items || vi.w < n_items) {
+        if (ki.w < n_items) {
+          const int cq = ki.h * AT_HD, ck = D + cq;
+          if (kj == 0) {
+            mbar_wait(q_empty, (n & 1) ^ 1);  // every QK of the previous item has completed
+            mbar_arrive_expect_tx(q_full, AT_QB);
+            tma_load_3d(sQ, &tmQ, q_full, cq, ki.b, ki.q0);
+            ++n;
+          }
+          const uint32_t ks = gk % AT_KST;
+          mbar_wait(&k_empty[ks], ((gk / AT_KST) & 1) ^ 1);
           mbar_arrive_expect_tx(&k_full[ks], AT_KB);
-          tma_load_3d(sK + ks * AT_KB, &tmKV, &k_full[ks], ck, it.b, j * AT_BN);
-          mbar_wait(&v_empty[vs], ((g >> 1) & 1) ^ 1);
+          tma_load_3d(sK + ks * AT_KB, &tmKV, &k_full[ks], ck, ki.b, kj * AT_BN);
+          ++gk;
+          if (++kj == ki.n_kv) {
+            kj = 0;
+            kk_ = items.next_work(ki, kk_ + 1);
+          }
+        }
+        if (vi.w < n_items && (gk >= gv + 3 || ki.w >= n_items)) {
+          const int cv = 2 * D + vi.h * AT_HD;
+          const uint32_t vs = gv & 1;
+          mbar_wait(&v_empty[vs], ((gv >> 1) & 1) ^ 1);
           mbar_arrive_expect_tx(&v_full[vs], AT_KB);
-          tma_load_3d(sV + vs * AT_KB, &tmKV, &v_full[vs], cv, it.b, j * AT_BN);
+          tma_load_3d(sV + vs * AT_KB, &tmKV, &v_full[vs], cv, vi.b, vj * AT_BN);
+          ++gv;
+          if (++vj == vi.n_kv) {
+            vj = 0;
+            vk_ = items.next_work(vi, vk_ + 1);
+          }
         }
       }
     }
@@ -183,9 +258,7 @@ __global__ void __launch_bounds__(192, 2)
       constexpr uint32_t IDESC_PV = idesc_bf16_f32(AT_BM, AT_HD, 0, 1);
       const uint64_t qdesc = desc_kmajor_sw128(smem_u32(sQ));
       AttnItem qk, pv;  // two cursors over the same item list: QK runs two key tiles ahead of PV
-      qk.w = pv.w = blockIdx.x;
-      attn_next_work(qk, lengths, L, H, nq, n_items, true);
-      attn_next_work(pv, lengths, L, H, nq, n_items, true);
+      int qk_k = items.next_work(qk, 0), pv_k = items.next_work(pv, 0);
       int qk_j = 0, pv_j = 0;
       uint32_t gq = 0, gp = 0, nqk = 0;  // global key-tile counters, items started by QK
       auto issue_qk = [&]() {
@@ -205,183 +278,243 @@ __global__ void __launch_bounds__(192, 2)
           umma_commit(q_empty);  // Q may be overwritten once these MMAs have completed
           qk_j = 0;
           ++nqk;
-          attn_next_work(qk, lengths, L, H, nq, n_items, false);
+          qk_k = items.next_work(qk, qk_k + 1);
         }
       };
       if (qk.w < n_items) issue_qk();
       if (qk.w < n_items) issue_qk();
       while (pv.w < n_items) {
         const uint32_t pb = gp & 1, ph = (gp >> 1) & 1;
-        mbar_wait(&p_full[pb], ph);  // S consumed, P in smem, O rescaled / read out if needed
+        mbar_wait(&p_full[pb], ph);  // S[pb] consumed, P[pb] in smem, O rescaled / read out
+        AT_TRACE(gp, 0);
         mbar_wait(&v_full[pb], ph);
         tc_fence_after();
         const uint32_t pa = smem_u32(sP + pb * AT_QB), va = smem_u32(sV + pb * AT_KB);
 #pragma unroll
         for (int kk = 0; kk < AT_BN / 16; ++kk)
-          umma_bf16_ss(tmem_O, desc_kmajor_sw128(pa) + 2 * kk, desc_mnmajor_sw128(va + kk * 2048, AT_KB),
-                       IDESC_PV, (pv_j | kk) != 0);
+          umma_bf16_ss(tmem_O + pb * AT_HD, desc_kmajor_sw128(pa) + 2 * kk,
+                       desc_mnmajor_sw128(va + kk * 2048, AT_KB), IDESC_PV, (pv_j >= 2) || kk != 0);
         umma_commit(&pv_done[pb]);
         umma_commit(&v_empty[pb]);
+        AT_TRACE(gp, 1);
+        // PV before QK: the group's next exp pass needs P[pb]/O[pb] free (PV done) as much as S
+        if (qk.w < n_items) issue_qk();
+        AT_TRACE(gp, 2);
         ++gp;
         if (++pv_j == pv.n_kv) {
           pv_j = 0;
-          attn_next_work(pv, lengths, L, H, nq, n_items, false);
+          pv_k = items.next_work(pv, pv_k + 1);
         }
-        if (qk.w < n_items) issue_qk();
       }
     }
   } else {
-    // ---- softmax / correction / output: thread <-> query row
+    // ---- softmax / correction / output: thread <-> (query row, key-tile parity)
+    const int grp = (warp - 2) >> 2;       // 0: even tiles, 1: odd tiles of the CTA's tile stream
     const int q = (warp & 3) * 32 + lane;  // row in the tile == TMEM lane
-    const int st = threadIdx.x - 64;       // 0..127
+    const int st = threadIdx.x - 64;       // 0..255
     const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t tS = tmem_base + lane_addr + grp * AT_BN;
+    const uint32_t tO = tmem_O + lane_addr + grp * AT_HD;        // this group's accumulator
+    const uint32_t tO_other = tmem_O + lane_addr + (grp ^ 1) * AT_HD;
     const int swz = q & 7;
-    // Penalty LUT, once per CTA: entry o <-> (key - query) = o - lut_off;
-    // pen2 = log2(max(1, |key - query|)).
+    uint64_t* my_s_full = &s_full[grp];
+    uint64_t* my_p_full = &p_full[grp];
+    uint64_t* my_pv_done = &pv_done[grp];
+    uint8_t* myP = sP + grp * AT_QB + q * 128;
+    // Penalty LUT, once per CTA: sLut[o] = -log2(max(1, |o - lut_off|)), (key - query) = o - lut_off
     const int lut_off = nq * AT_BM;
     if (LOGPEN) {
       const int n_lut = lut_off + ((L + AT_BN - 1) / AT_BN) * AT_BN;
-      for (int o = st; o < n_lut; o += 128) {
+      for (int o = st; o < n_lut; o += 256) {
         const int d = abs(o - lut_off);
-        sLut[o] = (d > 1) ? __log2f((float)d) : 0.0f;
+        sLut[o] = (d > 1) ? -__log2f((float)d) : 0.0f;
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, 256);
     }
-    uint32_t g = 0;  // key tiles consumed so far (all items)
+    uint32_t g = 0;  // key tiles of the CTA's stream before the current item
     AttnItem it;
-    for (it.w = blockIdx.x; it.w < n_items; it.w += gridDim.x) {
-      attn_decode(it, lengths, L, H, nq, n_items);
+    for (int k = 0;; ++k) {
+      items.get(it, k);
+      if (it.w >= n_items) break;
       const int i = it.q0 + q;
-      __nv_bfloat16* orow = out + ((size_t)i * B + it.b) * D + it.h * AT_HD;
+      __nv_bfloat16* orow = out + ((size_t)i * B + it.b) * D + it.h * AT_HD + grp * 32;
       if (it.n_kv == 0) {  // tile of padded queries: defined (finite) output, no pipeline work
         if (i < L) {
           uint4* op = reinterpret_cast<uint4*>(orow);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) op[j] = make_uint4(0, 0, 0, 0);
+          for (int j = 0; j < 4; ++j) op[j] = make_uint4(0, 0, 0, 0);
         }
         continue;
       }
       float m_used = -INFINITY, l = 0.0f;
-      for (int j = 0; j < it.n_kv; ++j, ++g) {
-        const uint32_t sb = g & 1, ph = (g >> 1) & 1;
+      int cnt = 0;            // tiles this group has folded into O[grp] for this item
+      uint32_t last_gg = 0;   // stream index of the group's last tile
+      for (int j = (int)((g ^ grp) & 1); j < it.n_kv; j += 2) {
+        const uint32_t gg = g + j;  // (gg & 1) == grp
+        const uint32_t ph = (gg >> 1) & 1;
         const int k0 = j * AT_BN;
         const int nvalid = min(AT_BN, it.len - k0);
-        mbar_wait(&s_full[sb], ph);
+        mbar_wait(my_s_full, ph);
+        if (warp == 2 || warp == 6) AT_TRACE(gg, 3);
         tc_fence_after();
-        uint32_t s0[32], s1[32];
-        tmem_ld32(tmem_base + lane_addr + sb * AT_BN, s0);
-        tmem_ld32(tmem_base + lane_addr + sb * AT_BN + 32, s1);
-        tmem_ld_wait();
+        // pass 1: row maximum (S is read again in pass 2: registers are the scarce resource)
         float mx = -INFINITY;
-        if (nvalid == AT_BN) {
-          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // 4 independent chains
+        {
+          uint32_t s0[32];
 #pragma unroll
-          for (int c = 0; c < 32; ++c)
-            m4[c & 3] = fmaxf(m4[c & 3], fmaxf(__uint_as_float(s0[c]), __uint_as_float(s1[c])));
-          mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-        } else {
+          for (int half = 0; half < 2; ++half) {
+            tmem_ld32(tS + half * 32, s0);
+            tmem_ld_wait();
+            if (nvalid == AT_BN) {
+              float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            if (c < nvalid) mx = fmaxf(mx, __uint_as_float(s0[c]));
-            if (c + 32 < nvalid) mx = fmaxf(mx, __uint_as_float(s1[c]));
+              for (int c = 0; c < 32; ++c) m4[c & 3] = fmaxf(m4[c & 3], __uint_as_float(s0[c]));
+              mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+            } else {
+#pragma unroll
+              for (int c = 0; c < 32; ++c)
+                if (half * 32 + c < nvalid) mx = fmaxf(mx, __uint_as_float(s0[c]));
+            }
           }
         }
         const float m_new = fmaxf(m_used, mx * kLog2e);
-        // lazy rescale: only when some row of the warp grew by more than 2^8 (always at j == 0)
+        // P[grp] and O[grp] were last used by this group's previous tile (stream index gg - 2)
+        if (warp == 2 || warp == 6) AT_TRACE(gg, 4);
+        if (gg >= 2) mbar_wait(my_pv_done, ph ^ 1);
+        if (warp == 2 || warp == 6) AT_TRACE(gg, 5);
+        // lazy rescale: only when some row of the warp grew by more than 2^8 (always at the first tile)
         const bool grow = m_new > m_used + kRescaleThreshold;
         if (__any_sync(0xffffffffu, grow)) {
           const float m_next = grow ? m_new : m_used;
-          if (j > 0) {
+          if (cnt > 0) {
             const float alpha = ex2(m_used - m_next);
-            mbar_wait(&pv_done[(g - 1) & 1], ((g - 1) >> 1) & 1);  // O of the previous tile final
             tc_fence_after();
-            uint32_t o0[32], o1[32];
-            tmem_ld32(tmem_O + lane_addr, o0);
-            tmem_ld32(tmem_O + lane_addr + 32, o1);
-            tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              o0[c] = __float_as_uint(__uint_as_float(o0[c]) * alpha);
-              o1[c] = __float_as_uint(__uint_as_float(o1[c]) * alpha);
+            for (int half = 0; half < 2; ++half) {
+              uint32_t o0[32];
+              tmem_ld32(tO + half * 32, o0);
+              tmem_ld_wait();
+#pragma unroll
+              for (int c = 0; c < 32; ++c) o0[c] = __float_as_uint(__uint_as_float(o0[c]) * alpha);
+              tmem_st32(tO + half * 32, o0);
             }
-            tmem_st32(tmem_O + lane_addr, o0);
-            tmem_st32(tmem_O + lane_addr + 32, o1);
             tmem_st_wait();
             l *= alpha;
           }
           m_used = m_next;
         }
-        if (g >= 2) mbar_wait(&pv_done[sb], ph ^ 1);  // P buffer sb free (PV of tile g-2 done)
-        const float* lrow = sLut + (lut_off - i) + k0;  // penalty of key k0+c for this row: lrow[c]
-        uint4* prow = reinterpret_cast<uint4*>(sP + sb * AT_QB + q * 128);
-        const float negm = -m_used;
-        // stage A (in place): t = s*log2e - m - pen2   (all 64 LDS independent -> full ILP)
+        // pass 2: p = 2^(s*log2e - m - pen2), row sum, bf16 pack -> swizzled K-major P row.
+        // Packed fp32 (FFMA2/FADD2): one issue slot per two elements for everything but the MUFU.
+        const uint32_t lut_addr = smem_u32(sLut + (lut_off - i) + k0);
+        const float2 negm2 = make_float2(-m_used, -m_used);
+        const float2 l2e2 = make_float2(kLog2e, kLog2e);
+        float2 sm2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          float t0 = fmaf(__uint_as_float(s0[c]), kLog2e, negm);
-          float t1 = fmaf(__uint_as_float(s1[c]), kLog2e, negm);
+        for (int half = 0; half < 2; ++half) {
+          uint32_t s0[32];
+          float pn[16];
+          tmem_ld32(tS + half * 32, s0);
           if (LOGPEN) {
-            t0 -= lrow[c];
-            t1 -= lrow[c + 32];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) pn[c] = lds32(lut_addr + (half * 32 + c) * 4);
           }
-          s0[c] = __float_as_uint(t0);
-          s1[c] = __float_as_uint(t1);
-        }
-        // stage B (in place): p = 2^t, masked keys -> 0
+          tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          s0[c] = __float_as_uint(ex2(__uint_as_float(s0[c])));
-          s1[c] = __float_as_uint(ex2(__uint_as_float(s1[c])));
-        }
-        if (nvalid != AT_BN) {
+          for (int sub = 0; sub < 2; ++sub) {  // 16 columns at a time: registers, not ILP, are scarce
+            float2 t[8];
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            if (c >= nvalid) s0[c] = 0u;
-            if (c + 32 >= nvalid) s1[c] = 0u;
+            for (int c = 0; c < 8; ++c) {
+              float2 add = negm2;
+              if (LOGPEN) add = fadd2(negm2, make_float2(pn[2 * c], pn[2 * c + 1]));
+              t[c] = ffma2(make_float2(__uint_as_float(s0[sub * 16 + 2 * c]),
+                                       __uint_as_float(s0[sub * 16 + 2 * c + 1])), l2e2, add);
+            }
+            if (LOGPEN && sub == 0) {  // penalties of the second 16 columns fly under the exps
+#pragma unroll
+              for (int c = 0; c < 16; ++c) pn[c] = lds32(lut_addr + (half * 32 + 16 + c) * 4);
+            }
+            if (nvalid != AT_BN) {  // last key tile of the utterance: masked keys -> p = 2^-inf = 0
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                if (half * 32 + sub * 16 + 2 * c >= nvalid) t[c].x = -INFINITY;
+                if (half * 32 + sub * 16 + 2 * c + 1 >= nvalid) t[c].y = -INFINITY;
+              }
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              t[c].x = ex2(t[c].x);
+              t[c].y = ex2(t[c].y);
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) sm2[c & 1] = fadd2(sm2[c & 1], t[c]);
+#pragma unroll
+            for (int gq = 0; gq < 2; ++gq) {
+              const int o = gq * 4;
+              reinterpret_cast<uint4*>(myP)[(half * 4 + sub * 2 + gq) ^ swz] =
+                  make_uint4(pack_bf16x2(t[o].x, t[o].y), pack_bf16x2(t[o + 1].x, t[o + 1].y),
+                             pack_bf16x2(t[o + 2].x, t[o + 2].y), pack_bf16x2(t[o + 3].x, t[o + 3].y));
+            }
           }
         }
-        // stage C: row sum (4 chains) + bf16 pack -> swizzled K-major P row
-        float sm4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int c = 0; c < 32; ++c) sm4[c & 3] += __uint_as_float(s0[c]) + __uint_as_float(s1[c]);
-        const float sum = (sm4[0] + sm4[1]) + (sm4[2] + sm4[3]);
-#pragma unroll
-        for (int gq = 0; gq < 8; ++gq) {
-          const uint32_t* sv = (gq < 4) ? s0 : s1;
-          const int o = (gq & 3) * 8;
-          prow[gq ^ swz] = make_uint4(
-              pack_bf16x2(__uint_as_float(sv[o]), __uint_as_float(sv[o + 1])),
-              pack_bf16x2(__uint_as_float(sv[o + 2]), __uint_as_float(sv[o + 3])),
-              pack_bf16x2(__uint_as_float(sv[o + 4]), __uint_as_float(sv[o + 5])),
-              pack_bf16x2(__uint_as_float(sv[o + 6]), __uint_as_float(sv[o + 7])));
-        }
-        l += sum;
+        l += (sm2[0].x + sm2[0].y) + (sm2[1].x + sm2[1].y);
         tc_fence_before();
         fence_proxy_async_smem();
-        mbar_arrive(&p_full[sb]);
+        mbar_arrive(my_p_full);
+        if (warp == 2 || warp == 6) AT_TRACE(gg, 6);
+        ++cnt;
+        last_gg = gg;
       }
-      // item epilogue: O / l -> bf16 -> global.  The next item's first PV (accumulate = 0) is issued
-      // only after all 128 threads arrive on its p_full, i.e. after every thread has read O here.
-      mbar_wait(&pv_done[(g - 1) & 1], ((g - 1) >> 1) & 1);
+      g += it.n_kv;
+      // ---- item epilogue: merge the two groups' partial results
+      if (cnt > 0) {
+        mbar_wait(my_pv_done, (last_gg >> 1) & 1);  // O[grp] final
+        tc_fence_after();
+      }
+      sXch[(grp * 2 + 0) * AT_BM + q] = m_used;  // -inf when this group had no tile
+      sXch[(grp * 2 + 1) * AT_BM + q] = l;
+      tc_fence_before();
+      named_bar_sync(2, 256);
       tc_fence_after();
-      const float inv = 1.0f / l;
-      uint32_t o0[32], o1[32];
-      tmem_ld32(tmem_O + lane_addr, o0);
-      tmem_ld32(tmem_O + lane_addr + 32, o1);
-      tmem_ld_wait();
+      const bool other_has = it.n_kv - cnt > 0;  // item-uniform
+      const float m_o = sXch[((grp ^ 1) * 2 + 0) * AT_BM + q];
+      const float l_o = sXch[((grp ^ 1) * 2 + 1) * AT_BM + q];
+      const float mm = fmaxf(m_used, m_o);            // finite: the item has at least one tile
+      const float a_me = (cnt > 0) ? ex2(m_used - mm) : 0.0f;
+      const float a_ot = other_has ? ex2(m_o - mm) : 0.0f;
+      const float inv = 1.0f / (l * a_me + l_o * a_ot);
+      // this group writes output columns [32*grp, 32*grp + 32) of the head
+      float acc[32];
+      {
+        uint32_t o0[32];
+        if (cnt > 0) {  // warp-uniform (depends on the item only)
+          tmem_ld32(tO + grp * 32, o0);
+          tmem_ld_wait();
+        }
+        const float w = a_me * inv;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc[c] = (cnt > 0) ? __uint_as_float(o0[c]) * w : 0.0f;
+        if (other_has) {  // its O buffer is final: the other group waited for it before the barrier
+          tmem_ld32(tO_other + grp * 32, o0);
+          tmem_ld_wait();
+          const float w2 = a_ot * inv;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) acc[c] = fmaf(__uint_as_float(o0[c]), w2, acc[c]);
+        }
+      }
       if (i < L) {
         uint4* op = reinterpret_cast<uint4*>(orow);
 #pragma unroll
-        for (int gq = 0; gq < 8; ++gq) {
-          const uint32_t* v = (gq < 4) ? o0 : o1;
-          const int o = (gq & 3) * 8;
-          op[gq] = make_uint4(
-              pack_bf16x2(__uint_as_float(v[o]) * inv, __uint_as_float(v[o + 1]) * inv),
-              pack_bf16x2(__uint_as_float(v[o + 2]) * inv, __uint_as_float(v[o + 3]) * inv),
-              pack_bf16x2(__uint_as_float(v[o + 4]) * inv, __uint_as_float(v[o + 5]) * inv),
-              pack_bf16x2(__uint_as_float(v[o + 6]) * inv, __uint_as_float(v[o + 7]) * inv));
+        for (int gq = 0; gq < 4; ++gq) {
+          const int o = gq * 8;
+          op[gq] = make_uint4(pack_bf16x2(acc[o], acc[o + 1]), pack_bf16x2(acc[o + 2], acc[o + 3]),
+                              pack_bf16x2(acc[o + 4], acc[o + 5]), pack_bf16x2(acc[o + 6], acc[o + 7]));
         }
       }
+      // both O buffers have been read by both groups before either group lets the MMA warp start
+      // the next item's PV (its p_full arrivals come after this barrier)
+      tc_fence_before();
+      named_bar_sync(3, 256);
+      if (warp == 2 || warp == 6) AT_TRACE(g - 1, 7 - 0);
     }
   }
   tc_fence_before();
@@ -393,6 +526,12 @@ __global__ void __launch_bounds__(192, 2)
 }
 
 }  // namespace fbkst
+
+// debug hook (not part of the public ABI): buffer of 64*8 int64, or NULL to disable
+extern "C" int fbkst_debug_set_attention_trace(long long* buf) {
+  cudaError_t e = cudaMemcpyToSymbol(fbkst::g_attn_trace, &buf, sizeof(buf));
+  return e == cudaSuccess ? 0 : -2;
+}
 
 using namespace fbkst;
 
@@ -429,9 +568,9 @@ extern "C" int fbkst_attention_fwd(const void* qkv, void* out, const int32_t* le
   int grid = num_sms() * per_sm;
   if (grid > n_items) grid = (int)n_items;
   if (log_penalty)
-    attention_fwd_kernel<1><<<grid, 192, smem, st>>>(tmQ, tmKV, (__nv_bfloat16*)out, lengths, L, B, H);
+    attention_fwd_kernel<1><<<grid, AT_THREADS, smem, st>>>(tmQ, tmKV, (__nv_bfloat16*)out, lengths, L, B, H);
   else
-    attention_fwd_kernel<0><<<grid, 192, smem, st>>>(tmQ, tmKV, (__nv_bfloat16*)out, lengths, L, B, H);
+    attention_fwd_kernel<0><<<grid, AT_THREADS, smem, st>>>(tmQ, tmKV, (__nv_bfloat16*)out, lengths, L, B, H);
   FBKST_CHECK_CUDA(cudaGetLastError());
   return FBKST_OK;
 }

@@ -57,10 +57,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #if FBKST_WATCHDOG
-  if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) {  // ~2 s at 2 GHz: never legitimate
+  // try_wait suspends the thread in hardware for a bounded time per attempt, so the loop body is
+  // only a counter (no clock reads: the spinning TMA/MMA warps share issue slots with the math warps)
+  for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
+    if (spins > (1u << 26)) {  // seconds: never legitimate
       printf("fbkst: mbarrier watchdog block=(%d,%d) thread=%d bar=%u parity=%u\n", blockIdx.x,
              blockIdx.y, threadIdx.x, smem_u32(bar), parity);
       __trap();
@@ -214,6 +214,26 @@ __host__ __device__ constexpr uint32_t idesc_bf16_f32(int M, int N, int a_mn_maj
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+// packed 2 x fp32 arithmetic (sm_100: FFMA2 / FADD2, one issue slot for two lanes of work)
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  uint64_t ra, rb, rc, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  uint64_t ra, rb, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
 }
 // streaming 16-byte load: read-only path, do not allocate in L1 (data touched exactly once)
 __device__ __forceinline__ uint4 ld_nc_na(const uint4* p) {

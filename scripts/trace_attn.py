@@ -1,0 +1,30 @@
+"""Timeline of CTA 0 of the attention kernel (debug hook fbkst_debug_set_attention_trace)."""
+import ctypes
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "fbk-fairseq-st_b200"))
+from fbkst_b200 import _lib, ops  # noqa: E402
+
+lib = _lib.load()
+lib.fbkst_debug_set_attention_trace.argtypes = [ctypes.c_void_p]
+d = torch.device("cuda:0")
+L, B, H = 375, 64, 8
+qkv = (torch.randn(L * B, 3 * H * 64, device=d) * 0.7).bfloat16()
+lengths = torch.full((B,), L, dtype=torch.int32, device=d)
+for _ in range(3):
+    ops.attention(qkv, lengths, L, B, H, True)
+buf = torch.zeros(64 * 8, dtype=torch.int64, device=d)
+assert lib.fbkst_debug_set_attention_trace(buf.data_ptr()) == 0
+ops.attention(qkv, lengths, L, B, H, True)
+torch.cuda.synchronize()
+lib.fbkst_debug_set_attention_trace(None)
+t = buf.view(64, 8).cpu()
+t0 = int(t[t > 0].min())
+names = ["mma:p_full", "mma:PV", "mma:QK+2", "sm:s_full", "sm:pass1", "sm:PO_free", "sm:arrive", "-"]
+print("tile " + " ".join("%11s" % n for n in names))
+for i in range(40):
+    print("%4d " % i + " ".join("%11d" % (int(v) - t0 if v > 0 else -1) for v in t[i]))
