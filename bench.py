@@ -467,10 +467,19 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # Only the JSON line may reach stdout: libraries (NCCL prints its version banner there) write
+    # to fd 1 behind Python's back, so fd 1 is pointed at stderr for the whole run.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
+
     if args.impl == "reference":
         r = run_reference(args, rank, world)
         if r is not None:
-            print(json.dumps(r), flush=True)
+            emit(r)
         return
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -478,10 +487,10 @@ def main():
     r = run_ours(args, rank, world, local_rank)
     if rank == 0:
         result, enc = r
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N=1 only
             sd = {k: v for k, v in enc.state_dict().items()}
             result["cpu_baseline"] = cpu_reference(args, enc_state=sd)
-        print(json.dumps(result), flush=True)
+        emit(result)
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
