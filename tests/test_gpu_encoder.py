@@ -170,3 +170,90 @@ def test_cuda_graph_mode_is_bit_identical():
             n = int(l[0] + 3) // 4
             assert torch.equal(o.ctc_out.float()[:n], co[:n])
     assert len(enc._graphs) == 3  # T = 320, 317, 200
+
+
+@pytest.mark.parametrize("strategy", ["weighted", "softmax"])
+def test_encoder_cfg3_long_ragged_vs_oracle(strategy):
+    """BASELINE configs[2] shape: big2 model, ragged 200-3000 frame utterances (L up to 750, several
+    query tiles and key tiles per utterance, partially valid last tiles), weighted / softmax pooling."""
+    cfg = dict(embed_dim=512, ffn_dim=2048, heads=8, layers=2, conv_channels=64, feat_dim=40,
+               vocab=505, distance_penalty="log", ctc_layer=1, ctc_strategy=strategy)
+    sd = O.init_state_dict(cfg, seed=2)
+    lens_in = [3000, 2177, 1203, 640, 201]
+    x, lens = O.synthetic_batch(lens_in, 40, seed=31)
+    labels = O.synthetic_ctc_bump(750, len(lens_in), 505, seed=11)
+    hook = O.bump_hook(labels, 30.0)
+    ref = O.encoder_forward(sd, cfg, x, lens, ctc_logits_hook=hook)
+    enc = build_encoder(cfg, sd)
+    enc.ctc_fc.register_forward_hook(lambda m, i, o: hook(o))
+    out = enc(x.cuda(), lens.cuda())
+    check_against(out, ref, lens)
+
+
+def test_encoder_cfg5_shape_vs_oracle():
+    """BASELINE configs[4] shape: 80-dim fbank, d1024 h16 ffn4096, 128 conv channels
+    (conv_transformer_giant), long utterances (T up to 5000 -> L = 1250), compression at layer 2."""
+    cfg = dict(embed_dim=1024, ffn_dim=4096, heads=16, layers=2, conv_channels=128, feat_dim=80,
+               vocab=305, distance_penalty="log", ctc_layer=2, ctc_strategy="avg")
+    sd = O.init_state_dict(cfg, seed=4)
+    lens_in = [5000, 3333]
+    x, lens = O.synthetic_batch(lens_in, 80, seed=41)
+    labels = O.synthetic_ctc_bump(1250, 2, 305, seed=13)
+    hook = O.bump_hook(labels, 30.0)
+    ref = O.encoder_forward(sd, cfg, x, lens, ctc_logits_hook=hook)
+    enc = build_encoder(cfg, sd)
+    enc.ctc_fc.register_forward_hook(lambda m, i, o: hook(o))
+    out = enc(x.cuda(), lens.cuda())
+    check_against(out, ref, lens)
+
+
+def test_encoder_full_size_properties():
+    """BASELINE configs[1] at FULL size (64 x 1500 x 40, 11 layers, V=8005) through size-independent
+    properties: (1) determinism: two runs are bit-identical; (2) batch-slot permutation: permuting
+    the utterances permutes the outputs (same padded extent on both sides) up to bf16
+    rounding, and the integer outputs (compressed lengths) exactly;
+    (3) compressed lengths equal the number of label changes of the injected plan; (4) padding rows
+    of the compressed output are exactly 0 and everything is finite."""
+    import bench
+    cfgb = bench.CONFIGS["cfg2"]
+    model = cfgb["model"]
+    torch.manual_seed(0)
+    from fbkst_b200.config import build_encoder as build
+    enc = build(model, None, device="cpu")
+    bench.randomise_norm_stats(enc, 1)
+    enc = enc.cuda().eval()
+    B, T, L = 64, 1500, 375
+    g = torch.Generator().manual_seed(5)
+    lens_in = torch.randint(700, T + 1, (B,), generator=g).sort(descending=True).values
+    lens_in[0] = T
+    x, lens = bench.make_batch(lens_in.tolist(), 40, 99)
+    plan = bench.label_plan(L, B, model["vocab"], seed=7).cuda()
+    state = dict(plan=plan)
+
+    def bump(m, i, o):
+        return o.scatter_add(2, state["plan"].unsqueeze(-1), torch.full_like(o[..., :1], 30.0))
+    enc.ctc_fc.register_forward_hook(bump)
+    from fbkst_b200 import ops
+    xn = ops.cmvn(x.cuda(), lens.to(torch.int32).cuda())  # as the bench: CMVN, then the encoder
+    o1 = enc(xn, lens.cuda())
+    o2 = enc(xn, lens.cuda())
+    assert torch.equal(o1.encoder_out, o2.encoder_out) and torch.equal(o1.src_lengths, o2.src_lengths)
+    assert torch.isfinite(o1.encoder_out).all()
+    sub = [((n + 1) // 2 + 1) // 2 for n in lens.tolist()]
+    pl = plan.cpu()
+    for b in range(B):
+        n = sub[b]
+        changes = 1 + int((pl[1:n, b] != pl[: n - 1, b]).sum())
+        assert int(o1.src_lengths[b]) == changes, b
+        assert bool(o1.encoder_padding_mask[b, changes:].all()) and not bool(o1.encoder_padding_mask[b, :changes].any())
+    perm = torch.randperm(B, generator=g)
+    state["plan"] = plan[:, perm.cuda()]
+    o3 = enc(xn[perm.cuda()].contiguous(), lens[perm].cuda())
+    assert torch.equal(o3.src_lengths.cpu(), o1.src_lengths.cpu()[perm])
+    L2 = o1.encoder_out.shape[0]
+    for k in range(0, B, 5):
+        b = int(perm[k])
+        n = int(o1.src_lengths[b])
+        # not bit for bit: the key tiles of an utterance are split between the two softmax groups
+        # by their position in the CTA's tile stream, which moves with the batch slot
+        assert rel_err(o3.encoder_out[:n, k], o1.encoder_out[:n, b]) < 5e-3, (k, b)
