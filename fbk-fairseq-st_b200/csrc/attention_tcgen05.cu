@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
 #ifdef FBKST_ATTN_TRACE
-  long long* trace = (blockIdx.x == 0 && (lane == 0)) ? g_attn_trace : nullptr;
+  long long* trace = (blockIdx.x == 0 && (lane == 0)) ? g_attn_trace : nullptr;  // lane 0 of each warp
 #endif
 
   extern __shared__ uint8_t smem_raw[];
@@ -210,7 +210,11 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // Whole warp in uniform control flow, one ELECTED lane issues: with `if (lane == 0)` ptxas wraps
+    // every UTMALDG / UTCHMMA in a divergence waterfall (ELECT / BRA.U.ANY loop + descriptor
+    // rebuild, ~14 instructions per MMA); in uniform code the descriptors sit in uniform registers
+    // and the four MMAs of a tile issue back to back.
+    {
       // Two cursors over the flattened key-tile stream: K runs two tiles ahead of V.  QK(t+2) is
       // issued while tile t is being soft-maxed, so K(t+2) must not queue behind V(t+1), whose
       // buffer frees only when PV(t-1) has completed (one producer thread, blocking waits).
@@ -223,14 +227,20 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
           const int cq = ki.h * AT_HD, ck = D + cq;
           if (kj == 0) {
             mbar_wait(q_empty, (n & 1) ^ 1);  // every QK of the previous item has completed
-            mbar_arrive_expect_tx(q_full, AT_QB);
-            tma_load_3d(sQ, &tmQ, q_full, cq, ki.b, ki.q0);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(q_full, AT_QB);
+              tma_load_3d(sQ, &tmQ, q_full, cq, ki.b, ki.q0);
+            }
+            __syncwarp();
             ++n;
           }
           const uint32_t ks = gk % AT_KST;
           mbar_wait(&k_empty[ks], ((gk / AT_KST) & 1) ^ 1);
-          mbar_arrive_expect_tx(&k_full[ks], AT_KB);
-          tma_load_3d(sK + ks * AT_KB, &tmKV, &k_full[ks], ck, ki.b, kj * AT_BN);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&k_full[ks], AT_KB);
+            tma_load_3d(sK + ks * AT_KB, &tmKV, &k_full[ks], ck, ki.b, kj * AT_BN);
+          }
+          __syncwarp();
           ++gk;
           if (++kj == ki.n_kv) {
             kj = 0;
@@ -241,8 +251,11 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
           const int cv = 2 * D + vi.h * AT_HD;
           const uint32_t vs = gv & 1;
           mbar_wait(&v_empty[vs], ((gv >> 1) & 1) ^ 1);
-          mbar_arrive_expect_tx(&v_full[vs], AT_KB);
-          tma_load_3d(sV + vs * AT_KB, &tmKV, &v_full[vs], cv, vi.b, vj * AT_BN);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&v_full[vs], AT_KB);
+            tma_load_3d(sV + vs * AT_KB, &tmKV, &v_full[vs], cv, vi.b, vj * AT_BN);
+          }
+          __syncwarp();
           ++gv;
           if (++vj == vi.n_kv) {
             vj = 0;
@@ -252,8 +265,8 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (see above)
+    {
       constexpr uint32_t IDESC_QK = idesc_bf16_f32(AT_BM, AT_BN, 0, 0);
       constexpr uint32_t IDESC_PV = idesc_bf16_f32(AT_BM, AT_HD, 0, 1);
       const uint64_t qdesc = desc_kmajor_sw128(smem_u32(sQ));
@@ -268,14 +281,18 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
         tc_fence_after();
         const uint64_t kdesc = desc_kmajor_sw128(smem_u32(sK + ks * AT_KB));
         const uint32_t d_tmem = tmem_base + (gq & 1) * AT_BN;
+        const bool last = qk_j + 1 == qk.n_kv;
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < AT_HD / 16; ++k)
-          umma_bf16_ss(d_tmem, qdesc + 2 * k, kdesc + 2 * k, IDESC_QK, k != 0);
-        umma_commit(&s_full[gq & 1]);
-        umma_commit(&k_empty[ks]);
+          for (int k = 0; k < AT_HD / 16; ++k)
+            umma_bf16_ss(d_tmem, qdesc + 2 * k, kdesc + 2 * k, IDESC_QK, k != 0);
+          umma_commit(&s_full[gq & 1]);
+          umma_commit(&k_empty[ks]);
+          if (last) umma_commit(q_empty);  // Q may be overwritten once these MMAs have completed
+        }
+        __syncwarp();
         ++gq;
         if (++qk_j == qk.n_kv) {
-          umma_commit(q_empty);  // Q may be overwritten once these MMAs have completed
           qk_j = 0;
           ++nqk;
           qk_k = items.next_work(qk, qk_k + 1);
@@ -290,12 +307,15 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
         mbar_wait(&v_full[pb], ph);
         tc_fence_after();
         const uint32_t pa = smem_u32(sP + pb * AT_QB), va = smem_u32(sV + pb * AT_KB);
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < AT_BN / 16; ++kk)
-          umma_bf16_ss(tmem_O + pb * AT_HD, desc_kmajor_sw128(pa) + 2 * kk,
-                       desc_mnmajor_sw128(va + kk * 2048, AT_KB), IDESC_PV, (pv_j >= 2) || kk != 0);
-        umma_commit(&pv_done[pb]);
-        umma_commit(&v_empty[pb]);
+          for (int kk = 0; kk < AT_BN / 16; ++kk)
+            umma_bf16_ss(tmem_O + pb * AT_HD, desc_kmajor_sw128(pa) + 2 * kk,
+                         desc_mnmajor_sw128(va + kk * 2048, AT_KB), IDESC_PV, (pv_j >= 2) || kk != 0);
+          umma_commit(&pv_done[pb]);
+          umma_commit(&v_empty[pb]);
+        }
+        __syncwarp();
         AT_TRACE(gp, 1);
         // PV before QK: the group's next exp pass needs P[pb]/O[pb] free (PV done) as much as S
         if (qk.w < n_items) issue_qk();

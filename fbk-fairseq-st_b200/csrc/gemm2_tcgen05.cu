@@ -152,30 +152,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Producer and MMA warps run in warp-uniform control flow and let ONE ELECTED lane issue: under
+  // `if (lane == 0)` ptxas wraps every UTMALDG / UTCHMMA in a divergence waterfall (ELECT +
+  // BRA.U.ANY loop, descriptors rebuilt per instruction); uniform code keeps them in uniform
+  // registers and issues the four MMAs of a k-block back to back.
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
-        const int row_a = m_blk * 2 * G2_BM + (int)rank * G2_BM;
-        const int row_b = n_blk * G2_BN + (int)rank * (G2_BN / 2);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
+      const int row_a = m_blk * 2 * G2_BM + (int)rank * G2_BM;
+      const int row_b = n_blk * G2_BN + (int)rank * (G2_BN / 2);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
           if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);
           const uint32_t leader_full = map_to_cta(smem_u32(&full_bar[stage]), 0);
           uint8_t* sa = smem + stage * G2_STAGE_BYTES;
           tma_load_2d_cg2(sa, &tmA, leader_full, kb * G2_BK, row_a);
           tma_load_2d_cg2(sa + G2_A_BYTES, &tmB, leader_full, kb * G2_BK, row_b);
-          if (++stage == G2_STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        __syncwarp();
+        if (++stage == G2_STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -190,16 +195,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
           const uint32_t sa = smem_u32(smem + stage * G2_STAGE_BYTES);
           const uint64_t adesc = desc_kmajor_sw128(sa);
           const uint64_t bdesc = desc_kmajor_sw128(sa + G2_A_BYTES);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < G2_BK / 16; ++k)
-            umma_bf16_ss_cg2(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
-          umma_commit_cg2_mc(&empty_bar[stage], 0x3);
+            for (int k = 0; k < G2_BK / 16; ++k)
+              umma_bf16_ss_cg2(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
+            umma_commit_cg2_mc(&empty_bar[stage], 0x3);
+            if (kb == num_kb - 1) umma_commit_cg2_mc(&tfull_bar[acc], 0x3);
+          }
+          __syncwarp();
           if (++stage == G2_STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit_cg2_mc(&tfull_bar[acc], 0x3);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }

@@ -65,3 +65,13 @@ def test_argument_errors_do_not_need_a_gpu(lib):
     assert rc == -1 and b"null operand" in lib.fbkst_last_error()
     rc = lib.fbkst_layernorm(1, 1, 1, 1, 0, 4, 100, ctypes.c_float(1e-5), None, 0, None)
     assert rc == -1 and b"unsupported D" in lib.fbkst_last_error()
+
+
+def test_torch_custom_ops_are_registered_for_cuda_only():
+    """torch.ops.fbkst.* exist (north_star: kernels exposed as PyTorch custom ops) and have no CPU
+    kernel: the dispatcher refuses CPU tensors instead of falling back."""
+    from fbkst_b200 import torch_ops
+    for name in torch_ops.OPS:
+        assert hasattr(torch.ops.fbkst, name), name
+    with pytest.raises((NotImplementedError, RuntimeError), match="CPU"):
+        torch.ops.fbkst.layernorm(torch.zeros(4, 128), torch.ones(128), torch.zeros(128), False, 1e-5)

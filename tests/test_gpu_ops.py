@@ -266,3 +266,36 @@ def test_ctc_full_size_properties():
             assert torch.allclose(out[: changes, b], torch.full((changes, D), 1.5), atol=1e-5)
             assert out[changes:, b].abs().max() == 0
         assert L2 == int(nl.max())
+
+
+def test_torch_custom_ops_match_direct_calls():
+    """torch.ops.fbkst.* end in the same extern "C" entry points as fbkst_b200.ops.*."""
+    from fbkst_b200 import ops, torch_ops  # noqa: F401
+    g = torch.Generator().manual_seed(0)
+    a = bf(torch.randn(300, 256, generator=g)).to(dev())
+    w = bf(torch.randn(384, 256, generator=g) * 0.05).to(dev())
+    bias = torch.randn(384, generator=g).to(dev())
+    res = torch.randn(300, 384, generator=g).to(dev())
+    assert torch.equal(torch.ops.fbkst.linear(a, w, bias, True, None, False), ops.linear(a, w, bias, relu=True))
+    assert torch.equal(torch.ops.fbkst.linear(a, w, bias, False, res, True),
+                       ops.linear(a, w, bias, residual=res, out_dtype=torch.float32))
+    x = torch.randn(300, 256, generator=g).to(dev())
+    gm, bt = torch.randn(256, generator=g).to(dev()), torch.randn(256, generator=g).to(dev())
+    assert torch.equal(torch.ops.fbkst.layernorm(x, gm, bt, False, 1e-5), ops.layernorm(x, gm, bt))
+    L, B, H = 100, 3, 2
+    qkv = bf(torch.randn(L * B, 3 * H * 64, generator=g) * 0.7).to(dev())
+    lens = torch.tensor([100, 64, 5], dtype=torch.int32, device=dev())
+    assert torch.equal(torch.ops.fbkst.attention(qkv, lens, L, B, H, True), ops.attention(qkv, lens, L, B, H, True))
+    V, D = 50, 128
+    logits = torch.randn(L * B, V, generator=g).to(dev())
+    xs = torch.randn(L * B, D, generator=g).to(dev())
+    lab, prob = torch.ops.fbkst.ctc_argmax(logits, lens, L, B, V, True)
+    seg_id, seg_start, weight, new_len, max_new = torch.ops.fbkst.ctc_segment(lab, prob, lens, "weighted", L, B)
+    out = torch.ops.fbkst.ctc_compress(xs, seg_id, seg_start, weight, lens, new_len, max_new, L, B)
+    lab2, prob2 = ops.ctc_argmax(logits, lens, L, B, V, True)
+    s2 = ops.ctc_segment(lab2, prob2, lens, "weighted", L, B)
+    out2 = ops.ctc_compress(xs, s2[0], s2[1], s2[2], lens, s2[3], s2[4], L, B)
+    n = int(max_new.item()) * B
+    assert torch.equal(lab, lab2) and torch.equal(new_len, s2[3]) and torch.equal(out[:n], out2[:n])
+    mask = torch.ops.fbkst.lengths_to_mask(lens, L)
+    assert mask.dtype == torch.bool and mask.shape == (B, L) and bool(mask[2, 5]) and not bool(mask[2, 4])
