@@ -10,8 +10,11 @@ namespace fbkst {
 // ------------------------------------------------------------------ CMVN (a1)
 // Pass 1: per (utterance, feature) sum and sum of squares in fp64 (unbiased variance needs
 // sumsq - sum^2/n; fp64 keeps the cancellation harmless).  grid = (chunks, B).
-__global__ void cmvn_stats_kernel(const float* __restrict__ x, const int* __restrict__ lengths,
-                                  double* __restrict__ ws, int T, int F, int rows_per_block) {
+// `starts` (optional): x is a RAGGED buffer [sum(len), F] and utterance b begins at frame starts[b]
+// (device collater, a2 of the "next" rows: data/collaters.py:43-56); otherwise x is padded [B,T,F].
+__global__ void cmvn_stats_kernel(const float* __restrict__ x, const long long* __restrict__ starts,
+                                  const int* __restrict__ lengths, double* __restrict__ ws, int T, int F,
+                                  int rows_per_block) {
   extern __shared__ double sred[];  // [2][blockDim.x]
   const int b = blockIdx.y;
   const int len = min(lengths[b], T);
@@ -21,7 +24,7 @@ __global__ void cmvn_stats_kernel(const float* __restrict__ x, const int* __rest
   const int f = threadIdx.x % F, g = threadIdx.x / F;
   double s = 0.0, ss = 0.0;
   if (g < groups) {
-    const float* xp = x + ((size_t)b * T) * F + f;
+    const float* xp = x + (starts ? (size_t)starts[b] : (size_t)b * T) * F + f;
     for (int t = t0 + g; t < t1; t += groups) {
       const double v = (double)__ldg(xp + (size_t)t * F);
       s += v;
@@ -46,15 +49,17 @@ __global__ void cmvn_stats_kernel(const float* __restrict__ x, const int* __rest
 
 // Pass 2: y = (x - mean) * inv with the reference's eps rule (data_utils.py:15-19): if ANY
 // feature of the utterance has var < 1e-8, inv = 1/(sqrt(var)+1e-8) for all features.
-__global__ void cmvn_apply_kernel(const float* __restrict__ x, float* __restrict__ y,
-                                  const int* __restrict__ lengths, const double* __restrict__ ws,
-                                  int T, int F, int rows_per_block) {
+// With `starts` the input is ragged and the output padded (collate + normalise in one pass); with
+// ws == nullptr nothing is normalised (pure zero-padded collate).
+__global__ void cmvn_apply_kernel(const float* __restrict__ x, const long long* __restrict__ starts,
+                                  float* __restrict__ y, const int* __restrict__ lengths,
+                                  const double* __restrict__ ws, int T, int F, int rows_per_block) {
   extern __shared__ float sstat[];  // mean[F], inv[F]
   const int b = blockIdx.y;
   const int len = min(lengths[b], T);
   int small = 0;
   float mean = 0.f, var = 0.f;
-  if (threadIdx.x < F) {
+  if (threadIdx.x < F && ws != nullptr) {
     const double n = (double)len;
     const double s = ws[((size_t)b * F + threadIdx.x) * 2 + 0];
     const double ss = ws[((size_t)b * F + threadIdx.x) * 2 + 1];
@@ -68,16 +73,18 @@ __global__ void cmvn_apply_kernel(const float* __restrict__ x, float* __restrict
   const int any_small = __syncthreads_or(small);
   if (threadIdx.x < F) {
     sstat[threadIdx.x] = mean;
-    sstat[F + threadIdx.x] = any_small ? 1.0f / (sqrtf(var) + 1e-8f) : 1.0f / sqrtf(var);
+    sstat[F + threadIdx.x] =
+        ws == nullptr ? 1.0f : (any_small ? 1.0f / (sqrtf(var) + 1e-8f) : 1.0f / sqrtf(var));
   }
   __syncthreads();
   const int t0 = blockIdx.x * rows_per_block;
   const int t1 = min(t0 + rows_per_block, T);
   const size_t base = ((size_t)b * T + t0) * F;
+  const size_t ibase = starts ? ((size_t)starts[b] + t0) * F : base;
   const int n = (t1 - t0) * F;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const int t = t0 + i / F, f = i % F;
-    y[base + i] = (t < len) ? (__ldg(x + base + i) - sstat[f]) * sstat[F + f] : 0.0f;
+    y[base + i] = (t < len) ? (__ldg(x + ibase + i) - sstat[f]) * sstat[F + f] : 0.0f;
   }
 }
 
@@ -279,8 +286,29 @@ extern "C" int fbkst_cmvn_f32(const float* x, float* y, const int32_t* lengths, 
   FBKST_CHECK_CUDA(cudaMemsetAsync(workspace, 0, sizeof(double) * 2 * B * F, st));
   const int rows = 128;
   dim3 grid((T + rows - 1) / rows, B);
-  cmvn_stats_kernel<<<grid, 256, 2 * 256 * sizeof(double), st>>>(x, lengths, workspace, T, F, rows);
-  cmvn_apply_kernel<<<grid, 256, 2 * F * sizeof(float), st>>>(x, y, lengths, workspace, T, F, rows);
+  cmvn_stats_kernel<<<grid, 256, 2 * 256 * sizeof(double), st>>>(x, nullptr, lengths, workspace, T, F, rows);
+  cmvn_apply_kernel<<<grid, 256, 2 * F * sizeof(float), st>>>(x, nullptr, y, lengths, workspace, T, F, rows);
+  FBKST_CHECK_CUDA(cudaGetLastError());
+  return FBKST_OK;
+}
+
+extern "C" int fbkst_collate_cmvn_f32(const float* packed, const int64_t* starts, const int32_t* lengths,
+                                      float* out, int B, int T, int F, int normalize, double* workspace,
+                                      fbkst_stream_t stream) {
+  FBKST_REQUIRE(packed && starts && lengths && out, "fbkst_collate_cmvn_f32: null pointer");
+  FBKST_REQUIRE(!normalize || workspace, "fbkst_collate_cmvn_f32: normalisation needs a workspace");
+  FBKST_REQUIRE(B > 0 && T > 0 && F > 0 && F <= 256, "fbkst_collate_cmvn_f32: bad shape B=%d T=%d F=%d",
+                B, T, F);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int rows = 128;
+  dim3 grid((T + rows - 1) / rows, B);
+  const long long* sp = reinterpret_cast<const long long*>(starts);
+  if (normalize) {
+    FBKST_CHECK_CUDA(cudaMemsetAsync(workspace, 0, sizeof(double) * 2 * B * F, st));
+    cmvn_stats_kernel<<<grid, 256, 2 * 256 * sizeof(double), st>>>(packed, sp, lengths, workspace, T, F, rows);
+  }
+  cmvn_apply_kernel<<<grid, 256, 2 * F * sizeof(float), st>>>(packed, sp, out, lengths,
+                                                             normalize ? workspace : nullptr, T, F, rows);
   FBKST_CHECK_CUDA(cudaGetLastError());
   return FBKST_OK;
 }

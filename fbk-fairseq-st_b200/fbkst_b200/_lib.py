@@ -18,6 +18,7 @@ SIGNATURES = {
     "fbkst_abi_version": [],
     "fbkst_device_ok": [],
     "fbkst_cmvn_f32": [P, P, P, I, I, I, P, P],
+    "fbkst_collate_cmvn_f32": [P, P, P, P, I, I, I, I, P, P],
     "fbkst_conv1_relu_bn": [P, P, P, P, P, P, I, I, I, I, P],
     "fbkst_conv2_relu_bn": [P, P, P, P, P, P, I, I, I, I, P],
     "fbkst_linear_bf16": [P, I64, P, I64, P, P, I64, P, I64, I, I, I, I, I, I, P, P, I, P],

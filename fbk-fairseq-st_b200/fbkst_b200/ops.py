@@ -45,6 +45,21 @@ def cmvn(x, lengths, out=None):
     return out
 
 
+def collate_cmvn(packed, starts, lengths, T, normalize=True, out=None):
+    """Ragged frames [sum(len), F] fp32 + starts [B] int64 + lengths [B] int32 -> padded [B,T,F]
+    (zeros beyond each length), per-utterance CMVN applied in the same pass if ``normalize``."""
+    lib = _lib.require_device()
+    _req(packed, torch.float32, "collate_cmvn.packed"); _req(starts, torch.int64, "collate_cmvn.starts")
+    _req(lengths, torch.int32, "collate_cmvn.lengths")
+    B, Fd = lengths.numel(), packed.shape[-1]
+    out = torch.empty(B, T, Fd, dtype=torch.float32, device=packed.device) if out is None else out
+    ws = torch.empty(B * Fd * 2, dtype=torch.float64, device=packed.device) if normalize else None
+    check(lib.fbkst_collate_cmvn_f32(packed.data_ptr(), starts.data_ptr(), lengths.data_ptr(),
+                                     out.data_ptr(), B, T, Fd, 1 if normalize else 0, _ptr(ws), _stream()))
+    _count(2 if normalize else 1)
+    return out
+
+
 def conv1_relu_bn(x, w, bias, scale, shift):
     lib = _lib.require_device()
     _req(x, torch.float32, "conv1.x")

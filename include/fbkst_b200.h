@@ -59,6 +59,18 @@ int fbkst_device_ok(void);
 int fbkst_cmvn_f32(const float* x, float* y, const int32_t* lengths, int B, int T, int F,
                    double* workspace, fbkst_stream_t stream);
 
+/* ---- next row N2: collate (+ optional CMVN) on device ---------------------------------------
+ * replaces examples/speech_recognition/data/collaters.py:43-56 (_collate_frames: zero-padded
+ * B x T x F batch) for features that arrive RAGGED: packed [sum(lengths), F] fp32 holds the
+ * utterances back to back, starts[b] (int64) is the first frame of the utterance that goes to
+ * batch slot b (the host has already sorted slots by descending length, collaters.py:89-92),
+ * lengths[b] its frame count.  out [B, T, F] fp32, rows t >= lengths[b] are 0.  normalize != 0
+ * additionally applies apply_mv_norm per utterance (data/data_utils.py:9-24) in the same pass;
+ * workspace: B*F*2 doubles (may be NULL when normalize == 0). */
+int fbkst_collate_cmvn_f32(const float* packed, const int64_t* starts, const int32_t* lengths,
+                           float* out, int B, int T, int F, int normalize, double* workspace,
+                           fbkst_stream_t stream);
+
 /* ---- a2 (conv 1): Conv2d(1->C,k3,s2,p1)+bias -> ReLU -> BatchNorm(eval affine) -----------
  * replaces conv_transformer.py:203-214 for i=0.  x [B,T,F] fp32; w [C,9] fp32; bias,
  * bn_scale, bn_shift [C] fp32 (scale = gamma/sqrt(var+eps), shift = beta - mean*scale);

@@ -299,3 +299,50 @@ def test_torch_custom_ops_match_direct_calls():
     assert torch.equal(lab, lab2) and torch.equal(new_len, s2[3]) and torch.equal(out[:n], out2[:n])
     mask = torch.ops.fbkst.lengths_to_mask(lens, L)
     assert mask.dtype == torch.bool and mask.shape == (B, L) and bool(mask[2, 5]) and not bool(mask[2, 4])
+
+
+# ------------------------------------------------------------------ next row N2: device collater
+def test_device_collater_reference_kat():
+    """The reference's collate KAT (tests/speech_recognition/test_collaters.py:23-50) through the
+    device collater: same ids / lengths / targets, src_tokens padded on the device."""
+    import numpy as np
+    from fbkst_b200.data import DeviceCollater
+    s1 = {"id": 0, "data": [np.array([[7, 8], [9, 10]]), np.array([4, 2, 3, 1])]}
+    s2 = {"id": 1, "data": [np.array([[1, 2], [3, 4], [5, 6]]), np.array([3, 2, 1])]}
+    batch = DeviceCollater(0, 1, pad_index=0, eos_index=1).collate([s1, s2])
+    assert batch["id"].tolist() == [1, 0] and batch["ntokens"] == 7 and batch["nsentences"] == 2
+    assert batch["net_input"]["src_tokens"].is_cuda
+    assert batch["net_input"]["src_tokens"].cpu().tolist() == [[[1, 2], [3, 4], [5, 6]], [[7, 8], [9, 10], [0, 0]]]
+    assert batch["net_input"]["prev_output_tokens"].tolist() == [[1, 3, 2, 0], [1, 4, 2, 3]]
+    assert batch["net_input"]["src_lengths"].tolist() == [3, 2]
+    assert batch["target"].tolist() == [[3, 2, 1, 0], [4, 2, 3, 1]]
+
+
+@pytest.mark.parametrize("normalize", [False, True])
+def test_device_collater_vs_oracle(normalize):
+    """Ragged utterances -> padded (and normalised) batch: bit-exact copy without CMVN, 1e-5 with."""
+    from oracle import collate_oracle as C
+    from fbkst_b200.data import DeviceCollater
+    g = torch.Generator().manual_seed(11)
+    lens = [1500, 3, 977, 1201, 640, 1, 1500, 333]
+    samples = [{"id": i, "data": [(torch.randn(n, 40, generator=g) * 3 + 1).numpy(),
+                                  torch.randint(3, 90, (4 + i,), generator=g).numpy()]}
+               for i, n in enumerate(lens)]
+    if normalize:  # unbiased variance of a single frame is undefined (NaN in the reference too)
+        samples = [s for s in samples if s["data"][0].shape[0] > 1]
+    ref = C.collate(samples, normalize=normalize)
+    col = DeviceCollater(0, 1, normalize=normalize)
+    for _ in range(2):  # second call reuses the pinned buffer
+        got = col.collate(samples)
+    assert got["net_input"]["src_lengths"].tolist() == ref["net_input"]["src_lengths"].tolist()
+    assert sorted(got["id"].tolist()) == sorted(ref["id"].tolist())
+    x = got["net_input"]["src_tokens"].cpu()
+    for k, i in enumerate(ref["id"].tolist()):
+        j = got["id"].tolist().index(i)
+        a, r = x[j], ref["net_input"]["src_tokens"][k]
+        if normalize:
+            assert rel_err(a, r) < 1e-5
+        else:
+            assert torch.equal(a, r)
+        assert torch.equal(got["target"][j], ref["target"][k])
+        assert torch.equal(got["net_input"]["prev_output_tokens"][j], ref["net_input"]["prev_output_tokens"][k])

@@ -109,3 +109,49 @@ def test_init_state_dict_matches_reference_keys():
     assert set(sd.keys()) == set(ref.keys())
     for k in ref:
         assert tuple(sd[k].shape) == tuple(ref[k].shape), k
+
+
+# ------------------------------------------------------------------ next row N2: collater
+def _kat_samples():
+    """tests/speech_recognition/test_collaters.py:23-31 of the reference."""
+    import numpy as np
+    frames1 = np.array([[7, 8], [9, 10]])
+    frames2 = np.array([[1, 2], [3, 4], [5, 6]])
+    target1 = np.array([4, 2, 3, 1])
+    target2 = np.array([3, 2, 1])
+    return [{"id": 0, "data": [frames1, target1]}, {"id": 1, "data": [frames2, target2]}]
+
+
+def test_collate_oracle_reference_kat():
+    """The reference's own known-answer vector (test_collaters.py:33-50) pins the collate oracle."""
+    from oracle import collate_oracle as C
+    batch = C.collate(_kat_samples(), pad_index=0, eos_index=1, move_eos_to_beginning=True)
+    assert batch["id"].tolist() == [1, 0]
+    assert batch["ntokens"] == 7 and batch["nsentences"] == 2
+    assert batch["net_input"]["src_tokens"].tolist() == [[[1, 2], [3, 4], [5, 6]], [[7, 8], [9, 10], [0, 0]]]
+    assert batch["net_input"]["prev_output_tokens"].tolist() == [[1, 3, 2, 0], [1, 4, 2, 3]]
+    assert batch["net_input"]["src_lengths"].tolist() == [3, 2]
+    assert batch["target"].tolist() == [[3, 2, 1, 0], [4, 2, 3, 1]]
+
+
+@pytest.mark.skipif(not R.available(), reason="live reference not mounted")
+def test_collate_oracle_vs_live_reference():
+    from oracle import collate_oracle as C
+    R.load()
+    from examples.speech_recognition.data.collaters import Seq2SeqCollater
+    g = torch.Generator().manual_seed(3)
+    samples = []
+    for i, n in enumerate([17, 40, 40, 5, 23]):
+        tl = 3 + i
+        samples.append({"id": i, "data": [torch.randn(n, 8, generator=g).numpy(),
+                                          torch.randint(3, 50, (tl,), generator=g).numpy()]})
+    ref = Seq2SeqCollater(0, 1, pad_index=1, eos_index=2).collate(samples)
+    got = C.collate(samples, pad_index=1, eos_index=2, move_eos_to_beginning=True)
+    assert torch.equal(ref["net_input"]["src_lengths"], got["net_input"]["src_lengths"])
+    # ties (two utterances of 40 frames) may be ordered either way by torch.sort: compare as sets
+    assert sorted(ref["id"].tolist()) == sorted(got["id"].tolist())
+    for k in range(5):
+        j = got["id"].tolist().index(int(ref["id"][k]))
+        assert torch.equal(ref["net_input"]["src_tokens"][k], got["net_input"]["src_tokens"][j])
+        assert torch.equal(ref["net_input"]["prev_output_tokens"][k], got["net_input"]["prev_output_tokens"][j])
+        assert torch.equal(ref["target"][k], got["target"][j])
