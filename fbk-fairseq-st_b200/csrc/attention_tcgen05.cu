@@ -197,6 +197,8 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
     tmem_alloc(tmem_slot, 256);
     tmem_relinquish();
   }
+  pdl_launch_dependents();
+  pdl_wait();  // barrier init / TMEM allocation above overlap the previous kernel's tail
   if (threadIdx.x >= 64 && threadIdx.x < 64 + AT_TABLE) {
     const int w = blockIdx.x + (threadIdx.x - 64) * gridDim.x;
     if (w < n_items) sItems[threadIdx.x - 64] = attn_decode_raw(w, lengths, L, H, nq);
@@ -588,9 +590,10 @@ extern "C" int fbkst_attention_fwd(const void* qkv, void* out, const int32_t* le
   int grid = num_sms() * per_sm;
   if (grid > n_items) grid = (int)n_items;
   if (log_penalty)
-    attention_fwd_kernel<1><<<grid, AT_THREADS, smem, st>>>(tmQ, tmKV, (__nv_bfloat16*)out, lengths, L, B, H);
+    FBKST_CHECK_CUDA(launch_pdl(attention_fwd_kernel<1>, dim3(grid), dim3(AT_THREADS), smem, st, tmQ, tmKV,
+                                (__nv_bfloat16*)out, lengths, L, B, H));
   else
-    attention_fwd_kernel<0><<<grid, AT_THREADS, smem, st>>>(tmQ, tmKV, (__nv_bfloat16*)out, lengths, L, B, H);
-  FBKST_CHECK_CUDA(cudaGetLastError());
+    FBKST_CHECK_CUDA(launch_pdl(attention_fwd_kernel<0>, dim3(grid), dim3(AT_THREADS), smem, st, tmQ, tmKV,
+                                (__nv_bfloat16*)out, lengths, L, B, H));
   return FBKST_OK;
 }

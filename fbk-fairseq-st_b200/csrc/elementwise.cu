@@ -159,6 +159,8 @@ __global__ void __launch_bounds__(256)
                      const float* __restrict__ beta, void* __restrict__ y, int out_f32, int M,
                      float eps, const int* __restrict__ m_limit, int m_limit_mult) {
   constexpr int D = NV * 128;
+  pdl_launch_dependents();
+  pdl_wait();
   if (m_limit != nullptr) M = min(M, __ldg(m_limit) * m_limit_mult);
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -341,12 +343,12 @@ extern "C" int fbkst_layernorm(const float* x, const float* gamma, const float* 
   const int f32 = out_dtype == FBKST_F32;
   const int grid = (M + 7) / 8;
   switch (D) {
-    case 128: layernorm_kernel<1><<<grid, 256, 0, st>>>(x, gamma, beta, y, f32, M, eps, m_limit, m_limit_mult); break;
-    case 256: layernorm_kernel<2><<<grid, 256, 0, st>>>(x, gamma, beta, y, f32, M, eps, m_limit, m_limit_mult); break;
-    case 384: layernorm_kernel<3><<<grid, 256, 0, st>>>(x, gamma, beta, y, f32, M, eps, m_limit, m_limit_mult); break;
-    case 512: layernorm_kernel<4><<<grid, 256, 0, st>>>(x, gamma, beta, y, f32, M, eps, m_limit, m_limit_mult); break;
-    case 768: layernorm_kernel<6><<<grid, 256, 0, st>>>(x, gamma, beta, y, f32, M, eps, m_limit, m_limit_mult); break;
-    case 1024: layernorm_kernel<8><<<grid, 256, 0, st>>>(x, gamma, beta, y, f32, M, eps, m_limit, m_limit_mult); break;
+    case 128: FBKST_CHECK_CUDA(launch_pdl(layernorm_kernel<1>, dim3(grid), dim3(256), 0, st, x, gamma, beta, y, f32, M, eps, m_limit, m_limit_mult)); break;
+    case 256: FBKST_CHECK_CUDA(launch_pdl(layernorm_kernel<2>, dim3(grid), dim3(256), 0, st, x, gamma, beta, y, f32, M, eps, m_limit, m_limit_mult)); break;
+    case 384: FBKST_CHECK_CUDA(launch_pdl(layernorm_kernel<3>, dim3(grid), dim3(256), 0, st, x, gamma, beta, y, f32, M, eps, m_limit, m_limit_mult)); break;
+    case 512: FBKST_CHECK_CUDA(launch_pdl(layernorm_kernel<4>, dim3(grid), dim3(256), 0, st, x, gamma, beta, y, f32, M, eps, m_limit, m_limit_mult)); break;
+    case 768: FBKST_CHECK_CUDA(launch_pdl(layernorm_kernel<6>, dim3(grid), dim3(256), 0, st, x, gamma, beta, y, f32, M, eps, m_limit, m_limit_mult)); break;
+    case 1024: FBKST_CHECK_CUDA(launch_pdl(layernorm_kernel<8>, dim3(grid), dim3(256), 0, st, x, gamma, beta, y, f32, M, eps, m_limit, m_limit_mult)); break;
     default:
       return set_error(FBKST_ERR_ARG, "fbkst_layernorm: unsupported D=%d (128..1024, multiple of 128)", D);
   }

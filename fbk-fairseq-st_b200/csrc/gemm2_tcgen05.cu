@@ -118,12 +118,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
   const uint32_t rank = cluster_ctarank();
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
-  // device-side row limit (rows valid after CTC compression): tiles beyond it are skipped
-  if (m_limit != nullptr) M = min(M, __ldg(m_limit) * m_limit_mult);
-  const int num_n = (N + G2_BN - 1) / G2_BN;
-  const int num_m = (M + 2 * G2_BM - 1) / (2 * G2_BM);
-  const int num_tiles = num_m * num_n;
-  const int num_kb = (K + G2_BK - 1) / G2_BK;
+  pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -151,6 +146,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Everything above is independent of the previous kernel's output (PDL prologue); nothing below
+  // may run before that kernel has completed.
+  pdl_wait();
+  // device-side row limit (rows valid after CTC compression): tiles beyond it are skipped
+  if (m_limit != nullptr) M = min(M, __ldg(m_limit) * m_limit_mult);
+  const int num_n = (N + G2_BN - 1) / G2_BN;
+  const int num_m = (M + 2 * G2_BM - 1) / (2 * G2_BM);
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (K + G2_BK - 1) / G2_BK;
 
   // Producer and MMA warps run in warp-uniform control flow and let ONE ELECTED lane issue: under
   // `if (lane == 0)` ptxas wraps every UTMALDG / UTCHMMA in a divergence waterfall (ELECT +
@@ -422,9 +426,8 @@ static int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, 
   const int max_clusters = num_sms() / 2;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
   static const int dbg = getenv("FBKST_GEMM_DBG") ? atoi(getenv("FBKST_GEMM_DBG")) : 0;
-  kern<<<2 * clusters, 384, G2_SMEM, stream>>>(tmA, tmB, tmO, tmR, M, N, K, bias, relu, dbg, m_limit,
-                                               m_limit_mult);
-  FBKST_CHECK_CUDA(cudaGetLastError());
+  FBKST_CHECK_CUDA(launch_pdl(kern, dim3(2 * clusters), dim3(384), G2_SMEM, stream, tmA, tmB, tmO, tmR, M,
+                              N, K, bias, relu, dbg, m_limit, m_limit_mult));
   return FBKST_OK;
 }
 

@@ -1,3 +1,5 @@
+#include <stdlib.h>
+
 #include "host_common.h"
 
 #include <stdarg.h>
@@ -82,6 +84,14 @@ int num_sms() {
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
     n = 148;
   return n;
+}
+
+bool pdl_enabled() {
+  static const int v = [] {
+    const char* e = getenv("FBKST_PDL");
+    return (e != nullptr && e[0] == '0') ? 0 : 1;
+  }();
+  return v != 0;
 }
 
 }  // namespace fbkst

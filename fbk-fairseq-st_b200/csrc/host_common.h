@@ -42,4 +42,29 @@ int make_tensor_map_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, u
 
 int num_sms();
 
+// 0 when FBKST_PDL=0 is set in the environment (A/B switch); default 1.
+bool pdl_enabled();
+
+// Launch `kernel` with programmatic stream serialisation (programmatic dependent launch): the grid
+// may be scheduled while the previous kernel of the stream is still draining, runs its prologue
+// (barrier init, TMEM allocation, tensor-map prefetch) and blocks in `griddepcontrol.wait` until
+// the predecessor has completed and flushed.  Every kernel launched this way MUST execute
+// pdl_wait() (ptx.cuh) before its first access to global memory.  Works under stream capture
+// (programmatic graph edges).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 }  // namespace fbkst

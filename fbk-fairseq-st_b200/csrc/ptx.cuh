@@ -26,6 +26,17 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ------------------------------------------------- programmatic dependent launch (PDL)
+// pdl_wait(): blocks until the previous kernel of the stream has completed and its writes are visible
+// (returns at once when the kernel was not launched with the PDL attribute).  Must precede the first
+// global-memory access of a kernel launched through launch_pdl().
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Lets the next kernel of the stream (if it was launched with the PDL attribute) start being
+// scheduled as SM resources free up, instead of after this grid has fully retired.
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
