@@ -45,8 +45,13 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t ran
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
   return r;
 }
+// Remote arrive on the LEADER's "accumulator free" barrier.  RELAXED on purpose: the only thing
+// the leader's MMA must not overtake is our tcgen05.ld of the accumulator, which has completed
+// (tcgen05.wait::ld) and is ordered by tcgen05.fence::before_thread_sync; no ordinary memory is
+// handed over.  `.release.cluster` compiled to MEMBAR.ALL.GPU + CCTL.IVALL per tile and warp --
+// 46 % of the epilogue warps' stall samples (profiles/r01a_ncu_gemm2.txt).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
                : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_cg2(uint32_t* smem_result, uint32_t ncols) {
