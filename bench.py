@@ -50,7 +50,7 @@ CTC_MARGIN = 30.0
 # captures (profiles/r01a_ncu_gemm2.txt: mean over the captured launches of each kernel)
 NCU_TRAFFIC = {
     "gemm2_kernel<bf16 out> (qkv, fc1, ctc_fc)": int((26.21 + 17.19 + 26.78 + 40.57) / 2 * 1e6),
-    "gemm2_kernel<f32 out + residual> (out_proj, fc2)": int((74.30 + 9.23 + 151.59 + 23.07) / 2 * 1e6),
+    "gemm2_kernel<f32 out + residual (+ bf16 copy, LN statistics)> (out_proj, fc2)": None,
 }
 
 
@@ -169,7 +169,8 @@ class KernelProfile:
             s.record()
             out = fn(*a, **k)
             e.record()
-            self.records.append((name, s, e, work(a, k, out)))
+            # linear_ln is the same kernel family as linear (folded-LayerNorm epilogues)
+            self.records.append(("linear" if name == "linear_ln" else name, s, e, work(a, k, out)))
             if name == "ctc_compress":
                 self.post = True  # later launches see only the compressed (valid) rows
             return out
@@ -183,14 +184,19 @@ class KernelProfile:
             M, K = a[0].shape
             M = valid_rows(M)
             N = a[1].shape[0]
-            by = (M * K + N * K) * 2 + M * N * (4 if out.dtype == torch.float32 else 2)
+            if isinstance(out, tuple):  # linear_ln producer side: (out, bf16 copy, row statistics)
+                out = out[0]
+                extra = M * N * 2 + M * ((N + 127) // 128) * 8
+            else:
+                extra = 0
+            by = (M * K + N * K) * 2 + M * N * (4 if out.dtype == torch.float32 else 2) + extra
             if k.get("residual") is not None:
                 by += M * N * 4
             # which kernel serves this launch (csrc/gemm2_tcgen05.cu, csrc/gemm_tcgen05.cu)
             if k.get("remap") is not None:
                 sub = "gemm_bf16_kernel (fc3: row remap + pos-emb epilogue)"
             elif k.get("residual") is not None:
-                sub = "gemm2_kernel<f32 out + residual> (out_proj, fc2)"
+                sub = "gemm2_kernel<f32 out + residual (+ bf16 copy, LN statistics)> (out_proj, fc2)"
             else:
                 sub = "gemm2_kernel<bf16 out> (qkv, fc1, ctc_fc)"
             return dict(flops=2.0 * M * N * K, bytes=by, sub=sub)
@@ -226,7 +232,12 @@ class KernelProfile:
 
         def other(a, k, out):
             return dict(flops=0.0, bytes=0)
-        for name, w in [("linear", lin), ("attention", att), ("layernorm", ln_), ("ctc_argmax", argmax),
+        def stats(a, k, out):
+            M, D = a[0].shape
+            return dict(flops=0.0, bytes=valid_rows(M) * D * (4 + 2))
+
+        for name, w in [("linear", lin), ("linear_ln", lin), ("row_stats_cast", stats), ("attention", att),
+                        ("layernorm", ln_), ("ctc_argmax", argmax),
                         ("ctc_compress", compress), ("ctc_segment", other), ("conv1_relu_bn", conv1),
                         ("conv2_relu_bn", conv2), ("cmvn", cmvn), ("cast_bf16", other),
                         ("lengths_to_mask", other)]:

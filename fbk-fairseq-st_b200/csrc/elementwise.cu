@@ -200,6 +200,41 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Row statistics + bf16 copy for the folded LayerNorm (gemm2_tcgen05.cu): for an x that does not
+// come out of a residual GEMM (fc3 output, CTC-compressed rows) this produces what that epilogue
+// would have: xb = bf16(x) and, per row and 128-column slice, (mean, M2) of the slice.
+template <int NV>
+__global__ void __launch_bounds__(256)
+    row_stats_cast_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xb,
+                          float2* __restrict__ stats, int M, const int* __restrict__ m_limit,
+                          int m_limit_mult) {
+  constexpr int D = NV * 128;
+  pdl_launch_dependents();
+  pdl_wait();
+  if (m_limit != nullptr) M = min(M, __ldg(m_limit) * m_limit_mult);
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  const float4* xp = reinterpret_cast<const float4*>(x + (size_t)row * D);
+  float4 v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = xp[i * 32 + lane];
+  float keep_mean = 0.f, keep_m2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float mean = warp_sum((v[i].x + v[i].y) + (v[i].z + v[i].w)) * (1.0f / 128.0f);
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    const float m2 = warp_sum((a * a + b * b) + (c * c + d * d));
+    if (lane == i) {
+      keep_mean = mean;
+      keep_m2 = m2;
+    }
+    reinterpret_cast<uint2*>(xb + (size_t)row * D)[i * 32 + lane] =
+        make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
+  }
+  if (lane < NV) stats[(size_t)row * NV + lane] = make_float2(keep_mean, keep_m2);
+}
+
 // ------------------------------------------------------ sinusoidal table (a4)
 __global__ void sinusoidal_table_kernel(float* __restrict__ table, int rows, int D) {
   const int half = D / 2;
@@ -351,6 +386,28 @@ extern "C" int fbkst_layernorm(const float* x, const float* gamma, const float* 
     case 1024: FBKST_CHECK_CUDA(launch_pdl(layernorm_kernel<8>, dim3(grid), dim3(256), 0, st, x, gamma, beta, y, f32, M, eps, m_limit, m_limit_mult)); break;
     default:
       return set_error(FBKST_ERR_ARG, "fbkst_layernorm: unsupported D=%d (128..1024, multiple of 128)", D);
+  }
+  FBKST_CHECK_CUDA(cudaGetLastError());
+  return FBKST_OK;
+}
+
+extern "C" int fbkst_row_stats_cast(const float* x, void* xb, float* row_stats, int M, int D,
+                                    const int32_t* m_limit, int m_limit_mult, fbkst_stream_t stream) {
+  FBKST_REQUIRE(x && xb && row_stats, "fbkst_row_stats_cast: null pointer");
+  FBKST_REQUIRE(M > 0, "fbkst_row_stats_cast: M must be positive");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = (M + 7) / 8;
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(xb);
+  float2* s2 = reinterpret_cast<float2*>(row_stats);
+  switch (D) {
+    case 128: FBKST_CHECK_CUDA(launch_pdl(row_stats_cast_kernel<1>, dim3(grid), dim3(256), 0, st, x, o, s2, M, m_limit, m_limit_mult)); break;
+    case 256: FBKST_CHECK_CUDA(launch_pdl(row_stats_cast_kernel<2>, dim3(grid), dim3(256), 0, st, x, o, s2, M, m_limit, m_limit_mult)); break;
+    case 384: FBKST_CHECK_CUDA(launch_pdl(row_stats_cast_kernel<3>, dim3(grid), dim3(256), 0, st, x, o, s2, M, m_limit, m_limit_mult)); break;
+    case 512: FBKST_CHECK_CUDA(launch_pdl(row_stats_cast_kernel<4>, dim3(grid), dim3(256), 0, st, x, o, s2, M, m_limit, m_limit_mult)); break;
+    case 768: FBKST_CHECK_CUDA(launch_pdl(row_stats_cast_kernel<6>, dim3(grid), dim3(256), 0, st, x, o, s2, M, m_limit, m_limit_mult)); break;
+    case 1024: FBKST_CHECK_CUDA(launch_pdl(row_stats_cast_kernel<8>, dim3(grid), dim3(256), 0, st, x, o, s2, M, m_limit, m_limit_mult)); break;
+    default:
+      return set_error(FBKST_ERR_ARG, "fbkst_row_stats_cast: unsupported D=%d (128..1024, multiple of 128)", D);
   }
   FBKST_CHECK_CUDA(cudaGetLastError());
   return FBKST_OK;

@@ -23,12 +23,16 @@ namespace fbkst {
 constexpr int G2_BM = 128;      // rows per CTA (256 per pair)
 constexpr int G2_BN = 256;      // tile columns (each CTA stages 128 of them)
 constexpr int G2_BK = 64;
-constexpr int G2_STAGES = 5;
 constexpr int G2_A_BYTES = G2_BM * G2_BK * 2;        // 16 KB
 constexpr int G2_B_BYTES = (G2_BN / 2) * G2_BK * 2;  // 16 KB
 constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
 constexpr int G2_EPI_BYTES = 8 * 2 * 4096;
-constexpr int G2_SMEM = G2_STAGES * G2_STAGE_BYTES + G2_EPI_BYTES + 512 + 1024;
+constexpr int G2_XB_BYTES = 8 * 4096;  // LNS: per-warp staging of the bf16 copy (32 rows x 64 columns)
+// The LayerNorm-statistics variant trades one operand stage for the bf16 staging buffers.
+constexpr int g2_stages(bool lns) { return lns ? 4 : 5; }
+constexpr int g2_smem(bool lns) {
+  return g2_stages(lns) * G2_STAGE_BYTES + G2_EPI_BYTES + (lns ? G2_XB_BYTES : 0) + 512 + 1024;
+}
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -99,19 +103,54 @@ __device__ __forceinline__ float4 bcast4_g2(const float4& v, int src_lane) {
                      __shfl_sync(0xffffffffu, v.z, src_lane), __shfl_sync(0xffffffffu, v.w, src_lane));
 }
 
-template <bool OUT_F32, bool RESID>
+// LayerNorm folded into the GEMMs around it (the reference's pre-LN block,
+// fairseq/modules/transformer_layer.py:108-133: x = x + f(LN(x))):
+//   LN(x) W^T + b = rstd * (x W''^T) + c,   W''[n,k] = gamma[k] W[n,k] - mean_k(gamma[k] W[n,k]),
+//                                           c[n] = b[n] + sum_k beta[k] W[n,k]
+// (the row mean drops out because every row of W'' sums to zero).  So the PRODUCER of x (out_proj /
+// fc2, LNS = true) also emits bf16(x) and, per row and 128-column slice, the (mean, M2) of that slice;
+// the CONSUMER (QKV / fc1, ln_stats != nullptr) merges the slices (Chan), and its epilogue is
+// fma(rstd, acc, c) instead of acc + b.  No LayerNorm kernel, no fp32 re-read of x.
+struct LnStatsIn {
+  const float2* stats;  // [M, parts] (mean, M2) per 128-column slice of the consumer's K dimension
+  int parts;
+  int dim;  // LayerNorm width (== K)
+  float eps;
+};
+
+// (mean, M2) of `parts` slices -> 1/sqrt(var + eps); slice p covers min(128, dim - 128 p) columns
+__device__ __forceinline__ float ln_rstd_from_slices(const float2* __restrict__ st, int parts, int dim,
+                                                     float eps) {
+  float n = 0.f, mean = 0.f, m2 = 0.f;
+  for (int p = 0; p < parts; ++p) {
+    const float2 v = __ldg(st + p);
+    const float c = (float)min(128, dim - 128 * p);
+    const float tot = n + c, delta = v.x - mean;
+    mean += delta * (c / tot);
+    m2 += v.y + delta * delta * (n * c / tot);
+    n = tot;
+  }
+  return rsqrtf(m2 / (float)dim + eps);
+}
+
+template <bool OUT_F32, bool RESID, bool LNS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
     gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, int M,
-                 int N, int K, const float* __restrict__ bias, int relu, int dbg,
-                 const int* __restrict__ m_limit, int m_limit_mult) {
+                 const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
+                 const __grid_constant__ CUtensorMap tmX, int M, int N, int K,
+                 const float* __restrict__ bias, int relu, int dbg, const int* __restrict__ m_limit,
+                 int m_limit_mult, const LnStatsIn ln_in, float2* __restrict__ stats_out) {
+  static_assert(!LNS || (OUT_F32 && RESID), "row statistics are produced by the residual epilogue");
+  constexpr int G2_STAGES = g2_stages(LNS);
   constexpr uint32_t TMEM_COLS = 512;  // two 256-column accumulator stages
   constexpr uint32_t IDESC = idesc_bf16_f32(256, G2_BN, 0, 0);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_epi = smem + G2_STAGES * G2_STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_epi + G2_EPI_BYTES);  // used in the leader
+  uint8_t* smem_xb = smem_epi + G2_EPI_BYTES;  // LNS only
+  uint64_t* full_bar =
+      reinterpret_cast<uint64_t*>(smem_epi + G2_EPI_BYTES + (LNS ? G2_XB_BYTES : 0));  // used in the leader
   uint64_t* empty_bar = full_bar + G2_STAGES;                                 // per CTA
   uint64_t* tfull_bar = empty_bar + G2_STAGES;                                // per CTA
   uint64_t* tempty_bar = tfull_bar + 2;                                       // used in the leader
@@ -130,6 +169,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmO);
     if (RESID) tma_prefetch_desc(&tmR);
+    if (LNS) tma_prefetch_desc(&tmX);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < G2_STAGES; ++s) {
@@ -267,6 +307,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         tc_fence_after();
         uint32_t v[32];
         tmem_ld32(taddr, v);
+        // LNS: statistics of this thread's row over the warp's <= 128 columns, shifted by the first
+        // value (single pass without cancellation), and the bf16 copy of x staged 64 columns at a time
+        float ln_shift = 0.f, ln_s1 = 0.f, ln_s2 = 0.f;
+        uint8_t* xrow = smem_xb + ew * 4096 + lane * 128;
 #pragma unroll 1
         for (int u = 0; u < 4; ++u) {
           const int col0 = n0 + u * 32;
@@ -276,6 +320,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
             tma_store_wait_read<0>();                    // its buffer was read by store(u-1)
             mbar_arrive_expect_tx(&rbar[bsel ^ 1], 4096);
             tma_load_2d(stg + (bsel ^ 1) * 4096, &tmR, &rbar[bsel ^ 1], col0 + 32, m0);
+          }
+          if (LNS && bsel == 0) {  // the bf16 staging buffer was read by the store issued at unit u-1
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
           }
           tmem_ld_wait();
           float f[32];
@@ -303,11 +351,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
             r.z += a2;
             r.w += a3;
             *sp = r;
+            if (LNS) {
+              if (u == 0 && g == 0) ln_shift = r.x;
+              const float d0 = r.x - ln_shift, d1 = r.y - ln_shift, d2 = r.z - ln_shift,
+                          d3 = r.w - ln_shift;
+              ln_s1 += (d0 + d1) + (d2 + d3);
+              ln_s2 = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, ln_s2))));
+              // columns (u&1)*32 + 4g .. +3 of the 64-column staging row: 8 bytes at offset
+              // (u&1)*64 + 8g, i.e. 16-byte chunk (u&1)*4 + g/2 (XOR-swizzled), half g&1
+              *reinterpret_cast<uint2*>(xrow + ((((bsel << 2) | (g >> 1)) ^ swz) << 4) + ((g & 1) << 3)) =
+                  make_uint2(pack_bf16x2(r.x, r.y), pack_bf16x2(r.z, r.w));
+            }
           }
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
             tma_store_2d(&tmO, stg + bsel * 4096, col0, m0);
+            if (LNS && (bsel == 1 || col0 + 32 >= N))
+              tma_store_2d(&tmX, smem_xb + ew * 4096, n0 + (u >> 1) * 64, m0);
             tma_store_commit();
           }
         }
@@ -315,7 +376,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(tempty_leader);
+        if (LNS && m0 + lane < M) {
+          const float cnt = (float)min(128, N - n0);
+          stats_out[(size_t)(m0 + lane) * ((N + 127) >> 7) + (n0 >> 7)] =
+              make_float2(ln_shift + ln_s1 / cnt, fmaxf(ln_s2 - ln_s1 * ln_s1 / cnt, 0.f));
+        }
       } else {
+        // folded LayerNorm: per-row 1/sigma from the producer's slice statistics (loaded before the
+        // accumulator wait so the latency hides under the main loop); 1 when there is no LayerNorm
+        float rs = 1.0f;
+        if (ln_in.stats != nullptr && m0 + lane < M)
+          rs = ln_rstd_from_slices(ln_in.stats + (size_t)(m0 + lane) * ln_in.parts, ln_in.parts,
+                                   ln_in.dim, ln_in.eps);
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
         constexpr int UNITS = OUT_F32 ? 4 : 2;  // staging rows are 128 B: 32 fp32 or 64 bf16 columns
@@ -341,8 +413,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
               const float4 bb = bcast4_g2(b4, u * 8 + g);
-              float a0 = __uint_as_float(v0[4 * g]) + bb.x, a1 = __uint_as_float(v0[4 * g + 1]) + bb.y,
-                    a2 = __uint_as_float(v0[4 * g + 2]) + bb.z, a3 = __uint_as_float(v0[4 * g + 3]) + bb.w;
+              float a0 = fmaf(rs, __uint_as_float(v0[4 * g]), bb.x),
+                    a1 = fmaf(rs, __uint_as_float(v0[4 * g + 1]), bb.y),
+                    a2 = fmaf(rs, __uint_as_float(v0[4 * g + 2]), bb.z),
+                    a3 = fmaf(rs, __uint_as_float(v0[4 * g + 3]), bb.w);
               if (relu) {
                 a0 = fmaxf(a0, 0.f);
                 a1 = fmaxf(a1, 0.f);
@@ -358,10 +432,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
               const int o = (g & 3) * 8;
               const float4 b0 = bcast4_g2(b4, u * 16 + 2 * g);
               const float4 b1 = bcast4_g2(b4, u * 16 + 2 * g + 1);
-              float a[8] = {__uint_as_float(src[o]) + b0.x,     __uint_as_float(src[o + 1]) + b0.y,
-                            __uint_as_float(src[o + 2]) + b0.z, __uint_as_float(src[o + 3]) + b0.w,
-                            __uint_as_float(src[o + 4]) + b1.x, __uint_as_float(src[o + 5]) + b1.y,
-                            __uint_as_float(src[o + 6]) + b1.z, __uint_as_float(src[o + 7]) + b1.w};
+              float a[8] = {fmaf(rs, __uint_as_float(src[o]), b0.x),     fmaf(rs, __uint_as_float(src[o + 1]), b0.y),
+                            fmaf(rs, __uint_as_float(src[o + 2]), b0.z), fmaf(rs, __uint_as_float(src[o + 3]), b0.w),
+                            fmaf(rs, __uint_as_float(src[o + 4]), b1.x), fmaf(rs, __uint_as_float(src[o + 5]), b1.y),
+                            fmaf(rs, __uint_as_float(src[o + 6]), b1.z), fmaf(rs, __uint_as_float(src[o + 7]), b1.w)};
               if (relu) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) a[j] = fmaxf(a[j], 0.f);
@@ -393,18 +467,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
   }
 }
 
-template <bool OUT_F32, bool RESID>
+template <bool OUT_F32, bool RESID, bool LNS>
 static int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
                         const float* resid, int64_t ldr, void* out, int64_t ldo, int M, int N, int K,
-                        int relu, const int* m_limit, int m_limit_mult, cudaStream_t stream) {
-  static_assert(G2_SMEM <= 232448, "shared memory budget exceeded");
-  auto kern = gemm2_kernel<OUT_F32, RESID>;
+                        int relu, const int* m_limit, int m_limit_mult, const LnStatsIn& ln_in,
+                        void* out_bf16, int64_t ldob, float* stats_out, cudaStream_t stream) {
+  constexpr int SMEM = g2_smem(LNS);
+  static_assert(SMEM <= 232448, "shared memory budget exceeded");
+  auto kern = gemm2_kernel<OUT_F32, RESID, LNS>;
   static bool configured = false;
   if (!configured) {
-    FBKST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM));
+    FBKST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured = true;
   }
-  CUtensorMap tmA, tmB, tmO, tmR;
+  CUtensorMap tmA, tmB, tmO, tmR, tmX;
   int rc = make_tensor_map_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, G2_BM, G2_BK);
   if (rc) return rc;
   rc = make_tensor_map_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, G2_BN / 2, G2_BK);
@@ -427,27 +503,46 @@ static int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, 
   } else {
     tmR = tmO;
   }
+  if (LNS) {
+    rc = make_tensor_map_2d_bf16(&tmX, out_bf16, (uint64_t)M, (uint64_t)N, (uint64_t)ldob, 32, 64);
+    if (rc) return rc;
+  } else {
+    tmX = tmO;
+  }
   const int tiles = ((M + 2 * G2_BM - 1) / (2 * G2_BM)) * ((N + G2_BN - 1) / G2_BN);
   const int max_clusters = num_sms() / 2;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
   static const int dbg = getenv("FBKST_GEMM_DBG") ? atoi(getenv("FBKST_GEMM_DBG")) : 0;
-  FBKST_CHECK_CUDA(launch_pdl(kern, dim3(2 * clusters), dim3(384), G2_SMEM, stream, tmA, tmB, tmO, tmR, M,
-                              N, K, bias, relu, dbg, m_limit, m_limit_mult));
+  FBKST_CHECK_CUDA(launch_pdl(kern, dim3(2 * clusters), dim3(384), SMEM, stream, tmA, tmB, tmO, tmR, tmX,
+                              M, N, K, bias, relu, dbg, m_limit, m_limit_mult, ln_in,
+                              reinterpret_cast<float2*>(stats_out)));
   return FBKST_OK;
 }
 
-// Entry used by fbkst_linear_bf16 (gemm_tcgen05.cu) for the plain / residual epilogues.
+// Entry used by fbkst_linear_bf16 / fbkst_linear_ln_bf16 (gemm_tcgen05.cu) for the plain / residual
+// epilogues.  stats_in (with its LayerNorm width == K and eps): consumer side of the folded
+// LayerNorm; out_bf16 + stats_out: producer side (residual epilogue only).
 int linear_pair_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
                          const float* resid, int64_t ldr, void* out, int64_t ldo, int M, int N, int K,
-                         int relu, int out_f32, const int* m_limit, int m_limit_mult, cudaStream_t stream) {
+                         int relu, int out_f32, const int* m_limit, int m_limit_mult,
+                         const float* stats_in, float ln_eps, void* out_bf16, int64_t ldob,
+                         float* stats_out, cudaStream_t stream) {
+  LnStatsIn ln_in;
+  ln_in.stats = reinterpret_cast<const float2*>(stats_in);
+  ln_in.parts = (K + 127) / 128;
+  ln_in.dim = K;
+  ln_in.eps = ln_eps;
+  if (stats_out != nullptr)
+    return launch_gemm2<true, true, true>(A, lda, W, ldw, bias, resid, ldr, out, ldo, M, N, K, relu,
+                                          m_limit, m_limit_mult, ln_in, out_bf16, ldob, stats_out, stream);
   if (resid != nullptr)
-    return launch_gemm2<true, true>(A, lda, W, ldw, bias, resid, ldr, out, ldo, M, N, K, relu, m_limit,
-                                    m_limit_mult, stream);
+    return launch_gemm2<true, true, false>(A, lda, W, ldw, bias, resid, ldr, out, ldo, M, N, K, relu,
+                                           m_limit, m_limit_mult, ln_in, nullptr, 0, nullptr, stream);
   if (out_f32)
-    return launch_gemm2<true, false>(A, lda, W, ldw, bias, nullptr, 0, out, ldo, M, N, K, relu, m_limit,
-                                     m_limit_mult, stream);
-  return launch_gemm2<false, false>(A, lda, W, ldw, bias, nullptr, 0, out, ldo, M, N, K, relu, m_limit,
-                                    m_limit_mult, stream);
+    return launch_gemm2<true, false, false>(A, lda, W, ldw, bias, nullptr, 0, out, ldo, M, N, K, relu,
+                                            m_limit, m_limit_mult, ln_in, nullptr, 0, nullptr, stream);
+  return launch_gemm2<false, false, false>(A, lda, W, ldw, bias, nullptr, 0, out, ldo, M, N, K, relu,
+                                           m_limit, m_limit_mult, ln_in, nullptr, 0, nullptr, stream);
 }
 
 }  // namespace fbkst

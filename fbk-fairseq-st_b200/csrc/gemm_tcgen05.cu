@@ -18,7 +18,9 @@ namespace fbkst {
 // gemm2_tcgen05.cu: CTA-pair (cta_group::2) kernel for the plain / residual epilogues
 int linear_pair_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
                          const float* resid, int64_t ldr, void* out, int64_t ldo, int M, int N, int K,
-                         int relu, int out_f32, const int* m_limit, int m_limit_mult, cudaStream_t stream);
+                         int relu, int out_f32, const int* m_limit, int m_limit_mult,
+                         const float* stats_in, float ln_eps, void* out_bf16, int64_t ldob,
+                         float* stats_out, cudaStream_t stream);
 
 struct EpiParams {
   const float* bias;
@@ -644,11 +646,44 @@ extern "C" int fbkst_linear_bf16(const void* A, int64_t lda, const void* W, int6
   static const bool single_cta = getenv("FBKST_GEMM_1CTA") != nullptr;  // A/B switch for profiling
   if (!single_cta)
     return linear_pair_dispatch(A, lda, W, ldw, bias, residual, ldr, out, ldo, M, N, K, relu,
-                                (flags & FBKST_EPI_OUT_F32) ? 1 : 0, m_limit, m_limit_mult, st);
+                                (flags & FBKST_EPI_OUT_F32) ? 1 : 0, m_limit, m_limit_mult, nullptr, 0.f,
+                                nullptr, 0, nullptr, st);
   if (residual != nullptr) {
     return launch_gemm_tma<true, true, 3>(A, lda, W, ldw, bias, residual, ldr, out, ldo, M, N, K, relu, st);
   }
   if (flags & FBKST_EPI_OUT_F32)
     return launch_gemm_tma<true, false, 4>(A, lda, W, ldw, bias, nullptr, 0, out, ldo, M, N, K, relu, st);
   return launch_gemm_tma<false, false, 4>(A, lda, W, ldw, bias, nullptr, 0, out, ldo, M, N, K, relu, st);
+}
+
+extern "C" int fbkst_linear_ln_bf16(const void* A, int64_t lda, const void* W, int64_t ldw,
+                                    const float* bias, const float* residual, int64_t ldr, void* out,
+                                    int64_t ldo, int M, int N, int K, int flags,
+                                    const float* row_stats_in, float ln_eps, void* out_bf16,
+                                    int64_t ldob, float* row_stats_out, const int32_t* m_limit,
+                                    int m_limit_mult, fbkst_stream_t stream) {
+  using namespace fbkst;
+  FBKST_REQUIRE(A && W && out, "fbkst_linear_ln_bf16: null operand");
+  FBKST_REQUIRE(M > 0 && N > 0 && K > 0, "fbkst_linear_ln_bf16: empty problem M=%d N=%d K=%d", M, N, K);
+  FBKST_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldo % 8 == 0,
+                "fbkst_linear_ln_bf16: K, lda, ldw, ldo must be multiples of 8");
+  FBKST_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "fbkst_linear_ln_bf16: out must be 16-byte aligned");
+  FBKST_REQUIRE(!(flags & (FBKST_EPI_ROW_REMAP | FBKST_EPI_POSEMB)),
+                "fbkst_linear_ln_bf16: row remap / position epilogues are not available here");
+  if (residual != nullptr)
+    FBKST_REQUIRE((flags & FBKST_EPI_OUT_F32) && ldr % 4 == 0,
+                  "fbkst_linear_ln_bf16: a residual requires fp32 output and ldr %% 4 == 0");
+  FBKST_REQUIRE((out_bf16 == nullptr) == (row_stats_out == nullptr),
+                "fbkst_linear_ln_bf16: out_bf16 and row_stats_out come together");
+  if (row_stats_out != nullptr) {
+    FBKST_REQUIRE(residual != nullptr, "fbkst_linear_ln_bf16: row statistics need the residual epilogue");
+    FBKST_REQUIRE(N % 32 == 0 && ldob % 8 == 0 && (reinterpret_cast<uintptr_t>(out_bf16) & 15) == 0,
+                  "fbkst_linear_ln_bf16: N %% 32, ldob %% 8 and 16-byte alignment required (N=%d)", N);
+  }
+  if (row_stats_in != nullptr)
+    FBKST_REQUIRE(residual == nullptr, "fbkst_linear_ln_bf16: row_stats_in applies to the plain epilogue");
+  return linear_pair_dispatch(A, lda, W, ldw, bias, residual, ldr, out, ldo, M, N, K,
+                              (flags & FBKST_EPI_RELU) ? 1 : 0, (flags & FBKST_EPI_OUT_F32) ? 1 : 0, m_limit,
+                              m_limit_mult, row_stats_in, ln_eps, out_bf16, ldob, row_stats_out,
+                              reinterpret_cast<cudaStream_t>(stream));
 }

@@ -147,7 +147,12 @@ class CtcProjection(nn.Linear):
     def forward(self, x):  # noqa: D401
         L, B, D = x.shape
         w, b = self._prepared()
-        a = ops.cast_bf16(x.reshape(L * B, D))
+        pre = getattr(self, "_bf16_operand", None)  # (data_ptr of x, bf16(x)) left by the fc2 epilogue
+        self._bf16_operand = None
+        if pre is not None and pre[0] == x.data_ptr() and pre[1].shape == (L * B, D):
+            a = pre[1]
+        else:
+            a = ops.cast_bf16(x.reshape(L * B, D))
         return ops.linear(a, w, b).view(L, B, -1)
 
     def _prepared(self):
@@ -259,24 +264,23 @@ def make_encoder_class(base):
                 P["w3"] = ops.prep_fc3_weight(self.fc3.weight.detach().float(), C, self.feat_out)
                 P["b3"] = self.fc3.bias.detach().float().contiguous()
                 D = self.embed_dim
-                scale = 64 ** -0.5  # head_dim ** -0.5, folded into the q projection (exact: 2^-3)
+                # head_dim ** -0.5 folded into the q rows of the in-projection (exact: 2^-3)
+                qscale = torch.ones(3 * D, device=self.fc3.weight.device)
+                qscale[:D] = 64 ** -0.5
                 layers = []
                 for lyr in self.layers:
+                    # the two LayerNorms of the block are folded into the GEMMs they feed
+                    # (ops.fold_layernorm; transformer_layer.py:108-110 and :126-131)
                     w, b = lyr.self_attn.qkv()
-                    w = w.detach().float().clone()
-                    b = b.detach().float().clone()
-                    w[:D] *= scale
-                    b[:D] *= scale
+                    wqkv, cqkv = ops.fold_layernorm(w, b, lyr.self_attn_layer_norm.weight,
+                                                    lyr.self_attn_layer_norm.bias, row_scale=qscale)
+                    w1, c1 = ops.fold_layernorm(lyr.fc1.weight, lyr.fc1.bias, lyr.final_layer_norm.weight,
+                                                lyr.final_layer_norm.bias)
                     layers.append(dict(
-                        ln1=(lyr.self_attn_layer_norm.weight.detach().float().contiguous(),
-                             lyr.self_attn_layer_norm.bias.detach().float().contiguous()),
-                        wqkv=ops.cast_bf16(w), bqkv=b.contiguous(),
+                        wqkv=wqkv, bqkv=cqkv, eps1=lyr.self_attn_layer_norm.eps,
                         wo=ops.cast_bf16(lyr.self_attn.out_proj.weight.detach().float()),
                         bo=lyr.self_attn.out_proj.bias.detach().float().contiguous(),
-                        ln2=(lyr.final_layer_norm.weight.detach().float().contiguous(),
-                             lyr.final_layer_norm.bias.detach().float().contiguous()),
-                        w1=ops.cast_bf16(lyr.fc1.weight.detach().float()),
-                        b1=lyr.fc1.bias.detach().float().contiguous(),
+                        w1=w1, b1=c1, eps2=lyr.final_layer_norm.eps,
                         w2=ops.cast_bf16(lyr.fc2.weight.detach().float()),
                         b2=lyr.fc2.bias.detach().float().contiguous()))
                 P["layers"] = layers
@@ -380,34 +384,55 @@ def make_encoder_class(base):
             # launched for the worst case with a device-side row limit and persistent, finite
             # workspaces; the single host sync of the forward is the final read of the new lengths.
             limit, new_len = None, None
+            # Folded LayerNorm: every x travels with its bf16 copy and per-row slice statistics, written
+            # by the epilogue that produced x (out_proj / fc2) or by row_stats_cast (fc3 output,
+            # compressed rows); QKV / fc1 apply 1/sigma in their epilogues.  No LayerNorm launches
+            # inside the layer stack.
+            xb, st = ops.row_stats_cast(x)
+            n_layers = len(P["layers"])
             for li, W in enumerate(P["layers"]):
+                ctc_here = self.ctc_compress_out and self.ctc_layer == li + 1
+                need_ln = li + 1 < n_layers or ctc_here  # the last x only feeds the final LayerNorm
                 if limit is None:
-                    h = ops.layernorm(x, *W["ln1"])
-                    qkv = ops.linear(h, W["wqkv"], W["bqkv"])
+                    qkv = ops.linear_ln(xb, W["wqkv"], W["bqkv"], stats_in=st, ln_eps=W["eps1"])
                     att = ops.attention(qkv, lengths, L, B, H, self.log_penalty)
-                    x = ops.linear(att, W["wo"], W["bo"], residual=x, out_dtype=torch.float32)
-                    h = ops.layernorm(x, *W["ln2"])
-                    f = ops.linear(h, W["w1"], W["b1"], relu=True)
-                    x = ops.linear(f, W["w2"], W["b2"], residual=x, out_dtype=torch.float32)
+                    x, xb, st = ops.linear_ln(att, W["wo"], W["bo"], residual=x, out_dtype=torch.float32,
+                                              ln_out=True)
+                    f = ops.linear_ln(xb, W["w1"], W["b1"], relu=True, stats_in=st, ln_eps=W["eps2"])
+                    if need_ln:
+                        x, xb, st = ops.linear_ln(f, W["w2"], W["b2"], residual=x, out_dtype=torch.float32,
+                                                  ln_out=True)
+                    else:
+                        x = ops.linear(f, W["w2"], W["b2"], residual=x, out_dtype=torch.float32)
                 else:
-                    h = ops.layernorm(x, *W["ln1"], out=ws["h"], rows_limit=limit)
-                    qkv = ops.linear(h, W["wqkv"], W["bqkv"], out=ws["qkv"], rows_limit=limit)
+                    lo = (ws["h"], ws["st"])
+                    qkv = ops.linear_ln(xb, W["wqkv"], W["bqkv"], stats_in=st, ln_eps=W["eps1"],
+                                        out=ws["qkv"], rows_limit=limit)
                     att = ops.attention(qkv, lengths, L, B, H, self.log_penalty, out=ws["att"])
-                    x1 = ops.linear(att, W["wo"], W["bo"], residual=x, out_dtype=torch.float32,
-                                    out=ws["x1"], rows_limit=limit)
-                    h = ops.layernorm(x1, *W["ln2"], out=ws["h"], rows_limit=limit)
-                    f = ops.linear(h, W["w1"], W["b1"], relu=True, out=ws["f"], rows_limit=limit)
-                    x = ops.linear(f, W["w2"], W["b2"], residual=x1, out_dtype=torch.float32,
-                                   out=ws["x0"], rows_limit=limit)
-                if self.ctc_compress_out and self.ctc_layer == li + 1:
+                    x1, xb, st = ops.linear_ln(att, W["wo"], W["bo"], residual=x, out_dtype=torch.float32,
+                                               out=ws["x1"], ln_out=lo, rows_limit=limit)
+                    f = ops.linear_ln(xb, W["w1"], W["b1"], relu=True, stats_in=st, ln_eps=W["eps2"],
+                                      out=ws["f"], rows_limit=limit)
+                    if need_ln:
+                        x, xb, st = ops.linear_ln(f, W["w2"], W["b2"], residual=x1, out_dtype=torch.float32,
+                                                  out=ws["x0"], ln_out=lo, rows_limit=limit)
+                    else:
+                        x = ops.linear(f, W["w2"], W["b2"], residual=x1, out_dtype=torch.float32,
+                                       out=ws["x0"], rows_limit=limit)
+                if ctc_here:
+                    self.ctc_fc._bf16_operand = (x.data_ptr(), xb)  # bf16(x) is already there
                     if want_states:
                         r["x_ctc"], x, lengths, len_host, L = self._ctc_compress(x, lengths, L, B)
                         r["mask2"] = ops.lengths_to_mask(lengths, L)[0]
                         r["len_host"], r["L"] = len_host, L
+                        if li + 1 < n_layers:
+                            xb, st = ops.row_stats_cast(x)
                     else:
                         r["x_ctc"], x, lengths, max_new = self._ctc_compress(x, lengths, L, B, out=ws["x0"])
                         new_len = lengths
                         limit = (max_new, B)
+                        if li + 1 < n_layers:
+                            xb, st = ops.row_stats_cast(x, out=(ws["h"], ws["st"]), rows_limit=limit)
                 if want_states:
                     states.append(x.view(L, B, D))
             r.update(x=x, limit=limit, new_len=new_len, states=states)
@@ -467,7 +492,8 @@ def make_encoder_class(base):
             D, Dff = self.embed_dim, self.layers[0].fc1.out_features
             z = lambda n, dt: torch.zeros(M, n, dtype=dt, device=dev)
             return dict(h=z(D, torch.bfloat16), qkv=z(3 * D, torch.bfloat16), att=z(D, torch.bfloat16),
-                        f=z(Dff, torch.bfloat16), x0=z(D, torch.float32), x1=z(D, torch.float32))
+                        f=z(Dff, torch.bfloat16), x0=z(D, torch.float32), x1=z(D, torch.float32),
+                        st=torch.zeros(M, (D + 127) // 128, 2, dtype=torch.float32, device=dev))
 
         def _workspace(self, M, dev):
             """The eager path keeps one workspace (for the last shape seen)."""

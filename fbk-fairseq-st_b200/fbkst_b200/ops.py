@@ -126,6 +126,84 @@ def linear(a, w, bias=None, relu=False, residual=None, out_dtype=torch.bfloat16,
     return out
 
 
+def linear_ln(a, w, bias=None, relu=False, residual=None, out_dtype=torch.bfloat16, out=None,
+              stats_in=None, ln_eps=1e-5, ln_out=None, rows_limit=None):
+    """``linear`` with the reference's pre-LayerNorm folded in (fbkst_linear_ln_bf16).
+    Consumer side: ``stats_in`` [M, ceil(K/128), 2] fp32 (per-row slice statistics of the LayerNorm
+    input whose bf16 copy is ``a``); ``w``/``bias`` are the folded W'' / c of ``fold_layernorm``.
+    Producer side (needs ``residual``): ``ln_out=(xb, stats)`` receives bf16(out) and the slice
+    statistics of out; pass ``ln_out=True`` to allocate them.  Returns out, or (out, xb, stats)."""
+    lib = _lib.require_device()
+    _req(a, torch.bfloat16, "linear_ln.a"); _req(w, torch.bfloat16, "linear_ln.w")
+    M, K = a.shape
+    N = w.shape[0]
+    if w.shape[1] != K:
+        raise ValueError("fbkst_b200.linear_ln: K mismatch %s vs %s" % (tuple(a.shape), tuple(w.shape)))
+    flags = (EPI_RELU if relu else 0) | (EPI_OUT_F32 if out_dtype == torch.float32 else 0)
+    ldr = 0
+    if residual is not None:
+        _req(residual, torch.float32, "linear_ln.residual")
+        ldr = residual.stride(0)
+    if out is None:
+        ldo = (N + 7) // 8 * 8
+        out = torch.empty(M, ldo, dtype=out_dtype, device=a.device)
+        if ldo != N:
+            out = out[:, :N]
+    if out.dtype != out_dtype or out.stride(-1) != 1:
+        raise ValueError("fbkst_b200.linear_ln: bad out tensor")
+    xb = st = None
+    if ln_out is not None:
+        if ln_out is True:
+            ln_out = (torch.empty(M, N, dtype=torch.bfloat16, device=a.device),
+                      torch.empty(M, (N + 127) // 128, 2, dtype=torch.float32, device=a.device))
+        xb, st = ln_out
+        _req(xb, torch.bfloat16, "linear_ln.xb"); _req(st, torch.float32, "linear_ln.stats")
+        if xb.shape != (M, N) or st.numel() < M * ((N + 127) // 128) * 2:
+            raise ValueError("fbkst_b200.linear_ln: bad ln_out buffers")
+    if stats_in is not None:
+        _req(stats_in, torch.float32, "linear_ln.stats_in")
+        if stats_in.numel() < M * ((K + 127) // 128) * 2:
+            raise ValueError("fbkst_b200.linear_ln: stats_in too small")
+    check(lib.fbkst_linear_ln_bf16(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _ptr(bias),
+                                   _ptr(residual), ldr, out.data_ptr(), out.stride(0), M, N, K, flags,
+                                   _ptr(stats_in), float(ln_eps), _ptr(xb), xb.stride(0) if xb is not None else 0,
+                                   _ptr(st), _ptr(rows_limit[0]) if rows_limit else 0,
+                                   rows_limit[1] if rows_limit else 0, _stream()))
+    _count()
+    return out if ln_out is None else (out, xb, st)
+
+
+def row_stats_cast(x, out=None, rows_limit=None):
+    """x [M,D] fp32 -> (bf16(x), slice statistics [M, D/128, 2]) for the folded LayerNorm."""
+    lib = _lib.require_device()
+    _req(x, torch.float32, "row_stats_cast.x")
+    M, D = x.shape
+    if out is None:
+        out = (torch.empty(M, D, dtype=torch.bfloat16, device=x.device),
+               torch.empty(M, (D + 127) // 128, 2, dtype=torch.float32, device=x.device))
+    xb, st = out
+    check(lib.fbkst_row_stats_cast(x.data_ptr(), xb.data_ptr(), st.data_ptr(), M, D,
+                                   _ptr(rows_limit[0]) if rows_limit else 0,
+                                   rows_limit[1] if rows_limit else 0, _stream()))
+    _count()
+    return xb, st
+
+
+def fold_layernorm(w, b, gamma, beta, row_scale=None):
+    """Weights of ``linear_ln``'s consumer side: W''[n,k] = gamma[k] W[n,k] - mean_k(gamma[k] W[n,k])
+    (bf16) and c[n] = b[n] + sum_k beta[k] W[n,k] (fp32), so that LN(x) W^T + b == rstd(x) * (x W''^T)
+    + c.  ``row_scale`` [N] optionally scales output rows (the q rows of the in-projection).
+    One-time parameter preparation (fp64 on the device), like ``prep_*``."""
+    w64, g64 = w.detach().double(), gamma.detach().double()
+    wg = w64 * g64[None, :]
+    wg = wg - wg.mean(dim=1, keepdim=True)
+    c = b.detach().double() + w64 @ beta.detach().double()
+    if row_scale is not None:
+        wg = wg * row_scale.double()[:, None]
+        c = c * row_scale.double()
+    return cast_bf16(wg.float().contiguous()), c.float().contiguous()
+
+
 def layernorm(x, gamma, beta, out_dtype=torch.bfloat16, eps=1e-5, out=None, rows_limit=None):
     lib = _lib.require_device()
     _req(x, torch.float32, "layernorm.x")

@@ -108,6 +108,32 @@ int fbkst_linear_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, co
                       const int32_t* lengths, const int32_t* m_limit, int m_limit_mult,
                       fbkst_stream_t stream);
 
+/* ---- a6/a8 fused: linear with the pre-LayerNorm of the reference's residual block folded in ---
+ * replaces the pairs  LayerNorm -> F.linear  of fairseq/modules/transformer_layer.py:108-110
+ * (self_attn_layer_norm -> in-projection, local_attention.py:178) and :126-131 (final_layer_norm
+ * -> fc1) without a LayerNorm kernel, using
+ *     LN(x) W^T + b = rstd(x) * (x W''^T) + c,
+ *     W''[n,k] = gamma[k] W[n,k] - mean_k(gamma[k] W[n,k]),   c[n] = b[n] + sum_k beta[k] W[n,k]
+ * (every row of W'' sums to zero, so the row mean of x drops out; W'' and c are prepared by the host).
+ * Same operands and flags as fbkst_linear_bf16 (no row remap / position table), plus
+ *   producer side (residual epilogue, i.e. out_proj / fc2):  out_bf16 [M,N] bf16 (pitch ldob)
+ *     receives bf16(out) and row_stats_out [M, ceil(N/128)] x 2 fp32 the (mean, M2) of each
+ *     128-column slice of every output row; both NULL to skip.  N % 32 == 0;
+ *   consumer side (plain epilogue, i.e. QKV / fc1 fed with out_bf16 as A and W'' as W):
+ *     row_stats_in [M, ceil(K/128)] x 2 fp32 as written by the producer (K == LayerNorm width);
+ *     the epilogue computes y = rstd * acc + bias with rstd = 1/sqrt(var + ln_eps); NULL: rstd = 1. */
+int fbkst_linear_ln_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                         const float* residual, int64_t ldr, void* out, int64_t ldo, int M, int N,
+                         int K, int flags, const float* row_stats_in, float ln_eps, void* out_bf16,
+                         int64_t ldob, float* row_stats_out, const int32_t* m_limit,
+                         int m_limit_mult, fbkst_stream_t stream);
+
+/* Row statistics + bf16 copy of an x that does not come out of a residual GEMM (fc3 output,
+ * CTC-compressed rows): xb = bf16(x), row_stats [M, D/128] x 2 fp32 as above.  Same D as
+ * fbkst_layernorm; m_limit as in fbkst_linear_bf16. */
+int fbkst_row_stats_cast(const float* x, void* xb, float* row_stats, int M, int D,
+                         const int32_t* m_limit, int m_limit_mult, fbkst_stream_t stream);
+
 /* ---- a8: LayerNorm over the last dim (eps 1e-5, affine) ----------------------------------
  * replaces fairseq/modules/layer_norm.py:29-32 call sites (transformer_layer.py:108,126;
  * conv_transformer.py:253-254).  x [M,D] fp32 -> y [M,D] bf16 or fp32.  D in {128,256,384,512,

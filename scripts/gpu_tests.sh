@@ -13,7 +13,7 @@ if ! grep -q passed gpurun_out/gemm.log || grep -q failed gpurun_out/gemm.log; t
   timeout 300 python scripts/debug_gemm.py > gpurun_out/debug_gemm.log 2>&1
   tail -n 40 gpurun_out/debug_gemm.log
 fi
-run small tests/test_gpu_ops.py -k "layernorm or cmvn or fc3_weight"
+run small tests/test_gpu_ops.py -k "layernorm or cmvn or fc3_weight or row_stats"
 run ctc tests/test_gpu_ops.py -k "ctc"
 run conv tests/test_gpu_ops.py -k "conv_stack"
 run attn tests/test_gpu_ops.py -k "attention"

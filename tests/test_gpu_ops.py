@@ -81,6 +81,114 @@ def test_layernorm(D):
     assert rel_err(ops.layernorm(x, gamma, beta).float(), ref) < 1e-2
 
 
+# --------------------------------------------------------- LayerNorm folded into the GEMMs
+def _slice_stats(x):
+    """(mean, M2) per 128-column slice, fp64 -> [M, parts, 2]."""
+    M, D = x.shape
+    parts = (D + 127) // 128
+    out = torch.zeros(M, parts, 2, dtype=torch.float64)
+    for p in range(parts):
+        sl = x[:, p * 128:(p + 1) * 128].double()
+        out[:, p, 0] = sl.mean(1)
+        out[:, p, 1] = ((sl - sl.mean(1, keepdim=True)) ** 2).sum(1)
+    return out
+
+
+@pytest.mark.parametrize("M,D", [(333, 128), (1000, 256), (777, 512), (300, 1024), (64, 384)])
+def test_row_stats_cast(M, D):
+    from fbkst_b200 import ops
+    g = torch.Generator().manual_seed(D + M)
+    x = (torch.randn(M, D, generator=g) * 2 + 3.0).to(dev())
+    xb, st = ops.row_stats_cast(x)
+    torch.cuda.synchronize()
+    assert torch.equal(xb, x.to(torch.bfloat16))
+    ref = _slice_stats(x.cpu())
+    assert rel_err(st[..., 0], ref[..., 0]) < 1e-5
+    assert rel_err(st[..., 1], ref[..., 1]) < 1e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 512, 512), (1000, 256, 1024), (513, 512, 2048), (77, 128, 256),
+                                   (640, 1024, 512), (130, 192, 64)])
+def test_linear_ln_producer(M, N, K):
+    """Residual epilogue that also emits bf16(out) and the per-slice row statistics of out."""
+    from fbkst_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    a = bf(torch.randn(M, K, generator=g)).to(dev())
+    w = bf(torch.randn(N, K, generator=g) / math.sqrt(K)).to(dev())
+    bias = torch.randn(N, generator=g).to(dev())
+    res = (torch.randn(M, N, generator=g) * 2 + 1.5).to(dev())
+    ref = a.float() @ w.float().t() + bias + res
+    out, xb, st = ops.linear_ln(a, w, bias, residual=res, out_dtype=torch.float32, ln_out=True)
+    torch.cuda.synchronize()
+    assert rel_err(out, ref) < 1e-4
+    assert torch.equal(xb, out.to(torch.bfloat16)), "bf16 copy must be the rounding of the fp32 output"
+    exp = _slice_stats(out.cpu())
+    assert rel_err(st[..., 0], exp[..., 0]) < 1e-5
+    assert rel_err(st[..., 1], exp[..., 1]) < 1e-4
+    # same fp32 result as the plain residual epilogue, bit for bit
+    assert torch.equal(out, ops.linear(a, w, bias, residual=res, out_dtype=torch.float32))
+
+
+@pytest.mark.parametrize("M,D,N", [(300, 512, 1536), (1000, 256, 768), (513, 1024, 4096), (77, 128, 256),
+                                   (200, 384, 1000)])
+def test_linear_ln_consumer(M, D, N):
+    """LN(x) W^T + b through the folded form: bf16(x), slice statistics, W'' and c."""
+    from fbkst_b200 import ops
+    g = torch.Generator().manual_seed(M + N + D)
+    x = (torch.randn(M, D, generator=g) * 1.7 + 0.6 * torch.randn(M, 1, generator=g)).to(dev())
+    gamma = (1 + 0.2 * torch.randn(D, generator=g)).to(dev())
+    beta = (0.3 * torch.randn(D, generator=g)).to(dev())
+    w = (torch.randn(N, D, generator=g) / math.sqrt(D)).to(dev())
+    b = torch.randn(N, generator=g).to(dev())
+    scale = torch.ones(N, device=dev())
+    scale[: N // 3] = 0.125
+    ref = (torch.nn.functional.layer_norm(x.double(), (D,), gamma.double(), beta.double(), 1e-5)
+           @ w.double().t() + b.double()) * scale.double()
+    xb, st = ops.row_stats_cast(x)
+    wf, cf = ops.fold_layernorm(w, b, gamma, beta, row_scale=scale)
+    out = ops.linear_ln(xb, wf, cf, stats_in=st, ln_eps=1e-5, out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    assert rel_err(out, ref) < 1e-2, rel_err(out, ref)
+    # not worse than the unfused bf16 path (LayerNorm kernel -> bf16 -> GEMM) beyond noise
+    h = ops.layernorm(x, gamma, beta)
+    unf = ops.linear(h, ops.cast_bf16(w * scale[:, None]), b * scale, out_dtype=torch.float32)
+    assert rel_err(out, ref) < 2.0 * rel_err(unf, ref) + 1e-3
+    outr = ops.linear_ln(xb, wf, cf, stats_in=st, relu=True)
+    assert rel_err(outr.float(), torch.relu(ref)) < 2e-2
+
+
+def test_linear_ln_chain_rows_limit():
+    """producer -> consumer chained on device with a device-side row limit (post-compression mode)."""
+    from fbkst_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    M, D, Dff, Bm = 512, 512, 2048, 8
+    a = bf(torch.randn(M, Dff, generator=g)).to(dev())
+    w2 = bf(torch.randn(D, Dff, generator=g) / math.sqrt(Dff)).to(dev())
+    b2 = torch.randn(D, generator=g).to(dev())
+    res = torch.randn(M, D, generator=g).to(dev())
+    gamma, beta = torch.ones(D, device=dev()), torch.zeros(D, device=dev())
+    w = (torch.randn(3 * D, D, generator=g) / math.sqrt(D)).to(dev())
+    b = torch.randn(3 * D, generator=g).to(dev())
+    wf, cf = ops.fold_layernorm(w, b, gamma, beta)
+    limit = torch.tensor([37], dtype=torch.int32, device=dev())  # 37 * 8 = 296 valid rows
+    rows = 37 * Bm
+    x = torch.zeros(M, D, device=dev())
+    xb = torch.zeros(M, D, dtype=torch.bfloat16, device=dev())
+    st = torch.zeros(M, D // 128, 2, device=dev())
+    ops.linear_ln(a, w2, b2, residual=res, out_dtype=torch.float32, out=x, ln_out=(xb, st),
+                  rows_limit=(limit, Bm))
+    y = torch.zeros(M, 3 * D, dtype=torch.bfloat16, device=dev())
+    ops.linear_ln(xb, wf, cf, stats_in=st, out=y, rows_limit=(limit, Bm))
+    torch.cuda.synchronize()
+    xr = a[:rows].float() @ w2.float().t() + b2 + res[:rows]
+    assert rel_err(x[:rows], xr) < 1e-4
+    yr = torch.nn.functional.layer_norm(xr, (D,)) @ w.t() + b
+    assert rel_err(y[:rows].float(), yr) < 2e-2
+    # warps whose 32-row block starts beyond the limit write nothing: rows >= 320 keep their zeros
+    assert float(y[320:].float().abs().max()) == 0.0
+    assert float(x[320:].abs().max()) == 0.0
+
+
 # ------------------------------------------------------------------------------------ CMVN
 def test_cmvn_golden(golden_dir):
     from fbkst_b200 import ops
