@@ -19,6 +19,9 @@ SOURCES = ["host_common.cu", "elementwise.cu", "ctc.cu", "gemm_tcgen05.cu", "gem
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+# extra defines for A/B experiments on the GPU box (e.g. FBKST_NVCC_FLAGS="-DFBKST_ATTN_TRACE");
+# part of the object digest, so switching them rebuilds
+FLAGS += os.environ.get("FBKST_NVCC_FLAGS", "").split()
 
 
 def _digest(path):

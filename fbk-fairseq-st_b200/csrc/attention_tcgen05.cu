@@ -174,6 +174,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
   uint64_t* pv_done = bars + 15;  // [2]
   uint64_t* q_empty = bars + 17;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* s_free = bars + 20;   // [2] softmax group -> MMA: S[grp] has been read for the last time
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -190,6 +191,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
       mbar_init(&s_full[s], 1);
       mbar_init(&p_full[s], 128);
       mbar_init(&pv_done[s], 1);
+      mbar_init(&s_free[s], 128);
     }
     fence_barrier_init();
   }
@@ -304,7 +306,17 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
       if (qk.w < n_items) issue_qk();
       while (pv.w < n_items) {
         const uint32_t pb = gp & 1, ph = (gp >> 1) & 1;
-        mbar_wait(&p_full[pb], ph);  // S[pb] consumed, P[pb] in smem, O rescaled / read out
+        // QK(gp+2) first: its accumulator S[pb] is free as soon as the group has pulled S(gp) into
+        // registers (s_free arrives a quarter into the exp pass), long before P(gp) is complete --
+        // the group finds S(gp+2) waiting when it finishes tile gp instead of idling for the
+        // PV-issue + QK-issue + MMA round trip (1500 of 4700 cycles per tile: profiles/r01c timeline).
+        if (qk.w < n_items) {
+          mbar_wait(&s_free[pb], ph);
+          tc_fence_after();
+          issue_qk();
+        }
+        AT_TRACE(gp, 2);
+        mbar_wait(&p_full[pb], ph);  // P[pb] in smem, O[pb] rescaled / read out
         AT_TRACE(gp, 0);
         mbar_wait(&v_full[pb], ph);
         tc_fence_after();
@@ -319,9 +331,6 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
         }
         __syncwarp();
         AT_TRACE(gp, 1);
-        // PV before QK: the group's next exp pass needs P[pb]/O[pb] free (PV done) as much as S
-        if (qk.w < n_items) issue_qk();
-        AT_TRACE(gp, 2);
         ++gp;
         if (++pv_j == pv.n_kv) {
           pv_j = 0;
@@ -431,51 +440,59 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
         const float2 negm2 = make_float2(-m_used, -m_used);
         const float2 l2e2 = make_float2(kLog2e, kLog2e);
         float2 sm2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t s0[32];
-          float pn[16];
-          tmem_ld32(tS + half * 32, s0);
+        uint64_t* my_s_free = &s_free[grp];
+        {
+          // S is pulled in 16-column pieces through two register buffers; a buffer is reloaded as soon
+          // as its scores have been turned into exponents' arguments, so the LAST read of S happens a
+          // quarter into the pass and the accumulator goes back to the MMA warp right there.
+          uint32_t sa[16], sb[16];
+          float pn[8];
+          tmem_ld16(tS, sa);
+          tmem_ld16(tS + 16, sb);
           if (LOGPEN) {
 #pragma unroll
-            for (int c = 0; c < 16; ++c) pn[c] = lds32(lut_addr + (half * 32 + c) * 4);
+            for (int c = 0; c < 8; ++c) pn[c] = lds32(lut_addr + c * 4);
           }
           tmem_ld_wait();
 #pragma unroll
-          for (int sub = 0; sub < 2; ++sub) {  // 16 columns at a time: registers, not ILP, are scarce
-            float2 t[8];
+          for (int ch = 0; ch < 8; ++ch) {  // 8 columns at a time: registers, not ILP, are scarce
+            uint32_t(&s0)[16] = (ch & 2) ? sb : sa;
+            const int o = (ch & 1) * 8;
+            float2 t[4];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
+            for (int c = 0; c < 4; ++c) {
               float2 add = negm2;
               if (LOGPEN) add = fadd2(negm2, make_float2(pn[2 * c], pn[2 * c + 1]));
-              t[c] = ffma2(make_float2(__uint_as_float(s0[sub * 16 + 2 * c]),
-                                       __uint_as_float(s0[sub * 16 + 2 * c + 1])), l2e2, add);
+              t[c] = ffma2(make_float2(__uint_as_float(s0[o + 2 * c]), __uint_as_float(s0[o + 2 * c + 1])),
+                           l2e2, add);
             }
-            if (LOGPEN && sub == 0) {  // penalties of the second 16 columns fly under the exps
+            if (ch == 1 || ch == 3) tmem_ld16(tS + (ch + 3) * 8, s0);  // columns 32.. / 48.. into the freed buffer
+            if (LOGPEN && ch < 7) {  // penalties of the next 8 columns fly under the exps
 #pragma unroll
-              for (int c = 0; c < 16; ++c) pn[c] = lds32(lut_addr + (half * 32 + 16 + c) * 4);
+              for (int c = 0; c < 8; ++c) pn[c] = lds32(lut_addr + ((ch + 1) * 8 + c) * 4);
+            }
+            if (ch == 3) {  // all of S(gg) is in registers: hand the accumulator back
+              tmem_ld_wait();
+              tc_fence_before();
+              mbar_arrive(my_s_free);
             }
             if (nvalid != AT_BN) {  // last key tile of the utterance: masked keys -> p = 2^-inf = 0
 #pragma unroll
-              for (int c = 0; c < 8; ++c) {
-                if (half * 32 + sub * 16 + 2 * c >= nvalid) t[c].x = -INFINITY;
-                if (half * 32 + sub * 16 + 2 * c + 1 >= nvalid) t[c].y = -INFINITY;
+              for (int c = 0; c < 4; ++c) {
+                if (ch * 8 + 2 * c >= nvalid) t[c].x = -INFINITY;
+                if (ch * 8 + 2 * c + 1 >= nvalid) t[c].y = -INFINITY;
               }
             }
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
+            for (int c = 0; c < 4; ++c) {
               t[c].x = ex2(t[c].x);
               t[c].y = ex2(t[c].y);
             }
 #pragma unroll
-            for (int c = 0; c < 8; ++c) sm2[c & 1] = fadd2(sm2[c & 1], t[c]);
-#pragma unroll
-            for (int gq = 0; gq < 2; ++gq) {
-              const int o = gq * 4;
-              reinterpret_cast<uint4*>(myP)[(half * 4 + sub * 2 + gq) ^ swz] =
-                  make_uint4(pack_bf16x2(t[o].x, t[o].y), pack_bf16x2(t[o + 1].x, t[o + 1].y),
-                             pack_bf16x2(t[o + 2].x, t[o + 2].y), pack_bf16x2(t[o + 3].x, t[o + 3].y));
-            }
+            for (int c = 0; c < 4; ++c) sm2[c & 1] = fadd2(sm2[c & 1], t[c]);
+            reinterpret_cast<uint4*>(myP)[ch ^ swz] =
+                make_uint4(pack_bf16x2(t[0].x, t[0].y), pack_bf16x2(t[1].x, t[1].y),
+                           pack_bf16x2(t[2].x, t[2].y), pack_bf16x2(t[3].x, t[3].y));
           }
         }
         l += (sm2[0].x + sm2[0].y) + (sm2[1].x + sm2[1].y);
