@@ -56,17 +56,19 @@ template <int IS_BF16>
 __global__ void __launch_bounds__(256)
     ctc_argmax_kernel(const void* __restrict__ logits, long long ldv,
                       const int* __restrict__ lengths, int* __restrict__ labels,
-                      float* __restrict__ top_prob, int rows, int B, int V) {
+                      float* __restrict__ top_prob, float* __restrict__ lse, int rows, int B,
+                      int V) {
   const int lane = threadIdx.x & 31;
   const int warps_per_grid = gridDim.x * (blockDim.x >> 5);
-  const bool want_sum = top_prob != nullptr;
+  const bool want_sum = top_prob != nullptr || lse != nullptr;
   for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows;
        row += warps_per_grid) {
     const int t = row / B, b = row - t * B;
     if (t >= __ldg(lengths + b)) {
       if (lane == 0) {
         labels[row] = -1;
-        if (want_sum) top_prob[row] = 0.0f;
+        if (top_prob) top_prob[row] = 0.0f;
+        if (lse) lse[row] = 0.0f;
       }
       continue;
     }
@@ -120,7 +122,8 @@ __global__ void __launch_bounds__(256)
     }
     if (lane == 0) {
       labels[row] = a.i;
-      if (want_sum) top_prob[row] = 1.0f / a.s;
+      if (top_prob) top_prob[row] = 1.0f / a.s;
+      if (lse) lse[row] = a.v + logf(a.s);
     }
   }
 }
@@ -142,7 +145,8 @@ template <int IS_BF16, int WANT_SUM>
 __global__ void __launch_bounds__(256)
     ctc_argmax_vec_kernel(const uint4* __restrict__ logits, long long row_vecs,
                           const int* __restrict__ lengths, int* __restrict__ labels,
-                          float* __restrict__ top_prob, int rows, int B, int V) {
+                          float* __restrict__ top_prob, float* __restrict__ lse, int rows, int B,
+                          int V) {
   constexpr int EPV = IS_BF16 ? 8 : 4;  // elements per 16-byte vector
   constexpr int UNROLL = 8;
   const int lane = threadIdx.x & 31;
@@ -152,7 +156,8 @@ __global__ void __launch_bounds__(256)
   if (t >= __ldg(lengths + b)) {
     if (lane == 0) {
       labels[row] = -1;
-      if (WANT_SUM) top_prob[row] = 0.0f;
+      if (WANT_SUM && top_prob) top_prob[row] = 0.0f;
+      if (WANT_SUM && lse) lse[row] = 0.0f;
     }
     return;
   }
@@ -269,7 +274,8 @@ __global__ void __launch_bounds__(256)
   }
   if (lane == 0) {
     labels[row] = a.i;
-    if (WANT_SUM) top_prob[row] = 1.0f / a.s;
+    if (WANT_SUM && top_prob) top_prob[row] = 1.0f / a.s;
+    if (WANT_SUM && lse) lse[row] = a.v + logf(a.s);  // log-sum-exp of the row (natural log)
   }
 }
 
@@ -472,9 +478,9 @@ __global__ void __launch_bounds__(256)
 
 using namespace fbkst;
 
-extern "C" int fbkst_ctc_argmax(const void* logits, int logits_dtype, int64_t ldv,
-                                const int32_t* lengths, int32_t* labels, float* top_prob, int L,
-                                int B, int V, fbkst_stream_t stream) {
+extern "C" int fbkst_ctc_argmax_lse(const void* logits, int logits_dtype, int64_t ldv,
+                                    const int32_t* lengths, int32_t* labels, float* top_prob,
+                                    float* lse, int L, int B, int V, fbkst_stream_t stream) {
   FBKST_REQUIRE(logits && lengths && labels, "fbkst_ctc_argmax: null pointer");
   FBKST_REQUIRE(L > 0 && B > 0 && V > 0 && ldv >= V, "fbkst_ctc_argmax: bad shape");
   FBKST_REQUIRE(logits_dtype == FBKST_BF16 || logits_dtype == FBKST_F32,
@@ -488,25 +494,33 @@ extern "C" int fbkst_ctc_argmax(const void* logits, int logits_dtype, int64_t ld
   if (aligned) {
     const uint4* lp = reinterpret_cast<const uint4*>(logits);
     const long long rv = (long long)((size_t)ldv * esz / 16);
-    if (logits_dtype == FBKST_BF16 && top_prob)
-      ctc_argmax_vec_kernel<1, 1><<<grid, 256, 0, st>>>(lp, rv, lengths, labels, top_prob, rows, B, V);
+    const bool sum = top_prob || lse;
+    if (logits_dtype == FBKST_BF16 && sum)
+      ctc_argmax_vec_kernel<1, 1><<<grid, 256, 0, st>>>(lp, rv, lengths, labels, top_prob, lse, rows, B, V);
     else if (logits_dtype == FBKST_BF16)
-      ctc_argmax_vec_kernel<1, 0><<<grid, 256, 0, st>>>(lp, rv, lengths, labels, top_prob, rows, B, V);
-    else if (top_prob)
-      ctc_argmax_vec_kernel<0, 1><<<grid, 256, 0, st>>>(lp, rv, lengths, labels, top_prob, rows, B, V);
+      ctc_argmax_vec_kernel<1, 0><<<grid, 256, 0, st>>>(lp, rv, lengths, labels, top_prob, lse, rows, B, V);
+    else if (sum)
+      ctc_argmax_vec_kernel<0, 1><<<grid, 256, 0, st>>>(lp, rv, lengths, labels, top_prob, lse, rows, B, V);
     else
-      ctc_argmax_vec_kernel<0, 0><<<grid, 256, 0, st>>>(lp, rv, lengths, labels, top_prob, rows, B, V);
+      ctc_argmax_vec_kernel<0, 0><<<grid, 256, 0, st>>>(lp, rv, lengths, labels, top_prob, lse, rows, B, V);
     FBKST_CHECK_CUDA(cudaGetLastError());
     return FBKST_OK;
   }
   const int cap = num_sms() * 8;
   if (grid > cap) grid = cap;
   if (logits_dtype == FBKST_BF16)
-    ctc_argmax_kernel<1><<<grid, 256, 0, st>>>(logits, ldv, lengths, labels, top_prob, rows, B, V);
+    ctc_argmax_kernel<1><<<grid, 256, 0, st>>>(logits, ldv, lengths, labels, top_prob, lse, rows, B, V);
   else
-    ctc_argmax_kernel<0><<<grid, 256, 0, st>>>(logits, ldv, lengths, labels, top_prob, rows, B, V);
+    ctc_argmax_kernel<0><<<grid, 256, 0, st>>>(logits, ldv, lengths, labels, top_prob, lse, rows, B, V);
   FBKST_CHECK_CUDA(cudaGetLastError());
   return FBKST_OK;
+}
+
+extern "C" int fbkst_ctc_argmax(const void* logits, int logits_dtype, int64_t ldv,
+                                const int32_t* lengths, int32_t* labels, float* top_prob, int L,
+                                int B, int V, fbkst_stream_t stream) {
+  return fbkst_ctc_argmax_lse(logits, logits_dtype, ldv, lengths, labels, top_prob, nullptr, L, B, V,
+                              stream);
 }
 
 extern "C" int fbkst_ctc_segment(const int32_t* labels, const float* top_prob,

@@ -29,6 +29,9 @@ SIGNATURES = {
     "fbkst_sinusoidal_table": [P, I, I, P],
     "fbkst_lengths_to_mask": [P, P, P, I, I, P],
     "fbkst_ctc_argmax": [P, I, I64, P, P, P, I, I, I, P],
+    "fbkst_ctc_argmax_lse": [P, I, I64, P, P, P, P, I, I, I, P],
+    "fbkst_ctc_uer": [P, P, P, I64, P, I, P, P, P, I, I, I, P],
+    "fbkst_ctc_loss_fwd": [P, I, I64, P, P, P, I64, P, I, P, P, I, I, I, I, P],
     "fbkst_ctc_segment": [P, P, P, I, P, P, P, P, P, I, I, P],
     "fbkst_ctc_compress": [P, P, P, P, P, P, P, P, I, I, I, P],
     "fbkst_cast_bf16": [P, P, I64, F, P],

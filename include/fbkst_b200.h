@@ -169,6 +169,14 @@ int fbkst_lengths_to_mask(const int32_t* lengths, uint8_t* mask, int32_t* any_pa
 int fbkst_ctc_argmax(const void* logits, int logits_dtype, int64_t ldv, const int32_t* lengths,
                      int32_t* labels, float* top_prob, int L, int B, int V, fbkst_stream_t stream);
 
+/* Same, plus lse[L*B] fp32 = log(sum_v exp(logits[row, v])) (natural log; 0 for padding rows), or
+ * NULL.  log_softmax(logits)[row, v] = logits[row, v] - lse[row]: what the CTC criterion needs
+ * (criterions/ctc_multi_loss.py:64-67 log_softmax over the fp32 logits) without materialising
+ * the L x B x V log-probabilities. */
+int fbkst_ctc_argmax_lse(const void* logits, int logits_dtype, int64_t ldv, const int32_t* lengths,
+                         int32_t* labels, float* top_prob, float* lse, int L, int B, int V,
+                         fbkst_stream_t stream);
+
 /* ---- a10 step 2 + a11: run-length segmentation and per-frame pooling weights ----------------
  * replaces conv_transformer.py:285-288 (groupby) and :385-426 (CTCCompressStrategy.*).
  * seg_id[L*B] int32: index of the run frame (t,b) belongs to (-1 for padding);
@@ -190,6 +198,32 @@ int fbkst_ctc_compress(const float* x, const int32_t* seg_id, const int32_t* seg
                        const float* weight, const int32_t* lengths, const int32_t* new_lengths,
                        const int32_t* max_new_len, float* out, int L, int B, int D,
                        fbkst_stream_t stream);
+
+/* ---- next row N1: the CTC criterion over ctc_out, on device ----------------------------------
+ * fbkst_ctc_uer replaces examples/speech_recognition/criterions/CTC_loss.py:31-74
+ * (compute_ctc_uer: per-utterance argmax().tolist(), python groupby, blank removal and
+ * EditDistance(False).align of utils/wer_utils.py:141-202 with costs match 0 / step 3 / mismatch 4).
+ * labels[L*B] int32 as written by fbkst_ctc_argmax on the CTC logits (row t*B+b; frames
+ * t >= in_lengths[b] are ignored); targets [B, ldt] int64 (fairseq's padded `target`), the first
+ * target_lengths[b] (int32, clamped to Umax) entries of row b are used.
+ * errors[B] int32 = number of non-match codes on the alignment path the reference backtracks
+ * (same strict-'<' tie-breaks), pred_lengths[B] int32 = tokens left after collapsing,
+ * totals[2] int64 = {sum of errors, sum of target lengths} (the reference's batch_errors and
+ * batch_total).  Integer work: bit-exact.  Both sequences empty: 0 errors (the reference raises). */
+int fbkst_ctc_uer(const int32_t* labels, const int32_t* in_lengths, const int64_t* targets,
+                  int64_t ldt, const int32_t* target_lengths, int blank, int32_t* errors,
+                  int32_t* pred_lengths, int64_t* totals, int L, int B, int Umax,
+                  fbkst_stream_t stream);
+
+/* fbkst_ctc_loss_fwd replaces the F.ctc_loss call of criterions/CTC_loss.py:143-151
+ * (reduction="sum", zero_infinity=True) including the log_softmax before it: logits [L*B, ldv]
+ * bf16/fp32 (row t*B+b, V valid columns), lse[L*B] from fbkst_ctc_argmax_lse.
+ * nll[B] fp32 = -log p(target_b | x_b) (0 where infinite), loss[1] fp32 = their sum in a fixed
+ * order.  Forward only (validation / scoring); fp32 log-space alpha recursion. */
+int fbkst_ctc_loss_fwd(const void* logits, int logits_dtype, int64_t ldv, const float* lse,
+                       const int32_t* in_lengths, const int64_t* targets, int64_t ldt,
+                       const int32_t* target_lengths, int blank, float* nll, float* loss, int L,
+                       int B, int V, int Umax, fbkst_stream_t stream);
 
 /* ---- weight preparation (fp32 master parameters -> kernel operand formats) ----------------- */
 /* dst[i] = bf16(src[i] * scale) */
