@@ -1,0 +1,85 @@
+"""Host-side mirror of the reference's CTC criterion arithmetic over the device path.
+
+Reference: ``examples/speech_recognition/criterions/CTC_loss.py`` -- ``compute_ctc_uer`` (:31-74) and
+the ``F.ctc_loss`` call of ``CTCCriterion.forward`` (:128-151), reached from ``ctc_multi_loss.py:27-41``
+with the encoder's ``ctc_out`` (T x B x V) and ``ctc_padding_mask``.
+
+The reference pulls every utterance's arg-max path to the host (``.tolist()``), collapses it with
+``itertools.groupby`` and runs a Python O(P*U) alignment per utterance, every training and validation
+step.  Here the frame arg-max, the log-sum-exp, the collapse, the alignment and the alpha recursion
+all run on the GPU; the only host transfer is the final read of 3 scalars.
+
+No CPU fallback: CPU tensors raise.
+"""
+import torch
+
+from . import ops
+
+
+def _time_major_rows(x):
+    """[T, B, V] logits/log-probs -> ([T*B, V] row view with row t*B+b, T, B, V) without copying
+    when the storage is time-major (also when `x` is the criterion's N x T x D transposed view)."""
+    if x.dim() != 3:
+        raise ValueError("fbkst_b200.criterion: expected a 3-D tensor")
+    if not x.is_cuda:
+        raise ValueError("fbkst_b200.criterion: expected a CUDA tensor (there is no CPU fallback)")
+    if x.dtype not in (torch.bfloat16, torch.float32):
+        x = x.float()
+    T, B, V = x.shape
+    if x.stride(2) != 1 or x.stride(0) != B * x.stride(1):
+        x = x.contiguous()
+    return x.as_strided((T * B, V), (x.stride(1), 1), x.storage_offset()), T, B, V
+
+
+def _i32(t, device):
+    return torch.as_tensor(t, device=device).to(torch.int32).contiguous()
+
+
+def ctc_uer_device(ctc_out, targets, input_lengths, target_lengths, blank_idx):
+    """Device tensors only, no synchronisation.  ctc_out T x B x V (logits or log-probs: the arg-max
+    is the same).  -> (errors [B] int32, totals [2] int64 = (batch_errors, batch_total))."""
+    rows, T, B, V = _time_major_rows(ctc_out)
+    dev = rows.device
+    il, tl = _i32(input_lengths, dev), _i32(target_lengths, dev)
+    labels, _ = ops.ctc_argmax(rows, il, T, B, V, want_prob=False)
+    tg = torch.as_tensor(targets, device=dev).to(torch.int64)
+    errors, _, totals = ops.ctc_uer(labels, il, tg, tl, blank_idx, T, B)
+    return errors, totals
+
+
+def compute_ctc_uer(logprobs, targets, input_lengths, target_lengths, blank_idx):
+    """Same signature and return value as the reference's ``compute_ctc_uer`` (CTC_loss.py:31-74):
+    logprobs N x T1 x D (the criterion passes the transposed view of the T x N x D tensor, which is
+    consumed without a copy), targets N x T2, lengths per sample.  Returns (batch_errors, batch_total)
+    as Python numbers (one device->host read of 16 bytes)."""
+    _, totals = ctc_uer_device(logprobs.transpose(0, 1), targets, input_lengths, target_lengths, blank_idx)
+    e, n = totals.tolist()
+    return float(e), float(n)
+
+
+def ctc_loss_and_uer(ctc_out, ctc_padding_mask, targets, target_lengths, blank_idx, pad_idx=None):
+    """What ``CTCCriterion.forward`` computes from the encoder output (CTC_loss.py:118-154):
+
+        lprobs = log_softmax(ctc_out.float());  input_lengths from the padding mask
+        loss   = F.ctc_loss(lprobs, targets, input_lengths, target_lengths, blank, "sum", zero_infinity)
+        errors, total = compute_ctc_uer(lprobs, targets, input_lengths, target_lengths, blank)
+
+    ctc_out T x B x V (bf16 or fp32 logits, ``encoder_out.ctc_out``), ctc_padding_mask B x T bool
+    (True = padding) or None or a [B] tensor of lengths.  One pass over the logits produces the frame
+    arg-max and the log-sum-exp; the log-probabilities are never materialised.
+    Returns device tensors (loss [1] fp32, nll [B] fp32, errors [B] int32, totals [2] int64)."""
+    rows, T, B, V = _time_major_rows(ctc_out)
+    dev = rows.device
+    if ctc_padding_mask is None:
+        il = torch.full((B,), T, dtype=torch.int32, device=dev)
+    elif ctc_padding_mask.dim() == 1:
+        il = _i32(ctc_padding_mask, dev)
+    else:  # data_utils.encoder_padding_mask_to_lengths: T - number of padded positions
+        m = ctc_padding_mask if ctc_padding_mask.shape[0] == B else ctc_padding_mask.t()
+        il = (T - m.sum(dim=1)).to(torch.int32)
+    tl = _i32(target_lengths, dev)
+    tg = torch.as_tensor(targets, device=dev).to(torch.int64)
+    labels, lse, _ = ops.ctc_argmax_lse(rows, il, T, B, V)
+    nll, loss = ops.ctc_loss_fwd(rows, lse, il, tg, tl, blank_idx, T, B, V)
+    errors, _, totals = ops.ctc_uer(labels, il, tg, tl, blank_idx, T, B)
+    return loss, nll, errors, totals

@@ -267,6 +267,64 @@ def ctc_argmax(logits, lengths, L, B, V, want_prob=True):
     return labels, prob
 
 
+def ctc_argmax_lse(logits, lengths, L, B, V, want_prob=False):
+    """As ctc_argmax, plus lse[L*B] fp32 = logsumexp of every valid row (0 for padding)."""
+    lib = _lib.require_device()
+    if logits.dtype not in (torch.bfloat16, torch.float32) or logits.stride(-1) != 1:
+        raise ValueError("fbkst_b200.ctc_argmax_lse: logits must be bf16/fp32 with unit column stride")
+    labels = torch.empty(L * B, dtype=torch.int32, device=logits.device)
+    lse = torch.empty(L * B, dtype=torch.float32, device=logits.device)
+    prob = torch.empty(L * B, dtype=torch.float32, device=logits.device) if want_prob else None
+    check(lib.fbkst_ctc_argmax_lse(logits.data_ptr(), BF16 if logits.dtype == torch.bfloat16 else F32,
+                                   logits.stride(0), lengths.data_ptr(), labels.data_ptr(), _ptr(prob),
+                                   lse.data_ptr(), L, B, V, _stream()))
+    _count()
+    return labels, lse, prob
+
+
+def ctc_uer(labels, in_lengths, targets, target_lengths, blank, L, B):
+    """compute_ctc_uer on device.  labels [L*B] int32 (from ctc_argmax), in_lengths / target_lengths
+    [B] int32, targets [B, U] int64 (padded).  -> errors [B] int32, pred_lengths [B] int32,
+    totals [2] int64 = (batch_errors, batch_total); nothing is synchronised."""
+    lib = _lib.require_device()
+    _req(labels, torch.int32, "ctc_uer.labels"); _req(in_lengths, torch.int32, "ctc_uer.in_lengths")
+    _req(target_lengths, torch.int32, "ctc_uer.target_lengths")
+    if targets.dtype != torch.int64 or targets.dim() != 2 or (targets.numel() and targets.stride(1) != 1):
+        raise ValueError("fbkst_b200.ctc_uer: targets must be [B, U] int64 with unit column stride")
+    U = targets.shape[1]
+    dev = labels.device
+    errors = torch.empty(B, dtype=torch.int32, device=dev)
+    plen = torch.empty(B, dtype=torch.int32, device=dev)
+    totals = torch.empty(2, dtype=torch.int64, device=dev)
+    check(lib.fbkst_ctc_uer(labels.data_ptr(), in_lengths.data_ptr(), targets.data_ptr() if U else 0,
+                            targets.stride(0) if U else 0, target_lengths.data_ptr(), int(blank),
+                            errors.data_ptr(), plen.data_ptr(), totals.data_ptr(), L, B, U, _stream()))
+    _count(2)
+    return errors, plen, totals
+
+
+def ctc_loss_fwd(logits, lse, in_lengths, targets, target_lengths, blank, L, B, V):
+    """F.ctc_loss(log_softmax(logits), ..., reduction="sum", zero_infinity=True) forward.
+    logits [L*B, >=V] bf16/fp32 rows t*B+b, lse from ctc_argmax_lse.  -> nll [B] fp32, loss [1] fp32."""
+    lib = _lib.require_device()
+    if logits.dtype not in (torch.bfloat16, torch.float32) or logits.stride(-1) != 1:
+        raise ValueError("fbkst_b200.ctc_loss_fwd: logits must be bf16/fp32 with unit column stride")
+    _req(lse, torch.float32, "ctc_loss_fwd.lse"); _req(in_lengths, torch.int32, "ctc_loss_fwd.in_lengths")
+    _req(target_lengths, torch.int32, "ctc_loss_fwd.target_lengths")
+    if targets.dtype != torch.int64 or targets.dim() != 2 or (targets.numel() and targets.stride(1) != 1):
+        raise ValueError("fbkst_b200.ctc_loss_fwd: targets must be [B, U] int64 with unit column stride")
+    U = targets.shape[1]
+    nll = torch.empty(B, dtype=torch.float32, device=logits.device)
+    loss = torch.empty(1, dtype=torch.float32, device=logits.device)
+    check(lib.fbkst_ctc_loss_fwd(logits.data_ptr(), BF16 if logits.dtype == torch.bfloat16 else F32,
+                                 logits.stride(0), lse.data_ptr(), in_lengths.data_ptr(),
+                                 targets.data_ptr() if U else 0, targets.stride(0) if U else 0,
+                                 target_lengths.data_ptr(), int(blank), nll.data_ptr(), loss.data_ptr(),
+                                 L, B, V, U, _stream()))
+    _count(2)
+    return nll, loss
+
+
 def ctc_segment(labels, top_prob, lengths, strategy, L, B):
     lib = _lib.require_device()
     dev = labels.device

@@ -19,4 +19,5 @@ run conv tests/test_gpu_ops.py -k "conv_stack"
 run attn tests/test_gpu_ops.py -k "attention"
 run encoder tests/test_gpu_encoder.py
 run misc tests/test_gpu_ops.py -k "custom_ops or collater"
-for f in gemm small ctc conv attn encoder misc; do echo "=== $f"; grep -E "^(E |FAILED|ERROR)|assert|Error" gpurun_out/$f.log | head -n 12; done
+run criterion tests/test_gpu_criterion.py
+for f in gemm small ctc conv attn encoder misc criterion; do echo "=== $f"; grep -E "^(E |FAILED|ERROR)|assert|Error" gpurun_out/$f.log | head -n 12; done
