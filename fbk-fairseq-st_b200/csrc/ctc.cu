@@ -383,95 +383,104 @@ __global__ void __launch_bounds__(128)
 }
 
 // out[s*B+b, :] = sum_{t in segment s of b} weight[t,b] * x[t*B+b, :].
-// INPUT-stationary: a warp task is (chunk of FR consecutive frames, utterance b, 128-column group);
-// a lane owns one float4 column, so a frame is one coalesced 512-byte warp load and all FR loads
-// of a task are issued up front -- their addresses depend on nothing but the task index, so they
-// fly in parallel with the per-frame metadata (run id, pooling weight) that lanes 0..FR-1 fetch.
-// The frames are then folded in time order; a run is written by the task in whose chunk it STARTS
-// (that task keeps reading past its chunk until the run ends), so every output row has exactly one
-// writer and a fixed summation order: no atomics, run-to-run identical results.
-// Why not one task per output row (rounds r01a/r01b in profiles/): run lengths are skewed (mean 4,
-// merged blank runs reach 60-80 frames), so per-run tasks either leave most of their load
-// registers idle or serialise on the longest run; 20-25 % of HBM peak both ways.
+// INPUT-stationary and PERSISTENT.  A warp task is (chunk of CH = 16 consecutive frames, utterance b,
+// 128-column group); the task OWNS the runs that START inside its chunk and reads exactly their
+// frames [begin, end) -- `end` may lie beyond the chunk when the last run continues -- so every frame
+// of x is read by exactly one task per column group (once from DRAM, never again from L2), every
+// output row has exactly one writer and a fixed summation order (ascending t): no atomics,
+// run-to-run identical results.
+//   * (begin, end) come from a 32-frame window of run ids [t0-1, t0+31) that the lanes fetch ONE TASK
+//     AHEAD (the previous iteration issues the loads), so the only memory round trip on a task's
+//     critical path is the batch of <= 16 frame loads (512 B per warp each, all issued before any is
+//     used) with the per-frame run id / pooling weight fetched by lanes 0..15 in the same flight.
+//   * runs longer than the window (merged blank runs reach 60-80 frames) take their end from
+//     seg_start[run + 1] and simply need more 16-frame batches; no per-batch metadata dependency.
+//   * the grid is sized to the resident-warp capacity and each warp walks tasks in a grid-stride
+//     loop: warps drift out of phase, so frame loads stream continuously instead of in waves
+//     (the one-task-per-warp version ran 2.6 waves of issue -> wait -> fold: 46 % of HBM peak,
+//     profiles/r01e_ncu_ctc.txt; one task per OUTPUT row was worse still: profiles/r01b).
 // The task of chunk c also zero-fills the padding rows new_len[b] <= s < max_new_len, s in chunk c.
-template <int FR>
+constexpr int CTC_CH = 16;
+
+__device__ __forceinline__ int ctc_window_sid(const int* __restrict__ seg_id, int task, int ncg, int B,
+                                              int L, int lane) {
+  const int b = (task / ncg) % B, c = task / (ncg * B);
+  const int t = c * CTC_CH - 1 + lane;
+  return (t >= 0 && t < L) ? __ldg(seg_id + (size_t)t * B + b) : (t < 0 ? -2 : -1);
+}
+
 __global__ void __launch_bounds__(256)
     ctc_compress_kernel(const float* __restrict__ x, const int* __restrict__ seg_id,
-                        const float* __restrict__ weight, const int* __restrict__ /*lengths*/,
-                        const int* __restrict__ new_lengths, const int* __restrict__ max_new_len,
-                        float* __restrict__ out, int L, int B, int D, int tasks) {
-  static_assert(FR <= 16, "metadata is fetched by lanes 0..FR-1, lane 16 looks one frame back");
+                        const int* __restrict__ seg_start, const float* __restrict__ weight,
+                        const int* __restrict__ lengths, const int* __restrict__ new_lengths,
+                        const int* __restrict__ max_new_len, float* __restrict__ out, int L, int B, int D,
+                        int tasks) {
+  constexpr int FR = CTC_CH;
   const int ncg = D >> 7;  // 128-column groups per row
   const int lane = threadIdx.x & 31;
-  const int task = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  int task = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (task >= tasks) return;
-  const int cg = task % ncg, b = (task / ncg) % B, c = task / (ncg * B);
-  const int t0 = c * FR;
   const size_t fstride = (size_t)B * (D >> 2);  // float4 elements between consecutive frames
-  const float4* xcol = reinterpret_cast<const float4*>(x + (size_t)b * D) + cg * 32 + lane;
-  float4* ocol = reinterpret_cast<float4*>(out + (size_t)b * D) + cg * 32 + lane;
-  // Nothing below waits for lengths[b]: fbkst_ctc_segment wrote seg_id = -1 and weight = 0 for every
-  // padding frame t < L, so the frame loads, the metadata loads and the bounds all go out together
-  // (one memory round trip per task).  Padding frames are loaded but never folded.
-  float4 v[FR];
-#pragma unroll
-  for (int k = 0; k < FR; ++k)
-    v[k] = (t0 + k < L) ? __ldg(xcol + (size_t)(t0 + k) * fstride) : make_float4(0.f, 0.f, 0.f, 0.f);
-  // metadata: lane k < FR <-> frame t0 + k; lane 16 <-> frame t0 - 1
-  const int tm = (lane == 16) ? t0 - 1 : t0 + lane;
-  const bool has = (lane < FR || lane == 16) && tm >= 0 && tm < L;
-  int sid = has ? __ldg(seg_id + (size_t)tm * B + b) : -1;
-  float wt = (has && lane < FR) ? __ldg(weight + (size_t)tm * B + b) : 0.0f;
-  const int nl = __ldg(new_lengths + b);
   const int mx = min(__ldg(max_new_len), L);
-  const int len = L;  // run extension stops at the first frame with another run id (-1 = padding)
-  const int prev = __shfl_sync(0xffffffffu, sid, 16);  // run id of frame t0 - 1 (-1: none)
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  int cur = -1;       // run being accumulated (warp-uniform)
-  bool owned = false; // it started inside this chunk
-#pragma unroll
-  for (int k = 0; k < FR; ++k) {
-    const int sk = __shfl_sync(0xffffffffu, sid, k);
-    const float wk = __shfl_sync(0xffffffffu, wt, k);
-    if (sk != cur) {
-      if (cur >= 0 && owned) ocol[(size_t)cur * fstride] = acc;
-      acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      cur = sk;
-      owned = sk != prev;
-    }
-    if (sk >= 0) {  // warp-uniform; padding frames may hold anything
-      acc.x = fmaf(wk, v[k].x, acc.x);
-      acc.y = fmaf(wk, v[k].y, acc.y);
-      acc.z = fmaf(wk, v[k].z, acc.z);
-      acc.w = fmaf(wk, v[k].w, acc.w);
-    }
-  }
-  if (cur >= 0 && owned) {
-    // the last run of the chunk may continue beyond it: keep folding until it ends
-    for (int t = t0 + FR; t < len; t += FR) {
-      const bool h2 = lane < FR && t + lane < len;
-      sid = h2 ? __ldg(seg_id + (size_t)(t + lane) * B + b) : -1;
-      wt = h2 ? __ldg(weight + (size_t)(t + lane) * B + b) : 0.0f;
-      const unsigned same = __ballot_sync(0xffffffffu, sid == cur) | ~((1u << FR) - 1u);
-      const int n = __ffs(~same) ? __ffs(~same) - 1 : FR;  // leading frames still in the run
-      if (n == 0) break;
-#pragma unroll
-      for (int k = 0; k < FR; ++k)
-        v[k] = (k < n) ? __ldg(xcol + (size_t)(t + k) * fstride) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int k = 0; k < FR; ++k) {
-        const float wk = (k < n) ? __shfl_sync(0xffffffffu, wt, k) : 0.0f;
-        acc.x = fmaf(wk, v[k].x, acc.x);
-        acc.y = fmaf(wk, v[k].y, acc.y);
-        acc.z = fmaf(wk, v[k].z, acc.z);
-        acc.w = fmaf(wk, v[k].w, acc.w);
+  int sidw = ctc_window_sid(seg_id, task, ncg, B, L, lane);
+  for (; task < tasks; task += nwarps) {
+    const int cg = task % ncg, b = (task / ncg) % B, c = task / (ncg * B);
+    const int t0 = c * FR;
+    const int sid = sidw;
+    if (task + nwarps < tasks) sidw = ctc_window_sid(seg_id, task + nwarps, ncg, B, L, lane);  // one task ahead
+    const int nl = __ldg(new_lengths + b);
+    const float4* xcol = reinterpret_cast<const float4*>(x + (size_t)b * D) + cg * 32 + lane;
+    float4* ocol = reinterpret_cast<float4*>(out + (size_t)b * D) + cg * 32 + lane;
+    // lane j <-> frame t0 - 1 + j.  Runs that start in the chunk: boundary at some lane 1..FR.
+    const int prv = __shfl_up_sync(0xffffffffu, sid, 1);
+    const unsigned bmask = __ballot_sync(0xffffffffu, lane >= 1 && lane <= FR && sid >= 0 && sid != prv);
+    if (bmask != 0) {  // warp-uniform
+      const int jb = __ffs(bmask) - 1;
+      const int s_last = __shfl_sync(0xffffffffu, sid, FR);  // run of the chunk's last frame (-1: padding)
+      int begin = t0 - 1 + jb, end;
+      if (s_last < 0) {
+        const unsigned em = __ballot_sync(0xffffffffu, lane > jb && sid < 0);
+        end = t0 - 1 + (__ffs(em) - 1);
+      } else {
+        const unsigned em = __ballot_sync(0xffffffffu, lane > FR && sid != s_last);
+        if (em != 0)
+          end = t0 - 1 + (__ffs(em) - 1);
+        else  // the run leaves the window: its end is the next run's start (or the utterance's end)
+          end = (s_last + 1 < nl) ? __ldg(seg_start + (size_t)(s_last + 1) * B + b) : min(__ldg(lengths + b), L);
       }
-      if (n < FR) break;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      int cur = -1;  // run being accumulated (warp-uniform)
+      for (int fb = begin; fb < end; fb += FR) {
+        float4 v[FR];
+#pragma unroll
+        for (int k = 0; k < FR; ++k)
+          v[k] = (fb + k < end) ? ld_nc_na(xcol + (size_t)(fb + k) * fstride) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool has = lane < FR && fb + lane < end;
+        const int sl = has ? __ldg(seg_id + (size_t)(fb + lane) * B + b) : -1;
+        const float wl = has ? __ldg(weight + (size_t)(fb + lane) * B + b) : 0.0f;
+#pragma unroll
+        for (int k = 0; k < FR; ++k) {
+          const int sk = __shfl_sync(0xffffffffu, sl, k);
+          const float wk = __shfl_sync(0xffffffffu, wl, k);
+          if (sk != cur) {  // warp-uniform
+            if (cur >= 0) ocol[(size_t)cur * fstride] = acc;
+            acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            cur = sk;
+          }
+          if (sk >= 0) {
+            acc.x = fmaf(wk, v[k].x, acc.x);
+            acc.y = fmaf(wk, v[k].y, acc.y);
+            acc.z = fmaf(wk, v[k].z, acc.z);
+            acc.w = fmaf(wk, v[k].w, acc.w);
+          }
+        }
+      }
+      if (cur >= 0) ocol[(size_t)cur * fstride] = acc;
     }
-    ocol[(size_t)cur * fstride] = acc;
+    // padding rows of the compressed output that fall into this chunk's index range
+    for (int s = max(t0, nl); s < min(t0 + FR, mx); ++s) ocol[(size_t)s * fstride] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  // padding rows of the compressed output that fall into this chunk's index range
-  for (int s = max(t0, nl); s < min(t0 + FR, mx); ++s) ocol[(size_t)s * fstride] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 }  // namespace fbkst
@@ -565,11 +574,18 @@ extern "C" int fbkst_ctc_compress(const float* x, const int32_t* seg_id, const i
     FBKST_CHECK_CUDA(cudaGetLastError());
     return FBKST_OK;
   }
-  constexpr int FR = 16;
-  const long long tasks = (long long)((L + FR - 1) / FR) * B * (D / 128);
+  const long long tasks = (long long)((L + CTC_CH - 1) / CTC_CH) * B * (D / 128);
   FBKST_REQUIRE(tasks < (1ll << 31), "fbkst_ctc_compress: too many tasks");
-  ctc_compress_kernel<FR><<<(int)((tasks + 7) / 8), 256, 0, st>>>(
-      x, seg_id, weight, lengths, new_lengths, max_new_len, out, L, B, D, (int)tasks);
+  // persistent: as many CTAs as can be resident (registers allow 2 x 256 threads per SM)
+  static int ctas_per_sm = 0;
+  if (ctas_per_sm == 0) {
+    FBKST_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, ctc_compress_kernel, 256, 0));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+  }
+  long long grid = (tasks + 7) / 8;
+  if (grid > (long long)num_sms() * ctas_per_sm) grid = (long long)num_sms() * ctas_per_sm;
+  ctc_compress_kernel<<<(int)grid, 256, 0, st>>>(x, seg_id, seg_start, weight, lengths, new_lengths,
+                                                 max_new_len, out, L, B, D, (int)tasks);
   FBKST_CHECK_CUDA(cudaGetLastError());
   return FBKST_OK;
 }

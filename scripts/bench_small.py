@@ -79,6 +79,6 @@ U = 60
 tgt = torch.randint(0, V - 1, (B, U), device=d)
 tlen = torch.randint(20, U + 1, (B,), device=d).to(torch.int32)
 labels, lse, _ = ops.ctc_argmax_lse(lg, lens, L, B, V)
-timeit("crit argmax+lse", lambda: ops.ctc_argmax_lse(lg, lens, L, B, V), L * B * V * 2 + L * B * 8)
+timeit("crit ctc_argmax_lse", lambda: ops.ctc_argmax_lse(lg, lens, L, B, V), L * B * V * 2 + L * B * 8)
 timeit("crit ctc_loss_fwd", lambda: ops.ctc_loss_fwd(lg, lse, lens, tgt, tlen, V - 1, L, B, V), L * B * (U + 1) * 2)
 timeit("crit ctc_uer", lambda: ops.ctc_uer(labels, lens, tgt, tlen, V - 1, L, B), L * B * 4)
