@@ -60,6 +60,32 @@ def collate_cmvn(packed, starts, lengths, T, normalize=True, out=None):
     return out
 
 
+def specaugment_(x, bands, n_freq, n_time):
+    """In-place SpecAugment masking: x [B,T,F] fp32, bands [B, n_freq+n_time, 2] int32 (start, width)."""
+    lib = _lib.require_device()
+    _req(x, torch.float32, "specaugment.x"); _req(bands, torch.int32, "specaugment.bands")
+    B, T, Fd = x.shape
+    if tuple(bands.shape) != (B, n_freq + n_time, 2):
+        raise ValueError("fbkst_b200.specaugment: bands must be [B, n_freq+n_time, 2]")
+    check(lib.fbkst_specaugment_f32(x.data_ptr(), bands.data_ptr(), B, T, Fd, n_freq, n_time, _stream()))
+    _count()
+    return x
+
+
+def time_stretch(x, windows, T_out):
+    """x [B,T,F] fp32, windows [n,4] int32 (first, last, count, flat out offset) -> (out [B,T_out,F],
+    ids [B,T_out] int32, -1 beyond the new length)."""
+    lib = _lib.require_device()
+    _req(x, torch.float32, "time_stretch.x"); _req(windows, torch.int32, "time_stretch.windows")
+    B, T, Fd = x.shape
+    ids = torch.empty(B, T_out, dtype=torch.int32, device=x.device)
+    out = torch.empty(B, T_out, Fd, dtype=torch.float32, device=x.device)
+    check(lib.fbkst_time_stretch_f32(x.data_ptr(), windows.data_ptr(), windows.shape[0], ids.data_ptr(),
+                                     out.data_ptr(), B, T, T_out, Fd, _stream()))
+    _count(2)
+    return out, ids
+
+
 def conv1_relu_bn(x, w, bias, scale, shift):
     lib = _lib.require_device()
     _req(x, torch.float32, "conv1.x")

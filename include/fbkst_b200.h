@@ -225,6 +225,28 @@ int fbkst_ctc_loss_fwd(const void* logits, int logits_dtype, int64_t ldv, const 
                        const int32_t* target_lengths, int blank, float* nll, float* loss, int L,
                        int B, int V, int Umax, fbkst_stream_t stream);
 
+/* ---- next row N3: training-time batch augmentation on device ------------------------------------
+ * fbkst_specaugment_f32 replaces examples/speech_recognition/modules/specaugment.py:55-112 (the
+ * per-spectrogram slice assignments of `specaugment`, called from tasks/speech_recognition.py:257-258).
+ * x [B, T, F] fp32 is masked IN PLACE: bands [B, n_freq + n_time, 2] int32 = (start, width) per
+ * utterance, the first n_freq are feature bands (x[b, :, f0:f0+f] = 0), the rest time bands
+ * (x[b, t0:t0+t, :] = 0); width 0 = nothing (utterances the `rate` draw skipped).  The host draws
+ * the bands with the reference's RNG calls in the reference's order.  Write-only kernel. */
+int fbkst_specaugment_f32(float* x, const int32_t* bands, int B, int T, int F, int n_freq, int n_time,
+                          fbkst_stream_t stream);
+
+/* fbkst_time_stretch_f32 replaces modules/time_stretch.py:18-57 (TimeStretch.forward +
+ * time_stretch_seq: per-window torch.linspace -> round -> long index lists, fancy-indexing per
+ * utterance, re-padding on the host and a second H2D).  x [B, T, F] fp32; windows [n_windows, 4] int32
+ * = (first, last, count, out_off): the window resamples frames first..last of its utterance to `count`
+ * frames written at flat position out_off (= b * T_out + offset) -- the host computes count =
+ * int(uniform(low, high) * window_size) with the reference's RNG calls; an utterance the `rate` draw
+ * skipped is one window (0, len-1, len, b*T_out).  ids [B, T_out] int32 receives the source frame of
+ * every output frame, bit-identical to the reference's index tensors (-1 beyond the new length);
+ * out [B, T_out, F] fp32 = x[b, ids[b, j], :] (0 where ids < 0).  16-byte aligned windows. */
+int fbkst_time_stretch_f32(const float* x, const int32_t* windows, int n_windows, int32_t* ids,
+                           float* out, int B, int T, int T_out, int F, fbkst_stream_t stream);
+
 /* ---- weight preparation (fp32 master parameters -> kernel operand formats) ----------------- */
 /* dst[i] = bf16(src[i] * scale) */
 int fbkst_cast_bf16(const float* src, void* dst, int64_t n, float scale, fbkst_stream_t stream);
