@@ -539,13 +539,23 @@ def make_encoder_class(base):
             return self.forward(**encoder_input)
 
         def reorder_encoder_out(self, encoder_out, new_order):
-            """conv_transformer.py:315-345: index_select batch dim by ``new_order`` (beam search)."""
+            """conv_transformer.py:315-345: index_select batch dim by ``new_order`` (beam search).
+            Same values as the reference; the tensors returned additionally remember which columns
+            of the ORIGINAL encoder output they hold (``cross_attention.reorder_tagged``), so
+            ``CrossAttention`` projects K/V once per utterance instead of once per hypothesis, and a
+            chain of reorders is one gather from the original.  With ``lazy_beam_reorder = True``
+            (opt-in; every consumer must be a ``CrossAttention``) nothing is gathered at all: the
+            un-replicated tensors travel with the row vector."""
+            from .cross_attention import reorder_tagged
+            lazy = getattr(self, "lazy_beam_reorder", False)
+            memo = {}
             if encoder_out.encoder_out is not None:
                 encoder_out = encoder_out._replace(
-                    encoder_out=encoder_out.encoder_out.index_select(1, new_order))
+                    encoder_out=reorder_tagged(encoder_out.encoder_out, 1, new_order, lazy, memo))
             if encoder_out.encoder_padding_mask is not None:
                 encoder_out = encoder_out._replace(
-                    encoder_padding_mask=encoder_out.encoder_padding_mask.index_select(0, new_order))
+                    encoder_padding_mask=reorder_tagged(encoder_out.encoder_padding_mask, 0, new_order,
+                                                        lazy, memo))
             if encoder_out.encoder_embedding is not None:
                 encoder_out = encoder_out._replace(
                     encoder_embedding=encoder_out.encoder_embedding.index_select(0, new_order))

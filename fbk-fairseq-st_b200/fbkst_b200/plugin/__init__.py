@@ -26,6 +26,7 @@ import examples.speech_recognition  # noqa: E402,F401  (registers the reference 
 from examples.speech_recognition.models import conv_transformer as _ref  # noqa: E402
 
 from fbkst_b200 import encoder as _enc  # noqa: E402
+from fbkst_b200.cross_attention import swap_cross_attention  # noqa: E402
 
 B200ConvolutionalTransformerEncoder = _enc.make_encoder_class(FairseqEncoder)
 # hand fairseq's own NamedTuple types to downstream isinstance checks
@@ -53,7 +54,23 @@ class B200ConvolutionalTransformerModel(_ref.ConvolutionalTransformerModel):
             args, src_dict if src_dict is not None else tgt_dict,
             audio_features=args.input_feat_per_channel)
         decoder = TransformerDecoder(args, tgt_dict, emb)
+        # encoder-decoder attention on the device kernel (K/V once per utterance, beam
+        # reorders move an index vector).  Same parameters / state_dict keys; inference only, so it
+        # is opt-in: --b200-cross-attention (generate.py), never needed for train.py.
+        if getattr(args, "b200_cross_attention", False):
+            swap_cross_attention(decoder)
+            encoder.lazy_beam_reorder = getattr(args, "b200_lazy_beam_reorder", False)
         return cls(encoder, decoder)
+
+    @staticmethod
+    def add_args(parser):
+        _ref.ConvolutionalTransformerModel.add_args(parser)
+        parser.add_argument("--b200-cross-attention", action="store_true",
+                            help="run the decoder's encoder-decoder attention on the sm_100a kernel "
+                                 "(inference: generate.py)")
+        parser.add_argument("--b200-lazy-beam-reorder", action="store_true",
+                            help="with --b200-cross-attention: never replicate the encoder output "
+                                 "x beam (reorder_encoder_out returns tagged aliases)")
 
 
 for _name, _fn in (("conv_transformer_b200", _ref.base_architecture),

@@ -65,5 +65,17 @@ _def("ctc_compress(Tensor x, Tensor seg_id, Tensor seg_start, Tensor weight, Ten
      ops.ctc_compress(x, seg_id, seg_start, weight, lengths, new_len, max_new, L, B))
 _def("lengths_to_mask(Tensor lengths, int L) -> Tensor", lambda lengths, L: ops.lengths_to_mask(lengths, L)[0])
 
+
+def _xattn(q, kv, mask, row_map, tgt_len, H, weights):
+    S, U = kv.shape[0], kv.shape[1]
+    out, w = ops.xattn(q, kv, mask, row_map, S, U, row_map.numel(), tgt_len, H, weights=weights)
+    if w is None:
+        w = torch.empty(0, dtype=torch.float32, device=q.device)
+    return out, w
+
+
+_def("xattn(Tensor q, Tensor kv, Tensor? mask, Tensor row_map, int tgt_len, int H, int weights)"
+     " -> (Tensor, Tensor)", _xattn)
+
 OPS = ["cmvn", "conv1_relu_bn", "conv2_relu_bn", "linear", "layernorm", "attention", "ctc_argmax",
-       "ctc_segment", "ctc_compress", "lengths_to_mask"]
+       "ctc_segment", "ctc_compress", "lengths_to_mask", "xattn"]

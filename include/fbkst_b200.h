@@ -247,6 +247,27 @@ int fbkst_specaugment_f32(float* x, const int32_t* bands, int B, int T, int F, i
 int fbkst_time_stretch_f32(const float* x, const int32_t* windows, int n_windows, int32_t* ids,
                            float* out, int B, int T, int T_out, int F, fbkst_stream_t stream);
 
+/* ---- next row N4: decoder cross-attention over the compressed encoder output ---------------------
+ * fbkst_xattn_fwd replaces the static_kv path of fairseq/modules/multihead_attention.py:108-367 as the
+ * decoder layer calls it (fairseq/modules/transformer_layer.py:339-348) during incremental generation,
+ * together with the x beam replication of the encoder output (conv_transformer.py:315-345,
+ * fairseq/sequence_generator.py:193-198) and the per-step re-gather of the cached keys/values
+ * (multihead_attention.py:407-420): K/V are projected once per UTTERANCE and rows address them through
+ * row_map, so replication/reordering never copies K/V.
+ *   q        [tgt_len * bsz, D] bf16, row r = t * bsz + b, already scaled by head_dim^-0.5 (:209)
+ *   kv       [S, U, 2D] bf16 time-major: columns [0, D) = k_proj(encoder_out), [D, 2D) = v_proj(...)
+ *   key_padding_mask [U, S] uint8 (1 = padding key, :330-335) or NULL
+ *   row_map  [bsz] int32: utterance (0..U-1) of hypothesis row b; out-of-range -> zero output row
+ *   out      [tgt_len * bsz, D] bf16 (heads concatenated; input of out_proj, :353)
+ *   attn_w   w_mode 0: unused; 1: [bsz, tgt_len, S] fp32 averaged over heads (:355-362);
+ *            2: [H, bsz, tgt_len, S] fp32 per head (need_head_weights)
+ *   head_ws  w_mode 1 only: caller-owned scratch [H, bsz, tgt_len, S] fp32 (per-head weights; the
+ *            average is taken over it in a fixed order)
+ * D = 64 * H, H <= 16; 32 * S + 14.4 KB of shared memory must fit in 200 KB (S <= ~5900). */
+int fbkst_xattn_fwd(const void* q, const void* kv, const uint8_t* key_padding_mask,
+                    const int32_t* row_map, void* out, float* attn_w, float* head_ws, int w_mode,
+                    int S, int U, int bsz, int tgt_len, int H, fbkst_stream_t stream);
+
 /* ---- weight preparation (fp32 master parameters -> kernel operand formats) ----------------- */
 /* dst[i] = bf16(src[i] * scale) */
 int fbkst_cast_bf16(const float* src, void* dst, int64_t n, float scale, fbkst_stream_t stream);

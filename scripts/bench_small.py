@@ -82,3 +82,42 @@ labels, lse, _ = ops.ctc_argmax_lse(lg, lens, L, B, V)
 timeit("crit ctc_argmax_lse", lambda: ops.ctc_argmax_lse(lg, lens, L, B, V), L * B * V * 2 + L * B * 8)
 timeit("crit ctc_loss_fwd", lambda: ops.ctc_loss_fwd(lg, lse, lens, tgt, tlen, V - 1, L, B, V), L * B * (U + 1) * 2)
 timeit("crit ctc_uer", lambda: ops.ctc_uer(labels, lens, tgt, tlen, V - 1, L, B), L * B * 4)
+
+# next row N4: one decoder step of encoder-decoder attention at the cfg2 generate shape (64 utterances
+# x beam 5, compressed S = 95, D 512, H 8).  Algorithmic bytes = the UNIQUE K/V (S*U*2D bf16) + q + out;
+# the reference's per-hypothesis cache would move bsz*2*S*D fp32 for the same step (printed for scale).
+if not only or "xattn" in only:
+    for S_, U_, beam_, H_ in ((95, 64, 5, 8), (375, 64, 5, 8), (1500, 8, 5, 16)):
+        D_ = 64 * H_
+        bsz_ = U_ * beam_
+        q_ = torch.randn(bsz_, D_, device=d).bfloat16()
+        kv_ = torch.randn(S_, U_, 2 * D_, device=d).bfloat16()
+        rm_ = torch.arange(U_, device=d).repeat_interleave(beam_).int()
+        mk_ = (torch.arange(S_, device=d)[None, :] >= torch.randint(S_ // 2, S_ + 1, (U_, 1), device=d))
+        nb = kv_.numel() * 2 + q_.numel() * 4
+        timeit("xattn S=%d U=%d beam=%d H=%d" % (S_, U_, beam_, H_),
+               lambda: ops.xattn(q_, kv_, mk_, rm_, S_, U_, bsz_, 1, H_, weights=0), nb)
+        timeit("xattn + head-avg weights", lambda: ops.xattn(q_, kv_, mk_, rm_, S_, U_, bsz_, 1, H_, weights=1),
+               nb + bsz_ * S_ * 4 * (2 * H_ + 1))
+        if not only or "xattn" in only:
+            # decode re-reads the same K/V every step: the steady state is L2-resident, not cold
+            # (20 calls captured in one CUDA graph, so the host launch path is not what is timed)
+            ops.xattn(q_, kv_, mk_, rm_, S_, U_, bsz_, 1, H_, weights=0)
+            torch.cuda.synchronize()
+            gr_ = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr_):
+                for _ in range(20):
+                    o_ = ops.xattn(q_, kv_, mk_, rm_, S_, U_, bsz_, 1, H_, weights=0)
+            gr_.replay()
+            torch.cuda.synchronize()
+            s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s_.record()
+            for _ in range(5):
+                gr_.replay()
+            e_.record()
+            torch.cuda.synchronize()
+            w_us = s_.elapsed_time(e_) / 100 * 1e3
+            print("    warm (graph of 20 back-to-back steps, K/V L2-resident): %.1f us/step, %.0f GB/s of K/V" %
+                  (w_us, nb / w_us / 1e3))
+        print("    (reference cache traffic for the step: %.1f MB fp32; unique K/V here: %.1f MB bf16)" %
+              (bsz_ * 2 * S_ * D_ * 4 / 1e6, kv_.numel() * 2 / 1e6))
