@@ -306,7 +306,7 @@ def run_ours(args, rank, world, local_rank):
     if model["ctc_layer"] > 0:
         enc.ctc_fc.register_forward_hook(bump)
 
-    n_batches = 4
+    n_batches = 9  # rotating inputs: 9 x 15.4 MB = 138 MB > the 126 MB L2 (cfg2)
     host = [make_batch(lengths, Fd, 1234 + rank * 100 + i) for i in range(n_batches)]
     host = [(x.pin_memory(), l) for x, l in host]
     dev_batches = [(x.to(dev), l) for x, l in host]
@@ -321,6 +321,14 @@ def run_ours(args, rank, world, local_rank):
 
     from fbkst_b200.pipeline import EncoderPipeline
     pipe = EncoderPipeline(enc, normalize=True, device=dev)
+
+    def run_device(n):
+        """n steps with the batches already in HBM, through the same compute lanes as the host-buffer
+        API (CMVN + encoder forward per batch, `lanes` batches in flight)."""
+        last = None
+        for o in pipe.run_device(dev_batches[i % n_batches] for i in range(n)):
+            last = o
+        return last
 
     def run_e2e(n):
         """n steps through the public host-buffer API: pinned host batch -> H2D -> CMVN -> encoder
@@ -338,31 +346,39 @@ def run_ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank) if rank == 0 else None  # samples warm-up + timed regions
     for i in range(args.warmup):
         step_resident(i)
+    run_device(args.warmup)
     run_e2e(args.warmup)
     barrier()
 
-    # ---- timed region 1: inputs resident in HBM; L2 flushed (untimed) between steps
+    # ---- timed region 1: inputs resident in HBM, K steps back to back (throughput: `lanes` batches in
+    # flight); rotating inputs larger than L2, and every step streams > 1 GB of activations through it
     launches0 = ops.LAUNCHES
-    evs = []
     barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     wall0 = time.perf_counter()
-    for i in range(args.steps):
-        flush.fill_(i & 0xFF)
-        # untimed GPU-side delay: the host enqueues step i while the GPU is still busy here, so host
-        # launch latency / scheduling jitter (N processes + the clock sampler on one box) never sits
-        # inside an event pair; what the events bracket is device time of the step
-        torch.cuda._sleep(LOOKAHEAD_CYCLES)
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        out = step_resident(i)
-        e.record()
-        evs.append((s, e))
+    ev0.record()
+    out = run_device(args.steps)
+    ev1.record()
     barrier()
     wall = time.perf_counter() - wall0
     launches = (ops.LAUNCHES - launches0) // args.steps
-    step_ms = [s.elapsed_time(e) for s, e in evs]
-    dev_ms = sum(step_ms)
+    dev_ms = ev0.elapsed_time(ev1)
     new_frames = float(out.src_lengths.sum().item())
+
+    # ---- informative: ONE forward at a time, L2 flushed (256 MB write, untimed) before each and ~1 ms of
+    # untimed GPU-side delay so that the host enqueues the step while the GPU is still busy (no launch
+    # latency inside the event pair): the cold-cache latency of a single batch
+    evs = []
+    for i in range(min(args.steps, 10)):
+        flush.fill_(i & 0xFF)
+        torch.cuda._sleep(LOOKAHEAD_CYCLES)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        step_resident(i)
+        e.record()
+        evs.append((s, e))
+    barrier()
+    step_ms = [s.elapsed_time(e) for s, e in evs]
 
     # ---- timed region 2: end to end from pinned host buffers (H2D + D2H inside)
     barrier()
@@ -423,17 +439,26 @@ def run_ours(args, rank, world, local_rank):
                     frames_per_step_per_gpu=frames, vocab=model["vocab"],
                     ctc_logit_injection="run-structured labels (geometric mean 3, 50%% blank), margin %g" % CTC_MARGIN,
                     compression_ratio=round(new_frames / sum(((n + 1) // 2 + 1) // 2 for n in lengths), 3),
-                    cache="L2 flushed (256 MB write, untimed, + ~1 ms untimed GPU delay so the host stays ahead) "
-                          "between timed steps; 4 rotating input batches",
+                    cache="%d rotating input batches (%.0f MB in total vs the 126 MB L2) plus the activations "
+                          "every step streams through L2 (> 1 GB at cfg2); no flush inside the timed region "
+                          "(steps run back to back, %d in flight); single_forward_ms is the flushed, "
+                          "one-at-a-time figure"
+                          % (n_batches, n_batches * host[0][0].numel() * 4 / 1e6, pipe.lanes),
+                    compute_lanes=pipe.lanes,
                     launch="eager" if args.no_graph else "CUDA graph replay of the encoder body",
                     parallelism="utterance-batch sharded x%d, no forward collective" % world),
         e2e=dict(value=round(world * frames / (e2e_ms * 1e-3 / args.steps), 1), unit="frames/s",
                  h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                 ms_per_step=round(e2e_ms / args.steps, 4)),
+                 ms_per_step=round(e2e_ms / args.steps, 4),
+                 api="fbkst_b200.pipeline.EncoderPipeline.run (pinned host batches in, pinned host "
+                     "encoder_out + lengths out; wall clock over all steps incl. pipeline fill/drain)",
+                 compute_lanes=pipe.lanes),
         gpu_launches=launches, clocks=clocks, roofline=roofline, kernels=kern,
-        wall_ms_per_step_incl_flush=round(wall * 1e3 / args.steps, 4), impl="ours",
-        step_ms=dict(min=round(min(step_ms), 4), median=round(statistics.median(step_ms), 4),
-                     max=round(max(step_ms), 4), note="rank 0, CUDA events per step"))
+        wall_ms_per_step=round(wall * 1e3 / args.steps, 4), impl="ours",
+        single_forward_ms=dict(min=round(min(step_ms), 4), median=round(statistics.median(step_ms), 4),
+                               max=round(max(step_ms), 4),
+                               note="rank 0: one forward at a time, L2 flushed (256 MB write) before each, "
+                                    "CUDA events per step; not the throughput figure"))
     return result, enc
 
 

@@ -109,15 +109,17 @@ __device__ __forceinline__ float2 ex2_poly2(float2 x) {
   return p;
 }
 
-// Optional timeline of CTA 0 (debug only; null in production): rows of 8 x int64 per key tile of
+// Optional timeline of CTA 0 (debug only; null in production): rows of 16 x int64 per key tile of
 // the CTA's stream: [0] MMA: p_full seen  [1] MMA: PV issued  [2] MMA: QK(+2) issued
 // [3] softmax: s_full seen  [4] pass 1 done  [5] P/O free  [6] p_full arrive  [7] item epilogue done (last tile row)
+// [8] MMA: s_free seen (before QK(+2))  [9] MMA: k_full seen (row = the tile being QK'd)  [10] producer: K issued
+// [11] producer: V issued  [12] MMA: v_full seen
 // Compiled in only with -DFBKST_ATTN_TRACE (scripts/trace_attn.py); the hooks cost a few percent.
 __device__ long long* g_attn_trace = nullptr;
 #ifdef FBKST_ATTN_TRACE
 #define AT_TRACE(tile, slot)                                                         \
   do {                                                                               \
-    if (trace != nullptr && (tile) < 64) trace[(tile) * 8 + (slot)] = clock64();    \
+    if (trace != nullptr && (tile) < 64) trace[(tile) * 16 + (slot)] = clock64();    \
   } while (0)
 #else
 #define AT_TRACE(tile, slot) \
@@ -272,6 +274,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
             tma_load_3d(sK + ks * AT_KB, &tmKV, &k_full[ks], ck, ki.b, kj * AT_BN);
           }
           __syncwarp();
+          AT_TRACE(gk, 10);
           ++gk;
           if (++kj == ki.n_kv) {
             kj = 0;
@@ -287,6 +290,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
             tma_load_3d(sV + vs * AT_KB, &tmKV, &v_full[vs], cv, vi.b, vj * AT_BN);
           }
           __syncwarp();
+          AT_TRACE(gv, 11);
           ++gv;
           if (++vj == vi.n_kv) {
             vj = 0;
@@ -309,6 +313,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
         if (qk_j == 0) mbar_wait(q_full, nqk & 1);
         const uint32_t ks = gq % AT_KST;
         mbar_wait(&k_full[ks], (gq / AT_KST) & 1);
+        AT_TRACE(gq, 9);
         tc_fence_after();
         const uint64_t kdesc = desc_kmajor_sw128(smem_u32(sK + ks * AT_KB));
         const uint32_t d_tmem = tmem_base + (gq & 1) * AT_BN;
@@ -339,6 +344,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
         // PV-issue + QK-issue + MMA round trip (1500 of 4700 cycles per tile: profiles/r01c timeline).
         if (qk.w < n_items) {
           mbar_wait(&s_free[pb], ph);
+          AT_TRACE(gp, 8);
           tc_fence_after();
           issue_qk();
         }
@@ -346,6 +352,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
         mbar_wait(&p_full[pb], ph);  // P[pb] in smem, O[pb] rescaled / read out
         AT_TRACE(gp, 0);
         mbar_wait(&v_full[pb], ph);
+        AT_TRACE(gp, 12);
         tc_fence_after();
         const uint32_t pa = smem_u32(sP + pb * AT_QB), va = smem_u32(sV + pb * AT_KB);
         if (elect_one()) {

@@ -242,6 +242,11 @@ def make_encoder_class(base):
             # opt-in: replay one captured CUDA graph per input shape instead of ~90 launches
             self.use_cuda_graph = False
             self._graphs = {}
+            # graphs (and the activations they own) are per lane: EncoderPipeline keeps one forward in
+            # flight per lane/stream and sets this before every launch
+            self.graph_lane = 0
+            self._len_pins = {}  # B -> ring of pinned int32 vectors for the new lengths (launch/finish)
+            self._len_pin_next = 0
 
         # ------------------------------------------------------------------ derived operand formats
         def _prepared(self):
@@ -312,6 +317,30 @@ def make_encoder_class(base):
                 return self._forward(src_tokens, src_lengths, return_all_hiddens)
 
         def _forward(self, src_tokens, src_lengths, return_all_hiddens):
+            return self._finish(self._launch(src_tokens, src_lengths, return_all_hiddens))
+
+        # The forward is split where its single host synchronisation sits: ``_launch`` enqueues every
+        # kernel (and, after CTC compression, an async copy of the new lengths into pinned memory),
+        # ``_finish`` waits for that copy and cuts the worst-case buffers to the exact output shape.
+        # ``forward`` runs both back to back; ``EncoderPipeline`` puts the next batch's ``_launch``
+        # between them so the GPU never waits for the host.
+        def launch(self, src_tokens, src_lengths):
+            """Asynchronous half of ``forward`` (inference, no hidden states): returns a handle for
+            ``finish``.  Buffers owned by a CUDA graph (``ctc_out``) stay valid until the next launch
+            with the same input shape on the same ``graph_lane``."""
+            if self.training and torch.is_grad_enabled():
+                raise NotImplementedError("fbkst_b200: training backward not implemented (see forward)")
+            if not src_tokens.is_cuda:
+                raise RuntimeError("fbkst_b200: src_tokens must be a CUDA tensor (no CPU fallback)")
+            with torch.no_grad():
+                return self._launch(src_tokens, src_lengths, False)
+
+        def finish(self, handle):
+            """Blocking half of ``forward``: the reference's output tuple for a ``launch`` handle."""
+            with torch.no_grad():
+                return self._finish(handle)
+
+        def _launch(self, src_tokens, src_lengths, return_all_hiddens):
             dev = src_tokens.device
             B, T, Fd = src_tokens.shape
             x_in = src_tokens if src_tokens.dtype == torch.float32 else src_tokens.float()
@@ -319,7 +348,6 @@ def make_encoder_class(base):
             # lengths: one host copy drives all shape logic (the reference syncs per utterance)
             len_host = src_lengths.tolist() if not src_lengths.is_cuda else src_lengths.cpu().tolist()
             len_host = [((n + 1) // 2 + 1) // 2 for n in len_host]  # ceil(ceil(n/2)/2), :213
-            D = self.embed_dim
             L = ((T + 1) // 2 + 1) // 2
             for _ in range(self.num_layers):
                 torch.empty(1).uniform_()  # LayerDrop draws: keep the CPU RNG stream of the reference
@@ -339,21 +367,40 @@ def make_encoder_class(base):
                 len_host, L = r["len_host"], r["L"]
                 mask = r["mask2"] if min(len_host) < L else None
             xf = ops.layernorm(x, *self._prepared()["lnf"], out_dtype=torch.float32, rows_limit=limit)
+            h = dict(xf=xf, mask=mask, ctc_mask=ctc_mask, states=states, len_host=len_host, L=L, B=B,
+                     x_ctc=r["x_ctc"], src_tokens=src_tokens, len_dtype=src_lengths.dtype, dev=dev,
+                     return_all_hiddens=return_all_hiddens, deferred=limit is not None)
             if limit is not None:
-                mask_full = ops.lengths_to_mask(new_len, L)[0]
-                len_host = new_len.cpu().tolist()  # the single host sync of the forward
+                h["mask_full"] = ops.lengths_to_mask(new_len, L)[0]
+                pin = self._len_pins.get(B)
+                if pin is None:
+                    pin = self._len_pins[B] = [torch.empty(B, dtype=torch.int32).pin_memory()
+                                               for _ in range(8)]
+                self._len_pin_next = (self._len_pin_next + 1) % len(pin)
+                h["new_len_pin"] = pin[self._len_pin_next]
+                h["new_len_pin"].copy_(new_len, non_blocking=True)
+                h["ev"] = torch.cuda.Event()
+                h["ev"].record()
+            return h
+
+        def _finish(self, h):
+            xf, mask, states, len_host, L, B = h["xf"], h["mask"], h["states"], h["len_host"], h["L"], h["B"]
+            D, dev = self.embed_dim, h["dev"]
+            if h["deferred"]:
+                h["ev"].synchronize()  # the single host sync of the forward
+                len_host = h["new_len_pin"].tolist()
                 L2 = max(len_host)
                 xf = xf[: L2 * B]
-                mask = None if min(len_host) >= L2 else mask_full[:, :L2].contiguous()
+                mask = None if min(len_host) >= L2 else h["mask_full"][:, :L2].contiguous()
                 L = L2
             xf = xf.view(L, B, D)
-            if return_all_hiddens:
+            if h["return_all_hiddens"]:
                 states[-1] = xf
-            out_lengths = torch.tensor(len_host, dtype=src_lengths.dtype).to(dev, non_blocking=True)
+            out_lengths = torch.tensor(len_host, dtype=h["len_dtype"]).to(dev, non_blocking=True)
             if self.ctc_compress_out:
-                return CTCAwareEncoderOut(xf, mask, None, states, src_tokens, out_lengths, r["x_ctc"],
-                                          ctc_mask)
-            return EncoderOut(xf, mask, None, states, src_tokens, out_lengths)
+                return CTCAwareEncoderOut(xf, mask, None, states, h["src_tokens"], out_lengths, h["x_ctc"],
+                                          h["ctc_mask"])
+            return EncoderOut(xf, mask, None, states, h["src_tokens"], out_lengths)
 
         def _body(self, P, x_in, lengths, len_host, L, B, want_states, ws):
             """Everything between the input batch and the final LayerNorm.  Shape-static when
@@ -441,7 +488,7 @@ def make_encoder_class(base):
         # ------------------------------------------------------------------------- CUDA graphs
         def _graph_key(self, B, T, Fd, dev):
             hooks = tuple(sorted(self.ctc_fc._forward_hooks)) if self.ctc_compress_out else ()
-            return (B, T, Fd, str(dev), self._prep_key, hooks)
+            return (B, T, Fd, str(dev), self._prep_key, hooks, self.graph_lane)
 
         def _replay(self, x_in, len_host, B, T, Fd, L):
             """Graph mode (``use_cuda_graph``): the ~90 launches of ``_body`` for one input shape are
@@ -458,8 +505,12 @@ def make_encoder_class(base):
                     self._graphs.pop(next(iter(self._graphs)))
                 G = self._capture(P, B, T, Fd, L, dev)
                 self._graphs[key] = G
-            G["len_pin"].copy_(torch.tensor(len_host, dtype=torch.int32))
-            G["lengths"].copy_(G["len_pin"], non_blocking=True)
+            # ring of pinned staging vectors: with ``launch``/``finish`` the host runs ahead of the
+            # GPU, so a staging vector is not rewritten before 7 later launches have been enqueued
+            G["pin_next"] = (G["pin_next"] + 1) % len(G["len_pin"])
+            pin = G["len_pin"][G["pin_next"]]
+            pin.copy_(torch.tensor(len_host, dtype=torch.int32))
+            G["lengths"].copy_(pin, non_blocking=True)
             G["x"].copy_(x_in, non_blocking=True)
             G["graph"].replay()
             ops._count(G["launches"])
@@ -469,7 +520,8 @@ def make_encoder_class(base):
             compress = self.ctc_compress_out and 0 < self.ctc_layer <= self.num_layers
             G = dict(x=torch.zeros(B, T, Fd, dtype=torch.float32, device=dev),
                      lengths=torch.full((B,), L, dtype=torch.int32, device=dev),
-                     len_pin=torch.empty(B, dtype=torch.int32).pin_memory(), P=P,
+                     len_pin=[torch.empty(B, dtype=torch.int32).pin_memory() for _ in range(8)],
+                     pin_next=0, P=P,
                      ws=self._make_workspace(L * B, dev) if compress else None)
             side = torch.cuda.Stream(dev)
             side.wait_stream(torch.cuda.current_stream(dev))
@@ -496,12 +548,14 @@ def make_encoder_class(base):
                         st=torch.zeros(M, (D + 127) // 128, 2, dtype=torch.float32, device=dev))
 
         def _workspace(self, M, dev):
-            """The eager path keeps one workspace (for the last shape seen)."""
+            """The eager path keeps one workspace per lane (for the last shape seen on it)."""
             key = (M, str(dev))
-            if self._ws_key != key:
-                self._ws = self._make_workspace(M, dev)
-                self._ws_key = key
-            return self._ws
+            if self._ws is None:
+                self._ws = {}
+            got = self._ws.get(self.graph_lane)
+            if got is None or got[0] != key:
+                got = self._ws[self.graph_lane] = (key, self._make_workspace(M, dev))
+            return got[1]
 
         def _ctc_compress(self, x, lengths, L, B, out=None):
             """conv_transformer.py:278-291 on device.  With ``out`` (workspace mode) nothing is read

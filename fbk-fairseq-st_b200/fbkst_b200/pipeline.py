@@ -1,9 +1,18 @@
 """Host-buffer serving loop for the encoder: the public end-to-end entry point.
 
 ``EncoderPipeline.run`` takes batches that live in (pinned) HOST memory and returns encoder outputs in
-HOST memory.  Three CUDA streams overlap the host->device copy of batch i+1, the kernels of batch i
-(fbank CMVN + encoder forward) and the device->host copy of batch i-1; all arithmetic still happens
-in the sm_100a kernels, PyTorch only moves bytes and orders streams.
+HOST memory.  All arithmetic happens in the sm_100a kernels; PyTorch only moves bytes and orders
+streams:
+
+  * one copy-in stream (pinned host batch -> device), one copy-out stream (result -> pinned host);
+  * ``lanes`` compute streams.  Batch i runs on lane ``i % lanes`` (fbank CMVN + encoder forward; each
+    lane replays its own CUDA graph, so it owns its activations).  Every kernel of the forward is a
+    persistent grid of one CTA (pair) per SM whose last wave leaves SMs idle; with two batches in
+    flight the CTAs of one lane's kernel start on the SMs the other lane's kernel has already left
+    (measured at cfg2: 2.70 -> 2.58 ms/step, profiles/r01g_overlap_probe.txt);
+  * the forward is used through its asynchronous half (``encoder.launch``): the host never waits for
+    batch i before batch i+1 .. i+lanes are enqueued, so the only host synchronisation of the forward
+    (the new lengths after CTC compression, needed for the output SHAPE) is hidden behind queued work.
 
 The per-batch work is exactly ``apply_mv_norm`` (data/fbank_dataset.py:44-45) followed by
 ``ConvolutionalTransformerEncoder.forward`` (models/conv_transformer.py:195-276).
@@ -16,16 +25,22 @@ from . import ops
 
 
 class EncoderPipeline:
-    def __init__(self, encoder, normalize=True, device=None):
+    def __init__(self, encoder, normalize=True, device=None, lanes=2):
         self.enc = encoder
         self.normalize = normalize
         self.device = device or next(encoder.parameters()).device
+        # eager launches share lazily created tables across lanes: keep one lane unless graphs are on
+        self.lanes = max(1, int(lanes)) if encoder.use_cuda_graph else 1
         self.s_in = torch.cuda.Stream(self.device)
-        self.s_compute = torch.cuda.Stream(self.device)
+        self.s_lane = [torch.cuda.Stream(self.device) for _ in range(self.lanes)]
         self.s_out = torch.cuda.Stream(self.device)
         self._dev_in = {}    # (slot, shape) -> device staging buffer
-        self._host_out = {}  # (slot, shape) -> pinned host buffer
-        self._busy = [None, None]  # event: compute finished reading input slot
+        self._host_out = {}  # (slot, shape, dtype) -> pinned host buffer
+        self._n_in = self.lanes + 2
+        self._consumed = [None] * self._n_in  # event: CMVN / encoder finished reading input slot
+        with torch.cuda.device(self.device):
+            encoder._prepared()  # derive the operand formats once, before any lane uses them
+            torch.cuda.synchronize(self.device)
 
     def _in_buffer(self, slot, shape):
         key = (slot, tuple(shape))
@@ -39,59 +54,94 @@ class EncoderPipeline:
             self._host_out[key] = torch.empty(shape, dtype=dtype).pin_memory()
         return self._host_out[key]
 
+    def _enqueue(self, i, batch):
+        """H2D of batch i on the copy-in stream, then CMVN + the asynchronous half of the forward on
+        lane i % lanes.  Nothing here waits on the host."""
+        x_host, lengths = batch
+        slot = i % self._n_in
+        if x_host.is_cuda:  # device-resident batch (run_device): nothing to stage
+            buf, ev_in = x_host, None
+        else:
+            buf = self._in_buffer(slot, x_host.shape)
+            with torch.cuda.stream(self.s_in):
+                if self._consumed[slot] is not None:
+                    self.s_in.wait_event(self._consumed[slot])
+                buf.copy_(x_host, non_blocking=True)
+                ev_in = torch.cuda.Event()
+                ev_in.record(self.s_in)
+        lane = i % self.lanes
+        s = self.s_lane[lane]
+        with torch.cuda.stream(s):
+            if ev_in is not None:
+                s.wait_event(ev_in)
+            if self.normalize:
+                len32 = lengths.to(torch.int32).to(self.device, non_blocking=True)
+                x = ops.cmvn(buf, len32)
+            else:
+                x = buf
+            self.enc.graph_lane = lane
+            try:
+                handle = self.enc.launch(x, lengths)
+            finally:
+                self.enc.graph_lane = 0
+            ev_done = torch.cuda.Event()
+            ev_done.record(s)
+        self._consumed[slot] = ev_done
+        return handle, ev_done
+
+    def _collect(self, j, handle, ev_done, to_host=True):
+        """Blocking half for batch j: exact output shape, D2H on the copy-out stream, wait for it."""
+        if not to_host:
+            # hand the result over to the caller's stream (ordered after batch j, not after the
+            # batches queued behind it on the lane)
+            self._caller.wait_event(ev_done)
+            with torch.cuda.stream(self._caller):
+                out = self.enc.finish(handle)
+            for t in (out.encoder_out, out.encoder_padding_mask, getattr(out, "ctc_padding_mask", None)):
+                if t is not None:
+                    t.record_stream(self._caller)  # allocated on the lane's stream
+            return out
+        with torch.cuda.stream(self.s_out):
+            # waits for the new lengths of batch j; the batches queued behind it keep the GPU busy
+            out = self.enc.finish(handle)
+            self.s_out.wait_event(ev_done)
+            eo = out.encoder_out
+            host = self._out_buffer(j & 1, eo.shape, eo.dtype)
+            host.copy_(eo, non_blocking=True)
+            ev_out = torch.cuda.Event()
+            ev_out.record(self.s_out)
+        if handle["deferred"]:
+            hl = handle["new_len_pin"].to(handle["len_dtype"])  # already on the host
+        else:
+            hl = torch.tensor(handle["len_host"], dtype=handle["len_dtype"])
+        ev_out.synchronize()
+        return host, hl
+
     def run(self, batches):
         """``batches``: iterable of ``(src_tokens [B,T,F] fp32 host tensor, src_lengths [B] int64 host
         tensor)``.  Yields ``(encoder_out [T'',B,D] fp32 host tensor, out_lengths [B] host tensor)`` in
-        order.  A yielded tensor is a view of a reusable pinned buffer: consume it before asking for
-        the batch after next."""
-        pending = collections.deque()
-        staged = None
-        it = iter(batches)
+        order.  A yielded ``encoder_out`` is a view of a reusable pinned buffer: consume it before
+        asking for the batch after next."""
+        return self._run(batches, True)
 
-        def stage(i, batch):
-            x_host, lengths = batch
-            buf = self._in_buffer(i & 1, x_host.shape)
-            with torch.cuda.stream(self.s_in):
-                if self._busy[i & 1] is not None:
-                    self.s_in.wait_event(self._busy[i & 1])
-                buf.copy_(x_host, non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(self.s_in)
-            return buf, lengths, ev
+    def run_device(self, batches):
+        """Same loop for batches that already live on the device: yields the encoder's output tuples
+        (device tensors, usable on the caller's current stream).  ``ctc_out`` aliases a buffer of the lane's CUDA
+        graph: it is valid until ``lanes`` more batches of the same shape have been yielded."""
+        return self._run(batches, False)
 
-        i = 0
-        first = next(it, None)
-        if first is None:
-            return
-        staged = stage(0, first)
-        while staged is not None:
-            x_dev, lengths, ev_in = staged
-            nxt = next(it, None)
-            staged = stage(i + 1, nxt) if nxt is not None else None  # H2D(i+1) overlaps compute(i)
-            with torch.cuda.stream(self.s_compute):
-                self.s_compute.wait_event(ev_in)
-                len32 = lengths.to(torch.int32).to(self.device, non_blocking=True)
-                x = ops.cmvn(x_dev, len32) if self.normalize else x_dev
-                out = self.enc(x, lengths)
-                ev_done = torch.cuda.Event()
-                ev_done.record(self.s_compute)
-            self._busy[i & 1] = ev_done
-            with torch.cuda.stream(self.s_out):
-                self.s_out.wait_event(ev_done)
-                eo = out.encoder_out
-                host = self._out_buffer(i & 1, eo.shape, eo.dtype)
-                host.copy_(eo, non_blocking=True)
-                hl = self._out_buffer(i & 1, out.src_lengths.shape, out.src_lengths.dtype)
-                hl.copy_(out.src_lengths, non_blocking=True)
-                ev_out = torch.cuda.Event()
-                ev_out.record(self.s_out)
-            pending.append((ev_out, host, hl, out))
-            if len(pending) > 1:  # D2H(i-1) has been overlapping compute(i)
-                e, h, l, _keep = pending.popleft()
-                e.synchronize()
-                yield h, l
-            i += 1
-        while pending:
-            e, h, l, _keep = pending.popleft()
-            e.synchronize()
-            yield h, l
+    def _run(self, batches, to_host):
+        caller = self._caller = torch.cuda.current_stream(self.device)
+        for s in self.s_lane:
+            s.wait_stream(caller)
+        inflight = collections.deque()
+        for i, batch in enumerate(batches):
+            inflight.append((i,) + self._enqueue(i, batch))
+            if len(inflight) > self.lanes:  # batches i-lanes+1 .. i stay queued behind this wait
+                j, handle, ev_done = inflight.popleft()
+                yield self._collect(j, handle, ev_done, to_host)
+        while inflight:
+            j, handle, ev_done = inflight.popleft()
+            yield self._collect(j, handle, ev_done, to_host)
+        for s in self.s_lane:
+            caller.wait_stream(s)

@@ -17,14 +17,15 @@ qkv = (torch.randn(L * B, 3 * H * 64, device=d) * 0.7).bfloat16()
 lengths = torch.full((B,), L, dtype=torch.int32, device=d)
 for _ in range(3):
     ops.attention(qkv, lengths, L, B, H, True)
-buf = torch.zeros(64 * 8, dtype=torch.int64, device=d)
+buf = torch.zeros(64 * 16, dtype=torch.int64, device=d)
 assert lib.fbkst_debug_set_attention_trace(buf.data_ptr()) == 0
 ops.attention(qkv, lengths, L, B, H, True)
 torch.cuda.synchronize()
 lib.fbkst_debug_set_attention_trace(None)
-t = buf.view(64, 8).cpu()
+t = buf.view(64, 16).cpu()[:, :13]
 t0 = int(t[t > 0].min())
-names = ["mma:p_full", "mma:PV", "mma:QK+2", "sm:s_full", "sm:pass1", "sm:PO_free", "sm:arrive", "-"]
+names = ["mma:p_full", "mma:PV", "mma:QK+2", "sm:s_full", "sm:pass1", "sm:PO_free", "sm:arrive", "epilogue",
+         "mma:s_free", "mma:k_full", "tma:K", "tma:V", "mma:v_full"]
 print("tile " + " ".join("%11s" % n for n in names))
 for i in range(40):
     print("%4d " % i + " ".join("%11d" % (int(v) - t0 if v > 0 else -1) for v in t[i]))

@@ -113,14 +113,17 @@ def test_training_mode_raises(golden_dir):
         enc(fx["src_tokens"].cuda(), fx["src_lengths"].cuda())
 
 
-def test_pipeline_matches_direct_calls(golden_dir):
-    """The host-buffer serving loop (3 streams) returns exactly what direct calls return."""
+@pytest.mark.parametrize("graph,lanes", [(False, 1), (True, 1), (True, 2), (True, 3)])
+def test_pipeline_matches_direct_calls(golden_dir, graph, lanes):
+    """The host-buffer serving loop (copy-in / compute lanes / copy-out streams, asynchronous
+    launch + deferred finish) returns exactly what direct calls return."""
     from fbkst_b200 import ops
     from fbkst_b200.pipeline import EncoderPipeline
     fx = torch.load(os.path.join(golden_dir, "enc_tiny_log.pt"), weights_only=False)
     enc = build_encoder(fx["cfg"], fx["state_dict"])
     batches = []
-    for i, lens in enumerate([[61, 47, 30], [90, 90], [33, 20, 20, 7], [61, 47, 30]]):
+    for i, lens in enumerate([[61, 47, 30], [90, 90], [33, 20, 20, 7], [61, 47, 30], [61, 40, 33],
+                              [61, 61, 61], [90, 12], [90, 90], [33, 31, 20, 9]]):
         x, l = O.synthetic_batch(lens, 40, seed=50 + i)
         batches.append(((x * 2 + 1).pin_memory(), l))
     direct = []
@@ -128,12 +131,24 @@ def test_pipeline_matches_direct_calls(golden_dir):
         xn = ops.cmvn(x.cuda(), l.to(torch.int32).cuda())
         o = enc(xn, l)
         direct.append((o.encoder_out.cpu(), o.src_lengths.cpu()))
-    pipe = EncoderPipeline(enc)
+    enc.use_cuda_graph = graph
+    pipe = EncoderPipeline(enc, lanes=lanes)
+    assert pipe.lanes == lanes
     got = [(h.clone(), l.clone()) for h, l in pipe.run(iter(batches))]
-    assert len(got) == len(direct)
-    for (a, la), (b, lb) in zip(got, direct):
+    got += [(h.clone(), l.clone()) for h, l in pipe.run(iter(batches))]  # second pass: cached graphs
+    assert len(got) == 2 * len(direct)
+    for (a, la), (b, lb) in zip(got, direct + direct):
         assert torch.equal(la, lb)
         assert torch.equal(a, b)
+    # device-resident batches through the same lanes
+    resident = [(ops.cmvn(x.cuda(), l.to(torch.int32).cuda()), l) for x, l in batches]
+    pipe_dev = EncoderPipeline(enc, normalize=False, lanes=lanes)
+    outs = [(o.encoder_out.clone(), o.src_lengths.clone()) for o in pipe_dev.run_device(iter(resident))]
+    torch.cuda.synchronize()
+    assert len(outs) == len(direct)
+    for (a, la), (b, lb) in zip(outs, direct):
+        assert torch.equal(la.cpu(), lb)
+        assert torch.equal(a.cpu(), b)
 
 
 def test_cuda_graph_mode_is_bit_identical():
