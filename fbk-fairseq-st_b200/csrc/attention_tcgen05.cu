@@ -29,6 +29,7 @@
 //   warps 2-5  softmax group 0 (even tiles of the CTA's tile stream), TMEM lane quarter = warp % 4
 //   warps 6-9  softmax group 1 (odd tiles)
 #include <math.h>
+#include <stdlib.h>
 
 #include "host_common.h"
 #include "ptx.cuh"
@@ -602,6 +603,440 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
   }
 }
 
+
+// =====================================================================================================
+// Decoupled variant (EXPERIMENT, off by default: FBKST_ATTN_DEC=1 selects it when two of its CTAs fit
+// an SM): the two softmax warpgroups of a CTA own DIFFERENT work items (group g takes items g, g+2,
+// g+4, ... of the CTA's list) instead of the even / odd key tiles of one item.  Hypothesis
+// (profiles/r01g_attention_timeline.txt): with split-KV the two groups start every item in lock step,
+// the item ends with a cross-group merge (two named barriers, both O buffers read by both groups) and
+// the faster group idles until the slower one has finished -- 5-6 k of the 14.5 k cycles of an item.
+// Here a group runs pass 1 / exp pass / its own 64-column epilogue back to back and never waits for
+// the other group; the only shared resources are the TMA warp and the MMA-issuing thread (both walk
+// the two groups' tile streams in the same fixed interleaved order, so a 3-slot K ring and the
+// single-buffered S / P / V / O of a group stay valid exactly as before).  Costs one more Q buffer.
+// MEASURED (profiles/r01g_attention_decoupled_ab.txt): parity green, but NOT faster -- cfg2 L=375
+// 62.5 vs 61.4 us, L=110 20.5 vs 18.4 us.  The timeline shows why: a group's tile period is ~4000
+// cycles of which the exp pass is 2100-2600 although on average only ~2.3 of the 4 groups of an SM
+// are in their exp pass (MUFU-throughput-bound would be ~1200): each softmax warp issues one
+// instruction per ~8 cycles (fixed-latency dependencies, 96-register cap -> little ILP), and the
+// group then waits 1300-1800 cycles for S of its next tile because the s_free -> QK -> s_full round
+// trip (~1500 cycles through the one in-order MMA thread) is longer than the half pass it is given.
+// The boundary idling it removes is replaced by that wait; the fix is ILP per softmax thread (S
+// row held in registers, 1 CTA/SM with 200+ registers), not more decoupling.
+constexpr int ATD_SMEM_FIXED = 2 * AT_QB + AT_KST * AT_KB + 2 * AT_KB + 2 * AT_QB /*P x2*/ +
+                               256 /*barriers*/ + 64 * 16 /*item table*/ + 1024 /*align*/;
+static inline int attention_dec_smem_bytes(int L) { return ATD_SMEM_FIXED + 4 * attention_lut_floats(L); }
+
+// Tile stream of one softmax group: items k = grp, grp + 2, ... of the CTA's list, key tiles in order.
+struct GrpCursor {
+  AttnItem it;
+  int k, j;      // index in the CTA's item list, key tile inside the item
+  uint32_t c, n; // tiles / items of this group before the current one
+  __device__ __forceinline__ void seek(const AttnList& items) {  // first item at or after k with work
+    for (;; k += 2) {
+      items.get(it, k);
+      if (it.w >= items.n_items || it.n_kv > 0) return;
+    }
+  }
+  __device__ __forceinline__ void init(const AttnList& items, int grp) {
+    k = grp; j = 0; c = 0; n = 0;
+    seek(items);
+  }
+  __device__ __forceinline__ bool valid(int n_items) const { return it.w < n_items; }
+  __device__ __forceinline__ void advance(const AttnList& items) {
+    ++c;
+    if (++j == it.n_kv) {
+      j = 0; ++n; k += 2;
+      seek(items);
+    }
+  }
+};
+
+template <int LOGPEN>
+__global__ void __launch_bounds__(AT_THREADS, 2)
+    attention_fwd_dec_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                             __nv_bfloat16* __restrict__ out, const int* __restrict__ lengths, int L, int B,
+                             int H) {
+  const int D = H * AT_HD;
+  const int nq = (L + AT_BM - 1) / AT_BM;
+  const int n_items = nq * B * H;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+#ifdef FBKST_ATTN_TRACE
+  long long* trace = (blockIdx.x == 0 && (lane == 0)) ? g_attn_trace : nullptr;
+#endif
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sQ = smem;                  // 2 x 16 KB: one per group
+  uint8_t* sK = sQ + 2 * AT_QB;        // AT_KST stages, shared by both groups (fixed interleaved order)
+  uint8_t* sV = sK + AT_KST * AT_KB;   // one per group
+  uint8_t* sP = sV + 2 * AT_KB;        // one per group
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * AT_QB);
+  int4* sItems = reinterpret_cast<int4*>(bars + 32);
+  float* sLut = reinterpret_cast<float*>(sItems + AT_TABLE);
+  uint64_t* q_full = bars + 0;    // [2]
+  uint64_t* q_empty = bars + 2;   // [2]
+  uint64_t* k_full = bars + 4;    // [3]
+  uint64_t* k_empty = bars + 7;   // [3]
+  uint64_t* v_full = bars + 10;   // [2]
+  uint64_t* v_empty = bars + 12;  // [2]
+  uint64_t* s_full = bars + 14;   // [2]
+  uint64_t* p_full = bars + 16;   // [2]
+  uint64_t* pv_done = bars + 18;  // [2]
+  uint64_t* s_free = bars + 20;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
+    for (int s = 0; s < AT_KST; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&q_full[s], 1);
+      mbar_init(&q_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+      mbar_init(&s_full[s], 1);
+      mbar_init(&p_full[s], 128);
+      mbar_init(&pv_done[s], 1);
+      mbar_init(&s_free[s], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  pdl_launch_dependents();
+  pdl_wait();
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + AT_TABLE) {
+    const int w = blockIdx.x + (threadIdx.x - 64) * gridDim.x;
+    if (w < n_items) sItems[threadIdx.x - 64] = attn_decode_raw(w, lengths, L, H, nq);
+  }
+  const AttnList items{sItems, lengths, L, H, nq, n_items};
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_O = tmem_base + 128;  // S[0] +0, S[1] +64, O[0] +128, O[1] +192
+
+  // Fixed interleaved order of the two groups' tile streams (identical in the TMA warp and the MMA
+  // warp): take the group whose turn it is, or the other one when that stream is exhausted; the turn
+  // flips after every tile.
+#define ATD_PICK(c0, c1, turn) (((turn) == 0) ? ((c0).valid(n_items) ? 0 : 1) : ((c1).valid(n_items) ? 1 : 0))
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    GrpCursor kc0, kc1, vc0, vc1;
+    kc0.init(items, 0); kc1.init(items, 1); vc0.init(items, 0); vc1.init(items, 1);
+    int kturn = 0, vturn = 0;
+    uint32_t gk = 0, gv = 0;
+    auto load_k = [&](GrpCursor& c, int g) {
+      const int cq = c.it.h * AT_HD, ck = D + cq;
+      if (c.j == 0) {
+        mbar_wait(&q_empty[g], (c.n & 1) ^ 1);  // every QK of the group's previous item has completed
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&q_full[g], AT_QB);
+          tma_load_3d(sQ + g * AT_QB, &tmQ, &q_full[g], cq, c.it.b, c.it.q0);
+        }
+        __syncwarp();
+      }
+      const uint32_t ks = gk % AT_KST;
+      mbar_wait(&k_empty[ks], ((gk / AT_KST) & 1) ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&k_full[ks], AT_KB);
+        tma_load_3d(sK + ks * AT_KB, &tmKV, &k_full[ks], ck, c.it.b, c.j * AT_BN);
+      }
+      __syncwarp();
+      ++gk;
+      c.advance(items);
+    };
+    auto load_v = [&](GrpCursor& c, int g) {
+      const int cv = 2 * D + c.it.h * AT_HD;
+      mbar_wait(&v_empty[g], (c.c & 1) ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&v_full[g], AT_KB);
+        tma_load_3d(sV + g * AT_KB, &tmKV, &v_full[g], cv, c.it.b, c.j * AT_BN);
+      }
+      __syncwarp();
+      ++gv;
+      c.advance(items);
+    };
+    for (;;) {
+      const bool k_left = kc0.valid(n_items) || kc1.valid(n_items);
+      const bool v_left = vc0.valid(n_items) || vc1.valid(n_items);
+      if (!k_left && !v_left) break;
+      if (k_left) {
+        if (ATD_PICK(kc0, kc1, kturn) == 0) load_k(kc0, 0); else load_k(kc1, 1);
+        kturn ^= 1;
+      }
+      if (v_left && (gk >= gv + 3 || !(kc0.valid(n_items) || kc1.valid(n_items)))) {
+        if (ATD_PICK(vc0, vc1, vturn) == 0) load_v(vc0, 0); else load_v(vc1, 1);
+        vturn ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t IDESC_QK = idesc_bf16_f32(AT_BM, AT_BN, 0, 0);
+    constexpr uint32_t IDESC_PV = idesc_bf16_f32(AT_BM, AT_HD, 0, 1);
+    GrpCursor qc0, qc1, pc0, pc1;
+    qc0.init(items, 0); qc1.init(items, 1); pc0.init(items, 0); pc1.init(items, 1);
+    int qturn = 0, pturn = 0;
+    uint32_t gq = 0;
+    // QK of the next tile of the QK order into S[g]; the caller has made sure S[g] is free
+    auto issue_qk = [&](GrpCursor& c, int g) {
+      if (c.j == 0) mbar_wait(&q_full[g], c.n & 1);
+      const uint32_t ks = gq % AT_KST;
+      mbar_wait(&k_full[ks], (gq / AT_KST) & 1);
+      tc_fence_after();
+      const uint64_t qdesc = desc_kmajor_sw128(smem_u32(sQ + g * AT_QB));
+      const uint64_t kdesc = desc_kmajor_sw128(smem_u32(sK + ks * AT_KB));
+      const uint32_t d_tmem = tmem_base + g * AT_BN;
+      const bool last = c.j + 1 == c.it.n_kv;
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < AT_HD / 16; ++k)
+          umma_bf16_ss(d_tmem, qdesc + 2 * k, kdesc + 2 * k, IDESC_QK, k != 0);
+        umma_commit(&s_full[g]);
+        umma_commit(&k_empty[ks]);
+        if (last) umma_commit(&q_empty[g]);  // Q[g] may be overwritten once these MMAs have completed
+      }
+      __syncwarp();
+      ++gq;
+      c.advance(items);
+    };
+    auto next_qk = [&]() {  // issue the next element of the QK order
+      if (ATD_PICK(qc0, qc1, qturn) == 0) issue_qk(qc0, 0); else issue_qk(qc1, 1);
+      qturn ^= 1;
+    };
+    // prologue: the first tile of each group (S[0] and S[1] are free)
+    if (qc0.valid(n_items) || qc1.valid(n_items)) next_qk();
+    {
+      // the second element is the other group's first tile unless that group has no work at all
+      const bool other_first = (qc0.valid(n_items) && qc0.c == 0) || (qc1.valid(n_items) && qc1.c == 0);
+      if (other_first) next_qk();
+    }
+    auto issue_pv = [&](GrpCursor& c, GrpCursor& qc, int g) {
+      const uint32_t ph = c.c & 1;
+      // QK of this group's NEXT tile first: S[g] is free as soon as the group has pulled S(c) into
+      // registers (half way through its exp pass), long before P(c) is complete.  By construction of
+      // the order that tile is the next element of the QK order iff it exists.
+      if (qc.valid(n_items) && qc.c == c.c + 1) {
+        mbar_wait(&s_free[g], ph);
+        tc_fence_after();
+        next_qk();
+      }
+      mbar_wait(&p_full[g], ph);  // P[g] in smem, O[g] rescaled / read out
+      mbar_wait(&v_full[g], ph);
+      tc_fence_after();
+      const uint32_t pa = smem_u32(sP + g * AT_QB), va = smem_u32(sV + g * AT_KB);
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < AT_BN / 16; ++kk)
+          umma_bf16_ss(tmem_O + g * AT_HD, desc_kmajor_sw128(pa) + 2 * kk,
+                       desc_mnmajor_sw128(va + kk * 2048, AT_KB), IDESC_PV, (c.j > 0) || kk != 0);
+        umma_commit(&pv_done[g]);
+        umma_commit(&v_empty[g]);
+      }
+      __syncwarp();
+      c.advance(items);
+    };
+    while (pc0.valid(n_items) || pc1.valid(n_items)) {
+      if (ATD_PICK(pc0, pc1, pturn) == 0) issue_pv(pc0, qc0, 0); else issue_pv(pc1, qc1, 1);
+      pturn ^= 1;
+    }
+  } else {
+    // ---- softmax / correction / output: thread <-> (query row of the group's own item)
+    const int grp = (warp - 2) >> 2;
+    const int q = (warp & 3) * 32 + lane;  // row in the tile == TMEM lane
+    const int st = threadIdx.x - 64;       // 0..255
+    const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t tS = tmem_base + lane_addr + grp * AT_BN;
+    const uint32_t tO = tmem_O + lane_addr + grp * AT_HD;
+    const int swz = q & 7;
+    uint64_t* my_s_full = &s_full[grp];
+    uint64_t* my_p_full = &p_full[grp];
+    uint64_t* my_pv_done = &pv_done[grp];
+    uint64_t* my_s_free = &s_free[grp];
+    uint8_t* myP = sP + grp * AT_QB + q * 128;
+    const int lut_off = nq * AT_BM;
+    if (LOGPEN) {
+      const int n_lut = lut_off + ((L + AT_BN - 1) / AT_BN) * AT_BN;
+      for (int o = st; o < n_lut; o += 256) {
+        const int d = abs(o - lut_off);
+        sLut[o] = (d > 1) ? -__log2f((float)d) : 0.0f;
+      }
+      named_bar_sync(1, 256);
+    }
+    uint32_t c = 0;  // key tiles of this group before the current one
+    AttnItem it;
+    for (int k = grp;; k += 2) {
+      items.get(it, k);
+      if (it.w >= n_items) break;
+      const int i = it.q0 + q;
+      __nv_bfloat16* orow = out + ((size_t)i * B + it.b) * D + it.h * AT_HD;
+      if (it.n_kv == 0) {  // tile of padded queries: defined (finite) output, no pipeline work
+        if (i < L) {
+          uint4* op = reinterpret_cast<uint4*>(orow);
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) op[jj] = make_uint4(0, 0, 0, 0);
+        }
+        continue;
+      }
+      float m_used = -INFINITY, l = 0.0f;
+      for (int j = 0; j < it.n_kv; ++j, ++c) {
+        const uint32_t ph = c & 1;
+        const int k0 = j * AT_BN;
+        const int nvalid = min(AT_BN, it.len - k0);
+        mbar_wait(my_s_full, ph);
+        if (warp == 2 || warp == 6) AT_TRACE(2 * c + grp, 3);
+        tc_fence_after();
+        // pass 1: row maximum (S is read again in pass 2: registers are the scarce resource)
+        float mx = -INFINITY;
+        {
+          uint32_t s0[32];
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            tmem_ld32(tS + half * 32, s0);
+            tmem_ld_wait();
+            if (nvalid == AT_BN) {
+              float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+              for (int cc = 0; cc < 32; ++cc) m4[cc & 3] = fmaxf(m4[cc & 3], __uint_as_float(s0[cc]));
+              mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+            } else {
+#pragma unroll
+              for (int cc = 0; cc < 32; ++cc)
+                if (half * 32 + cc < nvalid) mx = fmaxf(mx, __uint_as_float(s0[cc]));
+            }
+          }
+        }
+        const float m_new = fmaxf(m_used, mx * kLog2e);
+        if (warp == 2 || warp == 6) AT_TRACE(2 * c + grp, 4);
+        // P[grp] / O[grp] were last used by this group's previous tile
+        if (c >= 1) mbar_wait(my_pv_done, ph ^ 1);
+        if (warp == 2 || warp == 6) AT_TRACE(2 * c + grp, 5);
+        const bool grow = m_new > m_used + kRescaleThreshold;
+        if (__any_sync(0xffffffffu, grow)) {
+          const float m_next = grow ? m_new : m_used;
+          if (j > 0) {
+            const float alpha = ex2(m_used - m_next);
+            tc_fence_after();
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              uint32_t o0[32];
+              tmem_ld32(tO + half * 32, o0);
+              tmem_ld_wait();
+#pragma unroll
+              for (int cc = 0; cc < 32; ++cc) o0[cc] = __float_as_uint(__uint_as_float(o0[cc]) * alpha);
+              tmem_st32(tO + half * 32, o0);
+            }
+            tmem_st_wait();
+            l *= alpha;
+          }
+          m_used = m_next;
+        }
+        // pass 2 (same as the split-KV kernel): p = 2^(s*log2e - m - pen2), row sum, bf16 pack
+        const uint32_t lut_addr = smem_u32(sLut + (lut_off - i) + k0);
+        const float2 negm2 = make_float2(-m_used, -m_used);
+        const float2 l2e2 = make_float2(kLog2e, kLog2e);
+        float2 sm2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+        {
+          uint32_t sa[16], sb[16];
+          float pn[8];
+          tmem_ld16(tS, sa);
+          tmem_ld16(tS + 16, sb);
+          if (LOGPEN) {
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) pn[cc] = lds32(lut_addr + cc * 4);
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            uint32_t(&s0)[16] = (ch & 2) ? sb : sa;
+            const int o = (ch & 1) * 8;
+            float2 t[4];
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+              float2 add = negm2;
+              if (LOGPEN) add = fadd2(negm2, make_float2(pn[2 * cc], pn[2 * cc + 1]));
+              t[cc] = ffma2(make_float2(__uint_as_float(s0[o + 2 * cc]), __uint_as_float(s0[o + 2 * cc + 1])),
+                            l2e2, add);
+            }
+            if (ch == 1 || ch == 3) tmem_ld16(tS + (ch + 3) * 8, s0);
+            if (LOGPEN && ch < 7) {
+#pragma unroll
+              for (int cc = 0; cc < 8; ++cc) pn[cc] = lds32(lut_addr + ((ch + 1) * 8 + cc) * 4);
+            }
+            if (ch == 3) {  // all of S is in registers: hand the accumulator back
+              tmem_ld_wait();
+              tc_fence_before();
+              mbar_arrive(my_s_free);
+            }
+            if (nvalid != AT_BN) {
+#pragma unroll
+              for (int cc = 0; cc < 4; ++cc) {
+                if (ch * 8 + 2 * cc >= nvalid) t[cc].x = -INFINITY;
+                if (ch * 8 + 2 * cc + 1 >= nvalid) t[cc].y = -INFINITY;
+              }
+            }
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+              t[cc].x = ex2(t[cc].x);
+              t[cc].y = ex2(t[cc].y);
+            }
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) sm2[cc & 1] = fadd2(sm2[cc & 1], t[cc]);
+            reinterpret_cast<uint4*>(myP)[ch ^ swz] =
+                make_uint4(pack_bf16x2(t[0].x, t[0].y), pack_bf16x2(t[1].x, t[1].y),
+                           pack_bf16x2(t[2].x, t[2].y), pack_bf16x2(t[3].x, t[3].y));
+          }
+        }
+        l += (sm2[0].x + sm2[0].y) + (sm2[1].x + sm2[1].y);
+        tc_fence_before();
+        fence_proxy_async_smem();
+        mbar_arrive(my_p_full);
+        if (warp == 2 || warp == 6) AT_TRACE(2 * c + grp, 6);
+      }
+      // ---- item epilogue (this group only): O / l -> bf16, 128 B per query row
+      mbar_wait(my_pv_done, (c - 1) & 1);  // O[grp] final
+      tc_fence_after();
+      const float inv = 1.0f / l;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t o0[32];
+        tmem_ld32(tO + half * 32, o0);
+        tmem_ld_wait();
+        if (i < L) {
+          uint4* op = reinterpret_cast<uint4*>(orow + half * 32);
+#pragma unroll
+          for (int gq4 = 0; gq4 < 4; ++gq4) {
+            const int o = gq4 * 8;
+            op[gq4] = make_uint4(
+                pack_bf16x2(__uint_as_float(o0[o]) * inv, __uint_as_float(o0[o + 1]) * inv),
+                pack_bf16x2(__uint_as_float(o0[o + 2]) * inv, __uint_as_float(o0[o + 3]) * inv),
+                pack_bf16x2(__uint_as_float(o0[o + 4]) * inv, __uint_as_float(o0[o + 5]) * inv),
+                pack_bf16x2(__uint_as_float(o0[o + 6]) * inv, __uint_as_float(o0[o + 7]) * inv));
+          }
+        }
+      }
+      // O[grp] is overwritten by the PV of the group's next tile, which waits for this group's next
+      // p_full arrival (ordered after the TMEM reads above by the fence before that arrive)
+      if (warp == 2 || warp == 6) AT_TRACE(2 * (c - 1) + grp, 7);
+    }
+  }
+#undef ATD_PICK
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
 }  // namespace fbkst
 
 // debug hook (not part of the public ABI): buffer of 64*8 int64, or NULL to disable
@@ -634,7 +1069,28 @@ extern "C" int fbkst_attention_fwd(const void* qkv, void* out, const int32_t* le
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     FBKST_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<1>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    FBKST_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_dec_kernel<0>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    FBKST_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_dec_kernel<1>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
+  }
+  // decoupled groups (one item per softmax group): opt-in experiment, FBKST_ATTN_DEC=1, used when two
+  // of its CTAs fit an SM (L <~ 1100 with the penalty LUT); measured no faster than split-KV
+  static const bool dec_enabled = getenv("FBKST_ATTN_DEC") && atoi(getenv("FBKST_ATTN_DEC")) != 0;
+  const int smem_dec = attention_dec_smem_bytes(log_penalty ? L : 0);
+  const long long n_items_all = (long long)((L + AT_BM - 1) / AT_BM) * B * H;
+  if (dec_enabled && 2 * (smem_dec + 1024) <= 228 * 1024) {
+    FBKST_REQUIRE(n_items_all < (1ll << 30), "fbkst_attention_fwd: too many work items");
+    int grid = num_sms() * 2;
+    if (grid > n_items_all) grid = (int)n_items_all;
+    if (log_penalty)
+      FBKST_CHECK_CUDA(launch_pdl(attention_fwd_dec_kernel<1>, dim3(grid), dim3(AT_THREADS), smem_dec, st,
+                                  tmQ, tmKV, (__nv_bfloat16*)out, lengths, L, B, H));
+    else
+      FBKST_CHECK_CUDA(launch_pdl(attention_fwd_dec_kernel<0>, dim3(grid), dim3(AT_THREADS), smem_dec, st,
+                                  tmQ, tmKV, (__nv_bfloat16*)out, lengths, L, B, H));
+    return FBKST_OK;
   }
   const int smem = attention_smem_bytes(log_penalty ? L : 0);
   FBKST_REQUIRE(smem <= 227 * 1024, "fbkst_attention_fwd: L=%d needs %d B of shared memory", L, smem);
