@@ -222,6 +222,30 @@ def test_encoder_cfg5_shape_vs_oracle():
     check_against(out, ref, lens)
 
 
+@pytest.mark.parametrize("ctc_layer", [1, 2, 3])
+def test_encoder_cfg5_compression_sweep_vs_oracle(ctc_layer):
+    """BASELINE configs[4] sweeps the compression layer (4 / 8 / 12 of 12): here first / middle / last of a
+    3-layer d1024 h16 C128 F80 encoder -- compressing before any layer has run, between layers, and after
+    the last one (nothing but the final LayerNorm sees the compressed rows)."""
+    cfg = dict(embed_dim=1024, ffn_dim=4096, heads=16, layers=3, conv_channels=128, feat_dim=80,
+               vocab=305, distance_penalty="log", ctc_layer=ctc_layer, ctc_strategy="avg")
+    sd = O.init_state_dict(cfg, seed=6)
+    lens_in = [1210, 1000, 517]
+    x, lens = O.synthetic_batch(lens_in, 80, seed=43)
+    labels = O.synthetic_ctc_bump(303, 3, 305, seed=17)
+    hook = O.bump_hook(labels, 30.0)
+    ref = O.encoder_forward(sd, cfg, x, lens, ctc_logits_hook=hook)
+    enc = build_encoder(cfg, sd)
+    dev_hook = O.bump_hook(labels.cuda(), 30.0)  # device-resident plan: capturable in a CUDA graph
+    enc.ctc_fc.register_forward_hook(lambda m, i, o: dev_hook(o))
+    out = enc(x.cuda(), lens.cuda())
+    check_against(out, ref, lens)
+    enc.use_cuda_graph = True  # the graph path (worst-case grids + device-side row limits) as well
+    out_g = enc(x.cuda(), lens.cuda())
+    assert torch.equal(out_g.src_lengths, out.src_lengths)
+    assert torch.equal(out_g.encoder_out, out.encoder_out)
+
+
 def test_encoder_full_size_properties():
     """BASELINE configs[1] at FULL size (64 x 1500 x 40, 11 layers, V=8005) through size-independent
     properties: (1) determinism: two runs are bit-identical; (2) batch-slot permutation: permuting
