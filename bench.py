@@ -123,12 +123,13 @@ class ClockSampler:
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, interval_ms=20):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(
                 ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS,
-                 "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
+                 "--format=csv,noheader,nounits", "-lms", str(int(interval_ms))], stdout=self.f,
+                stderr=subprocess.DEVNULL) if interval_ms > 0 else None
         except OSError:
             self.p = None
 
@@ -334,8 +335,11 @@ def run_ours(args, rank, world, local_rank):
         """n steps through the public host-buffer API: pinned host batch -> H2D -> CMVN -> encoder
         -> D2H of encoder_out + lengths (copies overlap the kernels of the neighbouring steps)."""
         last = None
+        stamps = []
         for res, nl in pipe.run(host[i % n_batches] for i in range(n)):
             last = (res, nl)
+            stamps.append(time.perf_counter())
+        run_e2e.stamps = stamps
         return last
 
     def barrier():
@@ -343,11 +347,11 @@ def run_ours(args, rank, world, local_rank):
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None  # samples warm-up + timed regions
+    sampler = ClockSampler(local_rank, args.clock_interval_ms) if rank == 0 else None  # warm-up + timed regions
     for i in range(args.warmup):
         step_resident(i)
-    run_device(args.warmup)
-    run_e2e(args.warmup)
+    run_device(max(args.warmup, 8))  # every lane's graph, every staging slot and pinned buffer exists
+    run_e2e(max(args.warmup, 8))
     barrier()
 
     # ---- timed region 1: inputs resident in HBM, K steps back to back (throughput: `lanes` batches in
@@ -386,12 +390,13 @@ def run_ours(args, rank, world, local_rank):
     res, nl = run_e2e(args.steps)
     barrier()
     e2e_s = time.perf_counter() - t0
+    gaps = [b - a for a, b in zip(run_e2e.stamps, run_e2e.stamps[1:])] or [0.0]
     clocks = sampler.stop() if sampler else None
 
-    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    t = torch.tensor([dev_ms, e2e_s * 1e3, max(gaps) * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    dev_ms, e2e_ms = t.tolist()
+    dev_ms, e2e_ms, worst_gap_ms = t.tolist()
 
     # ---- per-kernel attribution (separate, untimed pass; same stream, CUDA events)
     kern = None
@@ -452,7 +457,12 @@ def run_ours(args, rank, world, local_rank):
                  ms_per_step=round(e2e_ms / args.steps, 4),
                  api="fbkst_b200.pipeline.EncoderPipeline.run (pinned host batches in, pinned host "
                      "encoder_out + lengths out; wall clock over all steps incl. pipeline fill/drain)",
-                 compute_lanes=pipe.lanes),
+                 compute_lanes=pipe.lanes,
+                 result_to_result_ms=dict(median=round(statistics.median(gaps) * 1e3, 3),
+                                          max=round(max(gaps) * 1e3, 3), at_step=gaps.index(max(gaps)) + 1,
+                                          max_over_ranks=round(worst_gap_ms, 3),
+                                          note="host clock between consecutive results (rank 0; max over "
+                                               "ranks separately)")),
         gpu_launches=launches, clocks=clocks, roofline=roofline, kernels=kern,
         wall_ms_per_step=round(wall * 1e3 / args.steps, 4), impl="ours",
         single_forward_ms=dict(min=round(min(step_ms), 4), median=round(statistics.median(step_ms), 4),
@@ -519,6 +529,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--clock-interval-ms", type=int, default=20,
+                    help="nvidia-smi sampling period for the `clocks` key (0 = no sampler)")
     ap.add_argument("--no-graph", action="store_true", help="launch kernel by kernel instead of graph replay")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

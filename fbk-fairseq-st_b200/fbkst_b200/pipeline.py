@@ -90,7 +90,10 @@ class EncoderPipeline:
         return handle, ev_done
 
     def _collect(self, j, handle, ev_done, to_host=True):
-        """Blocking half for batch j: exact output shape, D2H on the copy-out stream, wait for it."""
+        """Blocking half for batch j: exact output shape (waits for the batch's new lengths; the batches
+        queued behind it keep the GPU busy).  Host mode: the D2H copy is enqueued on the copy-out
+        stream and returned as (event, host tensor, host lengths) -- the caller waits for it AFTER it
+        has enqueued the next batch."""
         if not to_host:
             # hand the result over to the caller's stream (ordered after batch j, not after the
             # batches queued behind it on the lane)
@@ -102,7 +105,6 @@ class EncoderPipeline:
                     t.record_stream(self._caller)  # allocated on the lane's stream
             return out
         with torch.cuda.stream(self.s_out):
-            # waits for the new lengths of batch j; the batches queued behind it keep the GPU busy
             out = self.enc.finish(handle)
             self.s_out.wait_event(ev_done)
             eo = out.encoder_out
@@ -114,8 +116,7 @@ class EncoderPipeline:
             hl = handle["new_len_pin"].to(handle["len_dtype"])  # already on the host
         else:
             hl = torch.tensor(handle["len_host"], dtype=handle["len_dtype"])
-        ev_out.synchronize()
-        return host, hl
+        return ev_out, host, hl, out  # `out` keeps the device tensor alive until the copy has finished
 
     def run(self, batches):
         """``batches``: iterable of ``(src_tokens [B,T,F] fp32 host tensor, src_lengths [B] int64 host
@@ -135,13 +136,34 @@ class EncoderPipeline:
         for s in self.s_lane:
             s.wait_stream(caller)
         inflight = collections.deque()
+        copying = None  # host mode: the batch whose D2H copy is in flight
+
+        def deliver(c):
+            c[0].synchronize()
+            return c[1], c[2]
+
         for i, batch in enumerate(batches):
             inflight.append((i,) + self._enqueue(i, batch))
+            if copying is not None:  # its copy has been running while batch i was enqueued
+                yield deliver(copying)
+                copying = None
             if len(inflight) > self.lanes:  # batches i-lanes+1 .. i stay queued behind this wait
                 j, handle, ev_done = inflight.popleft()
-                yield self._collect(j, handle, ev_done, to_host)
-        while inflight:
-            j, handle, ev_done = inflight.popleft()
-            yield self._collect(j, handle, ev_done, to_host)
+                r = self._collect(j, handle, ev_done, to_host)
+                if to_host:
+                    copying = r
+                else:
+                    yield r
+        while inflight or copying is not None:
+            if copying is not None:
+                yield deliver(copying)
+                copying = None
+            if inflight:
+                j, handle, ev_done = inflight.popleft()
+                r = self._collect(j, handle, ev_done, to_host)
+                if to_host:
+                    copying = r
+                else:
+                    yield r
         for s in self.s_lane:
             caller.wait_stream(s)
