@@ -210,6 +210,8 @@ class KernelProfile:
             # which kernel serves this launch (csrc/gemm2_tcgen05.cu, csrc/gemm_tcgen05.cu)
             if k.get("remap") is not None:
                 sub = "gemm_bf16_kernel (fc3: row remap + pos-emb epilogue)"
+            elif k.get("residual") is None and out.dtype == torch.float32:
+                sub = "gemm2_kernel<f32 out> (fc3 + ReLU)"
             elif k.get("residual") is not None:
                 sub = "gemm2_kernel<f32 out + residual (+ bf16 copy, LN statistics)> (out_proj, fc2)"
             else:
@@ -251,7 +253,12 @@ class KernelProfile:
             M, D = a[0].shape
             return dict(flops=0.0, bytes=valid_rows(M) * D * (4 + 2))
 
-        for name, w in [("linear", lin), ("linear_ln", lin), ("row_stats_cast", stats), ("attention", att),
+        def embed(a, k, out):  # read fp32 (+ table rows), write fp32 + bf16
+            M, D = a[0].shape
+            return dict(flops=0.0, bytes=M * D * (4 + 4 + 4 + 2))
+
+        for name, w in [("linear", lin), ("linear_ln", lin), ("row_stats_cast", stats),
+                        ("embed_remap_stats", embed), ("attention", att),
                         ("layernorm", ln_), ("ctc_argmax", argmax),
                         ("ctc_compress", compress), ("ctc_segment", other), ("conv1_relu_bn", conv1),
                         ("conv2_relu_bn", conv2), ("cmvn", cmvn), ("cast_bf16", other),

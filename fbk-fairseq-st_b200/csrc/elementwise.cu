@@ -89,6 +89,12 @@ __global__ void cmvn_apply_kernel(const float* __restrict__ x, const long long* 
 }
 
 // ----------------------------------------------------------------- conv1 (a2)
+// MEASURED ALTERNATIVE (r01g, not kept): a persistent version that stages the (2*R1+1) x (F+2) input patch
+// of 8 output rows in shared memory (double-buffered, next patch prefetched into registers), reads the 9
+// taps with broadcast LDS and accumulates channel pairs with packed fp32 FMAs was SLOWER (75.8 us vs 67.6
+// us here at cfg2) although it removes every global-load stall from the pixel loop: the kernel is not
+// bound by its input loads.  The next step for conv1 is the tensor pipe (im2col K=9->16 in smem, one UMMA
+// per 128 pixels, TMEM epilogue), which cuts the instruction count ~4x.
 // Thread = (output row (b,t1), 8-channel group g): the 72 weights + 24 epilogue constants of the
 // group live in registers; the thread slides along the F1 output columns of its row (stride-2
 // window: 6 new inputs per pixel, no index division in the loop).  The 8 threads of a pixel write
@@ -229,6 +235,56 @@ __global__ void __launch_bounds__(256)
       keep_mean = mean;
       keep_m2 = m2;
     }
+    reinterpret_cast<uint2*>(xb + (size_t)row * D)[i * 32 + lane] =
+        make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
+  }
+  if (lane < NV) stats[(size_t)row * NV + lane] = make_float2(keep_mean, keep_m2);
+}
+
+// fc3 epilogue that is not a GEMM epilogue (conv_transformer.py:225-229): the fc3 GEMM writes relu(a W^T
+// + b) in the conv layout's row order (b, t); this kernel moves row (b, t) to the time-major row t*B + b,
+// adds the sinusoidal position (row t+1 of the table inside the utterance, the padding row 0 beyond
+// its length) and emits what row_stats_cast would: fp32 x, bf16 x and the per-slice LayerNorm statistics
+// of the first layer.  One warp per row: 2 KB coalesced reads and writes.  Measured (ncu, cfg2): CTA-pair
+// GEMM 21.7 us + this kernel 18.6 us, against 52.3 us for the single-CTA GEMM with the row-remapping
+// thread-per-row epilogue + 11.3 us for the separate row_stats_cast pass.
+template <int NV>
+__global__ void __launch_bounds__(256)
+    embed_remap_stats_kernel(const float* __restrict__ src, const float* __restrict__ table,
+                             long long ld_table, const int* __restrict__ lengths,
+                             float* __restrict__ x, __nv_bfloat16* __restrict__ xb,
+                             float2* __restrict__ stats, int L, int B) {
+  constexpr int D = NV * 128;
+  pdl_launch_dependents();
+  pdl_wait();
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // t * B + b
+  if (row >= L * B) return;
+  const int lane = threadIdx.x & 31;
+  const int t = row / B, b = row - t * B;
+  const float4* sp = reinterpret_cast<const float4*>(src + ((size_t)b * L + t) * D);
+  float4 v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = __ldg(sp + i * 32 + lane);
+  if (table != nullptr) {
+    const int prow = (t < __ldg(lengths + b)) ? t + 1 : 0;
+    const float4* tp = reinterpret_cast<const float4*>(table + (size_t)prow * ld_table);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 p = __ldg(tp + i * 32 + lane);
+      v[i].x += p.x; v[i].y += p.y; v[i].z += p.z; v[i].w += p.w;
+    }
+  }
+  float keep_mean = 0.f, keep_m2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float mean = warp_sum((v[i].x + v[i].y) + (v[i].z + v[i].w)) * (1.0f / 128.0f);
+    const float a = v[i].x - mean, bb = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    const float m2 = warp_sum((a * a + bb * bb) + (c * c + d * d));
+    if (lane == i) {
+      keep_mean = mean;
+      keep_m2 = m2;
+    }
+    reinterpret_cast<float4*>(x + (size_t)row * D)[i * 32 + lane] = v[i];
     reinterpret_cast<uint2*>(xb + (size_t)row * D)[i * 32 + lane] =
         make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
   }
@@ -409,6 +465,35 @@ extern "C" int fbkst_row_stats_cast(const float* x, void* xb, float* row_stats, 
     default:
       return set_error(FBKST_ERR_ARG, "fbkst_row_stats_cast: unsupported D=%d (128..1024, multiple of 128)", D);
   }
+  FBKST_CHECK_CUDA(cudaGetLastError());
+  return FBKST_OK;
+}
+
+extern "C" int fbkst_embed_remap_stats(const float* src, const float* table, int64_t ld_table,
+                                       const int32_t* lengths, float* x, void* xb, float* row_stats,
+                                       int L, int B, int D, fbkst_stream_t stream) {
+  FBKST_REQUIRE(src && x && xb && row_stats, "fbkst_embed_remap_stats: null pointer");
+  FBKST_REQUIRE(L > 0 && B > 0, "fbkst_embed_remap_stats: bad shape L=%d B=%d", L, B);
+  FBKST_REQUIRE(table == nullptr || (lengths != nullptr && ld_table % 4 == 0),
+                "fbkst_embed_remap_stats: a position table needs lengths and a row stride multiple of 4");
+  FBKST_REQUIRE((long long)L * B < (1ll << 31), "fbkst_embed_remap_stats: too many rows");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = (L * B + 7) / 8;
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(xb);
+  float2* s2 = reinterpret_cast<float2*>(row_stats);
+  const long long ldt = ld_table;
+#define FBKST_ERS(NV) FBKST_CHECK_CUDA(launch_pdl(embed_remap_stats_kernel<NV>, dim3(grid), dim3(256), 0, st, src, table, ldt, lengths, x, o, s2, L, B))
+  switch (D) {
+    case 128: FBKST_ERS(1); break;
+    case 256: FBKST_ERS(2); break;
+    case 384: FBKST_ERS(3); break;
+    case 512: FBKST_ERS(4); break;
+    case 768: FBKST_ERS(6); break;
+    case 1024: FBKST_ERS(8); break;
+    default:
+      return set_error(FBKST_ERR_ARG, "fbkst_embed_remap_stats: unsupported D=%d (128..1024, multiple of 128)", D);
+  }
+#undef FBKST_ERS
   FBKST_CHECK_CUDA(cudaGetLastError());
   return FBKST_OK;
 }

@@ -24,6 +24,7 @@ SIGNATURES = {
     "fbkst_linear_bf16": [P, I64, P, I64, P, P, I64, P, I64, I, I, I, I, I, I, P, P, I, P],
     "fbkst_linear_ln_bf16": [P, I64, P, I64, P, P, I64, P, I64, I, I, I, I, P, F, P, I64, P, P, I, P],
     "fbkst_row_stats_cast": [P, P, P, I, I, P, I, P],
+    "fbkst_embed_remap_stats": [P, P, I64, P, P, P, P, I, I, I, P],
     "fbkst_layernorm": [P, P, P, P, I, I, I, F, P, I, P],
     "fbkst_attention_fwd": [P, P, P, I, I, I, I, P],
     "fbkst_sinusoidal_table": [P, I, I, P],

@@ -414,14 +414,15 @@ def make_encoder_class(base):
             y = ops.conv2_relu_bn(y, P["w2"], P["b2"], *P["bn1"])  # [B, T2, F2, C]
             assert y.shape[1] == L
             a = y.view(B * L, -1)
-            if self.embed_positions is not None:
-                table = self._positions(L + 1, dev)
-                x = ops.linear(a, P["w3"], P["b3"], relu=True, out_dtype=torch.float32,
-                               remap=(L, B), posemb=(table, lengths))
-            else:
-                x = ops.linear(a, P["w3"], P["b3"], relu=True, out_dtype=torch.float32, remap=(L, B))
+            # fc3 + ReLU on the CTA-pair GEMM in the conv layout's (b, t) row order; the transpose to
+            # time-major rows, the positions and the first layer's LayerNorm statistics are one
+            # row-per-warp pass (:225-229)
+            h3 = ops.linear(a, P["w3"], P["b3"], relu=True, out_dtype=torch.float32)
+            table = self._positions(L + 1, dev) if self.embed_positions is not None else None
+            x, xb, st = ops.embed_remap_stats(h3, L, B, table, lengths if table is not None else None)
             if self.layernorm_embedding is not None:
                 x = ops.layernorm(x, *P["lne"], out_dtype=torch.float32)
+                xb, st = ops.row_stats_cast(x)
             mask = ops.lengths_to_mask(lengths, L)[0]
             r = dict(mask=mask, mask2=None, x_ctc=None, len_host=len_host, L=L, tables=table
                      if self.embed_positions is not None else None)
@@ -435,7 +436,6 @@ def make_encoder_class(base):
             # by the epilogue that produced x (out_proj / fc2) or by row_stats_cast (fc3 output,
             # compressed rows); QKV / fc1 apply 1/sigma in their epilogues.  No LayerNorm launches
             # inside the layer stack.
-            xb, st = ops.row_stats_cast(x)
             n_layers = len(P["layers"])
             for li, W in enumerate(P["layers"]):
                 ctc_here = self.ctc_compress_out and self.ctc_layer == li + 1

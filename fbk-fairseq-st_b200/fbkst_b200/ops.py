@@ -215,6 +215,30 @@ def row_stats_cast(x, out=None, rows_limit=None):
     return xb, st
 
 
+def embed_remap_stats(src, L, B, table=None, lengths=None):
+    """fc3 output [B*L, D] fp32 in (b, t) row order -> time-major x [L*B, D] fp32 (+ sinusoidal positions
+    from ``table`` masked by ``lengths``: conv_transformer.py:225-229), bf16(x) and the slice statistics
+    of ``row_stats_cast`` in one pass."""
+    lib = _lib.require_device()
+    _req(src, torch.float32, "embed_remap_stats.src")
+    M, D = src.shape
+    if M != L * B:
+        raise ValueError("embed_remap_stats: src has %d rows, expected L*B = %d" % (M, L * B))
+    if table is not None:
+        _req(table, torch.float32, "embed_remap_stats.table")
+        _req(lengths, torch.int32, "embed_remap_stats.lengths")
+        if table.shape[0] < L + 1 or table.shape[1] != D:
+            raise ValueError("embed_remap_stats: position table too small")
+    x = torch.empty(M, D, dtype=torch.float32, device=src.device)
+    xb = torch.empty(M, D, dtype=torch.bfloat16, device=src.device)
+    st = torch.empty(M, (D + 127) // 128, 2, dtype=torch.float32, device=src.device)
+    check(lib.fbkst_embed_remap_stats(src.data_ptr(), _ptr(table), table.stride(0) if table is not None else 0,
+                                      _ptr(lengths) if table is not None else 0, x.data_ptr(), xb.data_ptr(),
+                                      st.data_ptr(), L, B, D, _stream()))
+    _count()
+    return x, xb, st
+
+
 def fold_layernorm(w, b, gamma, beta, row_scale=None):
     """Weights of ``linear_ln``'s consumer side: W''[n,k] = gamma[k] W[n,k] - mean_k(gamma[k] W[n,k])
     (bf16) and c[n] = b[n] + sum_k beta[k] W[n,k] (fp32), so that LN(x) W^T + b == rstd(x) * (x W''^T)

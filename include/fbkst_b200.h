@@ -134,6 +134,14 @@ int fbkst_linear_ln_bf16(const void* A, int64_t lda, const void* W, int64_t ldw,
 int fbkst_row_stats_cast(const float* x, void* xb, float* row_stats, int M, int D,
                          const int32_t* m_limit, int m_limit_mult, fbkst_stream_t stream);
 
+/* ---- a3/a4 tail: conv_transformer.py:225-229 (transpose(0,1) of the fc3 output + positions) fused with
+ * the first layer's row statistics.  src [B*L, D] fp32 in (b, t) row order (the fc3 GEMM output) ->
+ * x [L*B, D] fp32 time-major (row t*B + b), x += table[t+1] inside the utterance / table[0] (the
+ * padding row) beyond lengths[b] when table != NULL, xb = bf16(x), row_stats as fbkst_row_stats_cast. */
+int fbkst_embed_remap_stats(const float* src, const float* table, int64_t ld_table,
+                            const int32_t* lengths, float* x, void* xb, float* row_stats, int L, int B,
+                            int D, fbkst_stream_t stream);
+
 /* ---- a8: LayerNorm over the last dim (eps 1e-5, affine) ----------------------------------
  * replaces fairseq/modules/layer_norm.py:29-32 call sites (transformer_layer.py:108,126;
  * conv_transformer.py:253-254).  x [M,D] fp32 -> y [M,D] bf16 or fp32.  D in {128,256,384,512,

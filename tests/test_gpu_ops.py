@@ -107,6 +107,33 @@ def test_row_stats_cast(M, D):
     assert rel_err(st[..., 1], ref[..., 1]) < 1e-5
 
 
+@pytest.mark.parametrize("L,B,D,pos", [(37, 5, 128, True), (95, 8, 512, True), (61, 3, 1024, True),
+                                       (50, 4, 256, False), (1, 1, 384, True)])
+def test_embed_remap_stats(L, B, D, pos):
+    """(b,t)-ordered fc3 output -> time-major rows + sinusoidal positions (table row t+1 inside the
+    utterance, the padding row beyond it: conv_transformer.py:225-229, positional_embedding_audio.py:20-26)
+    + bf16 copy + slice statistics; the fp32 result is bit-exact (one fp32 add per element)."""
+    from fbkst_b200 import ops
+    g = torch.Generator().manual_seed(L * 7 + D)
+    src = torch.randn(B * L, D, generator=g).to(dev())
+    lengths = torch.randint(1, L + 1, (B,), generator=g).to(torch.int32)
+    lengths[0] = L
+    table = ops.sinusoidal_table(L + 8, D, dev()) if pos else None
+    x, xb, st = ops.embed_remap_stats(src, L, B, table, lengths.to(dev()) if pos else None)
+    torch.cuda.synchronize()
+    ref = src.view(B, L, D).transpose(0, 1)
+    if pos:
+        t = torch.arange(L).view(L, 1)
+        rows = torch.where(t < lengths.view(1, B).long(), t + 1, torch.zeros_like(t)).to(dev())  # [L, B]
+        ref = ref + table[rows]
+    ref = ref.reshape(L * B, D).contiguous()
+    assert torch.equal(x, ref)
+    assert torch.equal(xb, ref.to(torch.bfloat16))
+    rs = _slice_stats(ref.cpu())
+    assert rel_err(st[..., 0], rs[..., 0]) < 1e-5
+    assert rel_err(st[..., 1], rs[..., 1]) < 1e-5
+
+
 @pytest.mark.parametrize("M,N,K", [(300, 512, 512), (1000, 256, 1024), (513, 512, 2048), (77, 128, 256),
                                    (640, 1024, 512), (130, 192, 64)])
 def test_linear_ln_producer(M, N, K):
