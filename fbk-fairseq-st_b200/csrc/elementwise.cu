@@ -1,6 +1,7 @@
 // HBM-bound kernels of the path: fbank CMVN, conv1 (Cin=1, K=9: no tensor cores), LayerNorm,
 // sinusoidal table, padding mask, and the weight-format preparation kernels.
 #include <math.h>
+#include <stdlib.h>
 
 #include "host_common.h"
 #include "ptx.cuh"
@@ -85,6 +86,99 @@ __global__ void cmvn_apply_kernel(const float* __restrict__ x, const long long* 
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const int t = t0 + i / F, f = i % F;
     y[base + i] = (t < len) ? (__ldg(x + ibase + i) - sstat[f]) * sstat[F + f] : 0.0f;
+  }
+}
+
+// float4 versions of the two CMVN passes for F % 4 == 0 (every reference recipe: F = 40 / 80): thread <->
+// (feature quad, row group), no integer division in the row loops, 16-byte loads and stores.  Same fp64
+// statistics, same eps rule; the scalar kernels above serve any other F.
+__global__ void __launch_bounds__(256)
+    cmvn_stats4_kernel(const float* __restrict__ x, const long long* __restrict__ starts,
+                       const int* __restrict__ lengths, double* __restrict__ ws, int T, int F,
+                       int rows_per_block) {
+  extern __shared__ double sred[];  // [2][RG][F]
+  const int Q = F >> 2, RG = blockDim.x / Q;
+  const int b = blockIdx.y;
+  const int len = min(lengths[b], T);
+  const int t0 = blockIdx.x * rows_per_block;
+  const int t1 = min(t0 + rows_per_block, len);
+  const int q = threadIdx.x % Q, rg = threadIdx.x / Q;
+  double s[4] = {0.0, 0.0, 0.0, 0.0}, ss[4] = {0.0, 0.0, 0.0, 0.0};
+  if (rg < RG) {
+    const float4* xp = reinterpret_cast<const float4*>(x + (starts ? (size_t)starts[b] : (size_t)b * T) * F) + q;
+#pragma unroll 4
+    for (int t = t0 + rg; t < t1; t += RG) {
+      const float4 v = __ldg(xp + (size_t)t * Q);
+      s[0] += (double)v.x; ss[0] += (double)v.x * (double)v.x;
+      s[1] += (double)v.y; ss[1] += (double)v.y * (double)v.y;
+      s[2] += (double)v.z; ss[2] += (double)v.z * (double)v.z;
+      s[3] += (double)v.w; ss[3] += (double)v.w * (double)v.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      sred[rg * F + q * 4 + j] = s[j];
+      sred[(RG + rg) * F + q * 4 + j] = ss[j];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < F && t0 < t1) {
+    double a = 0.0, c = 0.0;
+    for (int k = 0; k < RG; ++k) {
+      a += sred[k * F + threadIdx.x];
+      c += sred[(RG + k) * F + threadIdx.x];
+    }
+    atomicAdd(&ws[((size_t)b * F + threadIdx.x) * 2 + 0], a);
+    atomicAdd(&ws[((size_t)b * F + threadIdx.x) * 2 + 1], c);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    cmvn_apply4_kernel(const float* __restrict__ x, const long long* __restrict__ starts,
+                       float* __restrict__ y, const int* __restrict__ lengths,
+                       const double* __restrict__ ws, int T, int F, int rows_per_block) {
+  extern __shared__ float sstat[];  // mean[F], inv[F]
+  const int b = blockIdx.y;
+  const int len = min(lengths[b], T);
+  int small = 0;
+  float mean = 0.f, var = 0.f;
+  if (threadIdx.x < F && ws != nullptr) {
+    const double n = (double)len;
+    const double s = ws[((size_t)b * F + threadIdx.x) * 2 + 0];
+    const double ss = ws[((size_t)b * F + threadIdx.x) * 2 + 1];
+    const double m = s / n;
+    double v = (ss - s * m) / (n - 1.0);
+    if (v < 0.0) v = 0.0;
+    mean = (float)m;
+    var = (float)v;
+    small = var < 1e-8f;
+  }
+  const int any_small = __syncthreads_or(small);
+  if (threadIdx.x < F) {
+    sstat[threadIdx.x] = mean;
+    sstat[F + threadIdx.x] =
+        ws == nullptr ? 1.0f : (any_small ? 1.0f / (sqrtf(var) + 1e-8f) : 1.0f / sqrtf(var));
+  }
+  __syncthreads();
+  const int Q = F >> 2, RG = blockDim.x / Q;
+  const int q = threadIdx.x % Q, rg = threadIdx.x / Q;
+  if (rg >= RG) return;
+  const float4 m4 = reinterpret_cast<const float4*>(sstat)[q];
+  const float4 i4 = reinterpret_cast<const float4*>(sstat + F)[q];
+  const int t0 = blockIdx.x * rows_per_block;
+  const int t1 = min(t0 + rows_per_block, T);
+  const float4* xp = reinterpret_cast<const float4*>(x + (starts ? (size_t)starts[b] : (size_t)b * T) * F) + q;
+  float4* yp = reinterpret_cast<float4*>(y + (size_t)b * T * F) + q;
+#pragma unroll 4
+  for (int t = t0 + rg; t < t1; t += RG) {
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < len) {
+      const float4 v = __ldg(xp + (size_t)t * Q);
+      o.x = (v.x - m4.x) * i4.x;
+      o.y = (v.y - m4.y) * i4.y;
+      o.z = (v.z - m4.z) * i4.z;
+      o.w = (v.w - m4.w) * i4.w;
+    }
+    yp[(size_t)t * Q] = o;
   }
 }
 
@@ -379,8 +473,14 @@ extern "C" int fbkst_cmvn_f32(const float* x, float* y, const int32_t* lengths, 
   FBKST_CHECK_CUDA(cudaMemsetAsync(workspace, 0, sizeof(double) * 2 * B * F, st));
   const int rows = 128;
   dim3 grid((T + rows - 1) / rows, B);
-  cmvn_stats_kernel<<<grid, 256, 2 * 256 * sizeof(double), st>>>(x, nullptr, lengths, workspace, T, F, rows);
-  cmvn_apply_kernel<<<grid, 256, 2 * F * sizeof(float), st>>>(x, nullptr, y, lengths, workspace, T, F, rows);
+  if (F % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+    const int RG = 256 / (F / 4);
+    cmvn_stats4_kernel<<<grid, 256, 2 * RG * F * sizeof(double), st>>>(x, nullptr, lengths, workspace, T, F, rows);
+    cmvn_apply4_kernel<<<grid, 256, 2 * F * sizeof(float), st>>>(x, nullptr, y, lengths, workspace, T, F, rows);
+  } else {
+    cmvn_stats_kernel<<<grid, 256, 2 * 256 * sizeof(double), st>>>(x, nullptr, lengths, workspace, T, F, rows);
+    cmvn_apply_kernel<<<grid, 256, 2 * F * sizeof(float), st>>>(x, nullptr, y, lengths, workspace, T, F, rows);
+  }
   FBKST_CHECK_CUDA(cudaGetLastError());
   return FBKST_OK;
 }
@@ -396,12 +496,22 @@ extern "C" int fbkst_collate_cmvn_f32(const float* packed, const int64_t* starts
   const int rows = 128;
   dim3 grid((T + rows - 1) / rows, B);
   const long long* sp = reinterpret_cast<const long long*>(starts);
+  const bool vec4 = F % 4 == 0 && (reinterpret_cast<uintptr_t>(packed) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(out) & 15) == 0;
   if (normalize) {
     FBKST_CHECK_CUDA(cudaMemsetAsync(workspace, 0, sizeof(double) * 2 * B * F, st));
-    cmvn_stats_kernel<<<grid, 256, 2 * 256 * sizeof(double), st>>>(packed, sp, lengths, workspace, T, F, rows);
+    if (vec4)
+      cmvn_stats4_kernel<<<grid, 256, 2 * (256 / (F / 4)) * F * sizeof(double), st>>>(packed, sp, lengths,
+                                                                                    workspace, T, F, rows);
+    else
+      cmvn_stats_kernel<<<grid, 256, 2 * 256 * sizeof(double), st>>>(packed, sp, lengths, workspace, T, F, rows);
   }
-  cmvn_apply_kernel<<<grid, 256, 2 * F * sizeof(float), st>>>(packed, sp, out, lengths,
-                                                             normalize ? workspace : nullptr, T, F, rows);
+  if (vec4)
+    cmvn_apply4_kernel<<<grid, 256, 2 * F * sizeof(float), st>>>(packed, sp, out, lengths,
+                                                                normalize ? workspace : nullptr, T, F, rows);
+  else
+    cmvn_apply_kernel<<<grid, 256, 2 * F * sizeof(float), st>>>(packed, sp, out, lengths,
+                                                               normalize ? workspace : nullptr, T, F, rows);
   FBKST_CHECK_CUDA(cudaGetLastError());
   return FBKST_OK;
 }
@@ -415,6 +525,9 @@ extern "C" int fbkst_conv1_relu_bn(const float* x, const float* w, const float* 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int T1 = (T + 1) / 2, F1 = (F + 1) / 2;
   FBKST_REQUIRE((long long)B * T1 * F1 < (1ll << 31), "fbkst_conv1_relu_bn: too many pixels");
+  // default: the tcgen05 kernel (conv1_tcgen05.cu); FBKST_CONV1_SIMT=1 selects the SIMT kernel above
+  static const bool simt = getenv("FBKST_CONV1_SIMT") != nullptr;
+  if (!simt) return conv1_tc_dispatch(x, w, bias, bn_scale, bn_shift, y, B, T, F, C, T1, F1, st);
   const long long total = (long long)B * T1 * (C / 8);
   const int grid = grid_for(total, 256, 8);
   if (C == 64)

@@ -5,8 +5,8 @@ run() { local name=$1; shift; timeout 600 python -m pytest "$@" -x -q > gpurun_o
 run ops tests/test_gpu_ops.py -k "conv or linear or fc3"
 run encoder tests/test_gpu_encoder.py
 grep -E "^(E |FAILED|ERROR)|assert|Error|watchdog" gpurun_out/ops.log gpurun_out/encoder.log | head -n 20
-echo "== conv1 v2"; timeout 120 python scripts/bench_small.py 10 conv 2>&1 | tail -n 3
-echo "== conv1 v1"; FBKST_CONV1_V1=1 timeout 120 python scripts/bench_small.py 10 conv1 2>&1 | tail -n 2
+echo "== conv1 tcgen05"; timeout 120 python scripts/bench_small.py 10 conv 2>&1 | tail -n 3
+echo "== conv1 SIMT"; FBKST_CONV1_SIMT=1 timeout 120 python scripts/bench_small.py 10 conv1 2>&1 | tail -n 2
 timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; echo "bench exit=$?"
 python - <<'PY'
 import json
