@@ -210,6 +210,7 @@ static int launch_conv1_tc(const float* x, const float* w, const float* bias, co
   if (per_sm == 0) {
     FBKST_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C1_THREADS, SMEM));
     if (per_sm < 1) per_sm = 1;
+    if (per_sm > 4) per_sm = 4;  // measured at cfg2: 3 / 4 / 5 / 6 CTAs per SM -> 49 / 41 / 53 / 49 us
     if (const char* e = getenv("FBKST_CONV1_PER_SM")) per_sm = atoi(e) > 0 ? atoi(e) : per_sm;  // A/B switch
   }
   int grid = num_sms() * per_sm;
