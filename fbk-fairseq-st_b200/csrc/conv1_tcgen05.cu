@@ -14,6 +14,7 @@
 // Small CTAs (160 threads, ~42 KB smem, C TMEM columns), as many per SM as fit: while one CTA waits for
 // its loads or its MMA the others build / drain.  Inputs and weights are rounded to bf16 (the output is
 // bf16 anyway; accumulation stays fp32).
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "host_common.h"
@@ -196,6 +197,11 @@ static int launch_conv1_tc(const float* x, const float* w, const float* bias, co
   static bool configured = false;
   if (!configured) {
     FBKST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    // shared-memory carve-out: the driver default and 100 % measure the same (41 us); switch kept for A/B
+    int carve = -1;
+    if (const char* e = getenv("FBKST_CONV1_CARVEOUT")) carve = atoi(e);  // A/B switch (-1: driver default)
+    if (carve >= 0)
+      FBKST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     configured = true;
   }
   const long long n_pix = (long long)B * T1 * F1;
@@ -206,15 +212,20 @@ static int launch_conv1_tc(const float* x, const float* w, const float* bias, co
   int rc = make_tensor_map(&tmY, y, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 2, dims, strides, box, nullptr);
   if (rc) return rc;
   const int n_tiles = (int)((n_pix + 127) / 128);
-  static int per_sm = 0;
-  if (per_sm == 0) {
-    FBKST_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C1_THREADS, SMEM));
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 4) per_sm = 4;  // measured at cfg2: 3 / 4 / 5 / 6 CTAs per SM -> 49 / 41 / 53 / 49 us
-    if (const char* e = getenv("FBKST_CONV1_PER_SM")) per_sm = atoi(e) > 0 ? atoi(e) : per_sm;  // A/B switch
-  }
+  // CTAs per SM by hand: 43 KB (C=64) / 67 KB (C=128) of smem, 80-85 registers x 160 threads and C TMEM
+  // columns give 4 / 3.  cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for this kernel (it
+  // appears to charge a tcgen05.alloc-ing kernel the whole TMEM), which halves the throughput: measured
+  // 3 / 4 / 5 / 6 CTAs per SM -> 49 / 41 / 53 / 49 us at cfg2, 1 -> 86 us.
+  int per_sm = (C == 64) ? 4 : 3;
+  if (const char* e = getenv("FBKST_CONV1_PER_SM")) per_sm = atoi(e) > 0 ? atoi(e) : per_sm;  // A/B switch
   int grid = num_sms() * per_sm;
   if (grid > n_tiles) grid = n_tiles;
+  static const bool dbg = getenv("FBKST_CONV1_DBG") != nullptr;
+  if (dbg) {
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C1_THREADS, SMEM);
+    fprintf(stderr, "conv1_tc: grid %d, occupancy API %d CTAs/SM, smem %d\n", grid, occ, SMEM);
+  }
   kern<<<grid, C1_THREADS, SMEM, st>>>(tmY, x, w, bias, scale, shift, B, T, F, T1, F1, (int)n_pix);
   FBKST_CHECK_CUDA(cudaGetLastError());
   return FBKST_OK;
