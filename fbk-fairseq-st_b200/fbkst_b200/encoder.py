@@ -511,10 +511,21 @@ def make_encoder_class(base):
             pin = G["len_pin"][G["pin_next"]]
             pin.copy_(torch.tensor(len_host, dtype=torch.int32))
             G["lengths"].copy_(pin, non_blocking=True)
-            G["x"].copy_(x_in, non_blocking=True)
+            if x_in.data_ptr() != G["x"].data_ptr():  # the caller may have produced x in place (static_input)
+                G["x"].copy_(x_in, non_blocking=True)
             G["graph"].replay()
             ops._count(G["launches"])
             return G["out"]
+
+        def static_input(self, B, T, Fd, dev):
+            """Graph mode: the captured graph's input buffer [B,T,F] fp32 for this shape on the current
+            ``graph_lane`` (None before the first forward of that shape).  A producer that writes the
+            batch straight into it (e.g. ``ops.cmvn(raw, lengths, out=buf)``) and passes it to
+            ``launch`` / ``forward`` saves the device-to-device copy of the replay."""
+            if not self.use_cuda_graph:
+                return None
+            G = self._graphs.get(self._graph_key(B, T, Fd, dev))
+            return None if G is None else G["x"]
 
         def _capture(self, P, B, T, Fd, L, dev):
             compress = self.ctc_compress_out and 0 < self.ctc_layer <= self.num_layers

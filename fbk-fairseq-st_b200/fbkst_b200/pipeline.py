@@ -74,13 +74,14 @@ class EncoderPipeline:
         with torch.cuda.stream(s):
             if ev_in is not None:
                 s.wait_event(ev_in)
-            if self.normalize:
-                len32 = lengths.to(torch.int32).to(self.device, non_blocking=True)
-                x = ops.cmvn(buf, len32)
-            else:
-                x = buf
             self.enc.graph_lane = lane
             try:
+                if self.normalize:
+                    len32 = lengths.to(torch.int32).to(self.device, non_blocking=True)
+                    # CMVN writes straight into the lane's graph input when that graph already exists
+                    x = ops.cmvn(buf, len32, out=self.enc.static_input(*buf.shape, buf.device))
+                else:
+                    x = buf
                 handle = self.enc.launch(x, lengths)
             finally:
                 self.enc.graph_lane = 0
