@@ -605,25 +605,25 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
 
 
 // =====================================================================================================
-// Decoupled variant (EXPERIMENT, off by default: FBKST_ATTN_DEC=1 selects it when two of its CTAs fit
-// an SM): the two softmax warpgroups of a CTA own DIFFERENT work items (group g takes items g, g+2,
-// g+4, ... of the CTA's list) instead of the even / odd key tiles of one item.  Hypothesis
-// (profiles/r01g_attention_timeline.txt): with split-KV the two groups start every item in lock step,
-// the item ends with a cross-group merge (two named barriers, both O buffers read by both groups) and
-// the faster group idles until the slower one has finished -- 5-6 k of the 14.5 k cycles of an item.
-// Here a group runs pass 1 / exp pass / its own 64-column epilogue back to back and never waits for
-// the other group; the only shared resources are the TMA warp and the MMA-issuing thread (both walk
-// the two groups' tile streams in the same fixed interleaved order, so a 3-slot K ring and the
-// single-buffered S / P / V / O of a group stay valid exactly as before).  Costs one more Q buffer.
-// MEASURED (profiles/r01g_attention_decoupled_ab.txt): parity green, but NOT faster -- cfg2 L=375
-// 62.5 vs 61.4 us, L=110 20.5 vs 18.4 us.  The timeline shows why: a group's tile period is ~4000
-// cycles of which the exp pass is 2100-2600 although on average only ~2.3 of the 4 groups of an SM
-// are in their exp pass (MUFU-throughput-bound would be ~1200): each softmax warp issues one
-// instruction per ~8 cycles (fixed-latency dependencies, 96-register cap -> little ILP), and the
-// group then waits 1300-1800 cycles for S of its next tile because the s_free -> QK -> s_full round
-// trip (~1500 cycles through the one in-order MMA thread) is longer than the half pass it is given.
-// The boundary idling it removes is replaced by that wait; the fix is ILP per softmax thread (S
-// row held in registers, 1 CTA/SM with 200+ registers), not more decoupling.
+// Decoupled variant (default whenever two of its CTAs fit an SM, i.e. L <~ 1100 with the penalty LUT;
+// FBKST_ATTN_DEC=0 forces the split-KV kernel above, which also serves longer L): the two softmax
+// warpgroups of a CTA own DIFFERENT work items (group g takes items g, g+2, g+4, ... of the CTA's list)
+// instead of the even / odd key tiles of one item.  With split-KV the two groups start every item in
+// lock step, the item ends with a cross-group merge (two named barriers, both O buffers read by both
+// groups) and the faster group idles until the slower one has finished -- 5-6 k of the 14.5 k cycles
+// of an item (profiles/r01g_attention_timeline.txt).  Here a group runs pass 1 / exp pass / its own
+// 64-column epilogue back to back and never waits for the other group.  Costs one more Q buffer.
+// History (profiles/r01g_attention_decoupled_ab.txt):
+//   v1  one in-order thread issuing QK and PV for both groups: parity green, NOT faster (62.5 vs 61.4 us
+//       at cfg2) -- the group that finished first waited 1300-1800 cycles for its next S because the
+//       thread was blocked on the other group's p_full;
+//   v2  (this code) warp 1 issues QK only (blocking, in the fixed interleaved order); warp 0 is an
+//       event loop over non-blocking mbarrier.test_wait probes that issues K/Q loads, V loads and PV
+//       MMAs as their barriers complete: S-wait 170-250 cycles, 59.5 vs 61.4 us at L=375, ragged cfg3
+//       attention 0.644 vs 0.662 ms/step, nothing slower.
+// What still bounds it: a group's tile period is ~3500 cycles of which the exp pass is ~2500 with four
+// groups sharing one MUFU pipe (floor 2048) and ~0.55 IPC per scheduler; the next step is fewer issue
+// slots per element (S row kept in registers, one TMEM read), not more overlap.
 constexpr int ATD_SMEM_FIXED = 2 * AT_QB + AT_KST * AT_KB + 2 * AT_KB + 2 * AT_QB /*P x2*/ +
                                256 /*barriers*/ + 64 * 16 /*item table*/ + 1024 /*align*/;
 static inline int attention_dec_smem_bytes(int L) { return ATD_SMEM_FIXED + 4 * attention_lut_floats(L); }
@@ -729,65 +729,104 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
 #define ATD_PICK(c0, c1, turn) (((turn) == 0) ? ((c0).valid(n_items) ? 0 : 1) : ((c1).valid(n_items) ? 1 : 0))
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    GrpCursor kc0, kc1, vc0, vc1;
+    // ---------------------------------------------- TMA loads (Q, K, V) + PV issue, EVENT DRIVEN
+    // Three cursors walk the fixed interleaved order (K loads, V loads, PV issues); each step is taken
+    // as soon as ITS barrier(s) have completed (non-blocking test_wait), so a PV never queues behind a
+    // K load whose ring slot is still busy and vice versa.  The QK issuer (warp 1) has the blocking,
+    // strictly ordered waits.  (FBKST_ATTN_DEC: with one in-order thread issuing both QK and PV the
+    // group that finished its tile first waited for the other group's p_full before its next S was
+    // even requested: 1300-1800 of 4000 cycles per tile, profiles/r01g_attention_decoupled_ab.txt.)
+    constexpr uint32_t IDESC_PV = idesc_bf16_f32(AT_BM, AT_HD, 0, 1);
+    GrpCursor kc0, kc1, vc0, vc1, pc0, pc1;
     kc0.init(items, 0); kc1.init(items, 1); vc0.init(items, 0); vc1.init(items, 1);
-    int kturn = 0, vturn = 0;
-    uint32_t gk = 0, gv = 0;
-    auto load_k = [&](GrpCursor& c, int g) {
+    pc0.init(items, 0); pc1.init(items, 1);
+    int kturn = 0, vturn = 0, pturn = 0;
+    uint32_t gk = 0;
+    auto try_k = [&](GrpCursor& c, int g) -> bool {
+      const uint32_t ks = gk % AT_KST;
+      if (!mbar_test_wait(&k_empty[ks], ((gk / AT_KST) & 1) ^ 1)) return false;
+      if (c.j == 0 && !mbar_test_wait(&q_empty[g], (c.n & 1) ^ 1)) return false;
       const int cq = c.it.h * AT_HD, ck = D + cq;
-      if (c.j == 0) {
-        mbar_wait(&q_empty[g], (c.n & 1) ^ 1);  // every QK of the group's previous item has completed
-        if (elect_one()) {
+      if (elect_one()) {
+        if (c.j == 0) {
           mbar_arrive_expect_tx(&q_full[g], AT_QB);
           tma_load_3d(sQ + g * AT_QB, &tmQ, &q_full[g], cq, c.it.b, c.it.q0);
         }
-        __syncwarp();
-      }
-      const uint32_t ks = gk % AT_KST;
-      mbar_wait(&k_empty[ks], ((gk / AT_KST) & 1) ^ 1);
-      if (elect_one()) {
         mbar_arrive_expect_tx(&k_full[ks], AT_KB);
         tma_load_3d(sK + ks * AT_KB, &tmKV, &k_full[ks], ck, c.it.b, c.j * AT_BN);
       }
       __syncwarp();
       ++gk;
       c.advance(items);
+      return true;
     };
-    auto load_v = [&](GrpCursor& c, int g) {
+    auto try_v = [&](GrpCursor& c, int g) -> bool {
+      if (!mbar_test_wait(&v_empty[g], (c.c & 1) ^ 1)) return false;
       const int cv = 2 * D + c.it.h * AT_HD;
-      mbar_wait(&v_empty[g], (c.c & 1) ^ 1);
       if (elect_one()) {
         mbar_arrive_expect_tx(&v_full[g], AT_KB);
         tma_load_3d(sV + g * AT_KB, &tmKV, &v_full[g], cv, c.it.b, c.j * AT_BN);
       }
       __syncwarp();
-      ++gv;
       c.advance(items);
+      return true;
     };
+    auto try_pv = [&](GrpCursor& c, int g) -> bool {
+      const uint32_t ph = c.c & 1;
+      if (!mbar_test_wait(&p_full[g], ph) || !mbar_test_wait(&v_full[g], ph)) return false;
+      tc_fence_after();
+      const uint32_t pa = smem_u32(sP + g * AT_QB), va = smem_u32(sV + g * AT_KB);
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < AT_BN / 16; ++kk)
+          umma_bf16_ss(tmem_O + g * AT_HD, desc_kmajor_sw128(pa) + 2 * kk,
+                       desc_mnmajor_sw128(va + kk * 2048, AT_KB), IDESC_PV, (c.j > 0) || kk != 0);
+        umma_commit(&pv_done[g]);
+        umma_commit(&v_empty[g]);
+      }
+      __syncwarp();
+      c.advance(items);
+      return true;
+    };
+    uint32_t idle = 0;
     for (;;) {
       const bool k_left = kc0.valid(n_items) || kc1.valid(n_items);
       const bool v_left = vc0.valid(n_items) || vc1.valid(n_items);
-      if (!k_left && !v_left) break;
+      const bool p_left = pc0.valid(n_items) || pc1.valid(n_items);
+      if (!k_left && !v_left && !p_left) break;
+      bool progressed = false;
+      if (p_left) {  // PV first: it is what the softmax groups wait for
+        const bool ok = (ATD_PICK(pc0, pc1, pturn) == 0) ? try_pv(pc0, 0) : try_pv(pc1, 1);
+        if (ok) { pturn ^= 1; progressed = true; }
+      }
       if (k_left) {
-        if (ATD_PICK(kc0, kc1, kturn) == 0) load_k(kc0, 0); else load_k(kc1, 1);
-        kturn ^= 1;
+        const bool ok = (ATD_PICK(kc0, kc1, kturn) == 0) ? try_k(kc0, 0) : try_k(kc1, 1);
+        if (ok) { kturn ^= 1; progressed = true; }
       }
-      if (v_left && (gk >= gv + 3 || !(kc0.valid(n_items) || kc1.valid(n_items)))) {
-        if (ATD_PICK(vc0, vc1, vturn) == 0) load_v(vc0, 0); else load_v(vc1, 1);
-        vturn ^= 1;
+      if (v_left) {
+        const bool ok = (ATD_PICK(vc0, vc1, vturn) == 0) ? try_v(vc0, 0) : try_v(vc1, 1);
+        if (ok) { vturn ^= 1; progressed = true; }
       }
+      if (!progressed) __nanosleep(32);  // do not take issue slots from the softmax warps of this SMSP
+#if FBKST_WATCHDOG
+      idle = progressed ? 0 : idle + 1;
+      if (idle > (1u << 25)) {
+        printf("fbkst: attention event loop watchdog block=%d\n", blockIdx.x);
+        __trap();
+      }
+#endif
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
+    // ------------------------------------------------------------------ QK issuer (blocking, in order)
     constexpr uint32_t IDESC_QK = idesc_bf16_f32(AT_BM, AT_BN, 0, 0);
-    constexpr uint32_t IDESC_PV = idesc_bf16_f32(AT_BM, AT_HD, 0, 1);
-    GrpCursor qc0, qc1, pc0, pc1;
-    qc0.init(items, 0); qc1.init(items, 1); pc0.init(items, 0); pc1.init(items, 1);
-    int qturn = 0, pturn = 0;
+    GrpCursor qc0, qc1;
+    qc0.init(items, 0); qc1.init(items, 1);
+    int qturn = 0;
     uint32_t gq = 0;
-    // QK of the next tile of the QK order into S[g]; the caller has made sure S[g] is free
     auto issue_qk = [&](GrpCursor& c, int g) {
+      if (c.c >= 1) {  // S[g] must have been pulled into registers by the group's previous tile
+        mbar_wait(&s_free[g], (c.c - 1) & 1);
+      }
       if (c.j == 0) mbar_wait(&q_full[g], c.n & 1);
       const uint32_t ks = gq % AT_KST;
       mbar_wait(&k_full[ks], (gq / AT_KST) & 1);
@@ -808,45 +847,9 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
       ++gq;
       c.advance(items);
     };
-    auto next_qk = [&]() {  // issue the next element of the QK order
+    while (qc0.valid(n_items) || qc1.valid(n_items)) {
       if (ATD_PICK(qc0, qc1, qturn) == 0) issue_qk(qc0, 0); else issue_qk(qc1, 1);
       qturn ^= 1;
-    };
-    // prologue: the first tile of each group (S[0] and S[1] are free)
-    if (qc0.valid(n_items) || qc1.valid(n_items)) next_qk();
-    {
-      // the second element is the other group's first tile unless that group has no work at all
-      const bool other_first = (qc0.valid(n_items) && qc0.c == 0) || (qc1.valid(n_items) && qc1.c == 0);
-      if (other_first) next_qk();
-    }
-    auto issue_pv = [&](GrpCursor& c, GrpCursor& qc, int g) {
-      const uint32_t ph = c.c & 1;
-      // QK of this group's NEXT tile first: S[g] is free as soon as the group has pulled S(c) into
-      // registers (half way through its exp pass), long before P(c) is complete.  By construction of
-      // the order that tile is the next element of the QK order iff it exists.
-      if (qc.valid(n_items) && qc.c == c.c + 1) {
-        mbar_wait(&s_free[g], ph);
-        tc_fence_after();
-        next_qk();
-      }
-      mbar_wait(&p_full[g], ph);  // P[g] in smem, O[g] rescaled / read out
-      mbar_wait(&v_full[g], ph);
-      tc_fence_after();
-      const uint32_t pa = smem_u32(sP + g * AT_QB), va = smem_u32(sV + g * AT_KB);
-      if (elect_one()) {
-#pragma unroll
-        for (int kk = 0; kk < AT_BN / 16; ++kk)
-          umma_bf16_ss(tmem_O + g * AT_HD, desc_kmajor_sw128(pa) + 2 * kk,
-                       desc_mnmajor_sw128(va + kk * 2048, AT_KB), IDESC_PV, (c.j > 0) || kk != 0);
-        umma_commit(&pv_done[g]);
-        umma_commit(&v_empty[g]);
-      }
-      __syncwarp();
-      c.advance(items);
-    };
-    while (pc0.valid(n_items) || pc1.valid(n_items)) {
-      if (ATD_PICK(pc0, pc1, pturn) == 0) issue_pv(pc0, qc0, 0); else issue_pv(pc1, qc1, 1);
-      pturn ^= 1;
     }
   } else {
     // ---- softmax / correction / output: thread <-> (query row of the group's own item)
@@ -1075,9 +1078,9 @@ extern "C" int fbkst_attention_fwd(const void* qkv, void* out, const int32_t* le
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  // decoupled groups (one item per softmax group): opt-in experiment, FBKST_ATTN_DEC=1, used when two
-  // of its CTAs fit an SM (L <~ 1100 with the penalty LUT); measured no faster than split-KV
-  static const bool dec_enabled = getenv("FBKST_ATTN_DEC") && atoi(getenv("FBKST_ATTN_DEC")) != 0;
+  // decoupled groups (one item per softmax group) whenever two of its CTAs fit an SM (L <~ 1100 with the
+  // penalty LUT); FBKST_ATTN_DEC=0 forces the split-KV kernel (A/B switch)
+  static const bool dec_enabled = !(getenv("FBKST_ATTN_DEC") && atoi(getenv("FBKST_ATTN_DEC")) == 0);
   const int smem_dec = attention_dec_smem_bytes(log_penalty ? L : 0);
   const long long n_items_all = (long long)((L + AT_BM - 1) / AT_BM) * B * H;
   if (dec_enabled && 2 * (smem_dec + 1024) <= 228 * 1024) {
