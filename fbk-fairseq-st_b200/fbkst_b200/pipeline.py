@@ -30,7 +30,8 @@ class EncoderPipeline:
         self.normalize = normalize
         self.device = device or next(encoder.parameters()).device
         # eager launches share lazily created tables across lanes: keep one lane unless graphs are on
-        self.lanes = max(1, int(lanes)) if encoder.use_cuda_graph else 1
+        # at most 4: lanes + 1 forwards are in flight and the encoder's pinned length rings hold 8
+        self.lanes = min(4, max(1, int(lanes))) if encoder.use_cuda_graph else 1
         self.s_in = torch.cuda.Stream(self.device)
         self.s_lane = [torch.cuda.Stream(self.device) for _ in range(self.lanes)]
         self.s_out = torch.cuda.Stream(self.device)
