@@ -9,11 +9,14 @@ compression at layer 8 -> final LN).  Workload at N=1 = BASELINE.json configs[1]
 d512 h8 ffn2048, bf16, batch 64 x 1500 x 40).  For N>1 the path shards by utterance batch: every rank
 runs its own batch, no collective on the data path (scaling "weak").
 
-Prints ONE JSON line (rank 0).  Keys: see the bench contract in the task statement; in addition
-`roofline` (dominant kernel family = the tcgen05 linear kernel, timed live with CUDA events),
-`kernels` (per-kernel-family breakdown), `cpu_baseline` (the oracle port on the host cores, rank 0,
-bounded sample) and `e2e` (same metric through the public encoder API with HOST input buffers:
-pinned H2D of the batch and D2H of the result inside the timed region).
+Prints ONE JSON line (rank 0).  Keys: see the bench contract in the task statement.
+`value`: K steps back to back through `EncoderPipeline.run_device` (batches resident in HBM, two
+forwards in flight on two compute lanes), one CUDA-event pair around all K steps, max over ranks.
+`e2e`: the same K steps through `EncoderPipeline.run` from pinned HOST buffers (H2D of every batch and
+D2H of every result inside the timed wall-clock region).  `single_forward_ms`: one forward at a time with
+an L2 flush before each (informative).  `roofline`: dominant kernel family (the tcgen05 linear kernel),
+timed live with CUDA events in a separate launch-by-launch pass; `kernels`: the same pass for every
+kernel family; `cpu_baseline`: the oracle port on the host cores (rank 0, bounded sample).
 """
 import argparse
 import json
