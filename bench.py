@@ -64,10 +64,12 @@ CONFIGS = {
 CTC_MARGIN = 30.0
 LOOKAHEAD_CYCLES = int(1.0e-3 * 1.9e9)  # ~1 ms of untimed GPU delay before every timed step
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
-# captures (profiles/r01a_ncu_gemm2.txt: mean over the captured launches of each kernel)
+# captures (profiles/r01i_ncu_gemm2.txt: mean over the captured launches of each kernel: qkv + fc1,
+# out_proj + fc2 of a full-length layer; cold caches, so an upper bound for the L2-warm step)
 NCU_TRAFFIC = {
-    "gemm2_kernel<bf16 out> (qkv, fc1, ctc_fc)": int((26.21 + 17.19 + 26.78 + 40.57) / 2 * 1e6),
-    "gemm2_kernel<f32 out + residual (+ bf16 copy, LN statistics)> (out_proj, fc2)": None,
+    "gemm2_kernel<bf16 out> (qkv, fc1, ctc_fc)": int((26.99 + 17.42 + 27.55 + 39.86) / 2 * 1e6),
+    "gemm2_kernel<f32 out + residual (+ bf16 copy, LN statistics)> (out_proj, fc2)":
+        int((74.31 + 23.66 + 151.59 + 35.04) / 2 * 1e6),
 }
 
 
