@@ -249,6 +249,10 @@ class KernelProfile:
             C = out.shape[-1]
             return dict(flops=2.0 * out.numel() * 9 * C, bytes=a[0].numel() * 2 + out.numel() * 2)
 
+        def conv2p(a, k, out):
+            C = out.shape[-1]
+            return dict(flops=2.0 * out.numel() * 9 * C, bytes=a[0].numel() * 2 + out.numel() * 2)
+
         def cmvn(a, k, out):
             return dict(flops=0.0, bytes=a[0].numel() * 4 * 3)
 
@@ -266,7 +270,8 @@ class KernelProfile:
                         ("embed_remap_stats", embed), ("attention", att),
                         ("layernorm", ln_), ("ctc_argmax", argmax),
                         ("ctc_compress", compress), ("ctc_segment", other), ("conv1_relu_bn", conv1),
-                        ("conv2_relu_bn", conv2), ("cmvn", cmvn), ("cast_bf16", other),
+                        ("conv2_relu_bn", conv2), ("conv1_relu_bn_planes", conv1),
+                        ("conv2_relu_bn_planes", conv2p), ("cmvn", cmvn), ("cast_bf16", other),
                         ("lengths_to_mask", other)]:
             self._wrap(name, w)
         return self

@@ -20,6 +20,7 @@ struct Conv2Params {
   const float* shift;
   __nv_bfloat16* out;
   int B, T2, F2, R, tiles_per_utt;
+  int planes;  // input = four (t1, f1)-parity planes written by conv1_tc (unit-stride tap boxes)
 };
 
 template <int C, int STAGES>
@@ -32,8 +33,10 @@ __global__ void __launch_bounds__(256, 1)
   // stage holds only the A box (35 % fewer bytes through TMA / L2, two more A stages).  MEASURED: the
   // kernel time does not move (51.2 us at cfg2 either way) -- the kernel is bound by its A loads (the
   // epilogue and MMA warps wait on tfull / full barriers: profiles/r01g_ncu_front.txt), i.e. by the 4-D
-  // boxes with element strides {1,2,2,1}.  Next step: conv1 emits parity planes (its thread <-> pixel
-  // mapping is free) so that every tap becomes a unit-stride box.
+  // boxes?  No: with conv1 writing (t1, f1)-parity planes (p.planes) every tap is a UNIT-stride 5-D box and
+  // the time is again 51.2 us.  Neither bytes, nor pipeline depth, nor box shape: what is left is the
+  // single MMA-issuing thread's per-k-block round trip (wait full -> fence -> 4 x UMMA N=64 -> commit, ~770
+  // cycles per k-block against 128 of tensor work) -- the next experiment is two taps per stage.
   constexpr bool WRES = (C == 64);
   constexpr int STAGE_BYTES = A_BYTES + (WRES ? 0 : B_BYTES);
   constexpr int W_BYTES = WRES ? 9 * B_BYTES : 0;
@@ -99,7 +102,11 @@ __global__ void __launch_bounds__(256, 1)
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], a_tx + (WRES ? 0 : B_BYTES));
           uint8_t* sa = smem + stage * STAGE_BYTES;
-          tma_load_4d(sa, &tmX, &full_bar[stage], kc * 64, kw - 1, 2 * t0 + kh - 1, b);
+          if (p.planes)  // tap (kh, kw) reads conv1 pixel (2*t2 + kh - 1, 2*f2 + kw - 1): plane (kh != 1, kw != 1)
+            tma_load_5d(sa, &tmX, &full_bar[stage], kc * 64, kw == 0 ? -1 : 0, t0 + (kh == 0 ? -1 : 0), b,
+                        (kh != 1) * 2 + (kw != 1));
+          else
+            tma_load_4d(sa, &tmX, &full_bar[stage], kc * 64, kw - 1, 2 * t0 + kh - 1, b);
           if (!WRES) tma_load_2d(sa + A_BYTES, &tmW, &full_bar[stage], kc * 64, tap * C);
           if (++stage == STAGES) {
             stage = 0;
@@ -202,11 +209,20 @@ static int launch_conv2(const void* x, const void* w_taps, const Conv2Params& p,
     configured = true;
   }
   CUtensorMap tmX, tmW;
-  uint64_t dims[4] = {(uint64_t)C, (uint64_t)F1, (uint64_t)T1, (uint64_t)p.B};
-  uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)F1 * C * 2, (uint64_t)T1 * F1 * C * 2};
-  uint32_t box[4] = {64, (uint32_t)(2 * p.F2), (uint32_t)(2 * p.R), 1};
-  uint32_t es[4] = {1, 2, 2, 1};
-  int rc = make_tensor_map(&tmX, x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 4, dims, strides, box, es);
+  int rc;
+  if (p.planes) {  // [4 planes][B][T2][F2][C], unit-stride boxes of one plane
+    uint64_t dims[5] = {(uint64_t)C, (uint64_t)p.F2, (uint64_t)p.T2, (uint64_t)p.B, 4};
+    uint64_t strides[4] = {(uint64_t)C * 2, (uint64_t)p.F2 * C * 2, (uint64_t)p.T2 * p.F2 * C * 2,
+                           (uint64_t)p.B * p.T2 * p.F2 * C * 2};
+    uint32_t box[5] = {64, (uint32_t)p.F2, (uint32_t)p.R, 1, 1};
+    rc = make_tensor_map(&tmX, x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 5, dims, strides, box, nullptr);
+  } else {
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)F1, (uint64_t)T1, (uint64_t)p.B};
+    uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)F1 * C * 2, (uint64_t)T1 * F1 * C * 2};
+    uint32_t box[4] = {64, (uint32_t)(2 * p.F2), (uint32_t)(2 * p.R), 1};
+    uint32_t es[4] = {1, 2, 2, 1};
+    rc = make_tensor_map(&tmX, x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 4, dims, strides, box, es);
+  }
   if (rc) return rc;
   rc = make_tensor_map_2d_bf16(&tmW, w_taps, (uint64_t)9 * C, (uint64_t)C, (uint64_t)C, C, 64);
   if (rc) return rc;
@@ -219,9 +235,9 @@ static int launch_conv2(const void* x, const void* w_taps, const Conv2Params& p,
 
 }  // namespace fbkst
 
-extern "C" int fbkst_conv2_relu_bn(const void* x, const void* w_taps, const float* bias,
-                                   const float* bn_scale, const float* bn_shift, void* y, int B,
-                                   int T1, int F1, int C, fbkst_stream_t stream) {
+static int conv2_entry(const void* x, const void* w_taps, const float* bias, const float* bn_scale,
+                       const float* bn_shift, void* y, int B, int T1, int F1, int C, int planes,
+                       fbkst_stream_t stream) {
   using namespace fbkst;
   FBKST_REQUIRE(x && w_taps && bias && bn_scale && bn_shift && y, "fbkst_conv2_relu_bn: null pointer");
   FBKST_REQUIRE(C == 64 || C == 128, "fbkst_conv2_relu_bn: C must be 64 or 128 (got %d)", C);
@@ -238,7 +254,20 @@ extern "C" int fbkst_conv2_relu_bn(const void* x, const void* w_taps, const floa
   p.R = 128 / p.F2;
   if (p.R > p.T2) p.R = p.T2;
   p.tiles_per_utt = (p.T2 + p.R - 1) / p.R;
+  p.planes = planes;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (C == 64) return launch_conv2<64, 8>(x, w_taps, p, T1, F1, st);  // resident weights leave room for 8 A stages
   return launch_conv2<128, 6>(x, w_taps, p, T1, F1, st);
+}
+
+extern "C" int fbkst_conv2_relu_bn(const void* x, const void* w_taps, const float* bias,
+                                   const float* bn_scale, const float* bn_shift, void* y, int B,
+                                   int T1, int F1, int C, fbkst_stream_t stream) {
+  return conv2_entry(x, w_taps, bias, bn_scale, bn_shift, y, B, T1, F1, C, 0, stream);
+}
+
+extern "C" int fbkst_conv2_relu_bn_planes(const void* x_planes, const void* w_taps, const float* bias,
+                                          const float* bn_scale, const float* bn_shift, void* y, int B,
+                                          int T1, int F1, int C, fbkst_stream_t stream) {
+  return conv2_entry(x_planes, w_taps, bias, bn_scale, bn_shift, y, B, T1, F1, C, 1, stream);
 }

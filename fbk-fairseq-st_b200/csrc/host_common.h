@@ -44,7 +44,7 @@ int num_sms();
 
 // conv1 on the tensor pipe (conv1_tcgen05.cu); C is 64 or 128
 int conv1_tc_dispatch(const float* x, const float* w, const float* bias, const float* scale,
-                      const float* shift, void* y, int B, int T, int F, int C, int T1, int F1,
+                      const float* shift, void* y, int B, int T, int F, int C, int T1, int F1, int planes,
                       cudaStream_t st);
 
 // 0 when FBKST_PDL=0 is set in the environment (A/B switch); default 1.

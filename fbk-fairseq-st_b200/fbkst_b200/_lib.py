@@ -21,6 +21,8 @@ SIGNATURES = {
     "fbkst_collate_cmvn_f32": [P, P, P, P, I, I, I, I, P, P],
     "fbkst_conv1_relu_bn": [P, P, P, P, P, P, I, I, I, I, P],
     "fbkst_conv2_relu_bn": [P, P, P, P, P, P, I, I, I, I, P],
+    "fbkst_conv1_relu_bn_planes": [P, P, P, P, P, P, I, I, I, I, P],
+    "fbkst_conv2_relu_bn_planes": [P, P, P, P, P, P, I, I, I, I, P],
     "fbkst_linear_bf16": [P, I64, P, I64, P, P, I64, P, I64, I, I, I, I, I, I, P, P, I, P],
     "fbkst_linear_ln_bf16": [P, I64, P, I64, P, P, I64, P, I64, I, I, I, I, P, F, P, I64, P, P, I, P],
     "fbkst_row_stats_cast": [P, P, P, I, I, P, I, P],

@@ -111,6 +111,37 @@ def conv2_relu_bn(x, w_taps, bias, scale, shift):
     return y
 
 
+def conv1_relu_bn_planes(x, w, bias, scale, shift):
+    """conv1 -> four (t1, f1)-parity planes [4, B, ceil(T1/2), ceil(F1/2), C] bf16 (see the header)."""
+    lib = _lib.require_device()
+    _req(x, torch.float32, "conv1.x")
+    B, T, Fd = x.shape
+    C = w.shape[0]
+    T1, F1 = (T + 1) // 2, (Fd + 1) // 2
+    y = torch.empty(4, B, (T1 + 1) // 2, (F1 + 1) // 2, C, dtype=torch.bfloat16, device=x.device)
+    check(lib.fbkst_conv1_relu_bn_planes(x.data_ptr(), _req(w, torch.float32, "conv1.w").data_ptr(),
+                                         bias.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+                                         y.data_ptr(), B, T, Fd, C, _stream()))
+    _count()
+    return y
+
+
+def conv2_relu_bn_planes(x_planes, T1, F1, w_taps, bias, scale, shift):
+    """conv2 over the plane layout of ``conv1_relu_bn_planes``; output as ``conv2_relu_bn``."""
+    lib = _lib.require_device()
+    _req(x_planes, torch.bfloat16, "conv2.x_planes"); _req(w_taps, torch.bfloat16, "conv2.w_taps")
+    four, B, TH, FH, C = x_planes.shape
+    if four != 4 or TH != (T1 + 1) // 2 or FH != (F1 + 1) // 2:
+        raise ValueError("conv2_relu_bn_planes: plane shape %s does not match T1=%d F1=%d"
+                         % (tuple(x_planes.shape), T1, F1))
+    y = torch.empty(B, TH, FH, C, dtype=torch.bfloat16, device=x_planes.device)
+    check(lib.fbkst_conv2_relu_bn_planes(x_planes.data_ptr(), w_taps.data_ptr(), bias.data_ptr(),
+                                         scale.data_ptr(), shift.data_ptr(), y.data_ptr(), B, T1, F1, C,
+                                         _stream()))
+    _count()
+    return y
+
+
 def linear(a, w, bias=None, relu=False, residual=None, out_dtype=torch.bfloat16, out=None,
            remap=None, posemb=None, rows_limit=None):
     """out = epi(a @ w.T).  a [M,K] bf16, w [N,K] bf16, bias [N] fp32, residual [M,N] fp32.

@@ -88,6 +88,17 @@ int fbkst_conv2_relu_bn(const void* x, const void* w_taps, const float* bias,
                         const float* bn_scale, const float* bn_shift, void* y, int B, int T1,
                         int F1, int C, fbkst_stream_t stream);
 
+/* ---- a2, plane layout (default inside the encoder): conv1 writes FOUR (t1, f1)-parity planes
+ * [ (t1&1)*2 + (f1&1) ][B][ceil(T1/2)][ceil(F1/2)][C] bf16 (slots past T1 / F1 are zeros) instead of
+ * [B][T1][F1][C]; conv2's stride-2 taps then are unit-stride TMA boxes of one plane.  Same arithmetic, same
+ * conv2 output as the pair above (conv_transformer.py:203-214). */
+int fbkst_conv1_relu_bn_planes(const float* x, const float* w, const float* bias, const float* bn_scale,
+                               const float* bn_shift, void* y_planes, int B, int T, int F, int C,
+                               fbkst_stream_t stream);
+int fbkst_conv2_relu_bn_planes(const void* x_planes, const void* w_taps, const float* bias,
+                               const float* bn_scale, const float* bn_shift, void* y, int B, int T1,
+                               int F1, int C, fbkst_stream_t stream);
+
 /* ---- generic fused linear: out = epi(A @ W^T) on tcgen05 --------------------------------
  * replaces every F.linear / nn.Linear on the path (conv_transformer.py:227,279;
  * local_attention.py:178,141; fairseq/modules/transformer_layer.py:131-133).

@@ -268,6 +268,36 @@ def test_conv_stack(B, T, Fd, C):
     assert e2 < 1e-2, e2
 
 
+@pytest.mark.parametrize("B,T,Fd,C", [(2, 61, 40, 64), (3, 100, 40, 64), (2, 37, 80, 64), (2, 45, 80, 128),
+                                      (1, 7, 40, 64), (2, 130, 42, 64)])
+def test_conv_stack_planes_is_bit_identical(B, T, Fd, C):
+    """conv1 -> parity planes -> conv2 with unit-stride tap boxes gives exactly the conv2 output of the
+    [B,T1,F1,C] path (same products, same accumulation order), and the planes hold conv1's pixels at
+    (t1 & 1, f1 & 1, t1 >> 1, f1 >> 1) with zeros in the slots past T1 / F1 (odd T1 / F1 included)."""
+    from fbkst_b200 import ops
+    g = torch.Generator().manual_seed(B * T + Fd + C)
+    d = dev()
+    x = torch.randn(B, T, Fd, generator=g).to(d)
+    w1 = (torch.randn(C, 9, generator=g) * 0.6).to(d)
+    w2 = ops.prep_conv2_weight((torch.randn(C, C, 3, 3, generator=g) * (1.0 / math.sqrt(9 * C))).to(d))
+    b1, b2 = (torch.randn(C, generator=g) * 0.1).to(d), (torch.randn(C, generator=g) * 0.1).to(d)
+    sc = [(torch.rand(C, generator=g) + 0.5).to(d) for _ in range(2)]
+    sh = [(torch.randn(C, generator=g) * 0.1).to(d) for _ in range(2)]
+    y1 = ops.conv1_relu_bn(x, w1, b1, sc[0], sh[0])
+    y2 = ops.conv2_relu_bn(y1, w2, b2, sc[1], sh[1])
+    p1 = ops.conv1_relu_bn_planes(x, w1, b1, sc[0], sh[0])
+    T1, F1 = y1.shape[1], y1.shape[2]
+    q2 = ops.conv2_relu_bn_planes(p1, T1, F1, w2, b2, sc[1], sh[1])
+    torch.cuda.synchronize()
+    ref = torch.zeros_like(p1)
+    for pt in range(2):
+        for pf in range(2):
+            sub = y1[:, pt::2, pf::2]
+            ref[pt * 2 + pf, :, : sub.shape[1], : sub.shape[2]] = sub
+    assert torch.equal(p1, ref)
+    assert torch.equal(q2, y2)
+
+
 def test_fc3_weight_permutation():
     from fbkst_b200 import ops
     D, C, F2 = 128, 64, 10
