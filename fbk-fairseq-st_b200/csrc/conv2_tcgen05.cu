@@ -30,13 +30,10 @@ __global__ void __launch_bounds__(256, 1)
   constexpr int A_BYTES = 128 * 64 * 2;
   constexpr int B_BYTES = C * 64 * 2;
   // C == 64: all nine weight taps (72 KB) stay resident in shared memory for the life of the CTA and a
-  // stage holds only the A box (35 % fewer bytes through TMA / L2, two more A stages).  MEASURED: the
-  // kernel time does not move (51.2 us at cfg2 either way) -- the kernel is bound by its A loads (the
-  // epilogue and MMA warps wait on tfull / full barriers: profiles/r01g_ncu_front.txt), i.e. by the 4-D
-  // boxes?  No: with conv1 writing (t1, f1)-parity planes (p.planes) every tap is a UNIT-stride 5-D box and
-  // the time is again 51.2 us.  Neither bytes, nor pipeline depth, nor box shape: what is left is the
-  // single MMA-issuing thread's per-k-block round trip (wait full -> fence -> 4 x UMMA N=64 -> commit, ~770
-  // cycles per k-block against 128 of tensor work) -- the next experiment is two taps per stage.
+  // stage holds only the A box (35 % fewer bytes through TMA / L2, two more A stages).  MEASURED: on its
+  // own this did not move the kernel (51.2 us at cfg2), nor did unit-stride tap boxes over parity planes
+  // (p.planes): the bound was the issue code of the single-lane MMA / TMA warps (see the comment at the
+  // warp roles); with that fixed and the epilogue constants in shared memory conv2 runs in 37-40 us.
   constexpr bool WRES = (C == 64);
   constexpr int STAGE_BYTES = A_BYTES + (WRES ? 0 : B_BYTES);
   constexpr int W_BYTES = WRES ? 9 * B_BYTES : 0;
@@ -54,6 +51,8 @@ __global__ void __launch_bounds__(256, 1)
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* w_full = tempty_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+  // per-channel epilogue constants (bias | BN scale | BN shift), read as broadcast float4 LDS
+  float4* sConst = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(full_bar) + 256);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -80,71 +79,84 @@ __global__ void __launch_bounds__(256, 1)
     tmem_alloc(tmem_slot, TMEM_COLS);
     tmem_relinquish();
   }
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) {
+    const float* src = i < C ? p.bias : (i < 2 * C ? p.scale : p.shift);
+    reinterpret_cast<float*>(sConst)[i] = __ldg(src + (i % C));
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Both single-issuer roles run in warp-UNIFORM control flow with one elected lane issuing: with
+  // `if (lane == 0)` ptxas wraps every UTMALDG / UTCHMMA in a divergence waterfall (ELECT / BRA.U.ANY loop +
+  // descriptor rebuild); the MMA warp spent ~60 % of its samples in that issue code and a k-block took ~770
+  // cycles for 128 cycles of tensor work (profiles/r01g_ncu_front.txt).
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      if (WRES) {
+    int stage = 0;
+    uint32_t phase = 0;
+    if (WRES) {
+      if (elect_one()) {
         mbar_arrive_expect_tx(w_full, W_BYTES);
         for (int tap = 0; tap < 9; ++tap) tma_load_2d(sW + tap * B_BYTES, &tmW, w_full, 0, tap * C);
       }
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int b = tile / p.tiles_per_utt;
-        const int t0 = (tile - b * p.tiles_per_utt) * p.R;
-        for (int kb = 0; kb < NUM_KB; ++kb) {
-          const int tap = kb / KCH, kc = kb - tap * KCH;
-          const int kh = tap / 3, kw = tap - kh * 3;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+      __syncwarp();
+    }
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int b = tile / p.tiles_per_utt;
+      const int t0 = (tile - b * p.tiles_per_utt) * p.R;
+      for (int kb = 0; kb < NUM_KB; ++kb) {
+        const int tap = kb / KCH, kc = kb - tap * KCH;
+        const int kh = tap / 3, kw = tap - kh * 3;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * STAGE_BYTES;
+        if (elect_one()) {
           mbar_arrive_expect_tx(&full_bar[stage], a_tx + (WRES ? 0 : B_BYTES));
-          uint8_t* sa = smem + stage * STAGE_BYTES;
           if (p.planes)  // tap (kh, kw) reads conv1 pixel (2*t2 + kh - 1, 2*f2 + kw - 1): plane (kh != 1, kw != 1)
             tma_load_5d(sa, &tmX, &full_bar[stage], kc * 64, kw == 0 ? -1 : 0, t0 + (kh == 0 ? -1 : 0), b,
                         (kh != 1) * 2 + (kw != 1));
           else
             tma_load_4d(sa, &tmX, &full_bar[stage], kc * 64, kw - 1, 2 * t0 + kh - 1, b);
           if (!WRES) tma_load_2d(sa + A_BYTES, &tmW, &full_bar[stage], kc * 64, tap * C);
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      if (WRES) mbar_wait(w_full, 0);
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    if (WRES) mbar_wait(w_full, 0);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * C;
+      for (int kb = 0; kb < NUM_KB; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * C;
-        for (int kb = 0; kb < NUM_KB; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint64_t adesc = desc_kmajor_sw128(sa);
-          const uint64_t bdesc = desc_kmajor_sw128(WRES ? smem_u32(sW) + kb * B_BYTES : sa + A_BYTES);
+        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+        const uint64_t adesc = desc_kmajor_sw128(sa);
+        const uint64_t bdesc = desc_kmajor_sw128(WRES ? smem_u32(sW) + kb * B_BYTES : sa + A_BYTES);
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
           umma_commit(&empty_bar[stage]);
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+          if (kb == NUM_KB - 1) umma_commit(&tfull_bar[acc]);  // same thread as the MMAs it tracks
         }
-        umma_commit(&tfull_bar[acc]);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
   } else if (warp >= 4) {
     const int ew = warp - 4;
@@ -167,10 +179,12 @@ __global__ void __launch_bounds__(256, 1)
         if (r < valid_rows) {
           float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int ch = c * 32 + j;
-            const float a = fmaxf(__uint_as_float(v[j]) + __ldg(p.bias + ch), 0.0f);
-            f[j] = fmaf(a, __ldg(p.scale + ch), __ldg(p.shift + ch));
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 bb = sConst[c * 8 + j4], sc = sConst[C / 4 + c * 8 + j4], sh = sConst[C / 2 + c * 8 + j4];
+            f[4 * j4 + 0] = fmaf(fmaxf(__uint_as_float(v[4 * j4 + 0]) + bb.x, 0.0f), sc.x, sh.x);
+            f[4 * j4 + 1] = fmaf(fmaxf(__uint_as_float(v[4 * j4 + 1]) + bb.y, 0.0f), sc.y, sh.y);
+            f[4 * j4 + 2] = fmaf(fmaxf(__uint_as_float(v[4 * j4 + 2]) + bb.z, 0.0f), sc.z, sh.z);
+            f[4 * j4 + 3] = fmaf(fmaxf(__uint_as_float(v[4 * j4 + 3]) + bb.w, 0.0f), sc.w, sh.w);
           }
           uint4* o4 = reinterpret_cast<uint4*>(orow + c * 32);
 #pragma unroll
@@ -200,7 +214,7 @@ template <int C, int STAGES>
 static int launch_conv2(const void* x, const void* w_taps, const Conv2Params& p, int T1, int F1,
                         cudaStream_t stream) {
   constexpr int SMEM = (C == 64 ? STAGES * 128 * 64 * 2 + 9 * C * 64 * 2 : STAGES * (128 * 64 * 2 + C * 64 * 2)) +
-                       1024 + 256;
+                       1024 + 256 + 3 * C * 4;
   static_assert(SMEM <= 232448, "shared memory budget exceeded");
   auto kern = conv2_kernel<C, STAGES>;
   static bool configured = false;
