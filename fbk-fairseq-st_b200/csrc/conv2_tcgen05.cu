@@ -26,7 +26,7 @@ struct Conv2Params {
 template <int C, int STAGES>
 __global__ void __launch_bounds__(256, 1)
     conv2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
-                 Conv2Params p) {
+                 const __grid_constant__ CUtensorMap tmY, Conv2Params p) {
   constexpr int A_BYTES = 128 * 64 * 2;
   constexpr int B_BYTES = C * 64 * 2;
   // C == 64: all nine weight taps (72 KB) stay resident in shared memory for the life of the CTA and a
@@ -39,6 +39,8 @@ __global__ void __launch_bounds__(256, 1)
   constexpr int W_BYTES = WRES ? 9 * B_BYTES : 0;
   constexpr int KCH = C / 64;
   constexpr int NUM_KB = 9 * KCH;
+  // operand stages + resident taps + 256 B of barriers + 3*C floats of constants, rounded up to 1024
+  constexpr int SMEM_MAIN = ((STAGES * STAGE_BYTES + W_BYTES + 256 + 3 * C * 4) + 1023) / 1024 * 1024;
   constexpr uint32_t TMEM_COLS = 2 * C;
   constexpr uint32_t IDESC = idesc_bf16_f32(128, C, 0, 0);
 
@@ -53,6 +55,10 @@ __global__ void __launch_bounds__(256, 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
   // per-channel epilogue constants (bias | BN scale | BN shift), read as broadcast float4 LDS
   float4* sConst = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(full_bar) + 256);
+  // output staging [C/64 halves][128 rows][128 B], 128B-swizzled: one TMA store per tile and half with the
+  // box {64, F2, R} of the [B][T2][F2][C] output (rows past T2 are clipped by the map, rows >= R*F2 of the
+  // tile are not part of the box), instead of thread-per-row 16-byte stores (32 lines per instruction)
+  uint8_t* sOut = smem + SMEM_MAIN;
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -162,45 +168,54 @@ __global__ void __launch_bounds__(256, 1)
     const int ew = warp - 4;
     int acc = 0;
     uint32_t acc_phase = 0;
+    const int r = ew * 32 + lane;  // tile row == TMEM lane
+    uint8_t* srow = sOut + r * 128;
+    const bool issuer = (threadIdx.x == 128);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int b = tile / p.tiles_per_utt;
       const int t0 = (tile - b * p.tiles_per_utt) * p.R;
-      const int valid_rows = min(p.R, p.T2 - t0) * p.F2;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int r = ew * 32 + lane;
+      if (issuer) tma_store_wait_read<0>();  // the previous tile's store has finished reading the staging tile
+      asm volatile("bar.sync 1, 128;" ::: "memory");
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * C;
-      __nv_bfloat16* orow = p.out + ((size_t)((size_t)b * p.T2 + t0) * p.F2 + r) * C;
 #pragma unroll 1
       for (int c = 0; c < C / 32; ++c) {
         uint32_t v[32];
         tmem_ld32(taddr + c * 32, v);
         tmem_ld_wait();
-        if (r < valid_rows) {
-          float f[32];
+        float f[32];
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 bb = sConst[c * 8 + j4], sc = sConst[C / 4 + c * 8 + j4], sh = sConst[C / 2 + c * 8 + j4];
-            f[4 * j4 + 0] = fmaf(fmaxf(__uint_as_float(v[4 * j4 + 0]) + bb.x, 0.0f), sc.x, sh.x);
-            f[4 * j4 + 1] = fmaf(fmaxf(__uint_as_float(v[4 * j4 + 1]) + bb.y, 0.0f), sc.y, sh.y);
-            f[4 * j4 + 2] = fmaf(fmaxf(__uint_as_float(v[4 * j4 + 2]) + bb.z, 0.0f), sc.z, sh.z);
-            f[4 * j4 + 3] = fmaf(fmaxf(__uint_as_float(v[4 * j4 + 3]) + bb.w, 0.0f), sc.w, sh.w);
-          }
-          uint4* o4 = reinterpret_cast<uint4*>(orow + c * 32);
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 bb = sConst[c * 8 + j4], sc = sConst[C / 4 + c * 8 + j4], sh = sConst[C / 2 + c * 8 + j4];
+          f[4 * j4 + 0] = fmaf(fmaxf(__uint_as_float(v[4 * j4 + 0]) + bb.x, 0.0f), sc.x, sh.x);
+          f[4 * j4 + 1] = fmaf(fmaxf(__uint_as_float(v[4 * j4 + 1]) + bb.y, 0.0f), sc.y, sh.y);
+          f[4 * j4 + 2] = fmaf(fmaxf(__uint_as_float(v[4 * j4 + 2]) + bb.z, 0.0f), sc.z, sh.z);
+          f[4 * j4 + 3] = fmaf(fmaxf(__uint_as_float(v[4 * j4 + 3]) + bb.w, 0.0f), sc.w, sh.w);
+        }
+        uint8_t* hrow = srow + (c >> 1) * (128 * 128);
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            o4[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]),
-                               pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                               pack_bf16x2(f[8 * j + 4], f[8 * j + 5]),
-                               pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+        for (int j = 0; j < 4; ++j) {
+          const int chunk = (c & 1) * 4 + j;
+          *reinterpret_cast<uint4*>(hrow + ((chunk ^ (r & 7)) << 4)) =
+              make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                         pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (issuer) {
+#pragma unroll
+        for (int h = 0; h < C / 64; ++h) tma_store_4d(&tmY, sOut + h * (128 * 128), h * 64, 0, t0, b);
+        tma_store_commit();
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (issuer) tma_store_wait<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -213,8 +228,10 @@ __global__ void __launch_bounds__(256, 1)
 template <int C, int STAGES>
 static int launch_conv2(const void* x, const void* w_taps, const Conv2Params& p, int T1, int F1,
                         cudaStream_t stream) {
-  constexpr int SMEM = (C == 64 ? STAGES * 128 * 64 * 2 + 9 * C * 64 * 2 : STAGES * (128 * 64 * 2 + C * 64 * 2)) +
-                       1024 + 256 + 3 * C * 4;
+  constexpr int SMEM_MAIN =
+      (((C == 64 ? STAGES * 128 * 64 * 2 + 9 * C * 64 * 2 : STAGES * (128 * 64 * 2 + C * 64 * 2)) + 256 + 3 * C * 4) +
+       1023) / 1024 * 1024;
+  constexpr int SMEM = SMEM_MAIN + (C / 64) * 128 * 128 /*output staging*/ + 1024 /*alignment slack*/;
   static_assert(SMEM <= 232448, "shared memory budget exceeded");
   auto kern = conv2_kernel<C, STAGES>;
   static bool configured = false;
@@ -240,9 +257,17 @@ static int launch_conv2(const void* x, const void* w_taps, const Conv2Params& p,
   if (rc) return rc;
   rc = make_tensor_map_2d_bf16(&tmW, w_taps, (uint64_t)9 * C, (uint64_t)C, (uint64_t)C, C, 64);
   if (rc) return rc;
+  CUtensorMap tmY;
+  {
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)p.F2, (uint64_t)p.T2, (uint64_t)p.B};
+    uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)p.F2 * C * 2, (uint64_t)p.T2 * p.F2 * C * 2};
+    uint32_t box[4] = {64, (uint32_t)p.F2, (uint32_t)p.R, 1};
+    rc = make_tensor_map(&tmY, p.out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 4, dims, strides, box, nullptr);
+    if (rc) return rc;
+  }
   const int tiles = p.B * p.tiles_per_utt;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, 256, SMEM, stream>>>(tmX, tmW, p);
+  kern<<<grid, 256, SMEM, stream>>>(tmX, tmW, tmY, p);
   FBKST_CHECK_CUDA(cudaGetLastError());
   return FBKST_OK;
 }
