@@ -173,7 +173,7 @@ template <int LOGPEN>
 __global__ void __launch_bounds__(AT_THREADS, 2)
     attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                          __nv_bfloat16* __restrict__ out, const int* __restrict__ lengths, int L, int B,
-                         int H) {
+                         int H, const int* __restrict__ q_limit) {
   const int D = H * AT_HD;
   const int nq = (L + AT_BM - 1) / AT_BM;
   const int n_items = nq * B * H;
@@ -398,6 +398,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
       named_bar_sync(1, 256);
     }
     uint32_t g = 0;  // key tiles of the CTA's stream before the current item
+    const int q_lim = q_limit ? __ldg(q_limit) : L;  // (after pdl_wait: written by the previous kernel)
     AttnItem it;
     for (int k = 0;; ++k) {
       items.get(it, k);
@@ -405,7 +406,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
       const int i = it.q0 + q;
       __nv_bfloat16* orow = out + ((size_t)i * B + it.b) * D + it.h * AT_HD + grp * 32;
       if (it.n_kv == 0) {  // tile of padded queries: defined (finite) output, no pipeline work
-        if (i < L) {
+        if (i < L && it.q0 < q_lim) {  // tiles at or beyond the caller's row limit are never read: skip
           uint4* op = reinterpret_cast<uint4*>(orow);
 #pragma unroll
           for (int j = 0; j < 4; ++j) op[j] = make_uint4(0, 0, 0, 0);
@@ -657,7 +658,7 @@ template <int LOGPEN>
 __global__ void __launch_bounds__(AT_THREADS, 2)
     attention_fwd_dec_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                              __nv_bfloat16* __restrict__ out, const int* __restrict__ lengths, int L, int B,
-                             int H) {
+                             int H, const int* __restrict__ q_limit) {
   const int D = H * AT_HD;
   const int nq = (L + AT_BM - 1) / AT_BM;
   const int n_items = nq * B * H;
@@ -875,6 +876,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
       named_bar_sync(1, 256);
     }
     uint32_t c = 0;  // key tiles of this group before the current one
+    const int q_lim = q_limit ? __ldg(q_limit) : L;  // (after pdl_wait: written by the previous kernel)
     AttnItem it;
     for (int k = grp;; k += 2) {
       items.get(it, k);
@@ -882,7 +884,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
       const int i = it.q0 + q;
       __nv_bfloat16* orow = out + ((size_t)i * B + it.b) * D + it.h * AT_HD;
       if (it.n_kv == 0) {  // tile of padded queries: defined (finite) output, no pipeline work
-        if (i < L) {
+        if (i < L && it.q0 < q_lim) {  // tiles at or beyond the caller's row limit are never read: skip
           uint4* op = reinterpret_cast<uint4*>(orow);
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) op[jj] = make_uint4(0, 0, 0, 0);
@@ -1050,8 +1052,8 @@ extern "C" int fbkst_debug_set_attention_trace(long long* buf) {
 
 using namespace fbkst;
 
-extern "C" int fbkst_attention_fwd(const void* qkv, void* out, const int32_t* lengths, int L, int B,
-                                   int H, int log_penalty, fbkst_stream_t stream) {
+static int attention_entry(const void* qkv, void* out, const int32_t* lengths, int L, int B, int H,
+                           int log_penalty, const int32_t* q_limit, fbkst_stream_t stream) {
   FBKST_REQUIRE(qkv && out && lengths, "fbkst_attention_fwd: null pointer");
   FBKST_REQUIRE(L > 0 && B > 0 && H > 0, "fbkst_attention_fwd: bad shape L=%d B=%d H=%d", L, B, H);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -1089,10 +1091,10 @@ extern "C" int fbkst_attention_fwd(const void* qkv, void* out, const int32_t* le
     if (grid > n_items_all) grid = (int)n_items_all;
     if (log_penalty)
       FBKST_CHECK_CUDA(launch_pdl(attention_fwd_dec_kernel<1>, dim3(grid), dim3(AT_THREADS), smem_dec, st,
-                                  tmQ, tmKV, (__nv_bfloat16*)out, lengths, L, B, H));
+                                  tmQ, tmKV, (__nv_bfloat16*)out, lengths, L, B, H, q_limit));
     else
       FBKST_CHECK_CUDA(launch_pdl(attention_fwd_dec_kernel<0>, dim3(grid), dim3(AT_THREADS), smem_dec, st,
-                                  tmQ, tmKV, (__nv_bfloat16*)out, lengths, L, B, H));
+                                  tmQ, tmKV, (__nv_bfloat16*)out, lengths, L, B, H, q_limit));
     return FBKST_OK;
   }
   const int smem = attention_smem_bytes(log_penalty ? L : 0);
@@ -1105,9 +1107,21 @@ extern "C" int fbkst_attention_fwd(const void* qkv, void* out, const int32_t* le
   if (grid > n_items) grid = (int)n_items;
   if (log_penalty)
     FBKST_CHECK_CUDA(launch_pdl(attention_fwd_kernel<1>, dim3(grid), dim3(AT_THREADS), smem, st, tmQ, tmKV,
-                                (__nv_bfloat16*)out, lengths, L, B, H));
+                                (__nv_bfloat16*)out, lengths, L, B, H, q_limit));
   else
     FBKST_CHECK_CUDA(launch_pdl(attention_fwd_kernel<0>, dim3(grid), dim3(AT_THREADS), smem, st, tmQ, tmKV,
-                                (__nv_bfloat16*)out, lengths, L, B, H));
+                                (__nv_bfloat16*)out, lengths, L, B, H, q_limit));
   return FBKST_OK;
+}
+
+extern "C" int fbkst_attention_fwd(const void* qkv, void* out, const int32_t* lengths, int L, int B,
+                                   int H, int log_penalty, fbkst_stream_t stream) {
+  return attention_entry(qkv, out, lengths, L, B, H, log_penalty, nullptr, stream);
+}
+
+extern "C" int fbkst_attention_fwd_limited(const void* qkv, void* out, const int32_t* lengths, int L, int B,
+                                           int H, int log_penalty, const int32_t* q_limit,
+                                           fbkst_stream_t stream) {
+  FBKST_REQUIRE(q_limit != nullptr, "fbkst_attention_fwd_limited: null q_limit");
+  return attention_entry(qkv, out, lengths, L, B, H, log_penalty, q_limit, stream);
 }

@@ -29,6 +29,7 @@ SIGNATURES = {
     "fbkst_embed_remap_stats": [P, P, I64, P, P, P, P, I, I, I, P],
     "fbkst_layernorm": [P, P, P, P, I, I, I, F, P, I, P],
     "fbkst_attention_fwd": [P, P, P, I, I, I, I, P],
+    "fbkst_attention_fwd_limited": [P, P, P, I, I, I, I, P, P],
     "fbkst_sinusoidal_table": [P, I, I, P],
     "fbkst_lengths_to_mask": [P, P, P, I, I, P],
     "fbkst_ctc_argmax": [P, I, I64, P, P, P, I, I, I, P],

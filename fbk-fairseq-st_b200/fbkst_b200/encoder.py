@@ -467,7 +467,8 @@ def make_encoder_class(base):
                     lo = (ws["h"], ws["st"])
                     qkv = ops.linear_ln(xb, W["wqkv"], W["bqkv"], stats_in=st, ln_eps=W["eps1"],
                                         out=ws["qkv"], rows_limit=limit)
-                    att = ops.attention(qkv, lengths, L, B, H, self.log_penalty, out=ws["att"])
+                    att = ops.attention(qkv, lengths, L, B, H, self.log_penalty, out=ws["att"],
+                                        q_limit=limit[0])  # rows t >= max new length are never read
                     x1, xb, st = ops.linear_ln(att, W["wo"], W["bo"], residual=x, out_dtype=torch.float32,
                                                out=ws["x1"], ln_out=lo, rows_limit=limit)
                     f = ops.linear_ln(xb, W["w1"], W["b1"], relu=True, stats_in=st, ln_eps=W["eps2"],

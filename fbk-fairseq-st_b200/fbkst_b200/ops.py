@@ -298,8 +298,9 @@ def layernorm(x, gamma, beta, out_dtype=torch.bfloat16, eps=1e-5, out=None, rows
     return y
 
 
-def attention(qkv, lengths, L, B, H, log_penalty=True, out=None):
-    """qkv [L*B, 3*H*64] bf16 (row t*B+b) -> [L*B, H*64] bf16."""
+def attention(qkv, lengths, L, B, H, log_penalty=True, out=None, q_limit=None):
+    """qkv [L*B, 3*H*64] bf16 (row t*B+b) -> [L*B, H*64] bf16.  ``q_limit`` (device int32 [1]): the caller
+    only reads query rows t < q_limit; fully padded query tiles beyond it are not even zero-filled."""
     lib = _lib.require_device()
     _req(qkv, torch.bfloat16, "attention.qkv"); _req(lengths, torch.int32, "attention.lengths")
     if qkv.shape != (L * B, 3 * H * 64):
@@ -307,8 +308,13 @@ def attention(qkv, lengths, L, B, H, log_penalty=True, out=None):
                          (tuple(qkv.shape), L * B, 3 * H * 64))
     if out is None:
         out = torch.empty(L * B, H * 64, dtype=torch.bfloat16, device=qkv.device)
-    check(lib.fbkst_attention_fwd(qkv.data_ptr(), out.data_ptr(), lengths.data_ptr(), L, B, H,
-                                  1 if log_penalty else 0, _stream()))
+    if q_limit is not None:
+        _req(q_limit, torch.int32, "attention.q_limit")
+        check(lib.fbkst_attention_fwd_limited(qkv.data_ptr(), out.data_ptr(), lengths.data_ptr(), L, B, H,
+                                              1 if log_penalty else 0, q_limit.data_ptr(), _stream()))
+    else:
+        check(lib.fbkst_attention_fwd(qkv.data_ptr(), out.data_ptr(), lengths.data_ptr(), L, B, H,
+                                      1 if log_penalty else 0, _stream()))
     _count()
     return out
 

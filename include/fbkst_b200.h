@@ -169,6 +169,11 @@ int fbkst_layernorm(const float* x, const float* gamma, const float* beta, void*
  * entirely beyond lengths[b] are written as 0.  scores - ln(max(1,|i-j|)) if log_penalty. */
 int fbkst_attention_fwd(const void* qkv, void* out, const int32_t* lengths, int L, int B, int H,
                         int log_penalty, fbkst_stream_t stream);
+/* Same, for a caller that only consumes query rows t < *q_limit (device int32, e.g. the maximum length
+ * after CTC compression, known only on the device): query tiles that start at or beyond *q_limit AND
+ * lie entirely beyond lengths[b] are left untouched instead of being zero-filled. */
+int fbkst_attention_fwd_limited(const void* qkv, void* out, const int32_t* lengths, int L, int B, int H,
+                                int log_penalty, const int32_t* q_limit, fbkst_stream_t stream);
 
 /* ---- a4: sinusoidal position table (row 0 = zeros) ---------------------------------------
  * replaces fairseq/modules/sinusoidal_positional_embedding.py:36-58.  table [rows, D] fp32. */
