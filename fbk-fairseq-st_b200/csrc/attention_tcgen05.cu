@@ -1068,7 +1068,7 @@ static int attention_entry(const void* qkv, void* out, const int32_t* lengths, i
   if (rc) return rc;
   rc = make_tensor_map(&tmKV, qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3, dims, strides, boxk, nullptr);
   if (rc) return rc;
-  static bool configured = false;
+  static PerDeviceFlag configured;
   if (!configured) {
     FBKST_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<0>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -216,7 +216,7 @@ static int launch_conv1_tc(const float* x, const float* w, const float* bias, co
                            cudaStream_t st) {
   constexpr int SMEM = 128 * 128 + C * 128 + 4 * (C / 64) * 4096 + 3 * C * 4 + 64 + 1024;
   auto kern = conv1_tc_kernel<C>;
-  static bool configured = false;
+  static PerDeviceFlag configured;
   if (!configured) {
     FBKST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     // shared-memory carve-out: the driver default and 100 % measure the same (41 us); switch kept for A/B

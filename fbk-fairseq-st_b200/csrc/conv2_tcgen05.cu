@@ -234,7 +234,7 @@ static int launch_conv2(const void* x, const void* w_taps, const Conv2Params& p,
   constexpr int SMEM = SMEM_MAIN + (C / 64) * 128 * 128 /*output staging*/ + 1024 /*alignment slack*/;
   static_assert(SMEM <= 232448, "shared memory budget exceeded");
   auto kern = conv2_kernel<C, STAGES>;
-  static bool configured = false;
+  static PerDeviceFlag configured;
   if (!configured) {
     FBKST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured = true;

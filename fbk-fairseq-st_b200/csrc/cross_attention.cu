@@ -290,7 +290,7 @@ extern "C" int fbkst_xattn_fwd(const void* q, const void* kv, const uint8_t* key
                 "xattn_fwd: kv and out must be 16-byte aligned");
   const size_t smem = xattn_smem_bytes(S);
   FBKST_REQUIRE(smem <= 200 * 1024, "xattn_fwd: src_len %d too long (scores of 8 rows must fit in shared memory)", S);
-  static bool configured = false;
+  static PerDeviceFlag configured;
   if (smem > 48 * 1024 && !configured) {
     FBKST_CHECK_CUDA(cudaFuncSetAttribute(xattn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;

@@ -544,7 +544,7 @@ extern "C" int fbkst_ctc_segment(const int32_t* labels, const float* top_prob,
   FBKST_REQUIRE(L > 0 && B > 0 && L <= 24000, "fbkst_ctc_segment: L=%d out of range (1..24000)", L);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const size_t smem = sizeof(int) * (2 * (size_t)L + 1);
-  static bool configured = false;
+  static PerDeviceFlag configured;
   if (!configured) {
     FBKST_CHECK_CUDA(cudaFuncSetAttribute(ctc_segment_kernel,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

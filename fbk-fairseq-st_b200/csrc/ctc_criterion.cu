@@ -239,7 +239,7 @@ extern "C" int fbkst_ctc_uer(const int32_t* labels, const int32_t* in_lengths, c
   const size_t smem = sizeof(int) * ((size_t)L + 6 * ((size_t)Umax + 1) + (size_t)Umax);
   FBKST_REQUIRE(smem <= 200 * 1024, "fbkst_ctc_uer: L=%d / Umax=%d exceed shared memory", L, Umax);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  static bool configured = false;
+  static PerDeviceFlag configured;
   if (!configured) {
     FBKST_CHECK_CUDA(cudaFuncSetAttribute(ctc_uer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           200 * 1024));
@@ -275,7 +275,7 @@ extern "C" int fbkst_ctc_loss_fwd(const void* logits, int logits_dtype, int64_t 
   if (tch < 1) tch = 1;
   const size_t smem = fixed + per_frame * tch;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  static bool configured = false;
+  static PerDeviceFlag configured;
   if (!configured) {
     FBKST_CHECK_CUDA(cudaFuncSetAttribute(ctc_loss_fwd_kernel<0>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

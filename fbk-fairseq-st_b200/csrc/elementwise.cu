@@ -417,6 +417,18 @@ __global__ void lengths_to_mask_kernel(const int* __restrict__ lengths, uint8_t*
   if (__syncthreads_or(pad_seen) && threadIdx.x == 0) atomicOr(any_pad, 1);
 }
 
+// lengths after `times` stride-2 convolutions: n -> ceil(n / 2) each (conv_transformer.py:213), from the
+// int64 (fairseq) or int32 lengths wherever they live on the device: no host round trip for shape logic
+__global__ void subsample_lengths_kernel(const void* __restrict__ in, int in_is_i64, int* __restrict__ out,
+                                         int B, int times) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  long long n = in_is_i64 ? reinterpret_cast<const long long*>(in)[b]
+                          : (long long)reinterpret_cast<const int*>(in)[b];
+  for (int i = 0; i < times; ++i) n = (n + 1) >> 1;
+  out[b] = (int)n;
+}
+
 // ----------------------------------------------------------- weight preparation
 __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
                                  long long n, float scale) {
@@ -635,6 +647,15 @@ extern "C" int fbkst_lengths_to_mask(const int32_t* lengths, uint8_t* mask, int3
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   FBKST_CHECK_CUDA(cudaMemsetAsync(any_pad, 0, sizeof(int32_t), st));
   lengths_to_mask_kernel<<<grid_for((long long)B * L, 256), 256, 0, st>>>(lengths, mask, any_pad, B, L);
+  FBKST_CHECK_CUDA(cudaGetLastError());
+  return FBKST_OK;
+}
+
+extern "C" int fbkst_subsample_lengths(const void* lengths, int lengths_are_i64, int32_t* out, int B,
+                                       int times, fbkst_stream_t stream) {
+  FBKST_REQUIRE(lengths && out && B > 0 && times >= 0, "fbkst_subsample_lengths: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  subsample_lengths_kernel<<<(B + 127) / 128, 128, 0, st>>>(lengths, lengths_are_i64, out, B, times);
   FBKST_CHECK_CUDA(cudaGetLastError());
   return FBKST_OK;
 }

@@ -475,7 +475,7 @@ static int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, 
   constexpr int SMEM = g2_smem(LNS);
   static_assert(SMEM <= 232448, "shared memory budget exceeded");
   auto kern = gemm2_kernel<OUT_F32, RESID, LNS>;
-  static bool configured = false;
+  static PerDeviceFlag configured;
   if (!configured) {
     FBKST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured = true;

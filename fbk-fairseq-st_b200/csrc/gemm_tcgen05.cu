@@ -547,7 +547,7 @@ static int launch_gemm_tma(const void* A, int64_t lda, const void* W, int64_t ld
   constexpr int SMEM = STAGES * (BM * BK * 2 + BN * BK * 2) + 8 * (RESID ? 2 : 1) * 4096 + 1024 + 512;
   static_assert(SMEM <= 232448, "shared memory budget exceeded");
   auto kern = gemm_tma_kernel<OUT_F32, RESID, STAGES>;
-  static bool configured = false;
+  static PerDeviceFlag configured;
   if (!configured) {
     FBKST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured = true;
@@ -586,7 +586,7 @@ template <int BN, int STAGES>
 static int launch_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K,
                        const EpiParams& ep, cudaStream_t stream) {
   constexpr int SMEM = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 + 256;
-  static bool configured = false;
+  static PerDeviceFlag configured;
   auto kern = gemm_bf16_kernel<BN, STAGES>;
   if (!configured) {
     FBKST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));

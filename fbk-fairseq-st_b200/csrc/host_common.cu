@@ -77,12 +77,14 @@ int make_tensor_map_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, u
 }
 
 int num_sms() {
-  static int n = 0;
-  if (n) return n;
+  static std::atomic<int> cache[64];
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return 148;
+  int n = cache[dev].load(std::memory_order_relaxed);
+  if (n) return n;
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
     n = 148;
+  cache[dev].store(n, std::memory_order_relaxed);
   return n;
 }
 

@@ -7,6 +7,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/fbkst_b200.h"
 
 namespace fbkst {
@@ -40,7 +42,29 @@ int make_tensor_map(CUtensorMap* out, const void* base, CUtensorMapDataType dtyp
 int make_tensor_map_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
                             uint64_t ld, uint32_t box_rows, uint32_t box_cols);
 
-int num_sms();
+int num_sms();  // of the CURRENT device (cached per device)
+
+// "already configured on the CURRENT device" flag for one-time per-device setup at a call site
+// (cudaFuncSetAttribute is per device; a process may drive several GPUs).  Used as
+//   static PerDeviceFlag configured;  if (!configured) { ...; configured = true; }
+// Two threads racing on the same device both run the (idempotent) setup before either launches.
+class PerDeviceFlag {
+ public:
+  explicit operator bool() const { return (mask_.load(std::memory_order_acquire) >> dev()) & 1ull; }
+  bool operator!() const { return !static_cast<bool>(*this); }
+  PerDeviceFlag& operator=(bool v) {
+    if (v) mask_.fetch_or(1ull << dev(), std::memory_order_release);
+    return *this;
+  }
+
+ private:
+  static int dev() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d > 63) d = 0;
+    return d;
+  }
+  std::atomic<uint64_t> mask_{0};
+};
 
 // conv1 on the tensor pipe (conv1_tcgen05.cu); C is 64 or 128
 int conv1_tc_dispatch(const float* x, const float* w, const float* bias, const float* scale,

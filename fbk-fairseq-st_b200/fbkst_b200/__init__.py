@@ -6,4 +6,4 @@ There is no CPU or PyTorch fallback: every op raises if the library or a B200 is
 """
 from . import _lib  # noqa: F401
 
-__all__ = ["ops", "encoder", "data_utils"]
+__all__ = ["ops", "encoder", "data", "pipeline", "sharding", "augment", "criterion", "cross_attention"]

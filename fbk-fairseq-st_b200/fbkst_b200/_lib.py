@@ -32,6 +32,7 @@ SIGNATURES = {
     "fbkst_attention_fwd_limited": [P, P, P, I, I, I, I, P, P],
     "fbkst_sinusoidal_table": [P, I, I, P],
     "fbkst_lengths_to_mask": [P, P, P, I, I, P],
+    "fbkst_subsample_lengths": [P, I, P, I, I, P],
     "fbkst_ctc_argmax": [P, I, I64, P, P, P, I, I, I, P],
     "fbkst_ctc_argmax_lse": [P, I, I64, P, P, P, P, I, I, I, P],
     "fbkst_ctc_uer": [P, P, P, I64, P, I, P, P, P, I, I, I, P],

@@ -48,17 +48,39 @@ class DeviceCollater:
         self._pinned = None
 
     def _pack(self, frames):
-        """Utterances back to back in one pinned fp32 buffer (reused across batches)."""
+        """Utterances back to back in one pinned fp32 buffer.  Returns (view, release): the caller
+        enqueues the H2D copy of ``view`` and then calls ``release()``, which records a CUDA event
+        behind the copy; a pinned buffer is reused only once that event has completed, so a host
+        that runs ahead of the GPU never overwrites a batch whose copy has not executed yet."""
         total = sum(f.shape[0] for f in frames)
         fdim = frames[0].shape[1]
-        if self._pinned is None or self._pinned.numel() < total * fdim:
-            self._pinned = torch.empty(max(total * fdim, 1), dtype=torch.float32).pin_memory()
-        buf = self._pinned[: total * fdim].view(total, fdim)
+        need = max(total * fdim, 1)
+        if self._pinned is None:
+            self._pinned = []  # [buffer, event or None]
+        slot = None
+        for entry in self._pinned:
+            if entry[0].numel() >= need and (entry[1] is None or entry[1].query()):
+                slot = entry
+                break
+        if slot is None:
+            slot = [torch.empty(need, dtype=torch.float32).pin_memory(), None]
+            self._pinned.append(slot)
+            if len(self._pinned) > 8:  # bounded: drop a finished, smaller buffer
+                for i, entry in enumerate(self._pinned[:-1]):
+                    if entry[1] is None or entry[1].query():
+                        self._pinned.pop(i)
+                        break
+        buf = slot[0][: total * fdim].view(total, fdim)
         o = 0
         for f in frames:
             buf[o:o + f.shape[0]].copy_(f)
             o += f.shape[0]
-        return buf
+
+        def release():
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            slot[1] = ev
+        return buf, release
 
     def collate_frames(self, frames, order=None):
         """``frames``: list of [T_i, F] tensors/arrays.  Returns (src_tokens [B,T_max,F] on the device
@@ -71,7 +93,9 @@ class DeviceCollater:
         else:
             lens_sorted = lens.index_select(0, order)
         starts_all = torch.cumsum(lens, 0) - lens
-        packed = self._pack(frames).to(self.device, non_blocking=True)
+        staged, release = self._pack(frames)
+        packed = staged.to(self.device, non_blocking=True)
+        release()  # event behind the H2D copy guards the pinned buffer
         starts = starts_all.index_select(0, order).to(self.device, non_blocking=True)
         len32 = lens_sorted.to(torch.int32).to(self.device, non_blocking=True)
         src = ops.collate_cmvn(packed, starts, len32, int(lens_sorted.max()), normalize=self.normalize)

@@ -46,6 +46,28 @@ except Exception:  # standalone (tests, bench, the GPU box)
             return 1e6
 
 
+class _PinnedPool:
+    """Pinned int32 staging vectors, one per in-flight use.  A vector goes back to the pool only when
+    its user is done with it: ``give(t)`` after the host has read a D2H result, ``give(t, event)`` for
+    an H2D source (it is handed out again only once ``event`` -- recorded after the copy -- has
+    completed).  The host can run any number of launches ahead of the GPU without a staging vector
+    being rewritten under a copy that has not executed yet (the fixed 8-slot rings could)."""
+
+    def __init__(self):
+        self._free = {}
+
+    def take(self, n):
+        lst = self._free.setdefault(n, [])
+        for i, (t, ev) in enumerate(lst):
+            if ev is None or ev.query():
+                lst.pop(i)
+                return t
+        return torch.empty(n, dtype=torch.int32).pin_memory()
+
+    def give(self, t, event=None):
+        self._free.setdefault(t.numel(), []).append((t, event))
+
+
 class EncoderOut(NamedTuple):
     """fairseq/models/fairseq_encoder.py:11-21"""
     encoder_out: Tensor  # T x B x C
@@ -149,7 +171,12 @@ class _PositionalParams(nn.Module):
 class CtcProjection(nn.Linear):
     """``ctc_fc`` (conv_transformer.py:190): an ``nn.Linear`` whose forward is the tcgen05 GEMM,
     so forward hooks registered on it behave as on the reference module.  Input L x B x D fp32,
-    output L x B x V bf16 logits (rows padded to a multiple of 8 columns in memory)."""
+    output L x B x V logits in FP32 like the reference's (fp32 accumulators written unrounded; rows
+    padded to a multiple of 8 columns in memory): the CTC argmax, the pooling probabilities and the
+    CTC loss all see un-rounded logits, so near-ties between the top two labels are not turned into
+    exact ties by a bf16 store.  ``logits_dtype = torch.bfloat16`` is an opt-in that halves
+    the 2 x L*B*V*4 bytes this costs, for callers that accept bf16-rounded logits."""
+    logits_dtype = torch.float32
 
     def forward(self, x):  # noqa: D401
         L, B, D = x.shape
@@ -160,7 +187,7 @@ class CtcProjection(nn.Linear):
             a = pre[1]
         else:
             a = ops.cast_bf16(x.reshape(L * B, D))
-        return ops.linear(a, w, b).view(L, B, -1)
+        return ops.linear(a, w, b, out_dtype=self.logits_dtype).view(L, B, -1)
 
     def _prepared(self):
         key = (self.weight._version, self.bias._version, self.weight.data_ptr())
@@ -252,8 +279,7 @@ def make_encoder_class(base):
             # graphs (and the activations they own) are per lane: EncoderPipeline keeps one forward in
             # flight per lane/stream and sets this before every launch
             self.graph_lane = 0
-            self._len_pins = {}  # B -> ring of pinned int32 vectors for the new lengths (launch/finish)
-            self._len_pin_next = 0
+            self._pins = _PinnedPool()  # pinned staging vectors for lengths (H2D sources, D2H results)
 
         # ------------------------------------------------------------------ derived operand formats
         def _prepared(self):
@@ -352,61 +378,80 @@ def make_encoder_class(base):
             B, T, Fd = src_tokens.shape
             x_in = src_tokens if src_tokens.dtype == torch.float32 else src_tokens.float()
             x_in = x_in.contiguous()
-            # lengths: one host copy drives all shape logic (the reference syncs per utterance)
-            len_host = src_lengths.tolist() if not src_lengths.is_cuda else src_lengths.cpu().tolist()
-            len_host = [((n + 1) // 2 + 1) // 2 for n in len_host]  # ceil(ceil(n/2)/2), :213
             L = ((T + 1) // 2 + 1) // 2
+            # Lengths drive all shape logic.  Host lengths: used directly.  DEVICE lengths (fairseq's
+            # utils.move_to_cuda puts them there): subsampled on the device and read back together
+            # with the compressed lengths by the forward's single deferred host sync (``_finish``) --
+            # no blocking .cpu() at the top of the forward.  Only ``return_all_hiddens`` (exact
+            # per-layer shapes, which synchronises anyway) still needs them on the host up front.
+            len_dev = None
+            if src_lengths.is_cuda and not return_all_hiddens:
+                len_dev = ops.subsample_lengths(src_lengths.contiguous(), 2)
+                len_host = None
+            else:
+                len_host = src_lengths.tolist() if not src_lengths.is_cuda else src_lengths.cpu().tolist()
+                len_host = [((n + 1) // 2 + 1) // 2 for n in len_host]  # ceil(ceil(n/2)/2), :213
             for _ in range(self.num_layers):
                 torch.empty(1).uniform_()  # LayerDrop draws: keep the CPU RNG stream of the reference
             compress = self.ctc_compress_out and 0 < self.ctc_layer <= self.num_layers
             if self.use_cuda_graph and not return_all_hiddens:
-                r = self._replay(x_in, len_host, B, T, Fd, L)
+                r = self._replay(x_in, len_host, len_dev, B, T, Fd, L)
             else:
-                lengths = torch.tensor(len_host, dtype=torch.int32).to(dev, non_blocking=True)
+                lengths = len_dev if len_dev is not None else \
+                    torch.tensor(len_host, dtype=torch.int32).to(dev, non_blocking=True)
                 r = self._body(self._prepared(), x_in, lengths, len_host, L, B, return_all_hiddens,
                                self._workspace(L * B, dev) if compress and not return_all_hiddens else None)
             x, limit, new_len, states = r["x"], r["limit"], r["new_len"], r["states"]
-            mask = r["mask"] if min(len_host) < L else None  # :298-299: None when nothing is padded
-            if mask is not None and self.use_cuda_graph:
-                mask = mask.clone()  # do not hand out a buffer the next replay overwrites
+            mask_in = r["mask"]
+            if self.use_cuda_graph and not return_all_hiddens:
+                mask_in = mask_in.clone()  # do not hand out a buffer the next replay overwrites
+            # :298-299: the mask is None when nothing is padded (decided in _finish for device lengths)
+            mask = None if len_host is None or min(len_host) >= L else mask_in
             ctc_mask = mask
             if return_all_hiddens and compress:
                 len_host, L = r["len_host"], r["L"]
                 mask = r["mask2"] if min(len_host) < L else None
             xf = ops.layernorm(x, *self._prepared()["lnf"], out_dtype=torch.float32, rows_limit=limit)
-            h = dict(xf=xf, mask=mask, ctc_mask=ctc_mask, states=states, len_host=len_host, L=L, B=B,
-                     x_ctc=r["x_ctc"], src_tokens=src_tokens, len_dtype=src_lengths.dtype, dev=dev,
-                     return_all_hiddens=return_all_hiddens, deferred=limit is not None)
-            if limit is not None:
-                h["mask_full"] = ops.lengths_to_mask(new_len, L)[0]
-                pin = self._len_pins.get(B)
-                if pin is None:
-                    pin = self._len_pins[B] = [torch.empty(B, dtype=torch.int32).pin_memory()
-                                               for _ in range(8)]
-                self._len_pin_next = (self._len_pin_next + 1) % len(pin)
-                h["new_len_pin"] = pin[self._len_pin_next]
-                h["new_len_pin"].copy_(new_len, non_blocking=True)
+            deferred = limit is not None or len_host is None
+            h = dict(xf=xf, mask=mask, ctc_mask=ctc_mask, mask_in=mask_in, states=states, len_host=len_host,
+                     L=L, B=B, x_ctc=r["x_ctc"], src_tokens=src_tokens, len_dtype=src_lengths.dtype, dev=dev,
+                     return_all_hiddens=return_all_hiddens, deferred=deferred, compressed=limit is not None)
+            if deferred:
+                pin = h["pin"] = self._pins.take(2 * B)  # [subsampled input lengths | compressed lengths]
+                if len_host is None:
+                    pin[:B].copy_(r["lengths_in"], non_blocking=True)
+                if limit is not None:
+                    h["mask_full"] = ops.lengths_to_mask(new_len, L)[0]
+                    pin[B:].copy_(new_len, non_blocking=True)
                 h["ev"] = torch.cuda.Event()
                 h["ev"].record()
             return h
 
         def _finish(self, h):
-            xf, mask, states, len_host, L, B = h["xf"], h["mask"], h["states"], h["len_host"], h["L"], h["B"]
+            xf, mask, ctc_mask, states, L, B = h["xf"], h["mask"], h["ctc_mask"], h["states"], h["L"], h["B"]
+            len_host = h["len_host"]
             D, dev = self.embed_dim, h["dev"]
             if h["deferred"]:
                 h["ev"].synchronize()  # the single host sync of the forward
-                len_host = h["new_len_pin"].tolist()
-                L2 = max(len_host)
-                xf = xf[: L2 * B]
-                mask = None if min(len_host) >= L2 else h["mask_full"][:, :L2].contiguous()
-                L = L2
+                vals = h["pin"].tolist()
+                self._pins.give(h.pop("pin"))
+                if len_host is None:  # device lengths: the None-when-unpadded decision is made here
+                    len_host = vals[:B]
+                    mask = ctc_mask = h["mask_in"] if min(len_host) < L else None
+                if h["compressed"]:
+                    len_host = vals[B:]
+                    L2 = max(len_host)
+                    xf = xf[: L2 * B]
+                    mask = None if min(len_host) >= L2 else h["mask_full"][:, :L2].contiguous()
+                    L = L2
+            h["out_len_host"] = len_host
             xf = xf.view(L, B, D)
             if h["return_all_hiddens"]:
                 states[-1] = xf
             out_lengths = torch.tensor(len_host, dtype=h["len_dtype"]).to(dev, non_blocking=True)
             if self.ctc_compress_out:
                 return CTCAwareEncoderOut(xf, mask, None, states, h["src_tokens"], out_lengths, h["x_ctc"],
-                                          h["ctc_mask"])
+                                          ctc_mask)
             return EncoderOut(xf, mask, None, states, h["src_tokens"], out_lengths)
 
         def _body(self, P, x_in, lengths, len_host, L, B, want_states, ws):
@@ -436,8 +481,8 @@ def make_encoder_class(base):
                 x = ops.layernorm(x, *P["lne"], out_dtype=torch.float32)
                 xb, st = ops.row_stats_cast(x)
             mask = ops.lengths_to_mask(lengths, L)[0]
-            r = dict(mask=mask, mask2=None, x_ctc=None, len_host=len_host, L=L, tables=table
-                     if self.embed_positions is not None else None)
+            r = dict(mask=mask, mask2=None, x_ctc=None, len_host=len_host, L=L, lengths_in=lengths,
+                     tables=table if self.embed_positions is not None else None)
             states = [] if want_states else None
             # After CTC compression the number of valid rows is known only on the device.  Unless the
             # caller wants every hidden state (exact shapes per layer), the remaining layers are
@@ -503,7 +548,7 @@ def make_encoder_class(base):
             hooks = tuple(sorted(self.ctc_fc._forward_hooks)) if self.ctc_compress_out else ()
             return (B, T, Fd, str(dev), self._prep_key, hooks, self.graph_lane)
 
-        def _replay(self, x_in, len_host, B, T, Fd, L):
+        def _replay(self, x_in, len_host, len_dev, B, T, Fd, L):
             """Graph mode (``use_cuda_graph``): the ~90 launches of ``_body`` for one input shape are
             captured once and replayed with one ``cudaGraphLaunch``; the batch is copied into the
             graph's static input buffer (device-to-device) and the subsampled lengths into its static
@@ -518,12 +563,17 @@ def make_encoder_class(base):
                     self._graphs.pop(next(iter(self._graphs)))
                 G = self._capture(P, B, T, Fd, L, dev)
                 self._graphs[key] = G
-            # ring of pinned staging vectors: with ``launch``/``finish`` the host runs ahead of the
-            # GPU, so a staging vector is not rewritten before 7 later launches have been enqueued
-            G["pin_next"] = (G["pin_next"] + 1) % len(G["len_pin"])
-            pin = G["len_pin"][G["pin_next"]]
-            pin.copy_(torch.tensor(len_host, dtype=torch.int32))
-            G["lengths"].copy_(pin, non_blocking=True)
+            if len_dev is not None:
+                G["lengths"].copy_(len_dev, non_blocking=True)
+            else:
+                # pinned staging vector from the pool: handed out again only after the event recorded
+                # behind the H2D copy has completed (the host may run many launches ahead of the GPU)
+                pin = self._pins.take(B)
+                pin.copy_(torch.tensor(len_host, dtype=torch.int32))
+                G["lengths"].copy_(pin, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                self._pins.give(pin, ev)
             if x_in.data_ptr() != G["x"].data_ptr():  # the caller may have produced x in place (static_input)
                 G["x"].copy_(x_in, non_blocking=True)
             G["graph"].replay()
@@ -544,8 +594,7 @@ def make_encoder_class(base):
             compress = self.ctc_compress_out and 0 < self.ctc_layer <= self.num_layers
             G = dict(x=torch.zeros(B, T, Fd, dtype=torch.float32, device=dev),
                      lengths=torch.full((B,), L, dtype=torch.int32, device=dev),
-                     len_pin=[torch.empty(B, dtype=torch.int32).pin_memory() for _ in range(8)],
-                     pin_next=0, P=P,
+                     P=P,
                      ws=self._make_workspace(L * B, dev) if compress else None)
             side = torch.cuda.Stream(dev)
             side.wait_stream(torch.cuda.current_stream(dev))

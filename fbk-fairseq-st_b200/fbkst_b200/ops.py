@@ -340,6 +340,19 @@ def lengths_to_mask(lengths, L):
     return mask.view(torch.bool), any_pad
 
 
+def subsample_lengths(lengths, times=2):
+    """Device-resident lengths [B] int64/int32 -> int32 lengths after ``times`` stride-2 convolutions
+    (ceil(n/2) each, conv_transformer.py:213)."""
+    lib = _lib.require_device()
+    if not lengths.is_cuda or lengths.dtype not in (torch.int64, torch.int32) or not lengths.is_contiguous():
+        raise ValueError("fbkst_b200.subsample_lengths: expected a contiguous CUDA int64/int32 vector")
+    out = torch.empty(lengths.numel(), dtype=torch.int32, device=lengths.device)
+    check(lib.fbkst_subsample_lengths(lengths.data_ptr(), 1 if lengths.dtype == torch.int64 else 0,
+                                      out.data_ptr(), lengths.numel(), int(times), _stream()))
+    _count()
+    return out
+
+
 def ctc_argmax(logits, lengths, L, B, V, want_prob=True):
     """logits [L*B, >=V] bf16/fp32 (possibly a column-narrowed view) -> labels, top_prob."""
     lib = _lib.require_device()

@@ -30,7 +30,6 @@ class EncoderPipeline:
         self.normalize = normalize
         self.device = device or next(encoder.parameters()).device
         # eager launches share lazily created tables across lanes: keep one lane unless graphs are on
-        # at most 4: lanes + 1 forwards are in flight and the encoder's pinned length rings hold 8
         self.lanes = min(4, max(1, int(lanes))) if encoder.use_cuda_graph else 1
         self.s_in = torch.cuda.Stream(self.device)
         self.s_lane = [torch.cuda.Stream(self.device) for _ in range(self.lanes)]
@@ -114,10 +113,7 @@ class EncoderPipeline:
             host.copy_(eo, non_blocking=True)
             ev_out = torch.cuda.Event()
             ev_out.record(self.s_out)
-        if handle["deferred"]:
-            hl = handle["new_len_pin"].to(handle["len_dtype"])  # already on the host
-        else:
-            hl = torch.tensor(handle["len_host"], dtype=handle["len_dtype"])
+        hl = torch.tensor(handle["out_len_host"], dtype=handle["len_dtype"])  # set by finish (host)
         return ev_out, host, hl, out  # `out` keeps the device tensor alive until the copy has finished
 
     def run(self, batches):

