@@ -6,14 +6,14 @@
 // 72 FMAs + epilogue per pixel and 8-channel group, 128 registers) spends 65 us issuing instructions for
 // a 19 us write.  Here one tile = 128 consecutive output pixels (the channels-last output is one
 // contiguous [pixels, C] matrix):
-//   build     thread <-> pixel: 9 predicated loads (zero outside the image = the conv padding), bf16,
+//   build     thread <-> pixel: 9 predicated loads (zero outside the image = the conv padding), fp16,
 //             two 16-byte chunks into a K-major 128B-swizzled A tile (K padded 9 -> 16, ONE UMMA k-step)
 //   MMA       one tcgen05.mma M128 x N=C x K16 against the weight tile (built once per CTA), fp32 in TMEM
-//   epilogue  thread <-> TMEM lane <-> pixel: +bias -> ReLU -> BatchNorm affine -> bf16 -> swizzled smem
+//   epilogue  thread <-> TMEM lane <-> pixel: +bias -> ReLU -> BatchNorm affine -> fp16 -> swizzled smem
 //             row -> one TMA store per warp (32 pixels x 128 B), rows past the end clipped by the map
 // Small CTAs (160 threads, ~42 KB smem, C TMEM columns), as many per SM as fit: while one CTA waits for
-// its loads or its MMA the others build / drain.  Inputs and weights are rounded to bf16 (the output is
-// bf16 anyway; accumulation stays fp32).
+// its loads or its MMA the others build / drain.  Inputs, weights and the output are IEEE fp16 (saturating
+// conversions; accumulation stays fp32): the front end runs in fp16, not bf16 -- see ptx.cuh idesc_f16_f32.
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(C1_THREADS, 4)
                     const float* __restrict__ w, const float* __restrict__ bias,
                     const float* __restrict__ scale, const float* __restrict__ shift, int B, int T, int F,
                     int T1, int F1, int n_pix, int planes) {
-  constexpr uint32_t IDESC = idesc_bf16_f32(128, C, 0, 0);
+  constexpr uint32_t IDESC = idesc_f16_f32(128, C, 0, 0);
   constexpr int HALVES = C / 64;                 // 64-column (128-byte) output pieces per pixel
   constexpr int OUT_WARP_BYTES = HALVES * 4096;  // [half][32 rows][128 B] per epilogue warp
 
@@ -65,9 +65,9 @@ __global__ void __launch_bounds__(C1_THREADS, 4)
     for (int k = 0; k < 9; ++k) wv[k] = __ldg(w + n * 9 + k);
     uint8_t* rowp = sW + n * 128;
     *reinterpret_cast<uint4*>(rowp + ((0 ^ (n & 7)) << 4)) =
-        make_uint4(pack_bf16x2(wv[0], wv[1]), pack_bf16x2(wv[2], wv[3]), pack_bf16x2(wv[4], wv[5]),
-                   pack_bf16x2(wv[6], wv[7]));
-    *reinterpret_cast<uint4*>(rowp + ((1 ^ (n & 7)) << 4)) = make_uint4(pack_bf16x2(wv[8], 0.0f), 0u, 0u, 0u);
+        make_uint4(pack_f16x2(wv[0], wv[1]), pack_f16x2(wv[2], wv[3]), pack_f16x2(wv[4], wv[5]),
+                   pack_f16x2(wv[6], wv[7]));
+    *reinterpret_cast<uint4*>(rowp + ((1 ^ (n & 7)) << 4)) = make_uint4(pack_f16x2(wv[8], 0.0f), 0u, 0u, 0u);
   }
   for (int i = threadIdx.x; i < 3 * C; i += C1_THREADS) {
     const float* src = i < C ? bias : (i < 2 * C ? scale : shift);
@@ -152,9 +152,9 @@ __global__ void __launch_bounds__(C1_THREADS, 4)
       // slower: 57 vs 41 us at cfg2 -- the other CTAs of the SM already cover the load latency.)
       load_taps(tile);
       *reinterpret_cast<uint4*>(a_row + ((0 ^ sw) << 4)) =
-          make_uint4(pack_bf16x2(in[0], in[1]), pack_bf16x2(in[2], in[3]), pack_bf16x2(in[4], in[5]),
-                     pack_bf16x2(in[6], in[7]));
-      *reinterpret_cast<uint4*>(a_row + ((1 ^ sw) << 4)) = make_uint4(pack_bf16x2(in[8], 0.0f), 0u, 0u, 0u);
+          make_uint4(pack_f16x2(in[0], in[1]), pack_f16x2(in[2], in[3]), pack_f16x2(in[4], in[5]),
+                     pack_f16x2(in[6], in[7]));
+      *reinterpret_cast<uint4*>(a_row + ((1 ^ sw) << 4)) = make_uint4(pack_f16x2(in[8], 0.0f), 0u, 0u, 0u);
       fence_proxy_async_smem();
       tc_fence_before();  // orders the previous tile's TMEM reads before the MMA this arrival releases
       mbar_arrive(a_full);
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(C1_THREADS, 4)
       __syncwarp();
       mbar_wait(mma_done, ph);
       tc_fence_after();
-      // ---- epilogue: +bias -> ReLU -> BN affine -> bf16, 32 columns at a time
+      // ---- epilogue: +bias -> ReLU -> BN affine -> fp16, 32 columns at a time
 #pragma unroll
       for (int c32 = 0; c32 < C / 32; ++c32) {
         uint32_t v[32];
@@ -188,8 +188,8 @@ __global__ void __launch_bounds__(C1_THREADS, 4)
           }
           const int chunk = (c32 & 1) * 4 + j;  // 16-byte chunk inside the 128-byte half row
           *reinterpret_cast<uint4*>(orow + ((chunk ^ (lane & 7)) << 4)) =
-              make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
-                         pack_bf16x2(o[6], o[7]));
+              make_uint4(pack_f16x2(o[0], o[1]), pack_f16x2(o[2], o[3]), pack_f16x2(o[4], o[5]),
+                         pack_f16x2(o[6], o[7]));
         }
       }
       fence_proxy_async_smem();

@@ -5,7 +5,8 @@
 // input channels) is ONE TMA box over the channels-last conv1 output with element strides
 // {1,2,2,1}; the box's start coordinate (kw-1, 2*t0+kh-1) goes out of bounds at the borders and
 // TMA's zero fill is exactly the conv's zero padding.  K loop = 9 taps x (C/64) channel chunks.
-// Epilogue: +bias -> ReLU -> BatchNorm(eval) affine -> bf16, written channels-last, which is the
+// Operands (conv1 output, weights) and the output are IEEE fp16 (see ptx.cuh idesc_f16_f32).
+// Epilogue: +bias -> ReLU -> BatchNorm(eval) affine -> fp16, written channels-last, which is the
 // (t, f*C + c) operand layout of the fc3 GEMM (its weight columns are permuted to match).
 //
 // Same warp roles as gemm_tcgen05.cu (TMA / MMA / TMEM alloc / 4 epilogue warps), persistent.
@@ -42,7 +43,7 @@ __global__ void __launch_bounds__(256, 1)
   // operand stages + resident taps + 256 B of barriers + 3*C floats of constants, rounded up to 1024
   constexpr int SMEM_MAIN = ((STAGES * STAGE_BYTES + W_BYTES + 256 + 3 * C * 4) + 1023) / 1024 * 1024;
   constexpr uint32_t TMEM_COLS = 2 * C;
-  constexpr uint32_t IDESC = idesc_bf16_f32(128, C, 0, 0);
+  constexpr uint32_t IDESC = idesc_f16_f32(128, C, 0, 0);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps .shared
@@ -198,8 +199,8 @@ __global__ void __launch_bounds__(256, 1)
         for (int j = 0; j < 4; ++j) {
           const int chunk = (c & 1) * 4 + j;
           *reinterpret_cast<uint4*>(hrow + ((chunk ^ (r & 7)) << 4)) =
-              make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                         pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+              make_uint4(pack_f16x2(f[8 * j], f[8 * j + 1]), pack_f16x2(f[8 * j + 2], f[8 * j + 3]),
+                         pack_f16x2(f[8 * j + 4], f[8 * j + 5]), pack_f16x2(f[8 * j + 6], f[8 * j + 7]));
         }
       }
       tc_fence_before();

@@ -3,6 +3,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <cuda_fp16.h>
+
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -245,8 +247,8 @@ __global__ void __launch_bounds__(256, 2)
         a = fmaxf(a, 0.0f);
         o[j] = fmaf(a, sr[j], hr[j]);
       }
-      yp[(size_t)f1 * G] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
-                                      pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+      yp[(size_t)f1 * G] = make_uint4(pack_f16x2(o[0], o[1]), pack_f16x2(o[2], o[3]),
+                                      pack_f16x2(o[4], o[5]), pack_f16x2(o[6], o[7]));
     }
   }
 }
@@ -436,21 +438,24 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* _
        i += (long long)gridDim.x * blockDim.x)
     dst[i] = __float2bfloat16_rn(src[i] * scale);
 }
-__global__ void prep_conv2_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ o,
+__device__ __forceinline__ __half f2h_sat(float x) {
+  return __float2half_rn(fminf(fmaxf(x, -65504.0f), 65504.0f));
+}
+__global__ void prep_conv2_weight_kernel(const float* __restrict__ w, __half* __restrict__ o,
                                          int C) {
   const int total = 9 * C * C;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int ci = i % C, co = (i / C) % C, tap = i / (C * C);
-    o[i] = __float2bfloat16_rn(w[((size_t)co * C + ci) * 9 + tap]);
+    o[i] = f2h_sat(w[((size_t)co * C + ci) * 9 + tap]);
   }
 }
-__global__ void prep_fc3_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ o,
+__global__ void prep_fc3_weight_kernel(const float* __restrict__ w, __half* __restrict__ o,
                                        int D, int C, int F2) {
   const long long total = (long long)D * C * F2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C), f = (int)((i / C) % F2), d = (int)(i / ((long long)C * F2));
-    o[i] = __float2bfloat16_rn(w[((size_t)d * C + c) * F2 + f]);
+    o[i] = f2h_sat(w[((size_t)d * C + c) * F2 + f]);
   }
 }
 __global__ void prep_bn_affine_kernel(const float* gamma, const float* beta, const float* mean,
@@ -672,7 +677,7 @@ extern "C" int fbkst_cast_bf16(const float* src, void* dst, int64_t n, float sca
 extern "C" int fbkst_prep_conv2_weight(const float* w, void* w_taps, int C, fbkst_stream_t stream) {
   FBKST_REQUIRE(w && w_taps && C > 0, "fbkst_prep_conv2_weight: bad arguments");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  prep_conv2_weight_kernel<<<grid_for(9LL * C * C, 256), 256, 0, st>>>(w, (__nv_bfloat16*)w_taps, C);
+  prep_conv2_weight_kernel<<<grid_for(9LL * C * C, 256), 256, 0, st>>>(w, (__half*)w_taps, C);
   FBKST_CHECK_CUDA(cudaGetLastError());
   return FBKST_OK;
 }
@@ -682,7 +687,7 @@ extern "C" int fbkst_prep_fc3_weight(const float* w, void* w_perm, int D, int C,
   FBKST_REQUIRE(w && w_perm && D > 0 && C > 0 && F2 > 0, "fbkst_prep_fc3_weight: bad arguments");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   prep_fc3_weight_kernel<<<grid_for((long long)D * C * F2, 256), 256, 0, st>>>(
-      w, (__nv_bfloat16*)w_perm, D, C, F2);
+      w, (__half*)w_perm, D, C, F2);
   FBKST_CHECK_CUDA(cudaGetLastError());
   return FBKST_OK;
 }

@@ -139,11 +139,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
                  const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
                  const __grid_constant__ CUtensorMap tmX, int M, int N, int K,
                  const float* __restrict__ bias, int relu, int dbg, const int* __restrict__ m_limit,
-                 int m_limit_mult, const LnStatsIn ln_in, float2* __restrict__ stats_out) {
+                 int m_limit_mult, const LnStatsIn ln_in, float2* __restrict__ stats_out,
+                 const uint32_t idesc) {
   static_assert(!LNS || (OUT_F32 && RESID), "row statistics are produced by the residual epilogue");
   constexpr int G2_STAGES = g2_stages(LNS);
   constexpr uint32_t TMEM_COLS = 512;  // two 256-column accumulator stages
-  constexpr uint32_t IDESC = idesc_bf16_f32(256, G2_BN, 0, 0);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -247,7 +247,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < G2_BK / 16; ++k)
-              umma_bf16_ss_cg2(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
+              umma_bf16_ss_cg2(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
             umma_commit_cg2_mc(&empty_bar[stage], 0x3);
             if (kb == num_kb - 1) umma_commit_cg2_mc(&tfull_bar[acc], 0x3);
           }
@@ -471,7 +471,7 @@ template <bool OUT_F32, bool RESID, bool LNS>
 static int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
                         const float* resid, int64_t ldr, void* out, int64_t ldo, int M, int N, int K,
                         int relu, const int* m_limit, int m_limit_mult, const LnStatsIn& ln_in,
-                        void* out_bf16, int64_t ldob, float* stats_out, cudaStream_t stream) {
+                        void* out_bf16, int64_t ldob, float* stats_out, int ab_f16, cudaStream_t stream) {
   constexpr int SMEM = g2_smem(LNS);
   static_assert(SMEM <= 232448, "shared memory budget exceeded");
   auto kern = gemm2_kernel<OUT_F32, RESID, LNS>;
@@ -515,7 +515,8 @@ static int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, 
   static const int dbg = getenv("FBKST_GEMM_DBG") ? atoi(getenv("FBKST_GEMM_DBG")) : 0;
   FBKST_CHECK_CUDA(launch_pdl(kern, dim3(2 * clusters), dim3(384), SMEM, stream, tmA, tmB, tmO, tmR, tmX,
                               M, N, K, bias, relu, dbg, m_limit, m_limit_mult, ln_in,
-                              reinterpret_cast<float2*>(stats_out)));
+                              reinterpret_cast<float2*>(stats_out),
+                              ab_f16 ? idesc_f16_f32(256, G2_BN, 0, 0) : idesc_bf16_f32(256, G2_BN, 0, 0)));
   return FBKST_OK;
 }
 
@@ -526,7 +527,7 @@ int linear_pair_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw,
                          const float* resid, int64_t ldr, void* out, int64_t ldo, int M, int N, int K,
                          int relu, int out_f32, const int* m_limit, int m_limit_mult,
                          const float* stats_in, float ln_eps, void* out_bf16, int64_t ldob,
-                         float* stats_out, cudaStream_t stream) {
+                         float* stats_out, int ab_f16, cudaStream_t stream) {
   LnStatsIn ln_in;
   ln_in.stats = reinterpret_cast<const float2*>(stats_in);
   ln_in.parts = (K + 127) / 128;
@@ -534,15 +535,15 @@ int linear_pair_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw,
   ln_in.eps = ln_eps;
   if (stats_out != nullptr)
     return launch_gemm2<true, true, true>(A, lda, W, ldw, bias, resid, ldr, out, ldo, M, N, K, relu,
-                                          m_limit, m_limit_mult, ln_in, out_bf16, ldob, stats_out, stream);
+                                          m_limit, m_limit_mult, ln_in, out_bf16, ldob, stats_out, ab_f16, stream);
   if (resid != nullptr)
     return launch_gemm2<true, true, false>(A, lda, W, ldw, bias, resid, ldr, out, ldo, M, N, K, relu,
-                                           m_limit, m_limit_mult, ln_in, nullptr, 0, nullptr, stream);
+                                           m_limit, m_limit_mult, ln_in, nullptr, 0, nullptr, ab_f16, stream);
   if (out_f32)
     return launch_gemm2<true, false, false>(A, lda, W, ldw, bias, nullptr, 0, out, ldo, M, N, K, relu,
-                                            m_limit, m_limit_mult, ln_in, nullptr, 0, nullptr, stream);
+                                            m_limit, m_limit_mult, ln_in, nullptr, 0, nullptr, ab_f16, stream);
   return launch_gemm2<false, false, false>(A, lda, W, ldw, bias, nullptr, 0, out, ldo, M, N, K, relu,
-                                           m_limit, m_limit_mult, ln_in, nullptr, 0, nullptr, stream);
+                                           m_limit, m_limit_mult, ln_in, nullptr, 0, nullptr, ab_f16, stream);
 }
 
 }  // namespace fbkst

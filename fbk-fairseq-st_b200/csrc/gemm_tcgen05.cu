@@ -20,7 +20,7 @@ int linear_pair_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw,
                          const float* resid, int64_t ldr, void* out, int64_t ldo, int M, int N, int K,
                          int relu, int out_f32, const int* m_limit, int m_limit_mult,
                          const float* stats_in, float ln_eps, void* out_bf16, int64_t ldob,
-                         float* stats_out, cudaStream_t stream);
+                         float* stats_out, int ab_f16, cudaStream_t stream);
 
 struct EpiParams {
   const float* bias;
@@ -637,6 +637,8 @@ extern "C" int fbkst_linear_bf16(const void* A, int64_t lda, const void* W, int6
   ep.remap_outer = remap_outer;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (flags & (FBKST_EPI_ROW_REMAP | FBKST_EPI_POSEMB)) {  // row-remapping epilogue: direct stores
+    FBKST_REQUIRE(!(flags & FBKST_EPI_AB_F16), "fbkst_linear_bf16: fp16 operands need the CTA-pair kernel");
+    FBKST_REQUIRE(m_limit == nullptr, "fbkst_linear_bf16: m_limit is not supported with the row-remap epilogues");
     if (N % 256 == 0 || N > 1024) return launch_gemm<256, 4>(A, lda, W, ldw, M, N, K, ep, st);
     return launch_gemm<128, 6>(A, lda, W, ldw, M, N, K, ep, st);
   }
@@ -647,7 +649,10 @@ extern "C" int fbkst_linear_bf16(const void* A, int64_t lda, const void* W, int6
   if (!single_cta)
     return linear_pair_dispatch(A, lda, W, ldw, bias, residual, ldr, out, ldo, M, N, K, relu,
                                 (flags & FBKST_EPI_OUT_F32) ? 1 : 0, m_limit, m_limit_mult, nullptr, 0.f,
-                                nullptr, 0, nullptr, st);
+                                nullptr, 0, nullptr, (flags & FBKST_EPI_AB_F16) ? 1 : 0, st);
+  FBKST_REQUIRE(!(flags & FBKST_EPI_AB_F16), "fbkst_linear_bf16: fp16 operands need the CTA-pair kernel");
+  FBKST_REQUIRE(m_limit == nullptr, "fbkst_linear_bf16: m_limit is not supported by the single-CTA kernel "
+                                    "(FBKST_GEMM_1CTA)");
   if (residual != nullptr) {
     return launch_gemm_tma<true, true, 3>(A, lda, W, ldw, bias, residual, ldr, out, ldo, M, N, K, relu, st);
   }
@@ -685,5 +690,5 @@ extern "C" int fbkst_linear_ln_bf16(const void* A, int64_t lda, const void* W, i
   return linear_pair_dispatch(A, lda, W, ldw, bias, residual, ldr, out, ldo, M, N, K,
                               (flags & FBKST_EPI_RELU) ? 1 : 0, (flags & FBKST_EPI_OUT_F32) ? 1 : 0, m_limit,
                               m_limit_mult, row_stats_in, ln_eps, out_bf16, ldob, row_stats_out,
-                              reinterpret_cast<cudaStream_t>(stream));
+                              (flags & FBKST_EPI_AB_F16) ? 1 : 0, reinterpret_cast<cudaStream_t>(stream));
 }

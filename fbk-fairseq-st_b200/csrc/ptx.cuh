@@ -260,7 +260,21 @@ __host__ __device__ constexpr uint32_t idesc_bf16_f32(int M, int N, int a_mn_maj
          ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// Same with IEEE fp16 operands (11-bit significand: 4x finer than bf16).  Used by the conv front end,
+// whose six operand roundings in series (x, w1, y1, w2, y2, w3) otherwise dominate the encoder's
+// output error (profiles/r02_error_budget.md); fp32 accumulation as everywhere.
+__host__ __device__ constexpr uint32_t idesc_f16_f32(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // ------------------------------------------------------------------- helpers
+// two fp32 -> packed fp16x2, round to nearest even, SATURATING to +-65504 (never inf)
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -9,7 +9,7 @@ LIB_PATH = os.path.join(_HERE, "libfbkst_b200.so")
 ERR_ARG, ERR_CUDA, ERR_OOM = -1, -2, -3
 BF16, F32 = 0, 1
 CTC_STRATEGY = {"avg": 0, "weighted": 1, "softmax": 2}
-EPI_RELU, EPI_OUT_F32, EPI_ROW_REMAP, EPI_POSEMB = 1, 2, 4, 8
+EPI_RELU, EPI_OUT_F32, EPI_ROW_REMAP, EPI_POSEMB, EPI_AB_F16 = 1, 2, 4, 8, 16
 
 P, I, I64, F = c_void_p, c_int, c_int64, c_float
 

@@ -4,7 +4,7 @@ library or the GPU is missing (no fallback)."""
 import torch
 
 from . import _lib
-from ._lib import BF16, CTC_STRATEGY, EPI_OUT_F32, EPI_POSEMB, EPI_RELU, EPI_ROW_REMAP, F32, check
+from ._lib import BF16, CTC_STRATEGY, EPI_AB_F16, EPI_OUT_F32, EPI_POSEMB, EPI_RELU, EPI_ROW_REMAP, F32, check
 
 LAUNCHES = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
 
@@ -91,7 +91,7 @@ def conv1_relu_bn(x, w, bias, scale, shift):
     _req(x, torch.float32, "conv1.x")
     B, T, Fd = x.shape
     C = w.shape[0]
-    y = torch.empty(B, (T + 1) // 2, (Fd + 1) // 2, C, dtype=torch.bfloat16, device=x.device)
+    y = torch.empty(B, (T + 1) // 2, (Fd + 1) // 2, C, dtype=torch.float16, device=x.device)
     check(lib.fbkst_conv1_relu_bn(x.data_ptr(), _req(w, torch.float32, "conv1.w").data_ptr(),
                                   bias.data_ptr(), scale.data_ptr(), shift.data_ptr(),
                                   y.data_ptr(), B, T, Fd, C, _stream()))
@@ -101,9 +101,9 @@ def conv1_relu_bn(x, w, bias, scale, shift):
 
 def conv2_relu_bn(x, w_taps, bias, scale, shift):
     lib = _lib.require_device()
-    _req(x, torch.bfloat16, "conv2.x"); _req(w_taps, torch.bfloat16, "conv2.w_taps")
+    _req(x, torch.float16, "conv2.x"); _req(w_taps, torch.float16, "conv2.w_taps")
     B, T1, F1, C = x.shape
-    y = torch.empty(B, (T1 + 1) // 2, (F1 + 1) // 2, C, dtype=torch.bfloat16, device=x.device)
+    y = torch.empty(B, (T1 + 1) // 2, (F1 + 1) // 2, C, dtype=torch.float16, device=x.device)
     check(lib.fbkst_conv2_relu_bn(x.data_ptr(), w_taps.data_ptr(), bias.data_ptr(),
                                   scale.data_ptr(), shift.data_ptr(), y.data_ptr(), B, T1, F1, C,
                                   _stream()))
@@ -118,7 +118,7 @@ def conv1_relu_bn_planes(x, w, bias, scale, shift):
     B, T, Fd = x.shape
     C = w.shape[0]
     T1, F1 = (T + 1) // 2, (Fd + 1) // 2
-    y = torch.empty(4, B, (T1 + 1) // 2, (F1 + 1) // 2, C, dtype=torch.bfloat16, device=x.device)
+    y = torch.empty(4, B, (T1 + 1) // 2, (F1 + 1) // 2, C, dtype=torch.float16, device=x.device)
     check(lib.fbkst_conv1_relu_bn_planes(x.data_ptr(), _req(w, torch.float32, "conv1.w").data_ptr(),
                                          bias.data_ptr(), scale.data_ptr(), shift.data_ptr(),
                                          y.data_ptr(), B, T, Fd, C, _stream()))
@@ -129,12 +129,12 @@ def conv1_relu_bn_planes(x, w, bias, scale, shift):
 def conv2_relu_bn_planes(x_planes, T1, F1, w_taps, bias, scale, shift):
     """conv2 over the plane layout of ``conv1_relu_bn_planes``; output as ``conv2_relu_bn``."""
     lib = _lib.require_device()
-    _req(x_planes, torch.bfloat16, "conv2.x_planes"); _req(w_taps, torch.bfloat16, "conv2.w_taps")
+    _req(x_planes, torch.float16, "conv2.x_planes"); _req(w_taps, torch.float16, "conv2.w_taps")
     four, B, TH, FH, C = x_planes.shape
     if four != 4 or TH != (T1 + 1) // 2 or FH != (F1 + 1) // 2:
         raise ValueError("conv2_relu_bn_planes: plane shape %s does not match T1=%d F1=%d"
                          % (tuple(x_planes.shape), T1, F1))
-    y = torch.empty(B, TH, FH, C, dtype=torch.bfloat16, device=x_planes.device)
+    y = torch.empty(B, TH, FH, C, dtype=torch.float16, device=x_planes.device)
     check(lib.fbkst_conv2_relu_bn_planes(x_planes.data_ptr(), w_taps.data_ptr(), bias.data_ptr(),
                                          scale.data_ptr(), shift.data_ptr(), y.data_ptr(), B, T1, F1, C,
                                          _stream()))
@@ -144,17 +144,21 @@ def conv2_relu_bn_planes(x_planes, T1, F1, w_taps, bias, scale, shift):
 
 def linear(a, w, bias=None, relu=False, residual=None, out_dtype=torch.bfloat16, out=None,
            remap=None, posemb=None, rows_limit=None):
-    """out = epi(a @ w.T).  a [M,K] bf16, w [N,K] bf16, bias [N] fp32, residual [M,N] fp32.
+    """out = epi(a @ w.T).  a [M,K] bf16, w [N,K] bf16 (or both fp16), bias [N] fp32, residual [M,N] fp32.
     remap=(inner, outer): out row = (m % inner)*outer + m // inner.
     posemb=(table [P,N] fp32, lengths [outer] int32): adds table[pos(m)] (needs remap dims).
     rows_limit=(count [1] int32 device tensor, mult): only rows < count*mult are computed."""
     lib = _lib.require_device()
-    _req(a, torch.bfloat16, "linear.a"); _req(w, torch.bfloat16, "linear.w")
+    if a.dtype == torch.float16:  # the conv front end's operands are IEEE fp16 (conv2 output x fc3 weight)
+        _req(a, torch.float16, "linear.a"); _req(w, torch.float16, "linear.w")
+    else:
+        _req(a, torch.bfloat16, "linear.a"); _req(w, torch.bfloat16, "linear.w")
     M, K = a.shape
     N = w.shape[0]
     if w.shape[1] != K:
         raise ValueError("fbkst_b200.linear: K mismatch %s vs %s" % (tuple(a.shape), tuple(w.shape)))
-    flags = (EPI_RELU if relu else 0) | (EPI_OUT_F32 if out_dtype == torch.float32 else 0)
+    flags = (EPI_RELU if relu else 0) | (EPI_OUT_F32 if out_dtype == torch.float32 else 0) | \
+        (EPI_AB_F16 if a.dtype == torch.float16 else 0)
     inner = outer = 0
     lengths = None
     res, ldr = residual, 0
@@ -498,7 +502,7 @@ def prep_conv2_weight(w):
     lib = _lib.require_device()
     w = _req(w.contiguous(), torch.float32, "prep_conv2_weight.w")
     C = w.shape[0]
-    out = torch.empty(9, C, C, dtype=torch.bfloat16, device=w.device)
+    out = torch.empty(9, C, C, dtype=torch.float16, device=w.device)
     check(lib.fbkst_prep_conv2_weight(w.data_ptr(), out.data_ptr(), C, _stream()))
     _count()
     return out
@@ -508,7 +512,7 @@ def prep_fc3_weight(w, C, F2):
     lib = _lib.require_device()
     w = _req(w.contiguous(), torch.float32, "prep_fc3_weight.w")
     D = w.shape[0]
-    out = torch.empty(D, F2 * C, dtype=torch.bfloat16, device=w.device)
+    out = torch.empty(D, F2 * C, dtype=torch.float16, device=w.device)
     check(lib.fbkst_prep_fc3_weight(w.data_ptr(), out.data_ptr(), D, C, F2, _stream()))
     _count()
     return out

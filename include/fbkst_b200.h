@@ -44,7 +44,8 @@ enum {
   FBKST_EPI_RELU = 1,      /* y = max(y, 0) after the bias                                  */
   FBKST_EPI_OUT_F32 = 2,   /* out is fp32 (default bf16)                                    */
   FBKST_EPI_ROW_REMAP = 4, /* out row = (m % remap_inner) * remap_outer + m / remap_inner    */
-  FBKST_EPI_POSEMB = 8     /* residual is a [*, N] table indexed by position (see fc3)      */
+  FBKST_EPI_POSEMB = 8,    /* residual is a [*, N] table indexed by position (see fc3)      */
+  FBKST_EPI_AB_F16 = 16    /* A and W hold IEEE fp16 instead of bf16 (the conv front end)    */
 };
 
 const char* fbkst_last_error(void);
@@ -74,22 +75,24 @@ int fbkst_collate_cmvn_f32(const float* packed, const int64_t* starts, const int
 /* ---- a2 (conv 1): Conv2d(1->C,k3,s2,p1)+bias -> ReLU -> BatchNorm(eval affine) -----------
  * replaces conv_transformer.py:203-214 for i=0.  x [B,T,F] fp32; w [C,9] fp32; bias,
  * bn_scale, bn_shift [C] fp32 (scale = gamma/sqrt(var+eps), shift = beta - mean*scale);
- * y [B,T1,F1,C] bf16 channels-last, T1=ceil(T/2), F1=ceil(F/2).  C must be 64 or 128. */
+ * y [B,T1,F1,C] IEEE fp16 channels-last (saturating conversion), T1=ceil(T/2), F1=ceil(F/2).  C must
+ * be 64 or 128.  The conv front end (conv1, conv2, fc3 operands) runs in fp16, not bf16: its six
+ * operand roundings in series otherwise dominate the encoder's output error. */
 int fbkst_conv1_relu_bn(const float* x, const float* w, const float* bias, const float* bn_scale,
                         const float* bn_shift, void* y, int B, int T, int F, int C,
                         fbkst_stream_t stream);
 
 /* ---- a2 (conv 2): Conv2d(C->C,k3,s2,p1)+bias -> ReLU -> BatchNorm(eval affine) -----------
  * replaces conv_transformer.py:203-214 for i=1 as a TMA-fed implicit GEMM on tcgen05.
- * x [B,T1,F1,C] bf16 channels-last; w_taps [9][C][C] bf16 (tap = kh*3+kw, then out-ch,
- * in-ch); y [B,T2,F2,C] bf16 channels-last (T2=ceil(T1/2), F2=ceil(F1/2)), i.e. row
+ * x [B,T1,F1,C] fp16 channels-last; w_taps [9][C][C] fp16 (tap = kh*3+kw, then out-ch,
+ * in-ch); y [B,T2,F2,C] fp16 channels-last (T2=ceil(T1/2), F2=ceil(F1/2)), i.e. row
  * (b,t) of the fc3 operand with the flatten order (f, c). */
 int fbkst_conv2_relu_bn(const void* x, const void* w_taps, const float* bias,
                         const float* bn_scale, const float* bn_shift, void* y, int B, int T1,
                         int F1, int C, fbkst_stream_t stream);
 
 /* ---- a2, plane layout (default inside the encoder): conv1 writes FOUR (t1, f1)-parity planes
- * [ (t1&1)*2 + (f1&1) ][B][ceil(T1/2)][ceil(F1/2)][C] bf16 (slots past T1 / F1 are zeros) instead of
+ * [ (t1&1)*2 + (f1&1) ][B][ceil(T1/2)][ceil(F1/2)][C] fp16 (slots past T1 / F1 are zeros) instead of
  * [B][T1][F1][C]; conv2's stride-2 taps then are unit-stride TMA boxes of one plane.  Same arithmetic, same
  * conv2 output as the pair above (conv_transformer.py:203-214). */
 int fbkst_conv1_relu_bn_planes(const float* x, const float* w, const float* bias, const float* bn_scale,
@@ -303,9 +306,10 @@ int fbkst_xattn_fwd(const void* q, const void* kv, const uint8_t* key_padding_ma
 /* ---- weight preparation (fp32 master parameters -> kernel operand formats) ----------------- */
 /* dst[i] = bf16(src[i] * scale) */
 int fbkst_cast_bf16(const float* src, void* dst, int64_t n, float scale, fbkst_stream_t stream);
-/* conv2 weight [C,C,3,3] fp32 -> [9][C][C] bf16 (tap, out, in) */
+/* conv2 weight [C,C,3,3] fp32 -> [9][C][C] fp16 (tap, out, in) */
 int fbkst_prep_conv2_weight(const float* w, void* w_taps, int C, fbkst_stream_t stream);
-/* fc3 weight [D, C*F2] (flatten c*F2+f) fp32 -> [D, F2*C] (flatten f*C+c) bf16 */
+/* fc3 weight [D, C*F2] (flatten c*F2+f) fp32 -> [D, F2*C] (flatten f*C+c) fp16
+ * (the A operand of fc3 is conv2's fp16 output: call fbkst_linear_bf16 with FBKST_EPI_AB_F16) */
 int fbkst_prep_fc3_weight(const float* w, void* w_perm, int D, int C, int F2,
                           fbkst_stream_t stream);
 /* BatchNorm eval affine: scale = gamma / sqrt(var + eps), shift = beta - mean * scale */

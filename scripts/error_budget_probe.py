@@ -1,0 +1,108 @@
+import sys, math, torch, torch.nn.functional as F
+sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests'); sys.path.insert(0,'/root/repo/fbk-fairseq-st_b200')
+from oracle import encoder_oracle as O
+from helpers import parity_report
+torch.set_num_threads(8)
+bf=lambda t: t.to(torch.bfloat16).float()
+def layer(sd,p,x,mask,H,flags):
+    D=x.shape[-1]; L,B,_=x.shape
+    def ln_lin(x,g,b,W,bias,site):
+        if 'fold' in flags:
+            # folded: bf16(x) @ W''^T * rstd + c
+            mu=x.mean(-1,keepdim=True); var=x.var(-1,unbiased=False,keepdim=True); rstd=(var+1e-5).rsqrt()
+            wg=(W.double()*g.double()[None,:]); wg=wg-wg.mean(1,keepdim=True); c=bias.double()+W.double()@b.double()
+            xb=bf(x) if 'fold_center' not in flags else bf(x-mu)
+            return (xb@bf(wg.float()).t())*rstd+c.float()
+        y=F.layer_norm(x,(D,),g,b,1e-5)
+        if 'lnout' in flags: y=bf(y)
+        Wb=bf(W) if 'w' in flags else W
+        return y@Wb.t()+bias
+    r=x
+    qkv=ln_lin(x,sd[p+'self_attn_layer_norm.weight'],sd[p+'self_attn_layer_norm.bias'],sd[p+'self_attn.in_proj_weight'],sd[p+'self_attn.in_proj_bias'],'qkv')
+    if 'qkv' in flags: qkv=bf(qkv)
+    q,k,v=qkv.chunk(3,-1); hd=D//H
+    q=q*hd**-0.5
+    q=q.contiguous().view(L,B*H,hd).transpose(0,1);k=k.contiguous().view(L,B*H,hd).transpose(0,1);v=v.contiguous().view(L,B*H,hd).transpose(0,1)
+    s=torch.bmm(q,k.transpose(1,2))
+    if mask is not None:
+        s=s.view(B,H,L,L).masked_fill(mask.unsqueeze(1).unsqueeze(2),float('-inf')).view(B*H,L,L)
+    idx=torch.arange(L); dist=(idx[:,None]-idx[None,:]).abs().float()
+    s=s-torch.clamp(torch.log(dist),min=0.0)
+    pr=F.softmax(s,-1)
+    if 'p' in flags:
+        # flash: P unnormalised bf16 = exp(s-max), normalise by fp32 sum at end
+        m=s.max(-1,keepdim=True).values; e=torch.exp(s-m); l=e.sum(-1,keepdim=True); o=torch.bmm(bf(e),v)/l
+    else: o=torch.bmm(pr,v)
+    o=o.transpose(0,1).contiguous().view(L,B,D)
+    if 'att' in flags: o=bf(o)
+    Wo=sd[p+'self_attn.out_proj.weight']; Wo=bf(Wo) if 'w' in flags else Wo
+    x=r+o@Wo.t()+sd[p+'self_attn.out_proj.bias']
+    r=x
+    f=F.relu(ln_lin(x,sd[p+'final_layer_norm.weight'],sd[p+'final_layer_norm.bias'],sd[p+'fc1.weight'],sd[p+'fc1.bias'],'fc1'))
+    if 'f' in flags: f=bf(f)
+    W2=sd[p+'fc2.weight']; W2=bf(W2) if 'w' in flags else W2
+    return r+f@W2.t()+sd[p+'fc2.bias']
+cfg=dict(embed_dim=512, ffn_dim=2048, heads=8, layers=6, conv_channels=64, feat_dim=40, vocab=105, distance_penalty="log", ctc_layer=0)
+sd=O.init_state_dict(cfg,seed=1)
+x,lens=O.synthetic_batch([600,598,411,203],40,seed=77)
+x0,lengths=O.conv_subsample(sd,x,lens); x0=O.flatten_fc3(sd,x0); D=512
+x0=x0+O.positional_embedding(lengths,D).transpose(0,1)
+mask=O.create_mask(lengths)
+def run(flags):
+    y=x0
+    for l in range(cfg['layers']): y=layer(sd,'layers.%d.'%l,y,mask,8,flags)
+    return F.layer_norm(y,(D,),sd['layer_norm.weight'],sd['layer_norm.bias'],1e-5)
+ref=run(set())
+nl=lengths.tolist()
+for fl in [{'fold'},{'fold','fold_center'},{'lnout'},{'w'},{'qkv'},{'p'},{'att'},{'f'},{'fold','w','qkv','p','att','f'},{'fold','fold_center','w','qkv','p','att','f'},{'lnout','w','qkv','p','att','f'}]:
+    out=run(fl); rep=parity_report(out,ref,nl)
+    d=(out-ref); print(sorted(fl), 'max_rel %.4f elementwise %.4f rms_err %.5f'%(rep['max_rel'],rep['elementwise'],d.pow(2).mean().sqrt()/ref.pow(2).mean().sqrt()))
+print('x0 row mean/std', (x0.mean(-1).abs()/x0.std(-1)).mean())
+print("---- front end")
+def front(flags):
+    xx=x.unsqueeze(1)
+    if 'x' in flags: xx=bf(xx)
+    for i in range(2):
+        w=sd['convolutions.%d.weight'%i]
+        if 'cw' in flags: w=bf(w)
+        xx=F.conv2d(xx,w,sd['convolutions.%d.bias'%i],stride=2,padding=1); xx=F.relu(xx)
+        xx=F.batch_norm(xx,sd['bn.%d.running_mean'%i],sd['bn.%d.running_var'%i],sd['bn.%d.weight'%i],sd['bn.%d.bias'%i],False,0.0,1e-5)
+        if 'y' in flags: xx=bf(xx)
+    b,c,t,f=xx.shape
+    xx=xx.transpose(1,2).reshape(b,t,c*f).transpose(0,1)
+    w3=sd['fc3.weight']; w3=bf(w3) if 'w3' in flags else w3
+    h=F.relu(xx@w3.t()+sd['fc3.bias'])
+    return h+O.positional_embedding(lengths,D).transpose(0,1)
+def run2(fflags,lflags):
+    y=front(fflags)
+    for l in range(cfg['layers']): y=layer(sd,'layers.%d.'%l,y,mask,8,lflags)
+    return F.layer_norm(y,(D,),sd['layer_norm.weight'],sd['layer_norm.bias'],1e-5)
+for ff in [{'x'},{'cw'},{'y'},{'w3'},{'x','cw','y','w3'}]:
+    out=run2(ff,set()); rep=parity_report(out,ref,nl)
+    d=out-ref; print(sorted(ff),'max_rel %.4f elementwise %.4f rms_err %.5f'%(rep['max_rel'],rep['elementwise'],d.pow(2).mean().sqrt()/ref.pow(2).mean().sqrt()))
+out=run2({'x','cw','y','w3'},{'fold','w','qkv','p','att','f'}); rep=parity_report(out,ref,nl); print('all', rep)
+# just the front-end output itself
+f0=front(set()); f1=front({'x','cw','y','w3'}); print('front only', parity_report(f1,f0,nl))
+print("---- finer front end")
+def front2(flags):
+    xx=x.unsqueeze(1)
+    if 'x' in flags: xx=bf(xx)
+    for i in range(2):
+        w=sd['convolutions.%d.weight'%i]
+        if 'w%d'%(i+1) in flags: w=bf(w)
+        xx=F.conv2d(xx,w,sd['convolutions.%d.bias'%i],stride=2,padding=1); xx=F.relu(xx)
+        xx=F.batch_norm(xx,sd['bn.%d.running_mean'%i],sd['bn.%d.running_var'%i],sd['bn.%d.weight'%i],sd['bn.%d.bias'%i],False,0.0,1e-5)
+        if 'y%d'%(i+1) in flags: xx=bf(xx)
+    b,c,t,f=xx.shape
+    xx=xx.transpose(1,2).reshape(b,t,c*f).transpose(0,1)
+    w3=sd['fc3.weight']; w3=bf(w3) if 'w3' in flags else w3
+    h=F.relu(xx@w3.t()+sd['fc3.bias'])
+    return h+O.positional_embedding(lengths,D).transpose(0,1)
+LF={'fold','w','qkv','p','att','f'}
+def run3(fflags,lflags):
+    y=front2(fflags)
+    for l in range(cfg['layers']): y=layer(sd,'layers.%d.'%l,y,mask,8,lflags)
+    return F.layer_norm(y,(D,),sd['layer_norm.weight'],sd['layer_norm.bias'],1e-5)
+for ff in [{'x'},{'w1'},{'y1'},{'w2'},{'y2'},{'w3'},{'y1','y2'},{'y1','y2','w2','w3'},{'y2','w3'},{'y1','y2','w3'}, set()]:
+    out=run3(ff,LF); rep=parity_report(out,ref,nl)
+    d=out-ref; print(sorted(ff),'+layers: max_rel %.4f elementwise %.4f rms_err %.5f'%(rep['max_rel'],rep['elementwise'],d.pow(2).mean().sqrt()/ref.pow(2).mean().sqrt()))
