@@ -140,7 +140,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
                  const __grid_constant__ CUtensorMap tmX, int M, int N, int K,
                  const float* __restrict__ bias, int relu, int dbg, const int* __restrict__ m_limit,
                  int m_limit_mult, const LnStatsIn ln_in, float2* __restrict__ stats_out,
-                 const uint32_t idesc) {
+                 const uint32_t idesc, const int splits, const int split_rows) {
   static_assert(!LNS || (OUT_F32 && RESID), "row statistics are produced by the residual epilogue");
   constexpr int G2_STAGES = g2_stages(LNS);
   constexpr uint32_t TMEM_COLS = 512;  // two 256-column accumulator stages
@@ -198,8 +198,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
   if (m_limit != nullptr) M = min(M, __ldg(m_limit) * m_limit_mult);
   const int num_n = (N + G2_BN - 1) / G2_BN;
   const int num_m = (M + 2 * G2_BM - 1) / (2 * G2_BM);
-  const int num_tiles = num_m * num_n;
   const int num_kb = (K + G2_BK - 1) / G2_BK;
+  // Split-K (wgrad: few output tiles, K = tokens): tile index = (split, m_blk, n_blk); split s covers
+  // k-blocks [s*kb_per, min(num_kb, (s+1)*kb_per)) and stores its partial product at output rows
+  // m + s*split_rows (a [splits, split_rows, N] buffer reduced by a second kernel).  splits == 1: the
+  // ordinary GEMM.  The host guarantees that no split is empty.
+  const int tiles_mn = num_m * num_n;
+  const int num_tiles = tiles_mn * splits;
+  const int kb_per = (num_kb + splits - 1) / splits;
 
   // Producer and MMA warps run in warp-uniform control flow and let ONE ELECTED lane issue: under
   // `if (lane == 0)` ptxas wraps every UTMALDG / UTCHMMA in a divergence waterfall (ELECT +
@@ -209,10 +215,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
+      const int sp = tile / tiles_mn, t2 = tile - sp * tiles_mn;
+      const int m_blk = t2 / num_n, n_blk = t2 - m_blk * num_n;
       const int row_a = m_blk * 2 * G2_BM + (int)rank * G2_BM;
       const int row_b = n_blk * G2_BN + (int)rank * (G2_BN / 2);
-      for (int kb = 0; kb < num_kb; ++kb) {
+      const int kb0 = sp * kb_per, kb1 = min(num_kb, kb0 + kb_per);
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one()) {
           if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);
@@ -238,7 +246,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * G2_BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int sp = tile / tiles_mn;
+        const int kb0 = sp * kb_per, kb1 = min(num_kb, kb0 + kb_per);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * G2_STAGE_BYTES);
@@ -247,9 +257,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < G2_BK / 16; ++k)
-              umma_bf16_ss_cg2(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+              umma_bf16_ss_cg2(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, ((kb - kb0) | k) != 0);
             umma_commit_cg2_mc(&empty_bar[stage], 0x3);
-            if (kb == num_kb - 1) umma_commit_cg2_mc(&tfull_bar[acc], 0x3);
+            if (kb == kb1 - 1) umma_commit_cg2_mc(&tfull_bar[acc], 0x3);
           }
           __syncwarp();
           if (++stage == G2_STAGES) {
@@ -273,7 +283,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
     const int swz = lane & 7;
     int sbuf = 0;  // staging buffer toggle (non-residual path)
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
+      const int sp = tile / tiles_mn, t2 = tile - sp * tiles_mn;
+      const int m_blk = t2 / num_n, n_blk = t2 - m_blk * num_n;
+      const int m_store = sp * split_rows;  // row offset of this split's partial product
       const int m0 = m_blk * 2 * G2_BM + (int)rank * G2_BM + q * 32;
       const int n0 = n_blk * G2_BN + half * 128;
       const uint32_t tempty_leader = map_to_cta(smem_u32(&tempty_bar[acc]), 0);
@@ -448,7 +460,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0 && !(dbg & 1)) {
-            tma_store_2d(&tmO, stg + sbuf * 4096, col0, m0);
+            tma_store_2d(&tmO, stg + sbuf * 4096, col0, m0 + m_store);
             tma_store_commit();
           }
           sbuf ^= 1;
@@ -471,7 +483,8 @@ template <bool OUT_F32, bool RESID, bool LNS>
 static int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
                         const float* resid, int64_t ldr, void* out, int64_t ldo, int M, int N, int K,
                         int relu, const int* m_limit, int m_limit_mult, const LnStatsIn& ln_in,
-                        void* out_bf16, int64_t ldob, float* stats_out, int ab_f16, cudaStream_t stream) {
+                        void* out_bf16, int64_t ldob, float* stats_out, int ab_f16, int splits,
+                        int split_rows, cudaStream_t stream) {
   constexpr int SMEM = g2_smem(LNS);
   static_assert(SMEM <= 232448, "shared memory budget exceeded");
   auto kern = gemm2_kernel<OUT_F32, RESID, LNS>;
@@ -486,7 +499,7 @@ static int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, 
   rc = make_tensor_map_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, G2_BN / 2, G2_BK);
   if (rc) return rc;
   {
-    uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
+    uint64_t dims[2] = {(uint64_t)N, splits > 1 ? (uint64_t)splits * split_rows : (uint64_t)M};
     uint64_t strides[1] = {(uint64_t)ldo * (OUT_F32 ? 4 : 2)};
     uint32_t box[2] = {OUT_F32 ? 32u : 64u, 32u};
     rc = make_tensor_map(&tmO, out,
@@ -509,14 +522,15 @@ static int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, 
   } else {
     tmX = tmO;
   }
-  const int tiles = ((M + 2 * G2_BM - 1) / (2 * G2_BM)) * ((N + G2_BN - 1) / G2_BN);
+  const int tiles = ((M + 2 * G2_BM - 1) / (2 * G2_BM)) * ((N + G2_BN - 1) / G2_BN) * splits;
   const int max_clusters = num_sms() / 2;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
   static const int dbg = getenv("FBKST_GEMM_DBG") ? atoi(getenv("FBKST_GEMM_DBG")) : 0;
   FBKST_CHECK_CUDA(launch_pdl(kern, dim3(2 * clusters), dim3(384), SMEM, stream, tmA, tmB, tmO, tmR, tmX,
                               M, N, K, bias, relu, dbg, m_limit, m_limit_mult, ln_in,
                               reinterpret_cast<float2*>(stats_out),
-                              ab_f16 ? idesc_f16_f32(256, G2_BN, 0, 0) : idesc_bf16_f32(256, G2_BN, 0, 0)));
+                              ab_f16 ? idesc_f16_f32(256, G2_BN, 0, 0) : idesc_bf16_f32(256, G2_BN, 0, 0),
+                              splits, split_rows));
   return FBKST_OK;
 }
 
@@ -535,15 +549,36 @@ int linear_pair_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw,
   ln_in.eps = ln_eps;
   if (stats_out != nullptr)
     return launch_gemm2<true, true, true>(A, lda, W, ldw, bias, resid, ldr, out, ldo, M, N, K, relu,
-                                          m_limit, m_limit_mult, ln_in, out_bf16, ldob, stats_out, ab_f16, stream);
+                                          m_limit, m_limit_mult, ln_in, out_bf16, ldob, stats_out, ab_f16, 1, 0, stream);
   if (resid != nullptr)
     return launch_gemm2<true, true, false>(A, lda, W, ldw, bias, resid, ldr, out, ldo, M, N, K, relu,
-                                           m_limit, m_limit_mult, ln_in, nullptr, 0, nullptr, ab_f16, stream);
+                                           m_limit, m_limit_mult, ln_in, nullptr, 0, nullptr, ab_f16, 1, 0, stream);
   if (out_f32)
     return launch_gemm2<true, false, false>(A, lda, W, ldw, bias, nullptr, 0, out, ldo, M, N, K, relu,
-                                            m_limit, m_limit_mult, ln_in, nullptr, 0, nullptr, ab_f16, stream);
+                                            m_limit, m_limit_mult, ln_in, nullptr, 0, nullptr, ab_f16, 1, 0, stream);
   return launch_gemm2<false, false, false>(A, lda, W, ldw, bias, nullptr, 0, out, ldo, M, N, K, relu,
-                                           m_limit, m_limit_mult, ln_in, nullptr, 0, nullptr, ab_f16, stream);
+                                           m_limit, m_limit_mult, ln_in, nullptr, 0, nullptr, ab_f16, 1, 0, stream);
+}
+
+// Split-K GEMM for weight gradients: partial[s, m, n] = sum over the s-th slice of K of A[m, k] W[n, k]
+// (fp32, no bias), s < splits, stored at partial + (s * split_rows + m) * ldo.  split_rows >= M rounded
+// up to the 32-row store granularity (the caller allocates [splits, split_rows, ldo] floats).
+// *splits is clamped so that no slice is empty; the caller reduces the slices (fbkst_reduce_splits).
+int linear_pair_splitk(const void* A, int64_t lda, const void* W, int64_t ldw, float* partial, int64_t ldo,
+                       int M, int N, int K, int* splits, int split_rows, cudaStream_t stream) {
+  const int num_kb = (K + G2_BK - 1) / G2_BK;
+  int sp = *splits < 1 ? 1 : *splits;
+  if (sp > num_kb) sp = num_kb;
+  const int kb_per = (num_kb + sp - 1) / sp;
+  sp = (num_kb + kb_per - 1) / kb_per;  // no empty slice
+  *splits = sp;
+  LnStatsIn ln_in;
+  ln_in.stats = nullptr;
+  ln_in.parts = 0;
+  ln_in.dim = K;
+  ln_in.eps = 0.f;
+  return launch_gemm2<true, false, false>(A, lda, W, ldw, nullptr, nullptr, 0, partial, ldo, M, N, K, 0, nullptr,
+                                          0, ln_in, nullptr, 0, nullptr, 0, sp, split_rows, stream);
 }
 
 }  // namespace fbkst
