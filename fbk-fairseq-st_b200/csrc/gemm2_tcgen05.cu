@@ -581,4 +581,46 @@ int linear_pair_splitk(const void* A, int64_t lda, const void* W, int64_t ldw, f
                                           0, ln_in, nullptr, 0, nullptr, 0, sp, split_rows, stream);
 }
 
+// splits for a wgrad GEMM with `tiles_mn` output tiles over K = tokens: fill the CTA pairs about twice,
+// keep >= 8 k-blocks (512 tokens) per slice
+static int wgrad_splits(int M, int N, int K) {
+  const int tiles_mn = ((M + 2 * G2_BM - 1) / (2 * G2_BM)) * ((N + G2_BN - 1) / G2_BN);
+  const int pairs = num_sms() / 2;
+  int sp = (2 * pairs + tiles_mn - 1) / tiles_mn;
+  const int num_kb = (K + G2_BK - 1) / G2_BK;
+  const int max_sp = num_kb / 8 > 0 ? num_kb / 8 : 1;
+  if (sp > max_sp) sp = max_sp;
+  if (sp < 1) sp = 1;
+  const int kb_per = (num_kb + sp - 1) / sp;
+  return (num_kb + kb_per - 1) / kb_per;
+}
+
 }  // namespace fbkst
+
+extern "C" long long fbkst_linear_wgrad_workspace(int n_out, int k_in, int tokens) {
+  using namespace fbkst;
+  const int sp = wgrad_splits(n_out, k_in, tokens);
+  const long long split_rows = ((long long)n_out + 31) / 32 * 32;
+  const long long ldo = ((long long)k_in + 7) / 8 * 8;
+  return (long long)sp * split_rows * ldo;
+}
+
+// dW[n, k] = sum_m gT[n, m] * xT[k, m]  (fp32 out; both operands token-contiguous bf16): split-K over the
+// tokens on the CTA-pair tcgen05 kernel + a fixed-order reduction of the slices.  replaces the autograd of
+// every F.linear on the path (weight gradient).  workspace: fbkst_linear_wgrad_workspace(...) floats.
+extern "C" int fbkst_linear_wgrad_bf16(const void* gT, int64_t ldg, const void* xT, int64_t ldx, float* workspace,
+                                       float* dW, int64_t lddw, int n_out, int k_in, int tokens,
+                                       fbkst_stream_t stream) {
+  using namespace fbkst;
+  FBKST_REQUIRE(gT && xT && workspace && dW, "fbkst_linear_wgrad_bf16: null pointer");
+  FBKST_REQUIRE(n_out > 0 && k_in > 0 && tokens > 0, "fbkst_linear_wgrad_bf16: empty problem");
+  FBKST_REQUIRE(ldg % 8 == 0 && ldx % 8 == 0 && ldg >= tokens && ldx >= tokens,
+                "fbkst_linear_wgrad_bf16: operand pitches must be multiples of 8 and >= tokens");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int sp = wgrad_splits(n_out, k_in, tokens);
+  const int split_rows = (n_out + 31) / 32 * 32;
+  const int64_t ldo = ((int64_t)k_in + 7) / 8 * 8;
+  int rc = linear_pair_splitk(gT, ldg, xT, ldx, workspace, ldo, n_out, k_in, tokens, &sp, split_rows, st);
+  if (rc) return rc;
+  return fbkst_reduce_sum(workspace, sp, (int64_t)split_rows * ldo, n_out, k_in, ldo, dW, lddw, 1.0f, stream);
+}

@@ -1,7 +1,7 @@
 """ctypes binding of ``libfbkst_b200.so`` (declared in ``include/fbkst_b200.h``)."""
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
+from ctypes import c_char_p, c_float, c_int, c_int64, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfbkst_b200.so")
@@ -11,7 +11,7 @@ BF16, F32 = 0, 1
 CTC_STRATEGY = {"avg": 0, "weighted": 1, "softmax": 2}
 EPI_RELU, EPI_OUT_F32, EPI_ROW_REMAP, EPI_POSEMB, EPI_AB_F16 = 1, 2, 4, 8, 16
 
-P, I, I64, F = c_void_p, c_int, c_int64, c_float
+P, I, I64, F, U64 = c_void_p, c_int, c_int64, c_float, c_uint64
 
 # name -> argtypes; every entry point returns int (0 = ok) unless listed in _RESTYPES
 SIGNATURES = {
@@ -46,7 +46,20 @@ SIGNATURES = {
     "fbkst_prep_conv2_weight": [P, P, I, P],
     "fbkst_prep_fc3_weight": [P, P, I, I, I, P],
     "fbkst_prep_bn_affine": [P, P, P, P, F, P, P, I, P],
+    # training side
+    "fbkst_dropout_add_ln": [P, P, P, P, P, P, F, I, I, F, U64, I, P],
+    "fbkst_ln_bwd_blocks": [I],
+    "fbkst_ln_bwd": [P, P, P, P, I, P, F, I, I, P],
+    "fbkst_grad_prep": [P, I, I64, P, I64, F, I, I, P, I64, I, P, I64, P, I, I, I, F, U64, I, I, P],
+    "fbkst_reduce_sum": [P, I, I64, I, I, I64, P, I64, F, P],
+    "fbkst_linear_wgrad_bf16": [P, I64, P, I64, P, P, I64, I, I, I, P],
+    "fbkst_attention_train_fwd": [P, P, P, P, I, I, I, I, F, U64, I, P],
+    "fbkst_attn_delta": [P, P, P, I, I, P],
+    "fbkst_attention_train_bwd": [P, P, P, P, P, P, I, I, I, I, F, U64, I, P],
+    "fbkst_ctc_compress_bwd": [P, P, P, P, I, I, I, P],
+    "fbkst_dropout_inplace": [P, I, I64, F, U64, I, P],
 }
+_RESTYPES = {"fbkst_linear_wgrad_workspace": (c_int64, [I, I, I])}
 
 _lib = None
 
@@ -67,6 +80,10 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = c_int
+    for name, (restype, argtypes) in _RESTYPES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = restype
     _lib = lib
     return lib
 

@@ -528,3 +528,149 @@ def prep_bn_affine(gamma, beta, mean, var, eps=1e-5):
                                    _stream()))
     _count()
     return scale, shift
+
+
+# ------------------------------------------------------------------------------------- training side
+def dropout_add_ln(y, residual=None, gamma=None, beta=None, eps=1e-5, p=0.0, seed=0, site=0, want_x=True):
+    """x1 = residual + dropout(y); ln = LayerNorm(x1) in bf16 (when gamma is given).  -> (x1, ln)."""
+    lib = _lib.require_device()
+    _req(y, torch.float32, "dropout_add_ln.y")
+    M, D = y.shape
+    if residual is not None:
+        _req(residual, torch.float32, "dropout_add_ln.residual")
+    x1 = torch.empty_like(y) if want_x else None
+    ln = torch.empty(M, D, dtype=torch.bfloat16, device=y.device) if gamma is not None else None
+    check(lib.fbkst_dropout_add_ln(y.data_ptr(), _ptr(residual), _ptr(x1), _ptr(ln), _ptr(gamma), _ptr(beta),
+                                   float(eps), M, D, float(p), int(seed), int(site), _stream()))
+    _count()
+    return x1, ln
+
+
+def ln_bwd(dy, x, gamma, dx=None, eps=1e-5):
+    """LayerNorm backward.  dx: fp32 [M, D] holding the residual branch's gradient (accumulated into), or None.
+    -> (dx, dgamma [D], dbeta [D])."""
+    lib = _lib.require_device()
+    _req(dy, torch.float32, "ln_bwd.dy"); _req(x, torch.float32, "ln_bwd.x")
+    M, D = x.shape
+    acc = 1 if dx is not None else 0
+    if dx is None:
+        dx = torch.empty_like(x)
+    _req(dx, torch.float32, "ln_bwd.dx")
+    G = lib.fbkst_ln_bwd_blocks(M)
+    partial = torch.empty(G, 2, D, dtype=torch.float32, device=x.device)
+    check(lib.fbkst_ln_bwd(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), dx.data_ptr(), acc, partial.data_ptr(),
+                           float(eps), M, D, _stream()))
+    dgb = torch.empty(2, D, dtype=torch.float32, device=x.device)
+    check(lib.fbkst_reduce_sum(partial.data_ptr(), G, 2 * D, 1, 2 * D, 2 * D, dgb.data_ptr(), 2 * D, 1.0, _stream()))
+    _count(2)
+    return dx, dgb[0], dgb[1]
+
+
+def grad_prep(g, act=None, act_scale=1.0, remap=None, want_gb=True, want_gT=True, want_colsum=True, n_pad=None,
+              p=0.0, seed=0, site=0, dp_cols=None):
+    """See fbkst_grad_prep.  g [M, N] fp32/bf16 (unit column stride).  -> (gb [M, n_pad] bf16 or None,
+    gT [N, M] bf16 (a view of a [N, ceil8(M)] buffer) or None, colsum [N] fp32 or None)."""
+    lib = _lib.require_device()
+    if g.dtype not in (torch.float32, torch.bfloat16) or g.stride(-1) != 1 or g.dim() != 2:
+        raise ValueError("fbkst_b200.grad_prep: g must be a 2-D fp32/bf16 tensor with unit column stride")
+    M, N = g.shape
+    n_pad = N if n_pad is None else n_pad
+    dev = g.device
+    if act is not None:
+        _req(act, torch.bfloat16, "grad_prep.act")
+    gb = torch.empty(M, n_pad, dtype=torch.bfloat16, device=dev) if want_gb else None
+    ldt = (M + 7) // 8 * 8
+    gT = torch.empty(N, ldt, dtype=torch.bfloat16, device=dev) if want_gT else None
+    tiles = (M + 63) // 64
+    cs = torch.empty(tiles, n_pad, dtype=torch.float32, device=dev) if want_colsum else None
+    inner, outer = remap if remap is not None else (0, 0)
+    check(lib.fbkst_grad_prep(g.data_ptr(), 1 if g.dtype == torch.float32 else 0, g.stride(0), _ptr(act),
+                              act.stride(0) if act is not None else 0, float(act_scale), inner, outer,
+                              _ptr(gb), n_pad, n_pad, _ptr(gT), ldt, _ptr(cs), n_pad, M, N, float(p), int(seed),
+                              int(site), int(dp_cols if dp_cols is not None else N), _stream()))
+    _count()
+    colsum = None
+    if want_colsum:
+        colsum = torch.empty(n_pad, dtype=torch.float32, device=dev)
+        check(lib.fbkst_reduce_sum(cs.data_ptr(), tiles, n_pad, 1, n_pad, n_pad, colsum.data_ptr(), n_pad, 1.0,
+                                   _stream()))
+        _count()
+        colsum = colsum[:N]
+    return gb, (gT[:, :M] if gT is not None else None), colsum
+
+
+def transpose_bf16(x):
+    """[M, N] bf16/fp32 -> [N, M] bf16 (a view of a [N, ceil8(M)] buffer): the wgrad GEMM's token-contiguous
+    operand, or a transposed weight copy for the dgrad GEMM."""
+    return grad_prep(x, want_gb=False, want_gT=True, want_colsum=False)[1]
+
+
+def linear_wgrad(gT, xT):
+    """dW [n_out, k_in] fp32 = gT [n_out, tokens] @ xT [k_in, tokens]^T (both bf16, token-contiguous views)."""
+    lib = _lib.require_device()
+    if gT.dtype != torch.bfloat16 or xT.dtype != torch.bfloat16 or gT.stride(1) != 1 or xT.stride(1) != 1:
+        raise ValueError("fbkst_b200.linear_wgrad: operands must be bf16 with unit column stride")
+    n_out, tokens = gT.shape
+    k_in = xT.shape[0]
+    if xT.shape[1] != tokens:
+        raise ValueError("fbkst_b200.linear_wgrad: token counts differ")
+    ws = torch.empty(lib.fbkst_linear_wgrad_workspace(n_out, k_in, tokens), dtype=torch.float32, device=gT.device)
+    dW = torch.empty(n_out, k_in, dtype=torch.float32, device=gT.device)
+    check(lib.fbkst_linear_wgrad_bf16(gT.data_ptr(), gT.stride(0), xT.data_ptr(), xT.stride(0), ws.data_ptr(),
+                                      dW.data_ptr(), k_in, n_out, k_in, tokens, _stream()))
+    _count(2)
+    return dW
+
+
+def attention_train_fwd(qkv, lengths, L, B, H, log_penalty=True, p=0.0, seed=0, site=0):
+    """Training attention: qkv [L*B, 3*H*64] bf16 UNSCALED -> (out [L*B, H*64] bf16, lse [B*H, L] fp32)."""
+    lib = _lib.require_device()
+    _req(qkv, torch.bfloat16, "attention_train_fwd.qkv"); _req(lengths, torch.int32, "attention_train_fwd.lengths")
+    if qkv.shape != (L * B, 3 * H * 64):
+        raise ValueError("fbkst_b200.attention_train_fwd: bad qkv shape %s" % (tuple(qkv.shape),))
+    out = torch.empty(L * B, H * 64, dtype=torch.bfloat16, device=qkv.device)
+    lse = torch.empty(B * H, L, dtype=torch.float32, device=qkv.device)
+    check(lib.fbkst_attention_train_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), lengths.data_ptr(), L, B, H,
+                                        1 if log_penalty else 0, float(p), int(seed), int(site), _stream()))
+    _count()
+    return out, lse
+
+
+def attention_train_bwd(qkv, out, dout, lse, lengths, L, B, H, log_penalty=True, p=0.0, seed=0, site=0):
+    """-> dqkv [L*B, 3*H*64] bf16 given dout [L*B, H*64] bf16 (and the forward's out / lse)."""
+    lib = _lib.require_device()
+    _req(qkv, torch.bfloat16, "attention_train_bwd.qkv"); _req(dout, torch.bfloat16, "attention_train_bwd.dout")
+    _req(out, torch.bfloat16, "attention_train_bwd.out"); _req(lse, torch.float32, "attention_train_bwd.lse")
+    M = L * B
+    delta = torch.empty(M, H, dtype=torch.float32, device=qkv.device)
+    check(lib.fbkst_attn_delta(dout.data_ptr(), out.data_ptr(), delta.data_ptr(), M, H, _stream()))
+    dqkv = torch.empty(M, 3 * H * 64, dtype=torch.bfloat16, device=qkv.device)
+    check(lib.fbkst_attention_train_bwd(qkv.data_ptr(), dout.data_ptr(), lse.data_ptr(), delta.data_ptr(),
+                                        dqkv.data_ptr(), lengths.data_ptr(), L, B, H, 1 if log_penalty else 0,
+                                        float(p), int(seed), int(site), _stream()))
+    _count(3)
+    return dqkv
+
+
+def ctc_compress_bwd(dout, seg_id, weight, L, B):
+    lib = _lib.require_device()
+    _req(dout, torch.float32, "ctc_compress_bwd.dout")
+    D = dout.shape[-1]
+    dx = torch.empty(L * B, D, dtype=torch.float32, device=dout.device)
+    check(lib.fbkst_ctc_compress_bwd(dout.data_ptr(), seg_id.data_ptr(), weight.data_ptr(), dx.data_ptr(), L, B, D,
+                                     _stream()))
+    _count()
+    return dx
+
+
+def dropout_(x, p, seed, site):
+    """In-place dropout of a contiguous bf16 / fp32 tensor (numel % 4 == 0)."""
+    lib = _lib.require_device()
+    if p <= 0.0:
+        return x
+    if x.dtype not in (torch.float32, torch.bfloat16) or not x.is_contiguous():
+        raise ValueError("fbkst_b200.dropout_: contiguous bf16/fp32 tensor expected")
+    check(lib.fbkst_dropout_inplace(x.data_ptr(), 1 if x.dtype == torch.float32 else 0, x.numel(), float(p),
+                                    int(seed), int(site), _stream()))
+    _count()
+    return x

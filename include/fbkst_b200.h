@@ -317,6 +317,73 @@ int fbkst_prep_bn_affine(const float* gamma, const float* beta, const float* mea
                          const float* var, float eps, float* scale, float* shift, int C,
                          fbkst_stream_t stream);
 
+/* =====================================================================================================
+ * Training side (scope row T: cfg4).  The reference has no backward code: every gradient below is what
+ * torch.autograd derives from the Python calls cited.  Gradients are bf16 GEMM operands with fp32
+ * accumulation; parameter gradients are returned in fp32 in the reference's parameter layout.
+ * Dropout masks are regenerated from (seed, site, element position), never stored.
+ * ===================================================================================================== */
+
+/* x1 = residual + dropout(y, p);  ln_out = LayerNorm(x1) in bf16 (skipped when ln_out == NULL).
+ * replaces fairseq/modules/transformer_layer.py:120-122 / :133-135 (F.dropout + residual add) fused with
+ * the next sub-layer's LayerNorm (:108-110 / :126-128), and conv_transformer.py:229-232 with residual == NULL.
+ * y, residual, x1 [M, D] fp32 (x1 may be NULL); D a multiple of 128. */
+int fbkst_dropout_add_ln(const float* y, const float* residual, float* x1, void* ln_out_bf16, const float* gamma,
+                         const float* beta, float eps, int M, int D, float p, uint64_t seed, int site,
+                         fbkst_stream_t stream);
+
+/* LayerNorm backward (autograd of fairseq/modules/layer_norm.py:29-32): dx (+)= dLN(dy; x, gamma);
+ * partial [fbkst_ln_bwd_blocks(M), 2, D] fp32 receives per-block (dgamma | dbeta) sums, to be reduced with
+ * fbkst_reduce_sum.  accumulate != 0: dx already holds the residual branch's gradient. */
+int fbkst_ln_bwd_blocks(int M);
+int fbkst_ln_bwd(const float* dy, const float* x, const float* gamma, float* dx, int accumulate, float* partial,
+                 float eps, int M, int D, fbkst_stream_t stream);
+
+/* Gradient preparation for a linear layer's backward: from g [M, N] (fp32 or bf16, pitch ldg; optional row
+ * remap in_row(m) = (m % remap_inner) * remap_outer + m / remap_inner) produce
+ *   v = g, zeroed where the saved activation act[m, n] <= 0 (ReLU backward) and scaled by act_scale,
+ *       multiplied by the regenerated dropout keep-scale of element (in_row(m), n) of a [*, dp_cols] tensor;
+ *   gb [M, n_pad] bf16 (pitch ldb; columns N..n_pad-1 zero)   -- A operand of the dgrad GEMM        (optional)
+ *   gT [N, M] bf16 (pitch ldt)                                 -- A operand of the wgrad GEMM        (optional)
+ *   colsum [ceil(M/64), ld_cs] fp32 per-row-tile column sums   -- bias gradient after fbkst_reduce_sum (optional)
+ * replaces the autograd of F.relu / F.dropout / F.linear's bias (transformer_layer.py:120-135). */
+int fbkst_grad_prep(const void* g, int g_is_f32, int64_t ldg, const void* act_bf16, int64_t lda, float act_scale,
+                    int remap_inner, int remap_outer, void* gb, int64_t ldb, int n_pad, void* gT, int64_t ldt,
+                    float* colsum, int ld_cs, int M, int N, float p, uint64_t seed, int site, int dp_cols,
+                    fbkst_stream_t stream);
+
+/* out[r, c] = scale * sum_{g < G} in[g * g_stride + r * ldi + c]  (fixed summation order) */
+int fbkst_reduce_sum(const float* in, int G, int64_t g_stride, int rows, int cols, int64_t ldi, float* out,
+                     int64_t ldo, float scale, fbkst_stream_t stream);
+
+/* Weight gradient of a linear layer: dW[n, k] = sum_m gT[n, m] xT[k, m] (fp32), split-K over the tokens on
+ * the CTA-pair tcgen05 kernel + fixed-order reduction.  workspace: fbkst_linear_wgrad_workspace() floats. */
+long long fbkst_linear_wgrad_workspace(int n_out, int k_in, int tokens);
+int fbkst_linear_wgrad_bf16(const void* gT, int64_t ldg, const void* xT, int64_t ldx, float* workspace, float* dW,
+                            int64_t lddw, int n_out, int k_in, int tokens, fbkst_stream_t stream);
+
+/* Self-attention for training (local_attention.py:115-139 incl. F.dropout on the probabilities, :136):
+ * qkv [L*B, 3*H*64] bf16 UNSCALED (the kernel applies head_dim^-0.5, :98); out [L*B, H*64] bf16;
+ * lse [B*H, L] fp32 (log2 domain) is kept for the backward.  Query rows t >= lengths[b] give zeros. */
+int fbkst_attention_train_fwd(const void* qkv, void* out, float* lse, const int32_t* lengths, int L, int B, int H,
+                              int log_penalty, float dropout_p, uint64_t seed, int site, fbkst_stream_t stream);
+/* delta[m, h] = sum_d dO[m, h*64+d] * O[m, h*64+d]  (m = t*B+b) */
+int fbkst_attn_delta(const void* dO, const void* O, float* delta, int M, int H, fbkst_stream_t stream);
+/* dqkv [L*B, 3*H*64] bf16 = autograd of the call above w.r.t. q, k, v given dO [L*B, H*64] bf16: scores are
+ * recomputed tile by tile on tcgen05 (no L x L buffer); rows t >= lengths[b] get zero gradient. */
+int fbkst_attention_train_bwd(const void* qkv, const void* dO, const float* lse, const float* delta, void* dqkv,
+                              const int32_t* lengths, int L, int B, int H, int log_penalty, float dropout_p,
+                              uint64_t seed, int site, fbkst_stream_t stream);
+
+/* CTC-compression backward (conv_transformer.py:290: x.bmm(W) with W constant):
+ * dx[t*B+b, :] = weight[t, b] * dout[seg_id[t, b]*B + b, :], zero for padded frames. */
+int fbkst_ctc_compress_bwd(const float* dout, const int32_t* seg_id, const float* weight, float* dx, int L, int B,
+                           int D, fbkst_stream_t stream);
+
+/* in-place dropout of `numel` (multiple of 4) bf16 / fp32 elements (F.dropout, transformer_layer.py:133) */
+int fbkst_dropout_inplace(void* x, int is_f32, int64_t numel, float p, uint64_t seed, int site,
+                          fbkst_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -42,7 +42,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 def test_binding_covers_every_declared_symbol():
     from fbkst_b200 import _lib
-    bound = set(_lib.SIGNATURES) | {"fbkst_last_error"}
+    bound = set(_lib.SIGNATURES) | set(_lib._RESTYPES) | {"fbkst_last_error"}
     assert set(declared_symbols()) == bound
 
 

@@ -1,0 +1,230 @@
+"""GPU parity of the training-side kernels (scope row T), through the C ABI, against torch.autograd of
+the same fp32 formula on the same (bf16-rounded) inputs.
+
+Tolerances: fp32 streaming kernels 1e-5; bf16-output kernels 1e-2 of the tensor's max magnitude (one bf16
+rounding of the result); tensor-core gradients (bf16 operands, fp32 accumulation) 2e-2 (north_star)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from helpers import rel_err  # noqa: E402
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def bf(x):
+    return x.to(torch.bfloat16)
+
+
+# ----------------------------------------------------------------------- dropout + residual + LayerNorm
+@pytest.mark.parametrize("M,D", [(100, 128), (777, 512), (64, 1024)])
+def test_dropout_add_ln_no_dropout(M, D):
+    from fbkst_b200 import ops
+    g = torch.Generator().manual_seed(M + D)
+    y, r = torch.randn(M, D, generator=g).to(dev()), torch.randn(M, D, generator=g).to(dev())
+    gamma, beta = (1 + 0.1 * torch.randn(D, generator=g)).to(dev()), (0.1 * torch.randn(D, generator=g)).to(dev())
+    x1, ln = ops.dropout_add_ln(y, r, gamma, beta)
+    assert torch.equal(x1, y + r)
+    ref = torch.nn.functional.layer_norm(y + r, (D,), gamma, beta, 1e-5)
+    assert rel_err(ln.float(), ref) < 1e-2
+    x1b, ln_none = ops.dropout_add_ln(y, None)
+    assert ln_none is None and torch.equal(x1b, y)
+
+
+def test_dropout_mask_forward_backward_agree():
+    """The backward regenerates the forward's mask: grad_prep with the same (seed, site) on a tensor of
+    ones reproduces exactly the keep pattern dropout_add_ln applied; the keep rate is 1 - p."""
+    from fbkst_b200 import ops
+    M, D, p = 513, 512, 0.3
+    y = torch.ones(M, D, device=dev())
+    x1, _ = ops.dropout_add_ln(y, None, p=p, seed=1234567891011, site=7)
+    kept = x1 != 0
+    assert abs(kept.float().mean().item() - (1 - p)) < 5e-3
+    assert torch.allclose(x1[kept], torch.full_like(x1[kept], 1 / (1 - p)))
+    gb, gT, cs = ops.grad_prep(torch.ones(M, D, device=dev()), p=p, seed=1234567891011, site=7)
+    assert torch.equal(gb.float() != 0, kept)
+    assert torch.equal(gT.t().float() != 0, kept)
+    x2, _ = ops.dropout_add_ln(y, None, p=p, seed=1234567891011, site=8)  # another site: another mask
+    assert not torch.equal(x2 != 0, kept)
+    z = torch.ones(M, D, device=dev(), dtype=torch.bfloat16)
+    ops.dropout_(z, p, 1234567891011, 7)  # same counter layout for the in-place kernel
+    assert torch.equal(z != 0, kept)
+
+
+@pytest.mark.parametrize("M,D", [(100, 128), (3000, 512), (257, 1024)])
+def test_ln_bwd(M, D):
+    from fbkst_b200 import ops
+    g = torch.Generator().manual_seed(M * 3 + D)
+    x = (torch.randn(M, D, generator=g) * 2 + 0.5).to(dev()).requires_grad_(True)
+    gamma = (1 + 0.1 * torch.randn(D, generator=g)).to(dev()).requires_grad_(True)
+    beta = (0.1 * torch.randn(D, generator=g)).to(dev()).requires_grad_(True)
+    dy = torch.randn(M, D, generator=g).to(dev())
+    res = torch.randn(M, D, generator=g).to(dev())
+    torch.nn.functional.layer_norm(x, (D,), gamma, beta, 1e-5).backward(dy)
+    dx, dg, db = ops.ln_bwd(dy, x.detach(), gamma.detach(), dx=res.clone())
+    assert rel_err(dx, x.grad + res) < 1e-5
+    assert rel_err(dg, gamma.grad) < 1e-4 and rel_err(db, beta.grad) < 1e-4
+    dx2, _, _ = ops.ln_bwd(dy, x.detach(), gamma.detach())
+    assert rel_err(dx2, x.grad) < 1e-5
+
+
+# ----------------------------------------------------------------------- grad_prep (mask, transpose, sums)
+@pytest.mark.parametrize("M,N,f32", [(64, 64, True), (1000, 512, True), (333, 2048, False), (130, 8005, True)])
+def test_grad_prep(M, N, f32):
+    from fbkst_b200 import ops
+    g = torch.Generator().manual_seed(M + N)
+    x = torch.randn(M, N, generator=g).to(dev())
+    if not f32:
+        x = bf(x)
+    act = bf(torch.relu(torch.randn(M, N, generator=g))).to(dev())
+    n_pad = (N + 7) // 8 * 8
+    gb, gT, cs = ops.grad_prep(x, act=act, act_scale=1.25, n_pad=n_pad)
+    ref = bf(torch.where(act > 0, x.float() * 1.25, torch.zeros_like(x.float())))
+    assert gb.shape == (M, n_pad) and torch.equal(gb[:, :N], ref) and (gb[:, N:] == 0).all()
+    assert gT.shape == (N, M) and torch.equal(gT, ref.t())
+    assert rel_err(cs, ref.float().sum(0)) < 1e-5
+    t = ops.transpose_bf16(x)
+    assert torch.equal(t, bf(x).t())
+
+
+def test_grad_prep_row_remap():
+    """fc3's backward: the incoming gradient is time-major (t*B+b), the GEMM operands are in the conv
+    layout's (b*L+t) row order."""
+    from fbkst_b200 import ops
+    L, B, N = 37, 5, 256
+    g = torch.randn(L * B, N, device=dev())
+    act = bf(torch.relu(torch.randn(B * L, N, device=dev())))
+    gb, gT, cs = ops.grad_prep(g, act=act, remap=(L, B))
+    ref = bf(torch.where(act > 0, g.view(L, B, N).transpose(0, 1).reshape(B * L, N), torch.zeros_like(g)))
+    assert torch.equal(gb, ref) and torch.equal(gT, ref.t())
+
+
+# ----------------------------------------------------------------------- wgrad (split-K tcgen05 GEMM)
+@pytest.mark.parametrize("n_out,k_in,tokens", [(512, 512, 1000), (1536, 512, 24000), (2048, 512, 4099),
+                                                (8005, 512, 3000), (64, 576, 30000), (512, 640, 777)])
+def test_linear_wgrad(n_out, k_in, tokens):
+    from fbkst_b200 import ops
+    g = torch.Generator().manual_seed(n_out + tokens)
+    dy = bf(torch.randn(tokens, n_out, generator=g)).to(dev())
+    x = bf(torch.randn(tokens, k_in, generator=g)).to(dev())
+    dW = ops.linear_wgrad(ops.transpose_bf16(dy), ops.transpose_bf16(x))
+    ref = dy.float().t() @ x.float()
+    assert dW.shape == (n_out, k_in)
+    assert rel_err(dW, ref) < 1e-4
+    dW2 = ops.linear_wgrad(ops.transpose_bf16(dy), ops.transpose_bf16(x))
+    assert torch.equal(dW, dW2)  # fixed summation order
+
+
+# ----------------------------------------------------------------------- attention (training)
+def attn_train_ref(qkv, lengths, L, B, H, log_penalty, keep=None):
+    """local_attention.py:98-139 in fp32, differentiable; keep [B*H, L, L] = dropout keep-scale."""
+    D = H * 64
+    q, k, v = qkv.view(L, B, 3, H, 64).permute(2, 1, 3, 0, 4)  # [3] B H L 64
+    s = (q * 0.125) @ k.transpose(-1, -2)
+    key_pad = torch.arange(L, device=qkv.device)[None, :] >= lengths[:, None]
+    s = s.masked_fill(key_pad[:, None, None, :], float("-inf"))
+    if log_penalty:
+        i = torch.arange(L, device=qkv.device)
+        s = s - torch.clamp(torch.log((i[:, None] - i[None, :]).abs().float()), min=0)
+    p = torch.softmax(s, -1)
+    if keep is not None:
+        p = p * keep.view(B, H, L, L)
+    o = p @ v
+    return o.permute(2, 0, 1, 3).reshape(L * B, D)
+
+
+def valid_rows(lengths, L, B):
+    return (torch.arange(L, device=lengths.device)[:, None] < lengths[None, :]).reshape(L * B)
+
+
+@pytest.mark.parametrize("L,B,H,lens,pen", [
+    (64, 1, 1, [64], False), (128, 2, 2, [128, 128], True), (100, 3, 2, [100, 64, 5], True),
+    (375, 2, 8, [375, 201], True), (300, 2, 4, [300, 129], False), (700, 1, 2, [700], True)])
+def test_attention_train_fwd_bwd(L, B, H, lens, pen):
+    from fbkst_b200 import ops
+    g = torch.Generator().manual_seed(L + B + H)
+    D = H * 64
+    qkv = bf(torch.randn(L * B, 3 * D, generator=g)).to(dev())
+    lengths = torch.tensor(lens, dtype=torch.int32, device=dev())
+    out, lse = ops.attention_train_fwd(qkv, lengths, L, B, H, pen)
+    x = qkv.float().requires_grad_(True)
+    ref = attn_train_ref(x, lengths, L, B, H, pen)
+    vr = valid_rows(lengths, L, B)
+    assert torch.isfinite(out.float()).all()
+    assert rel_err(out.float()[vr], ref.detach()[vr]) < 1e-2
+    # the inference kernel computes the same thing from pre-scaled q
+    qs = qkv.clone()
+    qs[:, :D] = bf(qkv[:, :D].float() * 0.125)
+    inf = ops.attention(qs, lengths, L, B, H, pen)
+    assert rel_err(out.float()[vr], inf.float()[vr]) < 1e-2
+    # backward: padded query rows carry no gradient (the loss never reads them)
+    dout = bf(torch.randn(L * B, D, generator=g)).to(dev())
+    dout[~vr] = 0
+    ref.backward(dout.float())
+    dqkv = ops.attention_train_bwd(qkv, out, dout, lse, lengths, L, B, H, pen)
+    for name, sl in (("dq", slice(0, D)), ("dk", slice(D, 2 * D)), ("dv", slice(2 * D, 3 * D))):
+        e = rel_err(dqkv[:, sl].float(), x.grad[:, sl])
+        assert e < 2e-2, (name, e)
+    assert (dqkv.float()[~vr] == 0).all()  # padded rows: exact zeros in dq, dk, dv
+
+
+def test_attention_train_dropout_consistency():
+    """Attention dropout: the mask is a pure function of (seed, site, head-batch, q, k).  Extract it with
+    q = 0 (uniform probabilities) and v = one-hot keys, then check forward and backward against the fp32
+    formula using that mask."""
+    from fbkst_b200 import ops
+    L, B, H, p, seed, site = 64, 2, 2, 0.25, 987654321, 3
+    D = H * 64
+    lengths = torch.tensor([64, 64], dtype=torch.int32, device=dev())
+    probe = torch.zeros(L, B, 3, H, 64, device=dev())
+    probe[:, :, 2] = torch.eye(64, device=dev())[:, None, None, :]  # v[t] = e_t for every (b, h)
+    o, _ = ops.attention_train_fwd(bf(probe.view(L * B, 3 * D)), lengths, L, B, H, False, p=p, seed=seed, site=site)
+    keep = (o.float().view(L, B, H, 64) * 64).permute(1, 2, 0, 3).reshape(B * H, L, L)  # (1/64) * keep -> keep
+    frac = (keep == 0).float().mean().item()
+    assert abs(frac - p) < 0.03
+    assert torch.allclose(keep[keep != 0], torch.full_like(keep[keep != 0], 1 / (1 - p)), rtol=1e-2)
+    keep = torch.where(keep != 0, torch.full_like(keep, 1 / (1 - p)), torch.zeros_like(keep))
+    g = torch.Generator().manual_seed(5)
+    qkv = bf(torch.randn(L * B, 3 * D, generator=g)).to(dev())
+    out, lse = ops.attention_train_fwd(qkv, lengths, L, B, H, True, p=p, seed=seed, site=site)
+    x = qkv.float().requires_grad_(True)
+    ref = attn_train_ref(x, lengths, L, B, H, True, keep=keep)
+    assert rel_err(out.float(), ref.detach()) < 1e-2
+    dout = bf(torch.randn(L * B, D, generator=g)).to(dev())
+    ref.backward(dout.float())
+    dqkv = ops.attention_train_bwd(qkv, out, dout, lse, lengths, L, B, H, True, p=p, seed=seed, site=site)
+    assert rel_err(dqkv.float(), x.grad) < 2e-2
+
+
+# ----------------------------------------------------------------------- CTC compression backward
+def test_ctc_compress_bwd():
+    from fbkst_b200 import ops
+    L, B, D, V = 50, 3, 256, 40
+    g = torch.Generator().manual_seed(9)
+    lengths = torch.tensor([50, 33, 7], dtype=torch.int32, device=dev())
+    logits = torch.randn(L * B, V, generator=g)
+    runs = torch.randint(0, V, (L // 3 + 1, B), generator=g).repeat_interleave(3, 0)[:L]
+    logits.view(L, B, V).scatter_add_(2, runs.unsqueeze(-1), torch.full((L, B, 1), 20.0))
+    logits = logits.to(dev())
+    x = torch.randn(L * B, D, generator=g).to(dev())
+    labels, prob = ops.ctc_argmax(logits, lengths, L, B, V, True)
+    seg_id, seg_start, weight, new_len, max_new = ops.ctc_segment(labels, prob, lengths, "weighted", L, B)
+    out = ops.ctc_compress(x, seg_id, seg_start, weight, lengths, new_len, max_new, L, B)
+    dout = torch.randn(L * B, D, generator=g).to(dev())
+    dx = ops.ctc_compress_bwd(dout, seg_id, weight, L, B)
+    # dense restatement: out[s, b] = sum_t W[t, s] x[t, b]  (conv_transformer.py:290)
+    xr = x.clone().requires_grad_(True)
+    W = torch.zeros(B, L, L, device=dev())
+    sid, w = seg_id.view(L, B), weight.view(L, B)
+    for b in range(B):
+        for t in range(int(lengths[b])):
+            W[b, t, sid[t, b]] = w[t, b]
+    ref = torch.einsum("bts,tbd->sbd", W, xr.view(L, B, D)).reshape(L * B, D)
+    assert rel_err(out, ref.detach()) < 1e-5
+    ref.backward(dout)
+    assert rel_err(dx, xr.grad) < 1e-5
