@@ -226,8 +226,9 @@ struct GradPrepParams {
   int dp_cols;  // columns per row of the tensor the dropout mask was drawn for (counter pitch = dp_cols / 4)
 };
 
-template <int IN_F32>
+template <int IN_T>  // 0: bf16, 1: fp32, 2: IEEE fp16 (the conv front end's activations)
 __global__ void __launch_bounds__(256) grad_prep_kernel(const GradPrepParams p) {
+  constexpr int IN_F32 = IN_T == 1;
   __shared__ __align__(16) __nv_bfloat16 tileT[64][72];  // [n][m], 144-byte rows
   __shared__ float cs[16][65];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -250,6 +251,11 @@ __global__ void __launch_bounds__(256) grad_prep_kernel(const GradPrepParams p) 
           for (int j = 0; j < 4; ++j)
             if (n + j < p.N) v[j] = gp[j];
         }
+      } else if (IN_T == 2) {
+        const __half* gp = reinterpret_cast<const __half*>(p.g) + mi * p.ldg + n;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (n + j < p.N) v[j] = __half2float(gp[j]);
       } else {
         const __nv_bfloat16* gp = reinterpret_cast<const __nv_bfloat16*>(p.g) + mi * p.ldg + n;
         if (p.vec_ok && n + 3 < p.N) {
@@ -269,7 +275,8 @@ __global__ void __launch_bounds__(256) grad_prep_kernel(const GradPrepParams p) 
           if (n + j < p.N) v[j] = (__bfloat162float(ap[j]) > 0.f) ? v[j] * p.act_scale : 0.f;
       }
       if (p.dp.p > 0.f) {
-        const float4 k = dropout_scale4(p.dp, (unsigned long long)m * (p.dp_cols / 4) + (n >> 2));
+        // the mask lives in the layout of the tensor g was drawn for: its row is the (remapped) input row
+        const float4 k = dropout_scale4(p.dp, (unsigned long long)mi * (p.dp_cols / 4) + (n >> 2));
         v[0] *= k.x; v[1] *= k.y; v[2] *= k.z; v[3] *= k.w;
       }
     }
@@ -487,14 +494,16 @@ extern "C" int fbkst_grad_prep(const void* g, int g_is_f32, int64_t ldg, const v
   q.ld_cs = ld_cs;
   q.M = M;
   q.N = N;
-  const size_t esz = g_is_f32 ? 4 : 2;
+  const size_t esz = g_is_f32 == 1 ? 4 : 2;
   q.vec_ok = ((reinterpret_cast<uintptr_t>(g) % (4 * esz)) == 0 && (ldg * esz) % (4 * esz) == 0) ? 1 : 0;
   q.dp = make_dropout(p, seed, site);
   q.dp_cols = dp_cols > 0 ? dp_cols : 4;
   const int ncols = q.n_pad > N ? q.n_pad : N;
   dim3 grid((ncols + 63) / 64, (M + 63) / 64);
-  if (g_is_f32)
+  if (g_is_f32 == 1)
     grad_prep_kernel<1><<<grid, 256, 0, st>>>(q);
+  else if (g_is_f32 == 2)
+    grad_prep_kernel<2><<<grid, 256, 0, st>>>(q);
   else
     grad_prep_kernel<0><<<grid, 256, 0, st>>>(q);
   FBKST_CHECK_CUDA(cudaGetLastError());

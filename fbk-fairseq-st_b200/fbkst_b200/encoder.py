@@ -210,6 +210,11 @@ def make_encoder_class(base):
             if len(convs) != 2:
                 raise NotImplementedError("fbkst_b200: exactly two subsampling convolutions are supported")
             self.dropout = args.dropout
+            # training-mode dropout sites (local_attention.py:136; fairseq/modules/transformer_layer.py:43-46)
+            self.attention_dropout = float(getattr(args, "attention_dropout", 0.0) or 0.0)
+            self.activation_dropout = float(getattr(args, "activation_dropout", 0) or 0)
+            if self.activation_dropout == 0:
+                self.activation_dropout = float(getattr(args, "relu_dropout", 0) or 0)
             if getattr(args, "activation_fn", "relu") != "relu":
                 raise NotImplementedError("fbkst_b200: only activation_fn=relu is supported")
             if getattr(args, "attn_2d", False):
@@ -340,12 +345,15 @@ def make_encoder_class(base):
         # ------------------------------------------------------------------------------- forward
         def forward(self, src_tokens, src_lengths, cls_input: Optional[Tensor] = None,
                     return_all_hiddens: bool = False, **unused):
-            if self.training and torch.is_grad_enabled():
-                raise NotImplementedError(
-                    "fbkst_b200: the training backward of the encoder is not implemented yet; call "
-                    "eval() / torch.no_grad() (there is no PyTorch fallback)")
             if not src_tokens.is_cuda:
                 raise RuntimeError("fbkst_b200: src_tokens must be a CUDA tensor (no CPU fallback)")
+            # Training semantics (BatchNorm batch statistics, dropout) whenever the module is in train();
+            # the differentiable chain also serves eval() with gradients enabled (running statistics, no
+            # dropout).  Both run fbkst_b200.train: hand-written forward + backward kernels, no PyTorch
+            # arithmetic.  Everything else is the inference path.
+            if self.training or (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())):
+                from .train import forward_train
+                return forward_train(self, src_tokens, src_lengths, return_all_hiddens)
             with torch.no_grad():
                 return self._forward(src_tokens, src_lengths, return_all_hiddens)
 
@@ -361,8 +369,8 @@ def make_encoder_class(base):
             """Asynchronous half of ``forward`` (inference, no hidden states): returns a handle for
             ``finish``.  Buffers owned by a CUDA graph (``ctc_out``) stay valid until the next launch
             with the same input shape on the same ``graph_lane``."""
-            if self.training and torch.is_grad_enabled():
-                raise NotImplementedError("fbkst_b200: training backward not implemented (see forward)")
+            if self.training:
+                raise RuntimeError("fbkst_b200: launch/finish is the inference API (call eval())")
             if not src_tokens.is_cuda:
                 raise RuntimeError("fbkst_b200: src_tokens must be a CUDA tensor (no CPU fallback)")
             with torch.no_grad():

@@ -571,8 +571,8 @@ def grad_prep(g, act=None, act_scale=1.0, remap=None, want_gb=True, want_gT=True
     """See fbkst_grad_prep.  g [M, N] fp32/bf16 (unit column stride).  -> (gb [M, n_pad] bf16 or None,
     gT [N, M] bf16 (a view of a [N, ceil8(M)] buffer) or None, colsum [N] fp32 or None)."""
     lib = _lib.require_device()
-    if g.dtype not in (torch.float32, torch.bfloat16) or g.stride(-1) != 1 or g.dim() != 2:
-        raise ValueError("fbkst_b200.grad_prep: g must be a 2-D fp32/bf16 tensor with unit column stride")
+    if g.dtype not in (torch.float32, torch.bfloat16, torch.float16) or g.stride(-1) != 1 or g.dim() != 2:
+        raise ValueError("fbkst_b200.grad_prep: g must be a 2-D fp32/bf16/fp16 tensor with unit column stride")
     M, N = g.shape
     n_pad = N if n_pad is None else n_pad
     dev = g.device
@@ -584,7 +584,8 @@ def grad_prep(g, act=None, act_scale=1.0, remap=None, want_gb=True, want_gT=True
     tiles = (M + 63) // 64
     cs = torch.empty(tiles, n_pad, dtype=torch.float32, device=dev) if want_colsum else None
     inner, outer = remap if remap is not None else (0, 0)
-    check(lib.fbkst_grad_prep(g.data_ptr(), 1 if g.dtype == torch.float32 else 0, g.stride(0), _ptr(act),
+    check(lib.fbkst_grad_prep(g.data_ptr(), {torch.bfloat16: 0, torch.float32: 1, torch.float16: 2}[g.dtype],
+                              g.stride(0), _ptr(act),
                               act.stride(0) if act is not None else 0, float(act_scale), inner, outer,
                               _ptr(gb), n_pad, n_pad, _ptr(gT), ldt, _ptr(cs), n_pad, M, N, float(p), int(seed),
                               int(site), int(dp_cols if dp_cols is not None else N), _stream()))
@@ -674,3 +675,86 @@ def dropout_(x, p, seed, site):
                                     int(seed), int(site), _stream()))
     _count()
     return x
+
+
+def bn_batch_stats(y, gamma, beta, eps=1e-5, momentum=0.1, running_mean=None, running_var=None):
+    """Training-mode BatchNorm statistics of y [..., C] fp16 (channels-last): -> (mean, rstd, scale, shift) [C]
+    fp32; running_mean / running_var (fp32, updated in place) as nn.BatchNorm2d does."""
+    lib = _lib.require_device()
+    _req(y, torch.float16, "bn_batch_stats.y")
+    C = y.shape[-1]
+    P = y.numel() // C
+    dev = y.device
+    out = torch.empty(4, C, dtype=torch.float32, device=dev)
+    partial = torch.empty(lib.fbkst_bn_partial_blocks(), 2, C, dtype=torch.float32, device=dev)
+    check(lib.fbkst_bn_batch_stats(y.data_ptr(), P, C, gamma.data_ptr(), beta.data_ptr(), float(eps),
+                                   float(momentum), _ptr(running_mean), _ptr(running_var), out[0].data_ptr(),
+                                   out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(), partial.data_ptr(),
+                                   _stream()))
+    _count(2)
+    return out[0], out[1], out[2], out[3]
+
+
+def bn_apply(x, scale, shift, p=0.0, seed=0, site=0):
+    """y = dropout(scale[c] * x + shift[c]); x [..., C] fp16 channels-last -> fp16."""
+    lib = _lib.require_device()
+    _req(x, torch.float16, "bn_apply.x")
+    C = x.shape[-1]
+    y = torch.empty_like(x)
+    check(lib.fbkst_bn_apply(x.data_ptr(), y.data_ptr(), scale.data_ptr(), shift.data_ptr(), x.numel() // C, C,
+                             float(p), int(seed), int(site), _stream()))
+    _count()
+    return y
+
+
+def bn_relu_bwd(dy, relu_out, gamma, mean, rstd, batch_stats, p=0.0, seed=0, site=0):
+    """-> (dz bf16 like dy, dbeta [C], dgamma [C])."""
+    lib = _lib.require_device()
+    _req(dy, torch.bfloat16, "bn_relu_bwd.dy"); _req(relu_out, torch.float16, "bn_relu_bwd.relu_out")
+    C = dy.shape[-1]
+    P = dy.numel() // C
+    dz = torch.empty_like(dy)
+    sums = torch.empty(2, C, dtype=torch.float32, device=dy.device)
+    partial = torch.empty(lib.fbkst_bn_partial_blocks(), 2, C, dtype=torch.float32, device=dy.device)
+    check(lib.fbkst_bn_relu_bwd(dy.data_ptr(), relu_out.data_ptr(), gamma.data_ptr(), mean.data_ptr(),
+                                rstd.data_ptr(), 1 if batch_stats else 0, dz.data_ptr(), sums.data_ptr(),
+                                partial.data_ptr(), P, C, float(p), int(seed), int(site), _stream()))
+    _count(3)
+    return dz, sums[0], sums[1]
+
+
+def conv2_im2col_t(y1):
+    """y1 [B,T1,F1,C] fp16 -> colT [9*C, B*T2*F2] bf16 (a view of a pitch-padded buffer)."""
+    lib = _lib.require_device()
+    _req(y1, torch.float16, "conv2_im2col_t.y1")
+    B, T1, F1, C = y1.shape
+    P2 = B * ((T1 + 1) // 2) * ((F1 + 1) // 2)
+    ldt = (P2 + 7) // 8 * 8
+    colT = torch.empty(9 * C, ldt, dtype=torch.bfloat16, device=y1.device)
+    check(lib.fbkst_conv2_im2col_t(y1.data_ptr(), colT.data_ptr(), ldt, B, T1, F1, C, _stream()))
+    _count()
+    return colT[:, :P2]
+
+
+def conv2_col2im(dcol, B, T1, F1, C):
+    """dcol [B*T2*F2, 9*C] bf16 -> dy1 [B,T1,F1,C] bf16."""
+    lib = _lib.require_device()
+    _req(dcol, torch.bfloat16, "conv2_col2im.dcol")
+    dy1 = torch.empty(B, T1, F1, C, dtype=torch.bfloat16, device=dcol.device)
+    check(lib.fbkst_conv2_col2im(dcol.data_ptr(), dy1.data_ptr(), B, T1, F1, C, _stream()))
+    _count()
+    return dy1
+
+
+def conv1_wgrad(dz1, x):
+    """dz1 [B,T1,F1,C] bf16, x [B,T,F] fp32 -> (dW1 [C, 9] fp32, db1 [C] fp32)."""
+    lib = _lib.require_device()
+    _req(dz1, torch.bfloat16, "conv1_wgrad.dz1"); _req(x, torch.float32, "conv1_wgrad.x")
+    B, T, Fd = x.shape
+    C = dz1.shape[-1]
+    out = torch.empty(C, 10, dtype=torch.float32, device=x.device)
+    partial = torch.empty(lib.fbkst_bn_partial_blocks(), C, 10, dtype=torch.float32, device=x.device)
+    check(lib.fbkst_conv1_wgrad(dz1.data_ptr(), x.data_ptr(), out.data_ptr(), partial.data_ptr(), B, T, Fd, C,
+                                _stream()))
+    _count(2)
+    return out[:, :9], out[:, 9]

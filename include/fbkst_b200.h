@@ -339,7 +339,8 @@ int fbkst_ln_bwd_blocks(int M);
 int fbkst_ln_bwd(const float* dy, const float* x, const float* gamma, float* dx, int accumulate, float* partial,
                  float eps, int M, int D, fbkst_stream_t stream);
 
-/* Gradient preparation for a linear layer's backward: from g [M, N] (fp32 or bf16, pitch ldg; optional row
+/* Gradient preparation for a linear layer's backward: from g [M, N] (g_is_f32: 0 bf16, 1 fp32, 2 IEEE fp16;
+ * pitch ldg; optional row
  * remap in_row(m) = (m % remap_inner) * remap_outer + m / remap_inner) produce
  *   v = g, zeroed where the saved activation act[m, n] <= 0 (ReLU backward) and scaled by act_scale,
  *       multiplied by the regenerated dropout keep-scale of element (in_row(m), n) of a [*, dp_cols] tensor;
@@ -383,6 +384,34 @@ int fbkst_ctc_compress_bwd(const float* dout, const int32_t* seg_id, const float
 /* in-place dropout of `numel` (multiple of 4) bf16 / fp32 elements (F.dropout, transformer_layer.py:133) */
 int fbkst_dropout_inplace(void* x, int is_f32, int64_t numel, float p, uint64_t seed, int site,
                           fbkst_stream_t stream);
+
+/* ---- conv front end, training (conv_transformer.py:203-214).  Activations channels-last [pixels, C], fp16 in
+ * the forward, bf16 gradients; pixels = B*T'*F' of the PADDED batch (the reference does not mask: SURVEY F5). */
+int fbkst_bn_partial_blocks(void); /* rows of the `partial` scratch buffers below */
+/* nn.BatchNorm2d in training mode, statistics half: per-channel batch mean / biased variance of y (the ReLU
+ * output), running-stat update (momentum; unbiased variance; running_* may be NULL), mean / rstd for the
+ * backward and the affine (scale, shift) for fbkst_bn_apply.  partial: [fbkst_bn_partial_blocks(), 2, C]. */
+int fbkst_bn_batch_stats(const void* y_f16, int64_t pixels, int C, const float* gamma, const float* beta, float eps,
+                         float momentum, float* running_mean, float* running_var, float* mean, float* rstd,
+                         float* scale, float* shift, float* partial, fbkst_stream_t stream);
+/* y = dropout(scale[c] * x + shift[c], p)   (BatchNorm affine + F.dropout(p = max(dropout, .1)), :212-214) */
+int fbkst_bn_apply(const void* x_f16, void* y_f16, const float* scale, const float* shift, int64_t pixels, int C,
+                   float p, uint64_t seed, int site, fbkst_stream_t stream);
+/* autograd of dropout(BatchNorm(relu(z))) w.r.t. z: dz [pixels, C] bf16 from dy [pixels, C] bf16 and the saved
+ * ReLU output; batch_stats != 0: training-mode BatchNorm (mean / rstd of the batch), else running statistics.
+ * sums [2, C] fp32 receives (dbeta | dgamma). */
+int fbkst_bn_relu_bwd(const void* dy_bf16, const void* relu_out_f16, const float* gamma, const float* mean,
+                      const float* rstd, int batch_stats, void* dz_bf16, float* sums, float* partial,
+                      int64_t pixels, int C, float p, uint64_t seed, int site, fbkst_stream_t stream);
+/* conv2 weight-gradient operand: colT [(tap, ci), pixel] bf16 (pitch ldt) from conv1's output y1 [B,T1,F1,C] fp16 */
+int fbkst_conv2_im2col_t(const void* y1_f16, void* colT_bf16, int64_t ldt, int B, int T1, int F1, int C,
+                         fbkst_stream_t stream);
+/* conv2 input gradient: dy1 [B,T1,F1,C] bf16 = gather-sum over taps of dcol [B*T2*F2, 9*C] bf16 (= dz2 @ W2) */
+int fbkst_conv2_col2im(const void* dcol_bf16, void* dy1_bf16, int B, int T1, int F1, int C, fbkst_stream_t stream);
+/* conv1 weight + bias gradient: dw1b [C, 10] fp32 = (dW1[co, kh*3+kw] | db1[co]) from dz1 [B,T1,F1,C] bf16 and
+ * the input batch x [B,T,F] fp32.  partial: [fbkst_bn_partial_blocks(), C, 10]. */
+int fbkst_conv1_wgrad(const void* dz1_bf16, const float* x, float* dw1b, float* partial, int B, int T, int F, int C,
+                      fbkst_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -108,13 +108,6 @@ def test_reorder_and_non_torchscript(golden_dir):
     assert enc.output_batch_first is False
 
 
-def test_training_mode_raises(golden_dir):
-    fx = torch.load(os.path.join(golden_dir, "enc_tiny_log.pt"), weights_only=False)
-    enc = build_encoder(fx["cfg"], fx["state_dict"]).train()
-    with pytest.raises(NotImplementedError):
-        enc(fx["src_tokens"].cuda(), fx["src_lengths"].cuda())
-
-
 @pytest.mark.parametrize("graph,lanes", [(False, 1), (True, 1), (True, 2), (True, 3)])
 def test_pipeline_matches_direct_calls(golden_dir, graph, lanes):
     """The host-buffer serving loop (copy-in / compute lanes / copy-out streams, asynchronous

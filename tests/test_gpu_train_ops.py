@@ -225,6 +225,87 @@ def test_ctc_compress_bwd():
         for t in range(int(lengths[b])):
             W[b, t, sid[t, b]] = w[t, b]
     ref = torch.einsum("bts,tbd->sbd", W, xr.view(L, B, D)).reshape(L * B, D)
-    assert rel_err(out, ref.detach()) < 1e-5
+    n_rows = int(max_new.item()) * B  # rows beyond the longest compressed utterance are never written
+    assert rel_err(out[:n_rows], ref.detach()[:n_rows]) < 1e-5
+    dout[n_rows:] = 0
+    dx = ops.ctc_compress_bwd(dout, seg_id, weight, L, B)
     ref.backward(dout)
     assert rel_err(dx, xr.grad) < 1e-5
+
+
+# ----------------------------------------------------------------------- BatchNorm (training) + conv pieces
+@pytest.mark.parametrize("P,C", [(5000, 64), (777, 128)])
+def test_bn_train_forward_backward(P, C):
+    """nn.BatchNorm2d in training mode after a ReLU (conv_transformer.py:212): batch statistics over every
+    pixel, running-stat update (momentum 0.1, unbiased variance), and the autograd of BN(relu(z))."""
+    from fbkst_b200 import ops
+    g = torch.Generator().manual_seed(P + C)
+    z = (torch.randn(P, C, generator=g) * 1.5 + 0.3).half().to(dev())
+    r = torch.relu(z)
+    gamma = (1 + 0.2 * torch.randn(C, generator=g)).to(dev())
+    beta = (0.1 * torch.randn(C, generator=g)).to(dev())
+    rm, rv = torch.zeros(C, device=dev()), torch.ones(C, device=dev())
+    mean, rstd, sc, sh = ops.bn_batch_stats(r, gamma, beta, 1e-5, 0.1, rm, rv)
+    y = ops.bn_apply(r, sc, sh)
+    zr = z.float().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rm_ref, rv_ref = torch.zeros(C, device=dev()), torch.ones(C, device=dev())
+    yr = torch.nn.functional.batch_norm(torch.relu(zr).t().reshape(1, C, P, 1), rm_ref, rv_ref, gr, br, True, 0.1,
+                                        1e-5).reshape(C, P).t()
+    assert rel_err(y.float(), yr.detach()) < 2e-3
+    assert rel_err(rm, rm_ref) < 1e-4 and rel_err(rv, rv_ref) < 1e-4
+    dy = bf(torch.randn(P, C, generator=g)).to(dev())
+    (yr * dy.float()).sum().backward()
+    dz, dbeta, dgamma = ops.bn_relu_bwd(dy, r, gamma, mean, rstd, True)
+    assert rel_err(dz.float(), zr.grad) < 1e-2
+    assert rel_err(dgamma, gr.grad) < 1e-3 and rel_err(dbeta, br.grad) < 1e-3
+    # dropout: the backward regenerates bn_apply's mask
+    yd = ops.bn_apply(torch.ones_like(r), torch.ones(C, device=dev()), torch.zeros(C, device=dev()), 0.2, 77, 1)
+    kept = yd != 0
+    assert abs(kept.float().mean().item() - 0.8) < 1e-2
+    dzd, _, _ = ops.bn_relu_bwd(torch.ones(P, C, device=dev(), dtype=torch.bfloat16), torch.ones_like(r),
+                                torch.ones(C, device=dev()), torch.zeros(C, device=dev()), torch.ones(C, device=dev()),
+                                False, 0.2, 77, 1)
+    assert torch.equal(dzd != 0, kept)
+
+
+@pytest.mark.parametrize("B,T1,F1,C", [(2, 31, 20, 64), (3, 50, 20, 64), (2, 23, 40, 128)])
+def test_conv2_backward_pieces(B, T1, F1, C):
+    """conv2's weight and input gradients (im2col^T -> split-K GEMM; GEMM -> col2im) vs autograd of F.conv2d."""
+    from fbkst_b200 import ops
+    g = torch.Generator().manual_seed(B * T1 + C)
+    y1 = torch.randn(B, T1, F1, C, generator=g).half().to(dev())
+    w2 = (torch.randn(C, C, 3, 3, generator=g) / math.sqrt(9 * C)).to(dev())
+    T2, F2 = (T1 + 1) // 2, (F1 + 1) // 2
+    dz2 = bf(torch.randn(B, T2, F2, C, generator=g)).to(dev())
+    xr = y1.float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = bf(w2).float().requires_grad_(True)
+    out = torch.nn.functional.conv2d(xr, wr, None, stride=2, padding=1)
+    out.backward(dz2.float().permute(0, 3, 1, 2))
+    P2 = B * T2 * F2
+    colT = ops.conv2_im2col_t(y1)
+    ref_col = torch.nn.functional.unfold(y1.float().permute(0, 3, 1, 2), 3, padding=1, stride=2)  # B, C*9, T2*F2
+    ref_colT = ref_col.view(B, C, 9, T2 * F2).permute(2, 1, 0, 3).reshape(9 * C, P2)
+    assert torch.equal(colT.float(), bf(ref_colT).float())
+    dW2p = ops.linear_wgrad(ops.transpose_bf16(dz2.view(P2, C)), colT)
+    dW2 = dW2p.view(C, 3, 3, C).permute(0, 3, 1, 2)
+    assert rel_err(dW2, wr.grad) < 5e-3
+    w2d = ops.cast_bf16(w2.permute(2, 3, 1, 0).reshape(9 * C, C).contiguous())
+    dcol = ops.linear(dz2.view(P2, C), w2d)
+    dy1 = ops.conv2_col2im(dcol, B, T1, F1, C)
+    assert rel_err(dy1.float().permute(0, 3, 1, 2), xr.grad) < 2e-2
+
+
+def test_conv1_wgrad():
+    from fbkst_b200 import ops
+    B, T, Fd, C = 3, 61, 40, 64
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(B, T, Fd, generator=g).to(dev())
+    T1, F1 = (T + 1) // 2, (Fd + 1) // 2
+    dz1 = bf(torch.randn(B, T1, F1, C, generator=g)).to(dev())
+    w = torch.randn(C, 1, 3, 3, generator=g).to(dev()).requires_grad_(True)
+    b = torch.zeros(C, device=dev(), requires_grad=True)
+    torch.nn.functional.conv2d(x.unsqueeze(1), w, b, stride=2, padding=1).backward(dz1.float().permute(0, 3, 1, 2))
+    dW1, db1 = ops.conv1_wgrad(dz1, x)
+    assert rel_err(dW1.reshape(C, 1, 3, 3), w.grad) < 1e-4
+    assert rel_err(db1, b.grad) < 1e-4
