@@ -229,6 +229,8 @@ class EncoderTrainFn(torch.autograd.Function):
         xf = ops.layernorm(x, W["gf"], W["bf"], out_dtype=torch.float32, eps=enc.layer_norm.eps)
         S.update(layers=saved, x_last=x, L_out=cur_L)
         ctx.S, ctx.enc = S, enc
+        if getattr(enc, "keep_train_state", False):  # tests: the activation patterns of this forward
+            enc.last_train_state = S
         ctx.n_params = len(params)
         out = xf.view(cur_L, B, D)
         states[-1] = out

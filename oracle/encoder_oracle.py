@@ -80,8 +80,18 @@ def positional_embedding(lengths: Tensor, dim: int) -> Tensor:
 
 
 # --------------------------------------------------------------------------- a2
+def _relu(x: Tensor, masks: Optional[dict], key: str) -> Tensor:
+    """ReLU, or -- gradient-parity experiments only -- the same activation PATTERN as another
+    implementation: ``masks[key]`` (0/1, x's shape) replaces ``x > 0`` in both the value and the gradient.
+    A bf16 implementation flips the sign of pre-activations that are ~0; under random upstream gradients each
+    flipped unit moves a weight gradient by an O(1) term, which is noise, not a defect (tests/test_gpu_train.py)."""
+    if masks is None or key not in masks:
+        return F.relu(x)
+    return x * masks[key].to(x.dtype)
+
+
 def conv_subsample(sd: Dict[str, Tensor], src_tokens: Tensor, src_lengths: Tensor,
-                   bn_eps: float = 1e-5) -> Tuple[Tensor, Tensor]:
+                   bn_eps: float = 1e-5, relu_masks: Optional[dict] = None) -> Tuple[Tensor, Tensor]:
     """ST/models/conv_transformer.py:202-214 in eval mode: for each of the two
     convs: Conv2d(k3,s2,p1)+bias -> ReLU -> BatchNorm2d(running stats) ->
     lengths = ceil(lengths/2).  Runs over the zero-padded batch with NO masking
@@ -91,7 +101,7 @@ def conv_subsample(sd: Dict[str, Tensor], src_tokens: Tensor, src_lengths: Tenso
     for i in range(2):
         x = F.conv2d(x, sd["convolutions.%d.weight" % i], sd["convolutions.%d.bias" % i],
                      stride=2, padding=1)
-        x = F.relu(x)
+        x = _relu(x, relu_masks, "conv%d" % i)
         x = F.batch_norm(x, sd["bn.%d.running_mean" % i], sd["bn.%d.running_var" % i],
                          sd["bn.%d.weight" % i], sd["bn.%d.bias" % i], False, 0.0, bn_eps)
         lengths = torch.ceil(lengths.float() / 2).long()
@@ -99,12 +109,12 @@ def conv_subsample(sd: Dict[str, Tensor], src_tokens: Tensor, src_lengths: Tenso
 
 
 # --------------------------------------------------------------------------- a3
-def flatten_fc3(sd: Dict[str, Tensor], x: Tensor) -> Tensor:
+def flatten_fc3(sd: Dict[str, Tensor], x: Tensor, relu_masks: Optional[dict] = None) -> Tensor:
     """ST/models/conv_transformer.py:225-227 -- (B,C,T',F'') -> (T',B,C*F'') with
     channel-major flatten (index c*F''+f), then ReLU(fc3(.))."""
     b, c, t, f = x.shape
     x = x.transpose(1, 2).reshape(b, t, c * f).transpose(0, 1)
-    return F.relu(F.linear(x, sd["fc3.weight"], sd["fc3.bias"]))
+    return _relu(F.linear(x, sd["fc3.weight"], sd["fc3.bias"]), relu_masks, "fc3")
 
 
 # ----------------------------------------------------------------------- a7/a7'
@@ -142,7 +152,8 @@ def self_attention(sd: Dict[str, Tensor], prefix: str, x: Tensor, mask: Optional
 
 # --------------------------------------------------------------------------- a6
 def encoder_layer(sd: Dict[str, Tensor], prefix: str, x: Tensor, mask: Optional[Tensor],
-                  heads: int, log_penalty: bool, ln_eps: float = 1e-5) -> Tensor:
+                  heads: int, log_penalty: bool, ln_eps: float = 1e-5,
+                  relu_masks: Optional[dict] = None) -> Tensor:
     """fairseq/modules/transformer_layer.py:87-139 with normalize_before=True,
     eval mode (all dropouts off)."""
     D = x.shape[-1]
@@ -153,7 +164,7 @@ def encoder_layer(sd: Dict[str, Tensor], prefix: str, x: Tensor, mask: Optional[
     r = x
     x = F.layer_norm(x, (D,), sd[prefix + "final_layer_norm.weight"],
                      sd[prefix + "final_layer_norm.bias"], ln_eps)
-    x = F.relu(F.linear(x, sd[prefix + "fc1.weight"], sd[prefix + "fc1.bias"]))
+    x = _relu(F.linear(x, sd[prefix + "fc1.weight"], sd[prefix + "fc1.bias"]), relu_masks, prefix + "fc1")
     x = F.linear(x, sd[prefix + "fc2.weight"], sd[prefix + "fc2.bias"])
     return r + x
 
@@ -208,7 +219,8 @@ def ctc_compress(x: Tensor, logits: Tensor, lengths: Tensor, strategy: str):
 
 # --------------------------------------------------------------------------- a12
 def encoder_forward(sd: Dict[str, Tensor], cfg: dict, src_tokens: Tensor, src_lengths: Tensor,
-                    return_all_hiddens: bool = False, ctc_logits_hook=None) -> dict:
+                    return_all_hiddens: bool = False, ctc_logits_hook=None,
+                    relu_masks: Optional[dict] = None) -> dict:
     """ST/models/conv_transformer.py:195-276 in eval mode.
 
     ``cfg`` keys: embed_dim, heads, layers, distance_penalty ('log' or None),
@@ -219,15 +231,15 @@ def encoder_forward(sd: Dict[str, Tensor], cfg: dict, src_tokens: Tensor, src_le
     """
     heads = cfg["heads"]
     log_pen = cfg.get("distance_penalty", "log") == "log"
-    x, lengths = conv_subsample(sd, src_tokens, src_lengths)
-    x = flatten_fc3(sd, x)
+    x, lengths = conv_subsample(sd, src_tokens, src_lengths, relu_masks=relu_masks)
+    x = flatten_fc3(sd, x, relu_masks)
     D = x.shape[-1]
     x = x + positional_embedding(lengths, D).to(x.dtype).transpose(0, 1)
     mask = create_mask(lengths)
     states = [] if return_all_hiddens else None
     ctc_out, ctc_mask, segments = None, None, None
     for l in range(cfg["layers"]):
-        x = encoder_layer(sd, "layers.%d." % l, x, mask, heads, log_pen)
+        x = encoder_layer(sd, "layers.%d." % l, x, mask, heads, log_pen, relu_masks=relu_masks)
         if cfg.get("ctc_layer", 0) == l + 1:
             ctc_mask = mask
             ctc_out = F.linear(x, sd["ctc_fc.weight"], sd["ctc_fc.bias"])
