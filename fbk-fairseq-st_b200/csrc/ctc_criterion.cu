@@ -215,6 +215,189 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// CTC loss backward w.r.t. the LOGITS (autograd of F.ctc_loss(log_softmax(z)), CTC_loss.py:143-151):
+//   d nll / d z[t, c] = softmax(z[t])[c] - sum_{s : l'_s = c} gamma_t(s),
+//   gamma_t(s) = exp(alpha_t(s) + beta_t(s) - lp_t(l'_s) - ll)        (alpha, beta both include frame t)
+// (1) ctc_softmax_grad_kernel: the dense term g * softmax for the valid frames (zeros beyond each length):
+//     HBM streaming, one warp per row;
+// (2) ctc_loss_bwd_kernel: one CTA per utterance: alpha pass (kept in a global workspace), beta pass, and the
+//     sparse subtraction of g * gamma at the target / blank columns.  Infeasible alignments (ll = -inf,
+//     zero_infinity=True) get an all-zero gradient.  Duplicate labels are folded through a "next position
+//     with the same label" chain so that every (t, column) has exactly one writer (no atomics).
+template <int IS_BF16>
+__global__ void __launch_bounds__(256)
+    ctc_softmax_grad_kernel(const void* __restrict__ logits, long long ldv, const float* __restrict__ lse,
+                            const int* __restrict__ in_lengths, const float* __restrict__ grad_loss,
+                            float* __restrict__ dz, long long ldd, int rows, int B, int V) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int t = row / B, b = row - t * B;
+  float* op = dz + (size_t)row * ldd;
+  if (t >= __ldg(in_lengths + b)) {
+    for (int c = lane; c < V; c += 32) op[c] = 0.0f;
+    return;
+  }
+  const float g = __ldg(grad_loss), l = __ldg(lse + row);
+  for (int c = lane; c < V; c += 32)
+    op[c] = g * __expf(load_logit<IS_BF16>(logits, (size_t)row * ldv + c) - l);
+}
+
+// smem: beta[2][S] | gam[W] | lp[TCH][W] floats | tgt[U] | nxt[U] | hd[U] ints     (W = U + 1, column U = blank)
+template <int IS_BF16>
+__global__ void __launch_bounds__(256)
+    ctc_loss_bwd_kernel(const void* __restrict__ logits, long long ldv, const float* __restrict__ lse,
+                        const int* __restrict__ in_lengths, const long long* __restrict__ targets,
+                        long long ldt, const int* __restrict__ target_lengths, int blank,
+                        const float* __restrict__ grad_loss, float* __restrict__ alpha_ws,
+                        float* __restrict__ dz, long long ldd, int L, int B, int V, int Umax, int TCH) {
+  extern __shared__ float smf[];
+  const int Smax = 2 * Umax + 1, Wmax = Umax + 1;
+  float* beta = smf;
+  float* gam = beta + 2 * Smax;
+  float* lp = gam + Wmax;
+  int* tgt = reinterpret_cast<int*>(lp + (size_t)TCH * Wmax);
+  int* nxt = tgt + Umax;
+  int* hd = nxt + Umax;
+  __shared__ float red[8];
+  __shared__ float s_ll;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int len = max(0, min(in_lengths[b], L));
+  const int U = max(0, min(target_lengths[b], Umax));
+  const int S = 2 * U + 1, W = U + 1;
+  for (int j = tid; j < U; j += blockDim.x) tgt[j] = (int)targets[(size_t)b * ldt + j];
+  __syncthreads();
+  // nxt[u]: next position with the same label (-1: none); a position is a chain HEAD if no earlier one matches
+  for (int j = tid; j < U; j += blockDim.x) {
+    int n = -1;
+    for (int k = j + 1; k < U; ++k)
+      if (tgt[k] == tgt[j]) {
+        n = k;
+        break;
+      }
+    bool head = true;
+    for (int k = 0; k < j; ++k)
+      if (tgt[k] == tgt[j]) {
+        head = false;
+        break;
+      }
+    nxt[j] = n;
+    hd[j] = head ? 1 : 0;
+  }
+  if (len == 0) return;  // no frames: nothing to subtract (the dense kernel wrote zeros)
+  float* aw = alpha_ws + (size_t)b * L * Smax;
+  const float g = __ldg(grad_loss);
+  // ---- alpha pass (as ctc_loss_fwd_kernel), every alpha_t kept
+  for (int t0 = 0; t0 < len; t0 += TCH) {
+    const int nt = min(TCH, len - t0);
+    __syncthreads();
+    for (int e = tid; e < nt * W; e += blockDim.x) {
+      const int tt = e / W, u = e - tt * W;
+      const size_t row = (size_t)(t0 + tt) * B + b;
+      const int col = (u == U) ? blank : tgt[u];
+      lp[tt * W + u] = load_logit<IS_BF16>(logits, row * (size_t)ldv + col) - __ldg(lse + row);
+    }
+    __syncthreads();
+    for (int tt = 0; tt < nt; ++tt) {
+      const int t = t0 + tt;
+      const float* a0 = aw + (size_t)(t - 1) * Smax;
+      float* a1 = aw + (size_t)t * Smax;
+      const float* lpt = lp + tt * W;
+      for (int s = tid; s < S; s += blockDim.x) {
+        const int u = s >> 1;
+        const bool is_label = s & 1;
+        const float p = is_label ? lpt[u] : lpt[U];
+        float v;
+        if (t == 0) {
+          v = (s <= 1) ? p : -INFINITY;
+        } else {
+          const float x0 = a0[s];
+          const float x1 = s >= 1 ? a0[s - 1] : -INFINITY;
+          const float x2 = (is_label && s >= 3 && tgt[u] != tgt[u - 1]) ? a0[s - 2] : -INFINITY;
+          v = lse3(x0, x1, x2) + p;
+        }
+        a1[s] = v;
+      }
+      __syncthreads();  // alpha_t (global) visible to the whole CTA before step t + 1
+    }
+  }
+  if (tid == 0) {
+    const float* a = aw + (size_t)(len - 1) * Smax;
+    s_ll = (S > 1) ? lse3(a[S - 1], a[S - 2], -INFINITY) : a[0];
+  }
+  __syncthreads();
+  const float ll = s_ll;
+  if (isinf(ll) || isnan(ll)) {  // zero_infinity: no gradient for this utterance at all
+    for (int t = 0; t < len; ++t) {
+      float* op = dz + ((size_t)t * B + b) * ldd;
+      for (int c = tid; c < V; c += blockDim.x) op[c] = 0.0f;
+    }
+    return;
+  }
+  // ---- beta pass + sparse subtraction
+  int cur = 0;
+  for (int t1 = len; t1 > 0; t1 -= TCH) {
+    const int t0 = max(0, t1 - TCH), nt = t1 - t0;
+    __syncthreads();
+    for (int e = tid; e < nt * W; e += blockDim.x) {
+      const int tt = e / W, u = e - tt * W;
+      const size_t row = (size_t)(t0 + tt) * B + b;
+      const int col = (u == U) ? blank : tgt[u];
+      lp[tt * W + u] = load_logit<IS_BF16>(logits, row * (size_t)ldv + col) - __ldg(lse + row);
+    }
+    __syncthreads();
+    for (int tt = nt - 1; tt >= 0; --tt) {
+      const int t = t0 + tt;
+      const float* b0 = beta + cur * Smax;        // beta_{t+1}
+      float* b1 = beta + (cur ^ 1) * Smax;        // beta_t
+      const float* at = aw + (size_t)t * Smax;
+      const float* lpt = lp + tt * W;
+      float blank_part = 0.0f;
+      for (int s = tid; s < S; s += blockDim.x) {
+        const int u = s >> 1;
+        const bool is_label = s & 1;
+        const float p = is_label ? lpt[u] : lpt[U];
+        float v;
+        if (t == len - 1) {
+          v = (s >= S - 2) ? p : -INFINITY;
+        } else {
+          const float x0 = b0[s];
+          const float x1 = s + 1 < S ? b0[s + 1] : -INFINITY;
+          const float x2 = (is_label && s + 2 < S && tgt[u + 1] != tgt[u]) ? b0[s + 2] : -INFINITY;
+          v = lse3(x0, x1, x2) + p;
+        }
+        b1[s] = v;
+        const float lg = at[s] + v - p - ll;
+        const float gm = (lg == -INFINITY || isnan(lg)) ? 0.0f : __expf(lg);
+        if (is_label)
+          gam[u] = gm;
+        else
+          blank_part += gm;
+      }
+      // blank column: sum over the even states
+      blank_part = warp_sum(blank_part);
+      if (lane == 0) red[wid] = blank_part;
+      __syncthreads();
+      float* op = dz + ((size_t)t * B + b) * ldd;
+      if (tid == 0) {
+        float tot = 0.0f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+        op[blank] -= g * tot;
+      }
+      for (int u = tid; u < U; u += blockDim.x) {
+        if (!hd[u] || tgt[u] == blank) continue;  // one writer per column: the first position of each label
+        float tot = gam[u];
+        for (int k = nxt[u]; k >= 0; k = nxt[k]) tot += gam[k];
+        op[tgt[u]] -= g * tot;
+      }
+      cur ^= 1;
+      __syncthreads();
+    }
+  }
+}
+
 __global__ void ctc_loss_sum_kernel(const float* __restrict__ nll, float* __restrict__ loss, int B) {
   // fixed order: lane-strided partial sums, then a butterfly -> run-to-run identical
   float s = 0.0f;
@@ -295,6 +478,62 @@ extern "C" int fbkst_ctc_loss_fwd(const void* logits, int logits_dtype, int64_t 
                                                  tch);
   FBKST_CHECK_CUDA(cudaGetLastError());
   ctc_loss_sum_kernel<<<1, 32, 0, st>>>(nll, loss, B);
+  FBKST_CHECK_CUDA(cudaGetLastError());
+  return FBKST_OK;
+}
+
+extern "C" long long fbkst_ctc_loss_bwd_workspace(int L, int B, int Umax) {
+  return (long long)B * L * (2 * (long long)Umax + 1);
+}
+
+/* dlogits [L*B, ldd] fp32 = grad_loss[0] * d(sum_b nll_b)/d logits  (rows t*B+b; zero for frames beyond each
+ * input length and for utterances whose alignment is infeasible).  grad_loss: DEVICE scalar (the upstream
+ * gradient of the summed loss).  alpha_ws: fbkst_ctc_loss_bwd_workspace(L, B, Umax) floats. */
+extern "C" int fbkst_ctc_loss_bwd(const void* logits, int logits_dtype, int64_t ldv, const float* lse,
+                                  const int32_t* in_lengths, const int64_t* targets, int64_t ldt,
+                                  const int32_t* target_lengths, int blank, const float* grad_loss,
+                                  float* alpha_ws, float* dlogits, int64_t ldd, int L, int B, int V, int Umax,
+                                  fbkst_stream_t stream) {
+  FBKST_REQUIRE(logits && lse && in_lengths && target_lengths && grad_loss && alpha_ws && dlogits,
+                "fbkst_ctc_loss_bwd: null pointer");
+  FBKST_REQUIRE(L > 0 && B > 0 && V > 0 && ldv >= V && ldd >= V && blank >= 0 && blank < V && Umax >= 0 &&
+                    (Umax == 0 || (targets && ldt >= Umax)),
+                "fbkst_ctc_loss_bwd: bad shape");
+  FBKST_REQUIRE(logits_dtype == FBKST_BF16 || logits_dtype == FBKST_F32,
+                "fbkst_ctc_loss_bwd: dtype must be bf16 or fp32");
+  const size_t fixed = sizeof(float) * (2 * (2 * (size_t)Umax + 1) + (size_t)Umax + 1) + sizeof(int) * 3 * (size_t)Umax;
+  const size_t per_frame = sizeof(float) * ((size_t)Umax + 1);
+  FBKST_REQUIRE(fixed + per_frame <= 200 * 1024, "fbkst_ctc_loss_bwd: Umax=%d exceeds shared memory", Umax);
+  int tch = (int)((96 * 1024 - (fixed < 96 * 1024 ? fixed : 96 * 1024)) / per_frame);
+  if (tch > 32) tch = 32;
+  if (tch < 1) tch = 1;
+  const size_t smem = fixed + per_frame * tch;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  static PerDeviceFlag configured;
+  if (!configured) {
+    FBKST_CHECK_CUDA(cudaFuncSetAttribute(ctc_loss_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          200 * 1024));
+    FBKST_CHECK_CUDA(cudaFuncSetAttribute(ctc_loss_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          200 * 1024));
+    configured = true;
+  }
+  const int rows = L * B;
+  const long long* tg = reinterpret_cast<const long long*>(targets);
+  if (logits_dtype == FBKST_BF16) {
+    ctc_softmax_grad_kernel<1><<<(rows + 7) / 8, 256, 0, st>>>(logits, (long long)ldv, lse, in_lengths, grad_loss,
+                                                             dlogits, (long long)ldd, rows, B, V);
+    FBKST_CHECK_CUDA(cudaGetLastError());
+    ctc_loss_bwd_kernel<1><<<B, 256, smem, st>>>(logits, (long long)ldv, lse, in_lengths, tg, (long long)ldt,
+                                                 target_lengths, blank, grad_loss, alpha_ws, dlogits,
+                                                 (long long)ldd, L, B, V, Umax, tch);
+  } else {
+    ctc_softmax_grad_kernel<0><<<(rows + 7) / 8, 256, 0, st>>>(logits, (long long)ldv, lse, in_lengths, grad_loss,
+                                                             dlogits, (long long)ldd, rows, B, V);
+    FBKST_CHECK_CUDA(cudaGetLastError());
+    ctc_loss_bwd_kernel<0><<<B, 256, smem, st>>>(logits, (long long)ldv, lse, in_lengths, tg, (long long)ldt,
+                                                 target_lengths, blank, grad_loss, alpha_ws, dlogits,
+                                                 (long long)ldd, L, B, V, Umax, tch);
+  }
   FBKST_CHECK_CUDA(cudaGetLastError());
   return FBKST_OK;
 }

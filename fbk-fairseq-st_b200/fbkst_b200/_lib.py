@@ -58,6 +58,7 @@ SIGNATURES = {
     "fbkst_attention_train_bwd": [P, P, P, P, P, P, I, I, I, I, F, U64, I, P],
     "fbkst_ctc_compress_bwd": [P, P, P, P, I, I, I, P],
     "fbkst_dropout_inplace": [P, I, I64, F, U64, I, P],
+    "fbkst_ctc_loss_bwd": [P, I, I64, P, P, P, I64, P, I, P, P, P, I64, I, I, I, I, P],
     "fbkst_bn_partial_blocks": [],
     "fbkst_bn_batch_stats": [P, I64, I, P, P, F, F, P, P, P, P, P, P, P, P],
     "fbkst_bn_apply": [P, P, P, P, I64, I, F, U64, I, P],
@@ -66,7 +67,8 @@ SIGNATURES = {
     "fbkst_conv2_col2im": [P, P, I, I, I, I, P],
     "fbkst_conv1_wgrad": [P, P, P, P, I, I, I, I, P],
 }
-_RESTYPES = {"fbkst_linear_wgrad_workspace": (c_int64, [I, I, I])}
+_RESTYPES = {"fbkst_linear_wgrad_workspace": (c_int64, [I, I, I]),
+             "fbkst_ctc_loss_bwd_workspace": (c_int64, [I, I, I])}
 
 _lib = None
 

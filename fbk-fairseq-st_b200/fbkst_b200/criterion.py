@@ -57,6 +57,30 @@ def compute_ctc_uer(logprobs, targets, input_lengths, target_lengths, blank_idx)
     return float(e), float(n)
 
 
+class CtcLossFn(torch.autograd.Function):
+    """sum_b nll_b of F.ctc_loss(log_softmax(logits), ..., reduction="sum", zero_infinity=True), differentiable
+    w.r.t. the logits on the device kernels (alpha pass forward; dense softmax term + alpha/beta occupancies
+    backward).  The log-probabilities are never materialised (the reference's autograd keeps a T x B x V
+    log_softmax output alive for the backward)."""
+
+    @staticmethod
+    def forward(ctx, ctc_out, in_lengths, targets, target_lengths, blank_idx):
+        rows, T, B, V = _time_major_rows(ctc_out)
+        labels, lse, _ = ops.ctc_argmax_lse(rows, in_lengths, T, B, V)
+        nll, loss = ops.ctc_loss_fwd(rows, lse, in_lengths, targets, target_lengths, blank_idx, T, B, V)
+        ctx.save_for_backward(rows, lse, in_lengths, targets, target_lengths)
+        ctx.dims = (T, B, V, blank_idx, tuple(ctc_out.shape))
+        ctx.mark_non_differentiable(labels, nll)
+        return loss.reshape(()), labels, nll
+
+    @staticmethod
+    def backward(ctx, grad_loss, _gl, _gn):
+        rows, lse, il, tg, tl = ctx.saved_tensors
+        T, B, V, blank, shape = ctx.dims
+        dz = ops.ctc_loss_bwd(rows, lse, il, tg, tl, blank, grad_loss, T, B, V)  # [T*B, V], pitch ceil8(V)
+        return dz.view(T, B, V), None, None, None, None
+
+
 def ctc_loss_and_uer(ctc_out, ctc_padding_mask, targets, target_lengths, blank_idx, pad_idx=None):
     """What ``CTCCriterion.forward`` computes from the encoder output (CTC_loss.py:118-154):
 
@@ -83,3 +107,21 @@ def ctc_loss_and_uer(ctc_out, ctc_padding_mask, targets, target_lengths, blank_i
     nll, loss = ops.ctc_loss_fwd(rows, lse, il, tg, tl, blank_idx, T, B, V)
     errors, _, totals = ops.ctc_uer(labels, il, tg, tl, blank_idx, T, B)
     return loss, nll, errors, totals
+
+
+def ctc_loss_train(ctc_out, ctc_padding_mask, targets, target_lengths, blank_idx, mask_time_first=True):
+    """Differentiable CTC loss + UER counts for the training criterion.  ctc_out T x B x V logits (attached to
+    the autograd graph), ctc_padding_mask bool (True = padding), T x B if ``mask_time_first`` (what
+    CTCEncoderWrapperModel hands over, ctc_multi_loss.py:41) else B x T, or None.
+    -> (loss 0-dim tensor with grad_fn, errors total (device int64 [2]), input_lengths int32 [B])."""
+    T, B, V = ctc_out.shape
+    dev = ctc_out.device
+    if ctc_padding_mask is None:
+        il = torch.full((B,), T, dtype=torch.int32, device=dev)
+    else:
+        il = (T - ctc_padding_mask.sum(dim=0 if mask_time_first else 1)).to(torch.int32)
+    tl = _i32(target_lengths, dev)
+    tg = torch.as_tensor(targets, device=dev).to(torch.int64).contiguous()
+    loss, labels, _ = CtcLossFn.apply(ctc_out, il, tg, tl, int(blank_idx))
+    _, _, totals = ops.ctc_uer(labels, il, tg, tl, blank_idx, T, B)
+    return loss, totals, il

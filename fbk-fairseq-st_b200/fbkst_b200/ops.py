@@ -758,3 +758,24 @@ def conv1_wgrad(dz1, x):
                                 _stream()))
     _count(2)
     return out[:, :9], out[:, 9]
+
+
+def ctc_loss_bwd(logits, lse, in_lengths, targets, target_lengths, blank, grad_loss, L, B, V):
+    """d(sum_b nll_b)/d logits * grad_loss -> dlogits [L*B, V] fp32 view of a [L*B, ceil8(V)] buffer."""
+    lib = _lib.require_device()
+    if logits.dtype not in (torch.bfloat16, torch.float32) or logits.stride(-1) != 1:
+        raise ValueError("fbkst_b200.ctc_loss_bwd: logits must be bf16/fp32 with unit column stride")
+    _req(lse, torch.float32, "ctc_loss_bwd.lse"); _req(in_lengths, torch.int32, "ctc_loss_bwd.in_lengths")
+    _req(target_lengths, torch.int32, "ctc_loss_bwd.target_lengths")
+    U = targets.shape[1]
+    dev = logits.device
+    g = grad_loss.reshape(1).to(torch.float32).contiguous()
+    ldd = (V + 7) // 8 * 8
+    dz = torch.empty(L * B, ldd, dtype=torch.float32, device=dev)
+    ws = torch.empty(max(1, lib.fbkst_ctc_loss_bwd_workspace(L, B, U)), dtype=torch.float32, device=dev)
+    check(lib.fbkst_ctc_loss_bwd(logits.data_ptr(), BF16 if logits.dtype == torch.bfloat16 else F32, logits.stride(0),
+                                 lse.data_ptr(), in_lengths.data_ptr(), targets.data_ptr() if U else 0,
+                                 targets.stride(0) if U else 0, target_lengths.data_ptr(), int(blank), g.data_ptr(),
+                                 ws.data_ptr(), dz.data_ptr(), ldd, L, B, V, U, _stream()))
+    _count(2)
+    return dz[:, :V]

@@ -15,6 +15,8 @@ default (``:429-586``) is inherited.
 import os
 import sys
 
+import torch
+
 _PKG_PARENT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 if _PKG_PARENT not in sys.path:
     sys.path.insert(0, _PKG_PARENT)
@@ -71,6 +73,58 @@ class B200ConvolutionalTransformerModel(_ref.ConvolutionalTransformerModel):
         parser.add_argument("--b200-lazy-beam-reorder", action="store_true",
                             help="with --b200-cross-attention: never replicate the encoder output "
                                  "x beam (reorder_encoder_out returns tagged aliases)")
+
+
+# ---------------------------------------------------------------------------------------------------
+# the CTC half of ``ctc_multi_loss`` on the device kernels.  Same class, flags, sample fields,
+# logging keys and loss value as the reference criterion (criterions/ctc_multi_loss.py:107-194 +
+# CTC_loss.py:101-175); what changes is where the arithmetic runs: the frame arg-max, log-sum-exp, alpha /
+# beta recursions, the gradient w.r.t. the logits and the edit distance are CUDA kernels (fbkst_b200.criterion),
+# the T x B x V log-softmax is never materialised and nothing is pulled to the host per utterance.
+from fairseq import utils as _utils  # noqa: E402
+from fairseq.criterions import register_criterion  # noqa: E402
+from examples.speech_recognition.criterions import ctc_multi_loss as _cml  # noqa: E402
+from fbkst_b200 import criterion as _crit  # noqa: E402
+
+
+class B200CTCLoss(_cml.BaseCTCLoss):
+    def forward(self, model, sample, reduce=True, log_probs=True):
+        net_output = model(**sample["net_input"])  # FakeEncoderModel: the encoder's ctc_out + T x B padding mask
+        logits = net_output["encoder_out"]
+        if not torch.is_tensor(logits) or not logits.is_cuda:
+            raise RuntimeError("ctc_multi_loss_b200: CUDA logits expected (there is no CPU fallback; use "
+                               "--criterion ctc_multi_loss for the reference's CPU path)")
+        if getattr(model, "output_batch_first", False):
+            logits = logits.transpose(0, 1)
+        targets, target_lengths = sample["target"], sample["target_lengths"]
+        loss, totals, il = _crit.ctc_loss_train(logits, net_output["encoder_padding_mask"], targets,
+                                                target_lengths, self.blank_idx)
+        errors, total = (float(v) for v in totals.tolist())  # 16 bytes: the criterion's one host read
+        if self.args.sentence_avg:
+            sample_size = sample["target"].size(0)
+        elif getattr(self.args, "use_source_side_sample_size", False):
+            sample_size = int(il.sum().item())
+        else:
+            sample_size = sample["ntokens"]
+        logging_output = {
+            "loss": _utils.item(loss.data) if reduce else loss.data,
+            "ntokens": sample["ntokens"],
+            "nsentences": sample["target"].size(0),
+            "sample_size": sample_size,
+            "errors": errors,
+            "total": total,
+            "nframes": torch.sum(sample["net_input"]["src_lengths"]).item(),
+        }
+        return loss, sample_size, logging_output
+
+
+@register_criterion("ctc_multi_loss_b200")
+class B200CTCMultiLoss(_cml.CTCMultiLoss):
+    """``--criterion ctc_multi_loss_b200``: the reference's CTCMultiLoss with its CTC term on the GPU kernels."""
+
+    def __init__(self, args, task):
+        super().__init__(args, task)
+        self.ctc_criterion = B200CTCLoss(args, task)
 
 
 for _name, _fn in (("conv_transformer_b200", _ref.base_architecture),

@@ -385,6 +385,16 @@ int fbkst_ctc_compress_bwd(const float* dout, const int32_t* seg_id, const float
 int fbkst_dropout_inplace(void* x, int is_f32, int64_t numel, float p, uint64_t seed, int site,
                           fbkst_stream_t stream);
 
+/* ---- next row N1, backward: F.ctc_loss(log_softmax(logits), ..., "sum", zero_infinity=True) differentiated
+ * w.r.t. the logits (criterions/CTC_loss.py:143-151 under autograd).  dlogits [L*B, ldd] fp32 =
+ * grad_loss[0] * (softmax - occupancies) for frames t < in_lengths[b], zero elsewhere and for utterances
+ * with an infeasible alignment.  grad_loss: DEVICE scalar.  alpha_ws: fbkst_ctc_loss_bwd_workspace() floats. */
+long long fbkst_ctc_loss_bwd_workspace(int L, int B, int Umax);
+int fbkst_ctc_loss_bwd(const void* logits, int logits_dtype, int64_t ldv, const float* lse,
+                       const int32_t* in_lengths, const int64_t* targets, int64_t ldt,
+                       const int32_t* target_lengths, int blank, const float* grad_loss, float* alpha_ws,
+                       float* dlogits, int64_t ldd, int L, int B, int V, int Umax, fbkst_stream_t stream);
+
 /* ---- conv front end, training (conv_transformer.py:203-214).  Activations channels-last [pixels, C], fp16 in
  * the forward, bf16 gradients; pixels = B*T'*F' of the PADDED batch (the reference does not mask: SURVEY F5). */
 int fbkst_bn_partial_blocks(void); /* rows of the `partial` scratch buffers below */

@@ -11,6 +11,8 @@ edited; all fixes are monkeypatches applied in this process:
           NamedTuple attribute removed in Python 3.9)                 [SURVEY F1]
   shim 3  ``torch.Tensor.cuda`` no-op while running on CPU
           (local_attention.py:132 hard-codes ``.cuda()``)             [SURVEY F2]
+  shim 4  ``LocalAttention.in_proj_qkv`` clones its chunks when gradients are on
+          (in-place ``q *= scaling`` on a view, local_attention.py:98)  [SURVEY F11]
 """
 import argparse
 import contextlib
@@ -78,6 +80,21 @@ def cpu_cuda_noop():
         yield
     finally:
         torch.Tensor.cuda = orig
+
+
+@contextlib.contextmanager
+def grad_shims():
+    """Shim 4: with gradients enabled, ``q *= self.scaling`` (local_attention.py:98) modifies in
+    place a view returned by ``chunk`` (:152-153), which torch >= 1.x autograd rejects.  Cloning the three
+    chunks is the same arithmetic.  Needed only for gradient parity (eval() + grad) on the reference."""
+    load()
+    from examples.speech_recognition.modules.local_attention import LocalAttention
+    orig = LocalAttention.in_proj_qkv
+    LocalAttention.in_proj_qkv = lambda self, query: tuple(t.clone() for t in orig(self, query))
+    try:
+        yield
+    finally:
+        LocalAttention.in_proj_qkv = orig
 
 
 def make_dictionary(vocab: int):

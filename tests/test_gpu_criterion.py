@@ -131,3 +131,43 @@ def test_criterion_full_size_properties():
     assert torch.allclose(nll.double(), ref.double(), rtol=1e-4, atol=1e-3), (nll, ref)
     assert abs(loss.item() - ref.sum().item()) <= 1e-4 * max(1.0, abs(ref.sum().item()))
     assert ops.LAUNCHES > 0
+
+
+# ------------------------------------------------------------------ loss backward (N1, second half)
+@pytest.mark.parametrize("T,B,V,U", [(50, 4, 30, 12), (375, 6, 1005, 40), (120, 3, 8005, 25)])
+def test_ctc_loss_backward_vs_torch(T, B, V, U):
+    """d loss / d logits of the device CTC loss == autograd of F.ctc_loss(log_softmax(logits), ..., "sum",
+    zero_infinity=True) (criterions/CTC_loss.py:143-151), incl. repeated labels, ragged input / target
+    lengths and one infeasible utterance (target longer than its input: zero loss, zero gradient)."""
+    from fbkst_b200 import criterion as C
+    g = torch.Generator().manual_seed(T + V)
+    logits = torch.randn(T, B, V, generator=g).cuda()
+    in_len = torch.tensor([T] + [max(3, T - 7 * b) for b in range(1, B)], dtype=torch.long)
+    in_len[-1] = 4  # infeasible with a longer target
+    tgt_len = torch.tensor([min(U, max(1, int(in_len[b]) // 3)) for b in range(B)], dtype=torch.long)
+    tgt_len[-1] = min(U, 9)
+    blank = V - 1
+    targets = torch.randint(4, V - 1, (B, U), generator=g)
+    targets[0, 1] = targets[0, 0]  # repeated label (needs a blank in between)
+    targets[0, 3] = targets[0, 0]  # same label again later: one writer per column
+    for b in range(B):
+        targets[b, tgt_len[b]:] = 1
+    mask = (torch.arange(T)[None, :] >= in_len[:, None]).cuda()  # B x T, True = padding
+    x = logits.clone().requires_grad_(True)
+    lp = torch.log_softmax(x, -1)
+    flat = torch.cat([targets[b, :tgt_len[b]] for b in range(B)]).cuda()
+    ref = torch.nn.functional.ctc_loss(lp, flat, in_len.cuda(), tgt_len.cuda(), blank=blank, reduction="sum",
+                                       zero_infinity=True)
+    (ref * 0.7).backward()
+    y = logits.clone().requires_grad_(True)
+    loss, totals, il = C.ctc_loss_train(y, mask.t(), targets.cuda(), tgt_len.cuda(), blank)
+    assert abs(loss.item() - ref.item()) <= 1e-4 * abs(ref.item())
+    (loss * 0.7).backward()
+    err = (y.grad - x.grad).abs().max().item() / x.grad.abs().max().item()
+    assert err < 1e-4, err
+    assert y.grad[:, -1].abs().max() == 0  # infeasible utterance
+    assert y.grad[int(in_len[1]):, 1].abs().max() == 0  # frames beyond the input length
+    y2 = logits.clone().requires_grad_(True)
+    l2, _, _ = C.ctc_loss_train(y2, mask.t(), targets.cuda(), tgt_len.cuda(), blank)
+    (l2 * 0.7).backward()
+    assert torch.equal(y2.grad, y.grad)  # one writer per element: run-to-run identical

@@ -149,3 +149,84 @@ def test_generate_through_the_plugin(models):
         torch.backends.cudnn.allow_tf32 = old_tf32
         for h in handles:
             h.remove()
+
+
+class _CritTask(_Task):
+    def build_criterion(self, args):
+        from fairseq import criterions
+        return criterions.build_criterion(args, self)
+
+
+def test_train_step_through_the_criterion():
+    """fairseq's training call path (tasks/speech_recognition.py:234-263): criterion(model, sample) ->
+    loss.backward(), for the reference model with ``ctc_multi_loss`` and for ours with
+    ``--arch conv_transformer_big2_b200 --criterion ctc_multi_loss_b200`` (encoder forward/backward and the
+    CTC loss on the sm_100a kernels; decoder and label-smoothed CE are fairseq's in both).  Deterministic mode
+    (eval() + grad: no dropout, BatchNorm running statistics).  Loss values within 2e-2; every parameter's
+    gradient has cosine >= 0.99 with the reference's (see tests/test_gpu_train.py for why max-normalised
+    errors of ReLU-gated tensors are noise under bf16)."""
+    warnings.simplefilter("ignore")
+    R.load()
+    from fairseq import criterions, utils
+    utils.import_user_module(argparse.Namespace(user_dir=PLUGIN))
+    from fairseq.models import MODEL_REGISTRY
+    task = _CritTask()
+    task.source_dictionary = R.make_dictionary(120)
+    task.target_dictionary = R.make_dictionary(90)
+    extra = ["--label-smoothing", "0.1"]
+    a_ref = _args("conv_transformer_big2", extra)
+    a_our = _args("conv_transformer_big2_b200", extra)
+    a_our.criterion = "ctc_multi_loss_b200"
+    torch.manual_seed(7)
+    ref = MODEL_REGISTRY["conv_transformer"].build_model(a_ref, task)
+    ours = MODEL_REGISTRY["conv_transformer_b200"].build_model(a_our, task)
+    ours.load_state_dict(ref.state_dict(), strict=True)
+    ref, ours = ref.cuda().eval(), ours.cuda().eval()
+    crit_ref = criterions.build_criterion(a_ref, task).cuda()
+    crit_our = criterions.build_criterion(a_our, task).cuda()
+    assert type(crit_our).__name__ == "B200CTCMultiLoss"
+    lens_in = [801, 640, 523, 402]
+    B, L = len(lens_in), (max(lens_in) + 3) // 4
+    handles = _bump([ref, ours], L, B, len(task.source_dictionary), seed=23)
+    g = torch.Generator().manual_seed(1)
+    s = _sample(lens_in, 9)
+    U, U1 = 11, 9
+    tgt = torch.randint(4, 89, (B, U), generator=g)
+    tgt[:, -1] = task.target_dictionary.eos()
+    prev = torch.cat([torch.full((B, 1), task.target_dictionary.eos()), tgt[:, :-1]], 1)
+    tr = torch.randint(4, 118, (B, U1), generator=g)
+    trl = torch.tensor([9, 8, 7, 5])
+    for b in range(B):
+        tr[b, trl[b]:] = task.source_dictionary.pad()
+    sample = utils.move_to_cuda(dict(
+        net_input=dict(src_tokens=s["net_input"]["src_tokens"].cpu(), src_lengths=s["net_input"]["src_lengths"].cpu(),
+                       prev_output_tokens=prev),
+        target=tgt, transcript_target=tr, transcript_target_lengths=trl, ntokens=int(B * U), nsentences=B))
+    try:
+        with R.grad_shims():
+            loss_ref, ss_ref, log_ref = crit_ref(ref, sample)
+            loss_ref.backward()
+        loss_our, ss_our, log_our = crit_our(ours, sample)
+        loss_our.backward()
+        assert ss_ref == ss_our
+        assert abs(log_our["ctc_loss"] - log_ref["ctc_loss"]) <= 2e-2 * abs(log_ref["ctc_loss"])
+        assert abs(loss_our.item() - loss_ref.item()) <= 2e-2 * abs(loss_ref.item())
+        assert log_our["ctc_errors"] == log_ref["ctc_errors"] and log_our["ctc_total"] == log_ref["ctc_total"]
+        assert log_our["nframes"] == log_ref["nframes"]
+        pr = dict(ref.named_parameters())
+        low = {}
+        for name, p in ours.named_parameters():
+            gr = pr[name].grad
+            if gr is None or p.grad is None:
+                assert gr is None and p.grad is None, name
+                continue
+            a, r = p.grad.double().flatten(), gr.double().flatten()
+            if r.abs().max() < 1e-9 or name.endswith("k_proj.bias"):
+                continue
+            c = (torch.dot(a, r) / (a.norm() * r.norm()).clamp_min(1e-30)).item()
+            if c < 0.99:
+                low[name] = round(c, 4)
+        assert not low, low
+    finally:
+        for h in handles:
+            h.remove()

@@ -155,3 +155,40 @@ def test_collate_oracle_vs_live_reference():
         assert torch.equal(ref["net_input"]["src_tokens"][k], got["net_input"]["src_tokens"][j])
         assert torch.equal(ref["net_input"]["prev_output_tokens"][k], got["net_input"]["prev_output_tokens"][j])
         assert torch.equal(ref["target"][k], got["target"][j])
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not R.available(), reason="live reference not mounted")
+@pytest.mark.parametrize("penalty,strategy", [("log", "weighted"), (None, "avg")])
+def test_oracle_gradients_vs_live_reference(penalty, strategy):
+    """Gradient pin (scope row T): torch.autograd through the oracle equals torch.autograd through the LIVE
+    reference module in eval() + grad mode (BatchNorm running statistics, no dropout: the deterministic
+    setting), for every parameter -- so the GPU gradient-parity tests (tests/test_gpu_train.py), which
+    compare with the oracle, are anchored to the reference itself."""
+    import warnings
+    cfg = dict(embed_dim=128, ffn_dim=256, heads=2, layers=3, conv_channels=64, feat_dim=40, vocab=64,
+               distance_penalty=penalty, ctc_layer=2, ctc_strategy=strategy)
+    enc = R.build_reference_encoder(cfg, seed=3)
+    sd = {k: v.detach().clone() for k, v in enc.state_dict().items()}
+    x, lens = O.synthetic_batch([97, 64, 30], 40, seed=11)
+    labels = O.synthetic_ctc_bump(25, 3, 64, seed=2)
+    hook = O.bump_hook(labels, 30.0)
+    enc.ctc_fc.register_forward_hook(lambda m, i, o: hook(o))
+    g = torch.Generator().manual_seed(0)
+    with R.cpu_cuda_noop(), R.grad_shims(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = enc(x, lens, return_all_hiddens=True)
+        r_out = torch.randn(out.encoder_out.shape, generator=g)
+        r_ctc = torch.randn(out.ctc_out.shape, generator=g) * 0.05
+        ((out.encoder_out * r_out).sum() + (out.ctc_out * r_ctc).sum()).backward()
+    leaf = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k
+                and "_float_tensor" not in k else v) for k, v in sd.items()}
+    ref = O.encoder_forward(leaf, cfg, x, lens, ctc_logits_hook=hook)
+    assert_close(ref["encoder_out"].detach(), out.encoder_out.detach(), 1e-5)
+    ((ref["encoder_out"] * r_out).sum() + (ref["ctc_out"] * r_ctc).sum()).backward()
+    n = 0
+    for name, p in enc.named_parameters():
+        assert p.grad is not None and leaf[name].grad is not None, name
+        assert_close(leaf[name].grad, p.grad, 2e-4)
+        n += 1
+    assert n >= 40
