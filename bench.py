@@ -61,6 +61,12 @@ CONFIGS = {
                  lengths=[6000, 5600, 5200, 4800, 4400, 4000, 3500, 3000],
                  name="long-form 12L d1024 h16 ffn4096 C128, ctc-compress avg @8, batch 8 x 3000..6000 x 80"),
 }
+# BASELINE.json configs[3]: full ST training step -- the cfg2 encoder + a 6-layer decoder, joint CTC +
+# label-smoothed CE, bf16, NCCL gradient all-reduce (bench.py --config cfg4; see run_train)
+CONFIGS["cfg4"] = dict(model=CONFIGS["cfg2"]["model"], lengths=[1500] * 64,
+                       decoder=dict(layers=6, tgt_vocab=8000, tgt_len=64, transcript_len=48),
+                       name="EACL21 ST training step: cfg2 encoder (11L d512, log penalty, ctc-compress avg @8) + "
+                            "6-layer d512 decoder, ctc_multi_loss (CTC + label-smoothed CE), batch 64x1500x40 per GPU")
 CTC_MARGIN = 30.0
 LOOKAHEAD_CYCLES = int(1.0e-3 * 1.9e9)  # ~1 ms of untimed GPU delay before every timed step
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
@@ -573,6 +579,217 @@ def run_ours(args, rank, world, local_rank):
     return result, enc, parity_sample
 
 
+
+# ------------------------------------------------------------------------------ cfg4: training step
+def _reference_root():
+    env = os.environ.get("FBKST_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", os.path.join(ROOT, "baseline", "_ref")):
+        if os.path.isdir(os.path.join(cand, "examples", "speech_recognition")):
+            return cand
+    return None
+
+
+def run_train(args, rank, world, local_rank):
+    """BASELINE configs[3]: one optimisation step of the ST model the way fairseq's trainer runs it
+    (fairseq/trainer.py:335-443 -> tasks/speech_recognition.py:234-263): criterion(model, sample) with the
+    plugin's model (`--arch conv_transformer_big2_b200`: OUR encoder forward + backward kernels, fairseq's own
+    TransformerDecoder under bf16 autocast) and criterion (`ctc_multi_loss_b200`: CTC loss on our kernels +
+    fairseq's label-smoothed CE), loss.backward(), the reference's own LegacyDistributedDataParallel
+    (`--ddp-backend no_c10d`, README.md:142: ONE flat NCCL all-reduce after the backward), Adam step.
+    Everything outside the encoder / CTC loss is the reference's code, imported from baseline/_ref."""
+    root = _reference_root()
+    if root is None:
+        raise RuntimeError("cfg4 needs the reference package (baseline/_ref; run baseline/make_ref.py)")
+    plugin = os.path.join(ROOT, "fbk-fairseq-st_b200", "fbkst_b200", "plugin")
+    sys.path.insert(0, plugin)
+    import compat
+    compat.apply_numpy()
+    sys.path.insert(0, root)
+    import warnings
+    warnings.simplefilter("ignore")
+    from fairseq import criterions, options, utils
+    utils.import_user_module(argparse.Namespace(user_dir=plugin))
+    from fairseq.data import Dictionary
+    from fairseq.models import MODEL_REGISTRY
+    from fbkst_b200 import ops
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    cfg = CONFIGS[args.config]
+    model_cfg, dec, lengths = cfg["model"], cfg["decoder"], cfg["lengths"]
+    B, T, Fd = len(lengths), max(lengths), model_cfg["feat_dim"]
+
+    def make_dict(n, blank):
+        d = Dictionary()
+        for i in range(n - len(d) - (1 if blank else 0)):
+            d.add_symbol("w%d" % i)
+        if blank:
+            d.add_symbol("<ctc_blank>")
+        return d
+
+    class Task:
+        source_dictionary = make_dict(model_cfg["vocab"], True)
+        target_dictionary = make_dict(dec["tgt_vocab"], False)
+
+        def build_criterion(self, a):
+            return criterions.build_criterion(a, self)
+    task = Task()
+    parser = options.get_training_parser()
+    fa = options.parse_args_and_arch(parser, [
+        "/tmp/nodata", "--user-dir", plugin, "--arch", "conv_transformer_big2_b200",
+        "--task", "speech_translation_with_transcription", "--criterion", "ctc_multi_loss_b200",
+        "--underlying-criterion", "label_smoothed_cross_entropy", "--label-smoothing", "0.1",
+        "--ctc-encoder-layer", str(model_cfg["ctc_layer"]), "--ctc-compress-out",
+        "--ctc-compress-strategy", model_cfg["ctc_strategy"], "--no-attn-2d", "--distance-penalty", "log",
+        "--input-feat-per-channel", str(Fd), "--encoder-layers", str(model_cfg["layers"]),
+        "--encoder-embed-dim", str(model_cfg["embed_dim"]), "--encoder-ffn-embed-dim", str(model_cfg["ffn_dim"]),
+        "--encoder-attention-heads", str(model_cfg["heads"]), "--decoder-layers", str(dec["layers"]),
+        "--max-tokens", "12000", "--skip-normalization", "--dropout", "0.1", "--ddp-backend", "no_c10d"])
+    torch.manual_seed(0)
+    model = MODEL_REGISTRY["conv_transformer_b200"].build_model(fa, task).to(dev)
+    criterion = criterions.build_criterion(fa, task).to(dev)
+    model.train()
+    criterion.train()
+    n_params = sum(p.numel() for p in model.parameters())
+    n_enc = sum(p.numel() for p in model.encoder.parameters())
+    ddp = model
+    if world > 1:
+        from fairseq.legacy_distributed_data_parallel import LegacyDistributedDataParallel
+        ddp = LegacyDistributedDataParallel(model, world, process_group=None, buffer_size=2 ** 28)
+        for name in ("encoder", "decoder", "get_normalized_probs", "get_targets", "max_positions"):
+            setattr(ddp, name, getattr(model, name))  # what DistributedFairseqModel forwards
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, betas=(0.9, 0.98), fused=True)
+
+    L = ((T + 1) // 2 + 1) // 2
+    plan = label_plan(L, B, model_cfg["vocab"], seed=7 + rank).to(dev)
+    model.encoder.ctc_fc.register_forward_hook(
+        lambda m, i, o: o.scatter_add(2, plan.unsqueeze(-1), torch.full_like(o[..., :1], CTC_MARGIN)))
+    g = torch.Generator().manual_seed(99 + rank)
+    n_batches = 4
+    samples = []
+    for i in range(n_batches):
+        x, l = make_batch(lengths, Fd, 1234 + rank * 100 + i)
+        U, U1 = dec["tgt_len"], dec["transcript_len"]
+        tgt = torch.randint(4, dec["tgt_vocab"] - 1, (B, U), generator=g)
+        tgt[:, -1] = task.target_dictionary.eos()
+        prev = torch.cat([torch.full((B, 1), task.target_dictionary.eos()), tgt[:, :-1]], 1)
+        tr = torch.randint(4, model_cfg["vocab"] - 2, (B, U1), generator=g)
+        trl = torch.full((B,), U1, dtype=torch.long)
+        samples.append(utils.move_to_cuda(dict(
+            net_input=dict(src_tokens=x, src_lengths=l, prev_output_tokens=prev), target=tgt,
+            transcript_target=tr, transcript_target_lengths=trl, ntokens=B * U, nsentences=B)))
+    frames = float(sum(lengths))
+
+    marks = {}
+
+    def step(i, timed=None):
+        s = samples[i % n_batches]
+        ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+        e = [ev() for _ in range(5)] if timed is not None else None
+        torch.manual_seed(1000 + i)  # dropout seed source (fairseq: trainer.py:655-661)
+        opt.zero_grad(set_to_none=True)
+        if e:
+            e[0].record()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss, sample_size, log = criterion(ddp, s)
+        if e:
+            e[1].record()
+        loss.backward()  # the legacy DDP all-reduce fires at the end of the backward (one flat buffer)
+        if e:
+            e[2].record()
+        opt.step()
+        if e:
+            e[3].record()
+            timed.append(e)
+        return loss
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank, args.clock_interval_ms) if rank == 0 else None
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    launches0 = ops.LAUNCHES
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        last = step(i)
+    ev1.record()
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = (ops.LAUNCHES - launches0) // args.steps
+    # e2e: batches start in pinned HOST memory (H2D inside), the loss is read back on the host every step
+    host = [utils.apply_to_sample(lambda t: t.cpu().pin_memory(), s) for s in samples]
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        samples[i % n_batches] = utils.apply_to_sample(lambda t: t.to(dev, non_blocking=True), host[i % n_batches])
+        lv = step(i).item()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if sampler else None
+    # attribution (untimed region): forward / backward(+all-reduce) / optimizer split with CUDA events
+    timed = []
+    for i in range(3):
+        step(i, timed)
+    torch.cuda.synchronize()
+    split = dict(forward_and_loss_ms=round(sum(e[0].elapsed_time(e[1]) for e in timed) / 3, 3),
+                 backward_and_allreduce_ms=round(sum(e[1].elapsed_time(e[2]) for e in timed) / 3, 3),
+                 optimizer_ms=round(sum(e[2].elapsed_time(e[3]) for e in timed) / 3, 3))
+    # the all-reduce alone: the same flat buffer the legacy wrapper uses (fp32, all parameters)
+    ar_ms = None
+    if world > 1:
+        buf = torch.empty(n_params, dtype=torch.float32, device=dev)
+        torch.distributed.all_reduce(buf)
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(5):
+            torch.distributed.all_reduce(buf)
+        a1.record()
+        torch.cuda.synchronize()
+        ar_ms = a0.elapsed_time(a1) / 5
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    dev_ms, e2e_ms = t.tolist()
+    if rank != 0:
+        return None
+    ms_per_step = dev_ms / args.steps
+    h2d = sum(v.numel() * v.element_size() for v in
+              [host[0]["net_input"]["src_tokens"], host[0]["net_input"]["src_lengths"],
+               host[0]["net_input"]["prev_output_tokens"], host[0]["target"], host[0]["transcript_target"],
+               host[0]["transcript_target_lengths"]])
+    return dict(
+        metric="encoder fbank frames/sec", value=round(world * frames / (ms_per_step * 1e-3), 1), unit="frames/s",
+        n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=round(ms_per_step, 4),
+        higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
+        config=dict(workload=cfg["name"], per_gpu_batch="%dx%dx%d" % (B, T, Fd),
+                    frames_per_step_per_gpu=frames, parameters=n_params, encoder_parameters=n_enc,
+                    step="criterion(model, sample) [fairseq ctc_multi_loss_b200] -> backward -> flat gradient "
+                         "all-reduce (fairseq LegacyDistributedDataParallel, no_c10d) -> Adam",
+                    encoder="fbkst_b200 forward + backward kernels (train mode: BatchNorm batch statistics, "
+                            "dropout 0.1 / conv 0.1 / attention 0.1 / relu 0.1)",
+                    decoder="fairseq TransformerDecoder (PyTorch, bf16 autocast), label-smoothed CE",
+                    cache="%d rotating batches; every step streams several GB of saved activations" % n_batches,
+                    parallelism="data parallel x%d, one flat NCCL all-reduce per step" % world),
+        e2e=dict(value=round(world * frames / (e2e_ms * 1e-3 / args.steps), 1), unit="frames/s",
+                 h2d_bytes_per_step=h2d, d2h_bytes_per_step=4, ms_per_step=round(e2e_ms / args.steps, 4),
+                 api="fairseq criterion(model, sample) on the plugin model; pinned host sample in, loss.item() out"),
+        gpu_launches=launches, clocks=clocks, impl="ours", train_step_split=split,
+        allreduce=dict(ms=None if ar_ms is None else round(ar_ms, 3), bytes=n_params * 4,
+                       share_of_step=None if ar_ms is None else round(ar_ms / ms_per_step, 4),
+                       note="flat fp32 gradient buffer, torch.distributed NCCL all_reduce timed alone (5 reps)"),
+        final_loss=round(float(lv), 3),
+        roofline=None, cpu_baseline=None)
+
+
 # ------------------------------------------------------------------------------ CPU baseline
 def parity_numbers(ours, ref, lengths):
     """Both readings of the north_star's 2e-2 (bf16) over the valid positions of T x B x D outputs:
@@ -773,6 +990,14 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if args.config == "cfg4":
+        r = run_train(args, rank, world, local_rank)
+        if rank == 0:
+            emit(r)
+        if world > 1:
+            torch.distributed.barrier()
+            torch.distributed.destroy_process_group()
+        return
     r = run_ours(args, rank, world, local_rank)
     if rank == 0:
         result, enc, sample = r

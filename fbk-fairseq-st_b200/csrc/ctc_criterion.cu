@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(256)
   }
   const float g = __ldg(grad_loss), l = __ldg(lse + row);
   for (int c = lane; c < V; c += 32)
-    op[c] = g * __expf(load_logit<IS_BF16>(logits, (size_t)row * ldv + c) - l);
+    op[c] = g * expf(load_logit<IS_BF16>(logits, (size_t)row * ldv + c) - l);
 }
 
 // smem: beta[2][S] | gam[W] | lp[TCH][W] floats | tgt[U] | nxt[U] | hd[U] ints     (W = U + 1, column U = blank)
@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(256)
         }
         b1[s] = v;
         const float lg = at[s] + v - p - ll;
-        const float gm = (lg == -INFINITY || isnan(lg)) ? 0.0f : __expf(lg);
+        const float gm = (lg == -INFINITY || isnan(lg)) ? 0.0f : expf(lg);
         if (is_label)
           gam[u] = gm;
         else

@@ -21,6 +21,15 @@ _PKG_PARENT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__
 if _PKG_PARENT not in sys.path:
     sys.path.insert(0, _PKG_PARENT)
 
+# compat.py is loaded by PATH: fairseq imports this directory as a top-level module (fairseq/utils.py:344-359),
+# and importing it again as the package ``fbkst_b200.plugin`` would run the registrations twice
+import importlib.util as _ilu  # noqa: E402
+_spec = _ilu.spec_from_file_location("fbkst_b200_plugin_compat",
+                                     os.path.join(os.path.dirname(os.path.abspath(__file__)), "compat.py"))
+_compat = _ilu.module_from_spec(_spec)
+_spec.loader.exec_module(_compat)
+_compat.apply()  # (the numpy half is a no-op when the launcher already applied it)
+
 from fairseq.models import FairseqEncoder, register_model, register_model_architecture  # noqa: E402
 from fairseq.models.transformer import TransformerDecoder  # noqa: E402
 

@@ -164,7 +164,7 @@ def test_ctc_loss_backward_vs_torch(T, B, V, U):
     assert abs(loss.item() - ref.item()) <= 1e-4 * abs(ref.item())
     (loss * 0.7).backward()
     err = (y.grad - x.grad).abs().max().item() / x.grad.abs().max().item()
-    assert err < 1e-4, err
+    assert err < 1e-3, err  # fp32 on both sides (different summation orders in the alpha / beta recursions)
     assert y.grad[:, -1].abs().max() == 0  # infeasible utterance
     assert y.grad[int(in_len[1]):, 1].abs().max() == 0  # frames beyond the input length
     y2 = logits.clone().requires_grad_(True)
