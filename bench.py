@@ -714,6 +714,17 @@ def run_train(args, rank, world, local_rank):
     for i in range(max(args.warmup, 3)):
         step(i)
     barrier()
+    if os.environ.get("FBKST_TRAIN_PROFILE") and rank == 0:  # informative per-kernel table on stderr (untimed)
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for i in range(2):
+                step(i)
+            torch.cuda.synchronize()
+        rows = sorted(((getattr(e, "device_time_total", 0), e.count, e.key) for e in prof.key_averages()), reverse=True)
+        tot = sum(r[0] for r in rows if not r[2].startswith("Optimizer.step"))
+        sys.stderr.write("per-kernel device time over 2 training steps: %.2f ms/step\n" % (tot / 2e3))
+        for t, n, k in rows[:60]:
+            sys.stderr.write("%8.3f ms/step %5.1f%%  n=%-4d %s\n" % (t / 2e3, 100 * t / max(tot, 1), n // 2, k[:120]))
     launches0 = ops.LAUNCHES
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()

@@ -328,23 +328,56 @@ __global__ void __launch_bounds__(256) grad_prep_kernel(const GradPrepParams p) 
   }
 }
 
-// out[r, c] = scale * sum_{g < G} in[g * g_stride + r * ldi + c]   (fixed order)
+// out[r, c] = scale * sum_{g < G} in[g * g_stride + r * ldi + c], fixed summation order.
+// Block = 8 consecutive output elements x 32 g-lanes: lane l sums g = l, l + 32, ... (independent loads in
+// flight), then the 32 lane sums are added in lane order.  (The first version walked all G partials in one
+// thread: 375 dependent loads for a bias gradient -- 36 us per call, 4.3 ms of a training step.)
 __global__ void __launch_bounds__(256)
     reduce_sum_kernel(const float* __restrict__ in, int G, long long g_stride, int rows, int cols,
                       long long ldi, float* __restrict__ out, long long ldo, float scale) {
+  __shared__ float red[32][9];
+  const int e = threadIdx.x & 7, gl = threadIdx.x >> 3;
+  const long long total = (long long)rows * cols;
+  for (long long i0 = (long long)blockIdx.x * 8; i0 < total; i0 += (long long)gridDim.x * 8) {
+    const long long i = i0 + e;
+    float s = 0.f;
+    if (i < total) {
+      const int r = (int)(i / cols), c = (int)(i - (long long)r * cols);
+      const float* ip = in + (long long)r * ldi + c;
+      float s0 = 0.f, s1 = 0.f;
+      int g = gl;
+      for (; g + 32 < G; g += 64) {
+        s0 += ip[(long long)g * g_stride];
+        s1 += ip[(long long)(g + 32) * g_stride];
+      }
+      if (g < G) s0 += ip[(long long)g * g_stride];
+      s = s0 + s1;
+    }
+    red[gl][e] = s;
+    __syncthreads();
+    if (gl == 0 && i < total) {
+      float t = 0.f;
+#pragma unroll
+      for (int l = 0; l < 32; ++l) t += red[l][e];
+      const int r = (int)(i / cols), c = (int)(i - (long long)r * cols);
+      out[(long long)r * ldo + c] = t * scale;
+    }
+    __syncthreads();
+  }
+}
+
+// Few partials, many outputs (the split-K slices of a wgrad GEMM): one thread per output element.
+__global__ void __launch_bounds__(256)
+    reduce_sum_small_kernel(const float* __restrict__ in, int G, long long g_stride, int rows, int cols,
+                            long long ldi, float* __restrict__ out, long long ldo, float scale) {
   const long long total = (long long)rows * cols;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(i / cols), c = (int)(i - (long long)r * cols);
     const float* ip = in + (long long)r * ldi + c;
-    float s0 = 0.f, s1 = 0.f;
-    int g = 0;
-    for (; g + 1 < G; g += 2) {
-      s0 += ip[(long long)g * g_stride];
-      s1 += ip[(long long)(g + 1) * g_stride];
-    }
-    if (g < G) s0 += ip[(long long)g * g_stride];
-    out[(long long)r * ldo + c] = (s0 + s1) * scale;
+    float s = 0.f;
+    for (int g = 0; g < G; ++g) s += ip[(long long)g * g_stride];
+    out[(long long)r * ldo + c] = s * scale;
   }
 }
 
@@ -515,10 +548,17 @@ extern "C" int fbkst_reduce_sum(const float* in, int G, int64_t g_stride, int ro
   FBKST_REQUIRE(in && out && G > 0 && rows > 0 && cols > 0, "fbkst_reduce_sum: bad arguments");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const long long total = (long long)rows * cols;
-  long long grid = (total + 255) / 256;
-  const long long cap = (long long)num_sms() * 8;
-  if (grid > cap) grid = cap;
-  reduce_sum_kernel<<<(int)grid, 256, 0, st>>>(in, G, g_stride, rows, cols, ldi, out, ldo, scale);
+  if (G <= 16) {
+    long long grid = (total + 255) / 256;
+    const long long cap = (long long)num_sms() * 8;
+    if (grid > cap) grid = cap;
+    reduce_sum_small_kernel<<<(int)grid, 256, 0, st>>>(in, G, g_stride, rows, cols, ldi, out, ldo, scale);
+  } else {
+    long long grid = (total + 7) / 8;
+    const long long cap = (long long)num_sms() * 16;
+    if (grid > cap) grid = cap;
+    reduce_sum_kernel<<<(int)grid, 256, 0, st>>>(in, G, g_stride, rows, cols, ldi, out, ldo, scale);
+  }
   FBKST_CHECK_CUDA(cudaGetLastError());
   return FBKST_OK;
 }
