@@ -801,6 +801,130 @@ def run_train(args, rank, world, local_rank):
         roofline=None, cpu_baseline=None)
 
 
+
+# ------------------------------------------------------------------------------ cfg3: ragged, length-bucketed
+def run_ragged(args, rank, world, local_rank):
+    """BASELINE configs[2]: the cfg2 model with weighted / softmax pooling on RAGGED utterances (200..3000
+    frames), partitioned across the ranks by length-bucketed batch (fbkst_b200.sharding: sort by length, cut
+    into batches of <= 96 k padded frames with T quantised to 128 frames, deal every `world` consecutive
+    -- near-equal-cost -- batches to the ranks of one step).  Every rank runs DIFFERENT batches with different
+    shapes; no collective on the data path.  Weak scaling: the utterance pool grows with `world` so that every
+    rank runs `--steps` batches.  Reported: aggregate valid frames/s over the slowest rank's device time, the
+    per-rank time spread and the partition's padded-frame imbalance."""
+    import random
+    from fbkst_b200 import ops, sharding
+    from fbkst_b200.config import build_encoder
+    from fbkst_b200.pipeline import EncoderPipeline
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    cfg = CONFIGS["cfg3"]
+    model = dict(cfg["model"], ctc_strategy=args.ctc_strategy or cfg["model"]["ctc_strategy"])
+    Fd, PAD, MAXF = model["feat_dim"], 128, 96000
+    rng = random.Random(20210421)  # the same pool on every rank
+    pool = []
+    want = world * args.steps
+    while True:
+        pool += [rng.randint(200, 3000) for _ in range(64 * world)]
+        batches = sharding.bucket_by_length(pool, MAXF, pad_multiple=PAD)
+        if len(batches) >= want + 1:  # + 1: the last (shortest, partly filled) batch is dropped
+            break
+    # `want` batches spread over the whole length range (every k-th of the sorted batch list)
+    stride = (len(batches) - 1) // want
+    batches = [batches[i * stride] for i in range(want)] if stride >= 1 else batches[:want]
+    steps = sharding.shard_steps(batches, world)
+    imbalance = sharding.step_imbalance(pool, steps, PAD)
+    mine = [st[rank] for st in steps]
+
+    torch.manual_seed(0)
+    enc = build_encoder(model, None, device="cpu")
+    randomise_norm_stats(enc, 1)
+    enc = enc.to(dev).eval()
+    enc.use_cuda_graph = not args.no_graph
+    enc.max_graphs = 96
+    Lmax, Bmax = (3072 + 3) // 4, MAXF // 256
+    plan_big = label_plan(Lmax, Bmax, model["vocab"], seed=7).to(dev)
+    enc.ctc_fc.register_forward_hook(
+        lambda m, i, o: o.scatter_add(2, plan_big[: o.shape[0], : o.shape[1]].unsqueeze(-1),
+                                      torch.full_like(o[..., :1], CTC_MARGIN)))
+    g = torch.Generator().manual_seed(1234 + rank)
+    noise = torch.randn(MAXF + 3072, Fd, generator=g) * 3.0 + 1.0
+    dev_batches, frames, padded = [], 0.0, 0.0
+    for b in mine:
+        lens = [pool[i] for i in b]
+        T = sharding.padded_length(max(lens), PAD)
+        x = torch.zeros(len(b), T, Fd)
+        o = 0
+        for k, n in enumerate(lens):
+            x[k, :n] = noise[o:o + n]
+            o = (o + n) % 3000
+        dev_batches.append((x.to(dev), torch.tensor(lens, dtype=torch.long)))
+        frames += sum(lens)
+        padded += len(b) * T
+    shapes = sorted({tuple(x.shape[:2]) for x, _ in dev_batches})
+    pipe = EncoderPipeline(enc, normalize=True, device=dev)
+
+    def run(n_rep):
+        last = None
+        for _ in range(n_rep):
+            for o in pipe.run_device(iter(dev_batches)):
+                last = o
+        return last
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank, args.clock_interval_ms) if rank == 0 else None
+    run(2)  # every shape's graph on both lanes exists (untimed)
+    barrier()
+    import gc
+    gc.collect()
+    gc.freeze()
+    gc.disable()
+    launches0 = ops.LAUNCHES
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    out = run(1)
+    ev1.record()
+    barrier()
+    gc.enable()
+    my_ms = ev0.elapsed_time(ev1)
+    launches = (ops.LAUNCHES - launches0) // max(1, len(dev_batches))
+    clocks = sampler.stop() if sampler else None
+    stats = torch.tensor([my_ms, frames, padded], dtype=torch.float64, device=dev)
+    allr = [torch.zeros_like(stats) for _ in range(world)]
+    if world > 1:
+        torch.distributed.all_gather(allr, stats)
+    else:
+        allr = [stats]
+    if rank != 0:
+        return None
+    ms = [float(t[0]) for t in allr]
+    tot_frames = sum(float(t[1]) for t in allr)
+    tot_padded = sum(float(t[2]) for t in allr)
+    worst = max(ms)
+    return dict(
+        metric="encoder fbank frames/sec", value=round(tot_frames / (worst * 1e-3), 1), unit="frames/s",
+        n_gpus=world, steps=len(mine), warmup=2 * len(mine), ms_per_step=round(worst / len(mine), 4),
+        higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
+        config=dict(workload="cfg2 model, ctc-compress %s @8, RAGGED utterances 200..3000 frames, length-bucketed "
+                             "batches of <= 96 k padded frames (T quantised to 128), different batches per rank"
+                             % model["ctc_strategy"],
+                    utterances_in_pool=len(pool), steps_per_rank=len(mine), distinct_shapes_rank0=len(shapes),
+                    shapes_rank0=["%dx%d" % s for s in shapes[:4]] + ["..."] + ["%dx%d" % s for s in shapes[-2:]],
+                    valid_frames_total=tot_frames, padded_frames_total=tot_padded,
+                    padding_overhead=round(tot_padded / tot_frames - 1.0, 4),
+                    launch="eager" if args.no_graph else "CUDA graph replay, one graph per (shape, lane)",
+                    parallelism="utterance-batch sharded x%d by fbkst_b200.sharding, no forward collective" % world,
+                    cache="every batch is a different tensor (%.0f MB per rank in total)" % (padded * Fd * 4 / 1e6 / world)),
+        rank_time_ms=dict(min=round(min(ms), 3), max=round(worst, 3), mean=round(sum(ms) / len(ms), 3),
+                          spread=round(worst / min(ms), 4), per_rank=[round(m, 3) for m in ms]),
+        step_imbalance_padded_frames=round(imbalance, 4),
+        e2e=None, gpu_launches=launches, clocks=clocks, impl="ours", roofline=None, cpu_baseline=None)
+
+
 # ------------------------------------------------------------------------------ CPU baseline
 def parity_numbers(ours, ref, lengths):
     """Both readings of the north_star's 2e-2 (bf16) over the valid positions of T x B x D outputs:
@@ -968,7 +1092,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS) + ["cfg3r"],
+                    help="cfg2: headline; cfg3: one ragged bucket; cfg3r: ragged, length-bucketed, different batches "
+                         "per rank (BASELINE configs[2]); cfg4: training step; cfg5: long-form")
+    ap.add_argument("--ctc-strategy", default=None, choices=["avg", "weighted", "softmax"],
+                    help="cfg3r: pooling strategy (default weighted)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--clock-interval-ms", type=int, default=20,
                     help="nvidia-smi sampling period for the `clocks` key (0 = no sampler)")
@@ -1001,8 +1129,8 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    if args.config == "cfg4":
-        r = run_train(args, rank, world, local_rank)
+    if args.config in ("cfg4", "cfg3r"):
+        r = (run_train if args.config == "cfg4" else run_ragged)(args, rank, world, local_rank)
         if rank == 0:
             emit(r)
         if world > 1:

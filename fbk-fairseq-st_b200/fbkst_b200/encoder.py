@@ -281,6 +281,7 @@ def make_encoder_class(base):
             self._ws_key = None
             # opt-in: replay one captured CUDA graph per input shape instead of ~90 launches
             self.use_cuda_graph = False
+            self.max_graphs = 16  # cached graphs (each pins its activations: ~1.2 GB at 96 k frames, d512)
             self._graphs = {}
             # graphs (and the activations they own) are per lane: EncoderPipeline keeps one forward in
             # flight per lane/stream and sets this before every launch
@@ -568,7 +569,7 @@ def make_encoder_class(base):
             key = self._graph_key(B, T, Fd, dev)
             G = self._graphs.get(key)
             if G is None:
-                if len(self._graphs) >= 16:  # bounded: every graph pins its activations
+                if len(self._graphs) >= self.max_graphs:  # bounded: every graph pins its activations
                     self._graphs.pop(next(iter(self._graphs)))
                 G = self._capture(P, B, T, Fd, L, dev)
                 self._graphs[key] = G

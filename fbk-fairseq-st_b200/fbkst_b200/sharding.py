@@ -11,18 +11,29 @@ PADDED frames (``len(batch) * longest``, the quantity the kernels actually proce
 from typing import List, Sequence
 
 
-def bucket_by_length(lengths: Sequence[int], max_frames: int, max_sentences: int = 0) -> List[List[int]]:
+def padded_length(n: int, pad_multiple: int = 1) -> int:
+    """Frames the batch tensor is padded to: the longest utterance rounded up to ``pad_multiple``."""
+    return (n + pad_multiple - 1) // pad_multiple * pad_multiple if pad_multiple > 1 else n
+
+
+def bucket_by_length(lengths: Sequence[int], max_frames: int, max_sentences: int = 0,
+                     pad_multiple: int = 1) -> List[List[int]]:
     """Batches of utterance indices, longest first inside a batch (collater order,
-    ``data/collaters.py:89-92``); ``len(batch) * max(len) <= max_frames``."""
+    ``data/collaters.py:89-92``); ``len(batch) * padded(max(len)) <= max_frames``.
+
+    ``pad_multiple`` > 1 quantises the batch's time extent (T is rounded up to a multiple of it), so the
+    set of distinct batch SHAPES of an epoch is small: a ragged stream then re-uses the encoder's per-shape
+    CUDA graphs instead of re-capturing on every step (every batch of a given padded T is filled to the same
+    ``max_frames // T`` utterances, except the last one)."""
     if max_frames <= 0:
         raise ValueError("max_frames must be positive")
     order = sorted(range(len(lengths)), key=lambda i: (-lengths[i], i))
     batches, cur = [], []
     for i in order:
-        n = lengths[i]
+        n = padded_length(lengths[i], pad_multiple)
         if n > max_frames:
             raise ValueError("utterance %d has %d frames > max_frames=%d" % (i, n, max_frames))
-        longest = lengths[cur[0]] if cur else n
+        longest = padded_length(lengths[cur[0]], pad_multiple) if cur else n
         if cur and ((len(cur) + 1) * longest > max_frames or (max_sentences and len(cur) >= max_sentences)):
             batches.append(cur)
             cur = []
@@ -48,11 +59,11 @@ def batches_for_rank(lengths: Sequence[int], max_frames: int, rank: int, world: 
     return [st[rank] for st in steps]
 
 
-def step_imbalance(lengths: Sequence[int], steps: List[List[List[int]]]) -> float:
+def step_imbalance(lengths: Sequence[int], steps: List[List[List[int]]], pad_multiple: int = 1) -> float:
     """max over steps of (largest padded-frame count) / (mean padded-frame count) over busy ranks."""
     worst = 1.0
     for st in steps:
-        cost = [len(b) * max(lengths[i] for i in b) for b in st if b]
+        cost = [len(b) * padded_length(max(lengths[i] for i in b), pad_multiple) for b in st if b]
         if len(cost) > 1:
             worst = max(worst, max(cost) / (sum(cost) / len(cost)))
     return worst
