@@ -279,6 +279,39 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Merge of the per-chunk arg-max partials the ctc_fc GEMM epilogue leaves (gemm2_tcgen05.cu ArgmaxEpi): one
+// thread per row folds its ceil(V/128) partials in column order (strict '>' keeps the lowest index).
+__global__ void __launch_bounds__(256)
+    ctc_argmax_merge_kernel(const float4* __restrict__ partial, int chunks, const int* __restrict__ lengths,
+                            int* __restrict__ labels, float* __restrict__ top_prob, float* __restrict__ lse,
+                            int rows, int B) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  const int t = row / B, b = row - t * B;
+  if (t >= __ldg(lengths + b)) {
+    labels[row] = -1;
+    if (top_prob) top_prob[row] = 0.0f;
+    if (lse) lse[row] = 0.0f;
+    return;
+  }
+  float best = -INFINITY, sum = 0.0f;
+  int idx = 0x7fffffff;
+  const float4* p = partial + (size_t)row * chunks;
+  for (int c = 0; c < chunks; ++c) {
+    const float4 v = __ldg(p + c);
+    if (v.x > best) {
+      sum = sum * __expf(best - v.x) + v.z;
+      best = v.x;
+      idx = __float_as_int(v.y);
+    } else if (v.x != -INFINITY) {
+      sum += v.z * __expf(v.x - best);
+    }
+  }
+  labels[row] = idx;
+  if (top_prob) top_prob[row] = 1.0f / sum;
+  if (lse) lse[row] = best + logf(sum);
+}
+
 // One CTA per utterance.  smem: lab[L] | start[L+1] ints.
 __global__ void __launch_bounds__(512)
     ctc_segment_kernel(const int* __restrict__ labels, const float* __restrict__ top_prob,
@@ -586,6 +619,17 @@ extern "C" int fbkst_ctc_compress(const float* x, const int32_t* seg_id, const i
   if (grid > (long long)num_sms() * ctas_per_sm) grid = (long long)num_sms() * ctas_per_sm;
   ctc_compress_kernel<<<(int)grid, 256, 0, st>>>(x, seg_id, seg_start, weight, lengths, new_lengths,
                                                  max_new_len, out, L, B, D, (int)tasks);
+  FBKST_CHECK_CUDA(cudaGetLastError());
+  return FBKST_OK;
+}
+
+extern "C" int fbkst_ctc_argmax_merge(const float* partial, int chunks, const int32_t* lengths, int32_t* labels,
+                                      float* top_prob, float* lse, int L, int B, fbkst_stream_t stream) {
+  FBKST_REQUIRE(partial && lengths && labels && chunks > 0 && L > 0 && B > 0, "fbkst_ctc_argmax_merge: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int rows = L * B;
+  ctc_argmax_merge_kernel<<<(rows + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float4*>(partial), chunks,
+                                                             lengths, labels, top_prob, lse, rows, B);
   FBKST_CHECK_CUDA(cudaGetLastError());
   return FBKST_OK;
 }

@@ -133,15 +133,31 @@ __device__ __forceinline__ float ln_rstd_from_slices(const float2* __restrict__ 
   return rsqrtf(m2 / (float)dim + eps);
 }
 
-template <bool OUT_F32, bool RESID, bool LNS>
+// CTC projection epilogue (AM): while the fp32 logits of a tile pass through the epilogue registers, every
+// thread (= one output row) also folds its <= 128 columns into (max, first arg-max, sum of exp(x - max)) and
+// writes that partial to partial[row, chunk]; a tiny merge kernel (ctc.cu) turns the ceil(N/128) partials of a
+// row into the frame's label / top probability / log-sum-exp.  The 4-byte-per-element re-read of the logits
+// by a separate arg-max pass (768 MB at cfg2) disappears.  `bump_cols[row]`
+// (optional) adds `bump` to one column per row BEFORE the store and the arg-max: the run-structured logit
+// injection of the benchmarks / parity tests, equivalent to a forward hook on ctc_fc.
+struct ArgmaxEpi {
+  float4* partial;       // [M, chunks] (max, index as float bits, sum, -)
+  const int* bump_cols;  // [M] or nullptr
+  float bump;
+  int want_sum;
+  int chunks;
+};
+
+template <bool OUT_F32, bool RESID, bool LNS, bool AM = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
     gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
                  const __grid_constant__ CUtensorMap tmX, int M, int N, int K,
                  const float* __restrict__ bias, int relu, int dbg, const int* __restrict__ m_limit,
                  int m_limit_mult, const LnStatsIn ln_in, float2* __restrict__ stats_out,
-                 const uint32_t idesc, const int splits, const int split_rows) {
+                 const uint32_t idesc, const int splits, const int split_rows, const ArgmaxEpi am) {
   static_assert(!LNS || (OUT_F32 && RESID), "row statistics are produced by the residual epilogue");
+  static_assert(!AM || (OUT_F32 && !RESID), "the arg-max epilogue rides on the plain fp32 store");
   constexpr int G2_STAGES = g2_stages(LNS);
   constexpr uint32_t TMEM_COLS = 512;  // two 256-column accumulator stages
 
@@ -404,6 +420,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         tc_fence_after();
         constexpr int UNITS = OUT_F32 ? 4 : 2;  // staging rows are 128 B: 32 fp32 or 64 bf16 columns
         constexpr int UCOLS = OUT_F32 ? 32 : 64;
+        float am_best = -INFINITY, am_sum = 0.f;
+        int am_idx = 0x7fffffff;
+        const int am_bump = (AM && am.bump_cols != nullptr && m0 + lane < M) ? __ldg(am.bump_cols + m0 + lane) : -1;
 #pragma unroll 1
         for (int u = 0; u < UNITS; ++u) {
           const int col0 = n0 + u * UCOLS;
@@ -435,6 +454,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
                 a2 = fmaxf(a2, 0.f);
                 a3 = fmaxf(a3, 0.f);
               }
+              if (AM) {
+                const int c = col0 + 4 * g;
+                if (am_bump >= c && am_bump < c + 4) {
+                  a0 += (am_bump == c) ? am.bump : 0.f;
+                  a1 += (am_bump == c + 1) ? am.bump : 0.f;
+                  a2 += (am_bump == c + 2) ? am.bump : 0.f;
+                  a3 += (am_bump == c + 3) ? am.bump : 0.f;
+                }
+                // columns >= N of the last tile do not exist
+                const float x0 = (c < N) ? a0 : -INFINITY, x1 = (c + 1 < N) ? a1 : -INFINITY,
+                            x2 = (c + 2 < N) ? a2 : -INFINITY, x3 = (c + 3 < N) ? a3 : -INFINITY;
+                const float m4 = fmaxf(fmaxf(x0, x1), fmaxf(x2, x3));
+                if (m4 > am_best) {  // strict: an earlier (lower) column keeps equal values
+                  if (am.want_sum) am_sum *= exp2f((am_best - m4) * 1.4426950408889634f);
+                  am_best = m4;
+                  am_idx = c + ((x0 == m4) ? 0 : (x1 == m4) ? 1 : (x2 == m4) ? 2 : 3);
+                }
+                if (am.want_sum) {
+                  const float nb = -am_best * 1.4426950408889634f;
+                  am_sum += (exp2f(fmaf(x0, 1.4426950408889634f, nb)) + exp2f(fmaf(x1, 1.4426950408889634f, nb))) +
+                            (exp2f(fmaf(x2, 1.4426950408889634f, nb)) + exp2f(fmaf(x3, 1.4426950408889634f, nb)));
+                }
+              }
               *reinterpret_cast<float4*>(rowp + ((g ^ swz) << 4)) = make_float4(a0, a1, a2, a3);
             }
           } else {
@@ -465,6 +507,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
           }
           sbuf ^= 1;
         }
+        if (AM && m0 + lane < M)
+          am.partial[(size_t)(m0 + lane) * am.chunks + (n0 >> 7)] =
+              make_float4(am_best, __int_as_float(am_idx), am_sum, 0.f);
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
@@ -479,15 +524,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
   }
 }
 
-template <bool OUT_F32, bool RESID, bool LNS>
+template <bool OUT_F32, bool RESID, bool LNS, bool AM = false>
 static int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
                         const float* resid, int64_t ldr, void* out, int64_t ldo, int M, int N, int K,
                         int relu, const int* m_limit, int m_limit_mult, const LnStatsIn& ln_in,
                         void* out_bf16, int64_t ldob, float* stats_out, int ab_f16, int splits,
-                        int split_rows, cudaStream_t stream) {
+                        int split_rows, cudaStream_t stream, const ArgmaxEpi* am_in = nullptr) {
   constexpr int SMEM = g2_smem(LNS);
   static_assert(SMEM <= 232448, "shared memory budget exceeded");
-  auto kern = gemm2_kernel<OUT_F32, RESID, LNS>;
+  auto kern = gemm2_kernel<OUT_F32, RESID, LNS, AM>;
+  ArgmaxEpi am{};
+  if (am_in != nullptr) am = *am_in;
   static PerDeviceFlag configured;
   if (!configured) {
     FBKST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -530,7 +577,7 @@ static int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, 
                               M, N, K, bias, relu, dbg, m_limit, m_limit_mult, ln_in,
                               reinterpret_cast<float2*>(stats_out),
                               ab_f16 ? idesc_f16_f32(256, G2_BN, 0, 0) : idesc_bf16_f32(256, G2_BN, 0, 0),
-                              splits, split_rows));
+                              splits, split_rows, am));
   return FBKST_OK;
 }
 
@@ -558,6 +605,25 @@ int linear_pair_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw,
                                             m_limit, m_limit_mult, ln_in, nullptr, 0, nullptr, ab_f16, 1, 0, stream);
   return launch_gemm2<false, false, false>(A, lda, W, ldw, bias, nullptr, 0, out, ldo, M, N, K, relu,
                                            m_limit, m_limit_mult, ln_in, nullptr, 0, nullptr, ab_f16, 1, 0, stream);
+}
+
+// fp32 logits + per-row arg-max partials (see ArgmaxEpi): the ctc_fc projection of the inference path
+int linear_pair_argmax(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, float* out,
+                       int64_t ldo, int M, int N, int K, const int* bump_cols, float bump, int want_sum,
+                       float* partial, const int* m_limit, int m_limit_mult, cudaStream_t stream) {
+  LnStatsIn ln_in;
+  ln_in.stats = nullptr;
+  ln_in.parts = 0;
+  ln_in.dim = K;
+  ln_in.eps = 0.f;
+  ArgmaxEpi am;
+  am.partial = reinterpret_cast<float4*>(partial);
+  am.bump_cols = bump_cols;
+  am.bump = bump;
+  am.want_sum = want_sum;
+  am.chunks = (N + 127) / 128;
+  return launch_gemm2<true, false, false, true>(A, lda, W, ldw, bias, nullptr, 0, out, ldo, M, N, K, 0, m_limit,
+                                                m_limit_mult, ln_in, nullptr, 0, nullptr, 0, 1, 0, stream, &am);
 }
 
 // Split-K GEMM for weight gradients: partial[s, m, n] = sum over the s-th slice of K of A[m, k] W[n, k]
@@ -623,4 +689,20 @@ extern "C" int fbkst_linear_wgrad_bf16(const void* gT, int64_t ldg, const void* 
   int rc = linear_pair_splitk(gT, ldg, xT, ldx, workspace, ldo, n_out, k_in, tokens, &sp, split_rows, st);
   if (rc) return rc;
   return fbkst_reduce_sum(workspace, sp, (int64_t)split_rows * ldo, n_out, k_in, ldo, dW, lddw, 1.0f, stream);
+}
+
+/* a9 + a10 step 1 fused: logits = A W^T + bias (fp32, pitch ldo) AND, per row, the arg-max partials of every
+ * 128-column chunk (partial: [M, ceil(N/128)] float4), optionally after adding `bump` to column bump_cols[row].
+ * Follow with fbkst_ctc_argmax_merge.  replaces conv_transformer.py:279 + :282-284 without re-reading the logits. */
+extern "C" int fbkst_linear_argmax_f32(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                                       float* out, int64_t ldo, int M, int N, int K, const int32_t* bump_cols,
+                                       float bump, int want_sum, float* partial, const int32_t* m_limit,
+                                       int m_limit_mult, fbkst_stream_t stream) {
+  using namespace fbkst;
+  FBKST_REQUIRE(A && W && out && partial, "fbkst_linear_argmax_f32: null pointer");
+  FBKST_REQUIRE(M > 0 && N > 0 && K > 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldo % 4 == 0 && ldo >= N,
+                "fbkst_linear_argmax_f32: bad shape / pitch");
+  FBKST_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "fbkst_linear_argmax_f32: out must be 16-byte aligned");
+  return linear_pair_argmax(A, lda, W, ldw, bias, out, ldo, M, N, K, bump_cols, bump, want_sum, partial, m_limit,
+                            m_limit_mult, reinterpret_cast<cudaStream_t>(stream));
 }

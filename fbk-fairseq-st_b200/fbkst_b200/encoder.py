@@ -189,6 +189,12 @@ class CtcProjection(nn.Linear):
             a = ops.cast_bf16(x.reshape(L * B, D))
         return ops.linear(a, w, b, out_dtype=self.logits_dtype).view(L, B, -1)
 
+    def project_argmax(self, x2d, xb, lengths, L, B, want_prob, bump):
+        """Fused path (no forward hooks to honour): logits + frame arg-max from one GEMM (ops.linear_argmax)."""
+        w, b = self._prepared()
+        a = xb if xb is not None else ops.cast_bf16(x2d)
+        return ops.linear_argmax(a, w, b, lengths, L, B, want_prob=want_prob, bump=bump)
+
     def _prepared(self):
         key = (self.weight._version, self.bias._version, self.weight.data_ptr())
         if getattr(self, "_prep_key", None) != key:
@@ -286,6 +292,9 @@ def make_encoder_class(base):
             # graphs (and the activations they own) are per lane: EncoderPipeline keeps one forward in
             # flight per lane/stream and sets this before every launch
             self.graph_lane = 0
+            # benchmark / test logit injection without a forward hook (keeps the fused ctc_fc + arg-max epilogue):
+            # (labels [L, B] int32 device tensor, margin) -> logits[t, b, labels[t, b]] += margin   
+            self.ctc_logit_bump = None
             self._pins = _PinnedPool()  # pinned staging vectors for lengths (H2D sources, D2H results)
 
         # ------------------------------------------------------------------ derived operand formats
@@ -556,7 +565,8 @@ def make_encoder_class(base):
         # ------------------------------------------------------------------------- CUDA graphs
         def _graph_key(self, B, T, Fd, dev):
             hooks = tuple(sorted(self.ctc_fc._forward_hooks)) if self.ctc_compress_out else ()
-            return (B, T, Fd, str(dev), self._prep_key, hooks, self.graph_lane)
+            bump = None if self.ctc_logit_bump is None else (id(self.ctc_logit_bump[0]), self.ctc_logit_bump[1])
+            return (B, T, Fd, str(dev), self._prep_key, hooks, bump, self.graph_lane)
 
         def _replay(self, x_in, len_host, len_dev, B, T, Fd, L):
             """Graph mode (``use_cuda_graph``): the ~90 launches of ``_body`` for one input shape are
@@ -645,16 +655,36 @@ def make_encoder_class(base):
             back: returns (logits, out, new_len, max_new) as device tensors.  Otherwise one D2H copy
             (the new lengths) gives the exact output shape."""
             D = self.embed_dim
-            logits = self.ctc_fc(x.view(L, B, D))  # module call: forward hooks apply
-            V = logits.shape[-1]
-            try:
-                lg = logits.view(L * B, V)
-            except RuntimeError:
-                lg = logits.contiguous().view(L * B, V)
-            if lg.stride(-1) != 1:
-                lg = lg.contiguous()
             want_prob = self.ctc_compress_strategy != "avg"
-            labels, prob = ops.ctc_argmax(lg, lengths, L, B, V, want_prob)
+            fused = (not self.ctc_fc._forward_hooks and not self.ctc_fc._forward_pre_hooks
+                     and self.ctc_fc.logits_dtype == torch.float32)
+            if fused:
+                # ctc_fc on tcgen05 with the arg-max (+ sum exp) folded into its epilogue: the logits are written
+                # once and never re-read (conv_transformer.py:279 + :282-284)
+                pre = getattr(self.ctc_fc, "_bf16_operand", None)
+                self.ctc_fc._bf16_operand = None
+                xb = pre[1] if pre is not None and pre[0] == x.data_ptr() else None
+                bump = None
+                if self.ctc_logit_bump is not None:
+                    bl, bm = self.ctc_logit_bump
+                    if callable(bl):  # per-shape label plans (ragged streams): fn(L, B) -> [L, B] int32
+                        bl = bl(L, B)
+                    if tuple(bl.shape) != (L, B) or bl.dtype != torch.int32 or not bl.is_contiguous():
+                        raise ValueError("fbkst_b200: ctc_logit_bump labels must be a contiguous [L, B] int32 tensor")
+                    bump = (bl.view(L * B), float(bm))
+                lg, labels, prob, _ = self.ctc_fc.project_argmax(x, xb, lengths, L, B, want_prob, bump)
+                V = lg.shape[1]
+                logits = lg.view(L, B, V)
+            else:
+                logits = self.ctc_fc(x.view(L, B, D))  # module call: forward hooks apply
+                V = logits.shape[-1]
+                try:
+                    lg = logits.view(L * B, V)
+                except RuntimeError:
+                    lg = logits.contiguous().view(L * B, V)
+                if lg.stride(-1) != 1:
+                    lg = lg.contiguous()
+                labels, prob = ops.ctc_argmax(lg, lengths, L, B, V, want_prob)
             seg_id, seg_start, weight, new_len, max_new = ops.ctc_segment(
                 labels, prob, lengths, self.ctc_compress_strategy, L, B)
             res = ops.ctc_compress(x, seg_id, seg_start, weight, lengths, new_len, max_new, L, B, out=out)

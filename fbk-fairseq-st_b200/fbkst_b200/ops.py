@@ -172,7 +172,9 @@ def linear(a, w, bias=None, relu=False, residual=None, out_dtype=torch.bfloat16,
         _req(res, torch.float32, "linear.residual")
         ldr = res.stride(0)
     if out is None:
-        ldo = (N + 7) // 8 * 8
+        # rows start on 128-byte lines when N is not already a multiple of 8: the epilogue's 128-byte TMA store
+        # boxes then map to whole lines (V = 8005 logits: pitch 8032 instead of 8008)
+        ldo = N if N % 8 == 0 else ((N + 31) // 32 * 32 if out_dtype == torch.float32 else (N + 63) // 64 * 64)
         out = torch.empty(M, ldo, dtype=out_dtype, device=a.device)
         if ldo != N:
             out = out[:, :N]
@@ -355,6 +357,40 @@ def subsample_lengths(lengths, times=2):
                                       out.data_ptr(), lengths.numel(), int(times), _stream()))
     _count()
     return out
+
+
+def linear_argmax(a, w, bias, lengths, L, B, want_prob=True, want_lse=False, bump=None):
+    """ctc_fc with the frame arg-max folded into the GEMM epilogue.  a [L*B, K] bf16, w [V, K] bf16, bias [V]
+    fp32.  bump=(labels [L*B] int32, margin): logits[row, labels[row]] += margin before store and arg-max.
+    -> (logits [L*B, V] fp32 view of a 128-byte-pitched buffer, labels [L*B] int32, top_prob or None, lse or None)."""
+    lib = _lib.require_device()
+    _req(a, torch.bfloat16, "linear_argmax.a"); _req(w, torch.bfloat16, "linear_argmax.w")
+    _req(lengths, torch.int32, "linear_argmax.lengths")
+    M, K = a.shape
+    V = w.shape[0]
+    if M != L * B or w.shape[1] != K:
+        raise ValueError("fbkst_b200.linear_argmax: shape mismatch")
+    dev = a.device
+    ldo = (V + 31) // 32 * 32
+    out = torch.empty(M, ldo, dtype=torch.float32, device=dev)
+    chunks = (V + 127) // 128
+    partial = torch.empty(M, chunks, 4, dtype=torch.float32, device=dev)
+    bl, bm = (None, 0.0) if bump is None else bump
+    if bl is not None:
+        _req(bl, torch.int32, "linear_argmax.bump labels")
+        if bl.numel() != M:
+            raise ValueError("fbkst_b200.linear_argmax: bump labels must have L*B entries")
+    want_sum = want_prob or want_lse
+    check(lib.fbkst_linear_argmax_f32(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _ptr(bias),
+                                      out.data_ptr(), ldo, M, V, K, _ptr(bl), float(bm), 1 if want_sum else 0,
+                                      partial.data_ptr(), 0, 0, _stream()))
+    labels = torch.empty(M, dtype=torch.int32, device=dev)
+    prob = torch.empty(M, dtype=torch.float32, device=dev) if want_prob else None
+    lse = torch.empty(M, dtype=torch.float32, device=dev) if want_lse else None
+    check(lib.fbkst_ctc_argmax_merge(partial.data_ptr(), chunks, lengths.data_ptr(), labels.data_ptr(), _ptr(prob),
+                                     _ptr(lse), L, B, _stream()))
+    _count(2)
+    return out[:, :V], labels, prob, lse
 
 
 def ctc_argmax(logits, lengths, L, B, V, want_prob=True):

@@ -530,3 +530,45 @@ def test_device_collater_vs_oracle(normalize):
             assert torch.equal(a, r)
         assert torch.equal(got["target"][j], ref["target"][k])
         assert torch.equal(got["net_input"]["prev_output_tokens"][j], ref["net_input"]["prev_output_tokens"][k])
+
+
+# ------------------------------------------------------------- ctc_fc with the fused arg-max epilogue
+@pytest.mark.parametrize("L,B,V,K,want_prob", [(50, 3, 105, 256, True), (120, 4, 1005, 512, True),
+                                                (64, 5, 8005, 512, False), (33, 2, 8005, 512, True)])
+def test_linear_argmax_fused_epilogue(L, B, V, K, want_prob):
+    """logits identical to the plain fp32-output GEMM; labels = arg-max of THOSE logits (bit-exact, lowest
+    index on ties), top probability / log-sum-exp within 1e-4; the built-in bump equals a scatter-add hook."""
+    from fbkst_b200 import ops
+    g = torch.Generator().manual_seed(L + V)
+    a = bf(torch.randn(L * B, K, generator=g)).to(dev())
+    w = bf(torch.randn(V, K, generator=g) / math.sqrt(K)).to(dev())
+    bias = torch.randn(V, generator=g).to(dev())
+    lens = torch.tensor([L] + [max(1, L - 7 * b) for b in range(1, B)], dtype=torch.int32, device=dev())
+    plain = ops.linear(a, w, bias, out_dtype=torch.float32)
+    lg, labels, prob, lse = ops.linear_argmax(a, w, bias, lens, L, B, want_prob=want_prob, want_lse=True)
+    assert torch.equal(lg, plain)
+    valid = (torch.arange(L, device=dev())[:, None] < lens[None, :]).reshape(-1)
+    ref_lab = lg.argmax(-1).to(torch.int32)
+    assert torch.equal(labels[valid], ref_lab[valid]) and (labels[~valid] == -1).all()
+    ref_lse = torch.logsumexp(lg.double(), -1).float()
+    assert (lse[valid] - ref_lse[valid]).abs().max() < 1e-3
+    if want_prob:
+        ref_p = torch.softmax(lg.double(), -1).max(-1).values.float()
+        assert ((prob[valid] - ref_p[valid]).abs() / ref_p[valid]).max() < 1e-3
+    # ties -> lowest index: duplicate the winning weight row under a lower AND a higher index
+    w2 = w.clone()
+    bias2 = bias.clone()
+    top = int(ref_lab[0])
+    lo, hi = (top - 3) % V, (top + 5) % V
+    for j in (lo, hi):
+        w2[j] = w2[top]
+        bias2[j] = bias2[top]
+    _, lab2, _, _ = ops.linear_argmax(a, w2, bias2, lens, L, B, want_prob=False)
+    assert int(lab2[0]) == min(top, lo, hi)
+    # built-in bump == hook semantics
+    plan = torch.randint(0, V, (L * B,), generator=g).to(torch.int32).to(dev())
+    lgb, labb, _, _ = ops.linear_argmax(a, w, bias, lens, L, B, want_prob=False, bump=(plan, 30.0))
+    hooked = plain.clone()
+    hooked.scatter_add_(1, plan.long().unsqueeze(-1), torch.full((L * B, 1), 30.0, device=dev()))
+    assert torch.allclose(lgb, hooked, atol=1e-5)
+    assert torch.equal(labb[valid], plan[valid])

@@ -185,3 +185,30 @@ def test_unbumped_logits_same_logits_contract():
     assert out.src_lengths.cpu().tolist() == [len(s) for s in segs]
     # with random logits nearly every frame is its own run: the compression must not be degenerate
     assert max(len(s) for s in segs) > 300
+
+
+@pytest.mark.parametrize("strategy", ["avg", "weighted"])
+def test_fused_ctc_epilogue_equals_hook_path(strategy):
+    """The bench's logit injection through the fused ctc_fc + arg-max epilogue (enc.ctc_logit_bump) gives
+    exactly the compressed lengths of the forward-hook path and the same outputs (same kernels otherwise)."""
+    cfgb = bench.CONFIGS["cfg2"]
+    model = dict(cfgb["model"], ctc_strategy=strategy, layers=9)
+    lens_in = [1500, 1500, 1203, 997, 640, 333]
+    B, T, Fd = len(lens_in), 1500, 40
+    L = 375
+    enc = _bench_encoder(model)
+    plan = bench.label_plan(L, B, model["vocab"], seed=5)
+    x, lens = bench.make_batch(lens_in, Fd, 31)
+    handle, _ = _device_bump(enc, plan)
+    o_hook = enc(x.cuda(), lens.cuda())
+    handle.remove()
+    enc.ctc_logit_bump = (plan.to(torch.int32).cuda().contiguous(), bench.CTC_MARGIN)
+    o_fused = enc(x.cuda(), lens.cuda())
+    assert torch.equal(o_fused.src_lengths, o_hook.src_lengths)
+    nl = o_hook.src_lengths.tolist()
+    rep = parity_report(o_fused.encoder_out.float().cpu(), o_hook.encoder_out.float().cpu(), nl)
+    assert rep["max_rel"] < 1e-3, rep  # weighted: probabilities from exp2f partials vs the arg-max kernel's
+    assert torch.allclose(o_fused.ctc_out[:, :, :], o_hook.ctc_out, atol=1e-4)
+    enc.use_cuda_graph = True
+    o_graph = enc(x.cuda(), lens)
+    assert torch.equal(o_graph.encoder_out, o_fused.encoder_out)
