@@ -48,4 +48,9 @@ def build_encoder(cfg, state_dict=None, device="cuda:0"):
                                           audio_features=cfg["feat_dim"])
     if state_dict is not None:
         enc.load_state_dict(state_dict, strict=True)
+    # An inference encoder: eval() and frozen parameters.  (As with any nn.Module, a forward with gradients
+    # enabled and parameters that require them builds the differentiable chain -- fbkst_b200.train -- so
+    # callers that want gradients re-enable requires_grad; fairseq's generate / validate run under no_grad.)
+    for p in enc.parameters():
+        p.requires_grad_(False)
     return enc.to(device).eval()

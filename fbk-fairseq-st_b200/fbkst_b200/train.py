@@ -207,6 +207,10 @@ class EncoderTrainFn(torch.autograd.Function):
                 for hook in enc.ctc_fc._forward_hooks.values():  # test / bench logit injection
                     r = hook(enc.ctc_fc, (x2.view(cur_L, B, D),), hooked)
                     hooked = hooked if r is None else r
+                if enc.ctc_logit_bump is not None:  # the inference path's built-in injection, same semantics
+                    bl, bm = enc.ctc_logit_bump
+                    bl = bl(cur_L, B) if callable(bl) else bl
+                    hooked = hooked.scatter_add(2, bl.long().unsqueeze(-1), torch.full_like(hooked[..., :1], float(bm)))
                 lg = hooked.reshape(M, V) if hooked.stride(-1) == 1 else hooked.contiguous().view(M, V)
                 want_prob = enc.ctc_compress_strategy != "avg"
                 labels, prob = ops.ctc_argmax(lg, cur_len, cur_L, B, V, want_prob)

@@ -156,6 +156,8 @@ def test_training_mode_optimises():
                distance_penalty="log", ctc_layer=0, ctc_strategy="avg", dropout=0.1)
     sd = O.init_state_dict(cfg, seed=11)
     enc = build_encoder(cfg, sd).train()
+    for p in enc.parameters():
+        p.requires_grad_(True)
     x, lens = O.synthetic_batch([120, 99, 64], 40, seed=12)
     x, lens = x.cuda(), lens.cuda()
     target = torch.randn(30, 3, 128, device="cuda") * 0.1
