@@ -420,9 +420,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         tc_fence_after();
         constexpr int UNITS = OUT_F32 ? 4 : 2;  // staging rows are 128 B: 32 fp32 or 64 bf16 columns
         constexpr int UCOLS = OUT_F32 ? 32 : 64;
-        float am_best = -INFINITY, am_sum = 0.f;
+        float am_best = -INFINITY, am_sum = 0.f, am_bump_val = 0.f;
         int am_idx = 0x7fffffff;
         const int am_bump = (AM && am.bump_cols != nullptr && m0 + lane < M) ? __ldg(am.bump_cols + m0 + lane) : -1;
+        const bool am_tail = AM && (n0 + 128 > N);
 #pragma unroll 1
         for (int u = 0; u < UNITS; ++u) {
           const int col0 = n0 + u * UCOLS;
@@ -455,16 +456,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
                 a3 = fmaxf(a3, 0.f);
               }
               if (AM) {
+                // running (max, first arg-max[, sum exp]) of this row over the warp's columns.  ~1.5 instructions
+                // per element: the max changes O(log n) times per row, so the update branch is rare.  The logit
+                // bump and the columns >= N of the last tile are handled outside this loop.
                 const int c = col0 + 4 * g;
-                if (am_bump >= c && am_bump < c + 4) {
-                  a0 += (am_bump == c) ? am.bump : 0.f;
-                  a1 += (am_bump == c + 1) ? am.bump : 0.f;
-                  a2 += (am_bump == c + 2) ? am.bump : 0.f;
-                  a3 += (am_bump == c + 3) ? am.bump : 0.f;
+                float x0 = a0, x1 = a1, x2 = a2, x3 = a3;
+                if (am_tail) {  // tile-uniform: only the last column tile
+                  x0 = (c < N) ? a0 : -INFINITY;
+                  x1 = (c + 1 < N) ? a1 : -INFINITY;
+                  x2 = (c + 2 < N) ? a2 : -INFINITY;
+                  x3 = (c + 3 < N) ? a3 : -INFINITY;
                 }
-                // columns >= N of the last tile do not exist
-                const float x0 = (c < N) ? a0 : -INFINITY, x1 = (c + 1 < N) ? a1 : -INFINITY,
-                            x2 = (c + 2 < N) ? a2 : -INFINITY, x3 = (c + 3 < N) ? a3 : -INFINITY;
                 const float m4 = fmaxf(fmaxf(x0, x1), fmaxf(x2, x3));
                 if (m4 > am_best) {  // strict: an earlier (lower) column keeps equal values
                   if (am.want_sum) am_sum *= exp2f((am_best - m4) * 1.4426950408889634f);
@@ -476,6 +478,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
                   am_sum += (exp2f(fmaf(x0, 1.4426950408889634f, nb)) + exp2f(fmaf(x1, 1.4426950408889634f, nb))) +
                             (exp2f(fmaf(x2, 1.4426950408889634f, nb)) + exp2f(fmaf(x3, 1.4426950408889634f, nb)));
                 }
+                if (am_bump >= c && am_bump < c + 4)  // remember the un-bumped logit of the bump column
+                  am_bump_val = (am_bump == c) ? a0 : (am_bump == c + 1) ? a1 : (am_bump == c + 2) ? a2 : a3;
               }
               *reinterpret_cast<float4*>(rowp + ((g ^ swz) << 4)) = make_float4(a0, a1, a2, a3);
             }
@@ -499,6 +503,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
                              pack_bf16x2(a[6], a[7]));
             }
           }
+          if (AM && am_bump >= col0 && am_bump < col0 + UCOLS) {  // the stored logit carries the bump as well
+            const int j = am_bump - col0;
+            float* e = reinterpret_cast<float*>(rowp + (((j >> 2) ^ swz) << 4)) + (j & 3);
+            *e += am.bump;
+          }
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0 && !(dbg & 1)) {
@@ -507,9 +516,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
           }
           sbuf ^= 1;
         }
-        if (AM && m0 + lane < M)
+        if (AM && m0 + lane < M) {
+          if (am_bump >= n0 && am_bump < n0 + 128 && am_bump < N) {
+            // fold the bumped logit in: value v = orig + bump at column am_bump (orig is already counted)
+            const float v = am_bump_val + am.bump;
+            if (am.want_sum) {
+              const float mx = fmaxf(am_best, v);
+              am_sum = am_sum * exp2f((am_best - mx) * 1.4426950408889634f) -
+                       exp2f((am_bump_val - mx) * 1.4426950408889634f) + exp2f((v - mx) * 1.4426950408889634f);
+            }
+            if (v > am_best || (v == am_best && am_bump < am_idx)) {
+              am_best = v;
+              am_idx = am_bump;
+            }
+          }
           am.partial[(size_t)(m0 + lane) * am.chunks + (n0 >> 7)] =
               make_float4(am_best, __int_as_float(am_idx), am_sum, 0.f);
+        }
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
