@@ -656,8 +656,12 @@ def make_encoder_class(base):
             (the new lengths) gives the exact output shape."""
             D = self.embed_dim
             want_prob = self.ctc_compress_strategy != "avg"
+            # fused epilogue: measured 303 us against 217 (GEMM) + 116 (arg-max pass) at cfg2 for `avg`; with the
+            # sum of exponentials (weighted / softmax) the 8 epilogue warps become the bottleneck (374 us against
+            # 217 + 127), so those strategies keep the separate pass (scripts/bench_ctc_fc.py, profiles/r02j)
             fused = (not self.ctc_fc._forward_hooks and not self.ctc_fc._forward_pre_hooks
-                     and self.ctc_fc.logits_dtype == torch.float32)
+                     and self.ctc_fc.logits_dtype == torch.float32 and not want_prob
+                     and os.environ.get("FBKST_CTC_FUSED", "1") != "0")
             if fused:
                 # ctc_fc on tcgen05 with the arg-max (+ sum exp) folded into its epilogue: the logits are written
                 # once and never re-read (conv_transformer.py:279 + :282-284)

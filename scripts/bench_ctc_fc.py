@@ -36,3 +36,11 @@ timeit("ctc_argmax on fp32 logits (weighted)", lambda: ops.ctc_argmax(lg, lens, 
 timeit("fused ctc_fc + arg-max (avg)", lambda: ops.linear_argmax(a, w, bias, lens, L, B, want_prob=False))
 timeit("fused ctc_fc + arg-max (avg, bump)", lambda: ops.linear_argmax(a, w, bias, lens, L, B, want_prob=False, bump=(plan, 30.0)))
 timeit("fused ctc_fc + arg-max (weighted, bump)", lambda: ops.linear_argmax(a, w, bias, lens, L, B, want_prob=True, bump=(plan, 30.0)))
+
+# write-only / read-only HBM bandwidth for context (the fp32 logits are a 771 MB pure write)
+buf = torch.empty(1 << 30, dtype=torch.uint8, device="cuda")
+timeit("fill 1 GiB (write only)", lambda: buf.fill_(1))
+src = torch.empty(1 << 28, dtype=torch.float32, device="cuda")
+timeit("sum 1 GiB (read only)", lambda: src.sum())
+dst = torch.empty_like(src)
+timeit("copy 1 GiB -> 1 GiB (read + write)", lambda: dst.copy_(src))
