@@ -424,27 +424,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         int am_idx = 0x7fffffff;
         const int am_bump = (AM && am.bump_cols != nullptr && m0 + lane < M) ? __ldg(am.bump_cols + m0 + lane) : -1;
         const bool am_tail = AM && (n0 + 128 > N);
-        // fp32 output: 4 units of 32 columns.  The TMEM read of unit u + 1 is issued before unit u is
-        // processed (two register buffers, loop fully unrolled so that they alternate statically): the
-        // first version read, waited and processed one unit at a time and spent most of its issue slots
-        // stalled on the tcgen05.ld round trip (ncu r02_ctc_fc: long-scoreboard 5.8 per issue, tensor pipe
-        // 53 % on the ctc_fc shape against 83 % for the bf16-output epilogue).
-        uint32_t va[32], vb[32];
-        if (OUT_F32) tmem_ld32(taddr, va);
-#pragma unroll
+#pragma unroll 1
         for (int u = 0; u < UNITS; ++u) {
           const int col0 = n0 + u * UCOLS;
           if (col0 >= N) break;
-          uint32_t(&v0)[32] = (OUT_F32 && (u & 1)) ? vb : va;
-          uint32_t(&v1)[32] = vb;  // bf16 output: second half of the unit
-          if (!OUT_F32) {
-            tmem_ld32(taddr + u * UCOLS, va);
-            tmem_ld32(taddr + u * UCOLS + 32, vb);
-          }
+          uint32_t v0[32], v1[32];
+          tmem_ld32(taddr + u * UCOLS, v0);
+          if (!OUT_F32) tmem_ld32(taddr + u * UCOLS + 32, v1);
           if (lane == 0) tma_store_wait_read<1>();  // the buffer used two units ago is free again
           tmem_ld_wait();
-          if (OUT_F32 && u + 1 < UNITS && col0 + UCOLS < N)
-            tmem_ld32(taddr + (u + 1) * UCOLS, (u & 1) ? va : vb);  // prefetch the next unit
           if (u == UNITS - 1 || col0 + UCOLS >= N) {  // all TMEM reads of this tile done: release it
             tc_fence_before();
             __syncwarp();
