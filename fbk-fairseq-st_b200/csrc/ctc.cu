@@ -280,36 +280,44 @@ __global__ void __launch_bounds__(256)
 }
 
 // Merge of the per-chunk arg-max partials the ctc_fc GEMM epilogue leaves (gemm2_tcgen05.cu ArgmaxEpi): one
-// thread per row folds its ceil(V/128) partials in column order (strict '>' keeps the lowest index).
+// WARP per row: lane l folds chunks l, l + 32, ... (coalesced 16-byte loads, increasing column order: strict
+// '>' keeps the lowest index), then a (value, index) butterfly.  (One thread per row walked 63 strided float4
+// loads: 41 us at cfg2 in the ncu launch list, r02k.)
 __global__ void __launch_bounds__(256)
     ctc_argmax_merge_kernel(const float4* __restrict__ partial, int chunks, const int* __restrict__ lengths,
                             int* __restrict__ labels, float* __restrict__ top_prob, float* __restrict__ lse,
                             int rows, int B) {
-  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
   const int t = row / B, b = row - t * B;
   if (t >= __ldg(lengths + b)) {
-    labels[row] = -1;
-    if (top_prob) top_prob[row] = 0.0f;
-    if (lse) lse[row] = 0.0f;
+    if (lane == 0) {
+      labels[row] = -1;
+      if (top_prob) top_prob[row] = 0.0f;
+      if (lse) lse[row] = 0.0f;
+    }
     return;
   }
-  float best = -INFINITY, sum = 0.0f;
-  int idx = 0x7fffffff;
+  const bool want_sum = top_prob != nullptr || lse != nullptr;
+  ArgMax a{-INFINITY, 0x7fffffff, 0.0f};
   const float4* p = partial + (size_t)row * chunks;
-  for (int c = 0; c < chunks; ++c) {
+  for (int c = lane; c < chunks; c += 32) {
     const float4 v = __ldg(p + c);
-    if (v.x > best) {
-      sum = sum * __expf(best - v.x) + v.z;
-      best = v.x;
-      idx = __float_as_int(v.y);
-    } else if (v.x != -INFINITY) {
-      sum += v.z * __expf(v.x - best);
-    }
+    argmax_merge(a, v.x, __float_as_int(v.y), v.z, want_sum);
   }
-  labels[row] = idx;
-  if (top_prob) top_prob[row] = 1.0f / sum;
-  if (lse) lse[row] = best + logf(sum);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float v = __shfl_xor_sync(0xffffffffu, a.v, o);
+    const int i = __shfl_xor_sync(0xffffffffu, a.i, o);
+    const float s2 = __shfl_xor_sync(0xffffffffu, a.s, o);
+    argmax_merge(a, v, i, s2, want_sum);
+  }
+  if (lane == 0) {
+    labels[row] = a.i;
+    if (top_prob) top_prob[row] = 1.0f / a.s;
+    if (lse) lse[row] = a.v + logf(a.s);
+  }
 }
 
 // One CTA per utterance.  smem: lab[L] | start[L+1] ints.
@@ -628,7 +636,7 @@ extern "C" int fbkst_ctc_argmax_merge(const float* partial, int chunks, const in
   FBKST_REQUIRE(partial && lengths && labels && chunks > 0 && L > 0 && B > 0, "fbkst_ctc_argmax_merge: bad arguments");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int rows = L * B;
-  ctc_argmax_merge_kernel<<<(rows + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float4*>(partial), chunks,
+  ctc_argmax_merge_kernel<<<(rows + 7) / 8, 256, 0, st>>>(reinterpret_cast<const float4*>(partial), chunks,
                                                              lengths, labels, top_prob, lse, rows, B);
   FBKST_CHECK_CUDA(cudaGetLastError());
   return FBKST_OK;

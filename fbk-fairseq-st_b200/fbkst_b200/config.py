@@ -30,13 +30,13 @@ def make_args(cfg):
     a.ctc_compress_strategy = cfg.get("ctc_strategy", "avg")
     a.ctc_encoder_layer = cfg.get("ctc_layer", 0)
     a.criterion = "ctc_multi_loss"
-    a.max_source_positions = 100000
+    a.max_source_positions = cfg.get("max_source_positions", 100000)
     a.encoder_layerdrop = 0.0
     a.dropout = cfg.get("dropout", 0.1)
     a.attention_dropout = cfg.get("attention_dropout", 0.1)  # base_architecture defaults (:432-433)
     a.relu_dropout = cfg.get("relu_dropout", 0.1)
     a.encoder_normalize_before = True
-    a.encoder_learned_pos = False
+    a.encoder_learned_pos = bool(cfg.get("learned_pos", False))
     a.no_token_positional_embeddings = False
     a.layernorm_embedding = False
     return a

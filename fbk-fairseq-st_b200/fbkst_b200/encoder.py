@@ -163,9 +163,16 @@ class _SinusoidalParams(nn.Module):
 
 
 class _PositionalParams(nn.Module):
-    def __init__(self):
+    """``PositionalEmbeddingAudio`` (modules/positional_embedding_audio.py:13-19) as a parameter container:
+    sinusoidal (one persistent buffer) or, with ``--encoder-learned-pos``, an ``nn.Embedding`` with
+    ``padding_idx = 0`` exactly like ``LearnedPositionalEmbedding(num_embeddings, dim, 0)`` (same state_dict key
+    ``embed_positions.embeddings.weight``, same default initialisation).  Both are read the same way by the
+    kernel: row t + 1 for frame t < length, the padding row 0 beyond (fairseq/utils.py:192-202)."""
+
+    def __init__(self, learned=False, num_embeddings=0, dim=0):
         super().__init__()
-        self.embeddings = _SinusoidalParams()
+        self.learned = learned
+        self.embeddings = nn.Embedding(num_embeddings, dim, padding_idx=0) if learned else _SinusoidalParams()
 
 
 class CtcProjection(nn.Linear):
@@ -235,8 +242,6 @@ def make_encoder_class(base):
             self.log_penalty = penalty == "log"
             if not getattr(args, "encoder_normalize_before", True):
                 raise NotImplementedError("fbkst_b200: only pre-LayerNorm encoders (all reference archs)")
-            if getattr(args, "encoder_learned_pos", False):
-                raise NotImplementedError("fbkst_b200: learned positional embeddings are not supported")
 
             self.convolutions = nn.ModuleList()
             cin = 1
@@ -262,7 +267,8 @@ def make_encoder_class(base):
             self.feat_out = flat
             self.fc3 = _linear(flat * cin, D)
             self.embed_positions = None if getattr(args, "no_token_positional_embeddings", False) \
-                else _PositionalParams()
+                else _PositionalParams(bool(getattr(args, "encoder_learned_pos", False)),
+                                       int(getattr(args, "max_source_positions", 0) or 0), D)
             self.encoder_layerdrop = getattr(args, "encoder_layerdrop", 0.0)
             self.layers = nn.ModuleList(
                 [_EncoderLayerParams(D, args.encoder_ffn_embed_dim, self.log_penalty)
@@ -347,6 +353,12 @@ def make_encoder_class(base):
             return P
 
         def _positions(self, rows, device):
+            if self.embed_positions.learned:  # --encoder-learned-pos: the embedding matrix IS the table
+                w = self.embed_positions.embeddings.weight
+                if w.shape[0] < rows:
+                    raise ValueError("fbkst_b200: %d positions needed but --max-source-positions is %d"
+                                     % (rows, w.shape[0]))
+                return w.detach().float().contiguous()
             t = self._pos_table
             if t is None or t.shape[0] < rows or t.device != device:
                 t = ops.sinusoidal_table(max(rows, 1024), self.embed_dim, device)

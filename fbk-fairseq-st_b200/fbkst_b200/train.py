@@ -350,6 +350,9 @@ def forward_train(enc, src_tokens, src_lengths, return_all_hiddens):
         raise NotImplementedError("fbkst_b200: LayerDrop is not supported in training (--encoder-layerdrop 0)")
     if enc.layernorm_embedding is not None:
         raise NotImplementedError("fbkst_b200: layernorm_embedding is not supported in training")
+    if enc.embed_positions is not None and enc.embed_positions.learned:
+        raise NotImplementedError("fbkst_b200: learned positional embeddings are inference-only (no reference "
+                                  "architecture enables --encoder-learned-pos)")
     len_host = src_lengths.tolist()
     # one 63-bit seed per step from torch's CPU generator (fairseq re-seeds it per update: trainer.py:655-661)
     seed = int(torch.empty((), dtype=torch.int64).random_().item()) if enc.training else 0

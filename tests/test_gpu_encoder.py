@@ -291,3 +291,34 @@ def test_encoder_full_size_properties():
         # not bit for bit: the key tiles of an utterance are split between the two softmax groups
         # by their position in the CTA's tile stream, which moves with the batch slot
         assert rel_err(o3.encoder_out[:n, k], o1.encoder_out[:n, b]) < 5e-3, (k, b)
+
+
+def test_learned_positional_embeddings():
+    """--encoder-learned-pos (positional_embedding_audio.py:13-17): the embedding matrix is read like the
+    sinusoidal table (row t+1 inside the utterance, padding row 0 beyond).  Checked against the oracle with the
+    positional term swapped for the same lookup."""
+    import torch.nn.functional as F
+    cfg = dict(embed_dim=128, ffn_dim=256, heads=2, layers=2, conv_channels=64, feat_dim=40, vocab=64,
+               distance_penalty="log", ctc_layer=0, ctc_strategy="avg", learned_pos=True, max_source_positions=64)
+    sd = O.init_state_dict(cfg, seed=21)
+    del sd["embed_positions.embeddings._float_tensor"]
+    g = torch.Generator().manual_seed(3)
+    W = torch.randn(64, 128, generator=g) * 0.3
+    W[0] = 0  # padding_idx row
+    sd["embed_positions.embeddings.weight"] = W
+    enc = build_encoder(cfg, sd)
+    assert "embed_positions.embeddings.weight" in enc.state_dict()
+    x, lens = O.synthetic_batch([120, 99, 64], 40, seed=5)
+    out = enc(x.cuda(), lens.cuda())
+    # oracle with the learned lookup in place of the sinusoidal one
+    orig = O.positional_embedding
+    try:
+        def learned(lengths, dim):
+            t = torch.arange(int(lengths.max())).unsqueeze(0)
+            pos = torch.where(t < lengths.unsqueeze(1), t + 1, torch.zeros_like(t))
+            return F.embedding(pos, W)
+        O.positional_embedding = learned
+        ref = O.encoder_forward({k: v for k, v in sd.items() if "embed_positions" not in k}, cfg, x, lens)
+    finally:
+        O.positional_embedding = orig
+    check_against(out, ref, lens)
