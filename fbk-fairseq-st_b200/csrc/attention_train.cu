@@ -17,7 +17,9 @@
 // Recomputing S in the backward (instead of storing P) keeps HBM traffic at the q/k/v/dO level: no L^2 buffer.
 //
 // This is the correctness-first training path: one tile in flight per CTA, two CTAs per SM cover each other's
-// round trips.  Query rows at or beyond the utterance's length get zero output / zero gradient (the reference
+// round trips.  256 threads per CTA: TWO threads per own row (warps w and w + 4 share a TMEM lane quarter),
+// each handling 32 of a tile's 64 columns -- the first version (one thread per row, 8 warps per SM) was bound by
+// the latency of its dependent instruction chains (253 us per cfg2 layer for FWD, tensor pipe 5 %: r02k ncu).  Query rows at or beyond the utterance's length get zero output / zero gradient (the reference
 // computes finite garbage there that nothing reads: the loss masks padded positions).
 #include <math.h>
 
@@ -73,7 +75,7 @@ __device__ __forceinline__ void tr_store_chunk(uint8_t* tile, int row, int chunk
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256, 2)
     attn_train_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
                       const __grid_constant__ CUtensorMap tmDO128, const __grid_constant__ CUtensorMap tmDO64,
                       const AttnTrainParams p) {
@@ -81,12 +83,14 @@ __global__ void __launch_bounds__(128)
   const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
   const int r0 = blockIdx.x * TR_OWN;
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int rl = tid & 127;   // own row inside the block == TMEM lane
+  const int ch = tid >> 7;    // which 32 of a tile's 64 columns this thread handles
   const int len = min(__ldg(p.lengths + b), L);
-  const int row = r0 + tid;  // this thread's own row (query for FWD / DQ, key for DKV)
+  const int row = r0 + rl;  // this thread's own row (query for FWD / DQ, key for DKV)
 
   // ---- blocks with nothing to compute: defined zeros, no pipeline (CTA-uniform branch)
   if (r0 >= len) {
-    if (row < L) {
+    if (row < L && ch == 0) {
       if (MODE == TR_FWD) {
         uint4* op = reinterpret_cast<uint4*>(p.out + ((size_t)row * B + b) * D + h * TR_HD);
 #pragma unroll
@@ -124,7 +128,8 @@ __global__ void __launch_bounds__(128)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
   float* sLse = reinterpret_cast<float*>(bars + 8);   // [2][64]   (DKV)
   float* sDelta = sLse + 128;                         // [2][64]   (DKV)
-  float* sLut = sDelta + 128;                         // [2 * lut_off]
+  float* sXch = sDelta + 128;                         // [2][2][128]  (FWD: (m | l) of the two column halves)
+  float* sLut = sXch + 512;                           // [2 * lut_off]
   const int lut_off = ((L + 127) / 128) * 128;        // entry o <-> (k - q) = o - lut_off
 
   if (tid == 0) {
@@ -147,7 +152,7 @@ __global__ void __launch_bounds__(128)
     tmem_relinquish();
   }
   // penalty LUT in log2 domain, negated: sLut[o] = -log2(max(1, |o - lut_off|))  (conv_transformer_layer.py:26-27)
-  for (int o = tid; o < 2 * lut_off; o += 128) {
+  for (int o = tid; o < 2 * lut_off; o += 256) {
     const int d = abs(o - lut_off);
     sLut[o] = (p.log_penalty && d > 1) ? -__log2f((float)d) : 0.0f;
   }
@@ -155,11 +160,11 @@ __global__ void __launch_bounds__(128)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
-  const uint32_t tS = tmem_base + lane_addr;            // columns   0.. 63: S (or S^T)
-  const uint32_t tP = tmem_base + lane_addr + 64;       // columns  64..127: dP (or dP^T)
-  const uint32_t tA0 = tmem_base + lane_addr + 128;     // columns 128..191: accumulator 0 (O / dQ / dV)
-  const uint32_t tA1 = tmem_base + lane_addr + 192;     // columns 192..255: accumulator 1 (dK)
+  const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+  const uint32_t tS = tmem_base + lane_addr + ch * 32;        // columns   0.. 63: S (or S^T); this thread's half
+  const uint32_t tP = tmem_base + lane_addr + 64 + ch * 32;   // columns  64..127: dP (or dP^T)
+  const uint32_t tA0 = tmem_base + lane_addr + 128 + ch * 32; // columns 128..191: accumulator 0 (O / dQ / dV)
+  const uint32_t tA1 = tmem_base + lane_addr + 192 + ch * 32; // columns 192..255: accumulator 1 (dK)
 
   constexpr uint32_t IDESC_S = idesc_bf16_f32(TR_OWN, TR_OTH, 0, 0);
   constexpr uint32_t IDESC_ACC = idesc_bf16_f32(TR_OWN, TR_HD, 0, 1);
@@ -229,33 +234,44 @@ __global__ void __launch_bounds__(128)
       mbar_wait(bar_s, n_s & 1);
       ++n_s;
       tc_fence_after();
-      float s2[64];
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
+      float s2[32];
+      {
         uint32_t v[32];
-        tmem_ld32(tS + half * 32, v);
+        tmem_ld32(tS, v);
         tmem_ld_wait();
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
-          const int k = j * TR_OTH + half * 32 + c;
+          const int k = j * TR_OTH + ch * 32 + c;
           const float x = fmaf(__uint_as_float(v[c]), p.scale_log2e, sLut[k - row + lut_off]);
-          s2[half * 32 + c] = (k < len) ? x : -INFINITY;
+          s2[c] = (k < len) ? x : -INFINITY;
         }
       }
       float tm = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 64; ++c) tm = fmaxf(tm, s2[c]);
-      const float m_new = fmaxf(m_run, tm);  // finite: every tile j < n_oth holds at least one valid key
-      float acc = 0.0f;
+      for (int c = 0; c < 32; ++c) tm = fmaxf(tm, s2[c]);
+      const float m_new = fmaxf(m_run, tm);
+      if (m_new != -INFINITY) {  // this half of the tile holds at least one valid key (or an earlier one did)
+        float acc = 0.0f;
 #pragma unroll
-      for (int c = 0; c < 64; ++c) acc += tr_ex2(s2[c] - m_new);
-      l_run = l_run * tr_ex2(m_run - m_new) + acc;
-      m_run = m_new;
+        for (int c = 0; c < 32; ++c) acc += tr_ex2(s2[c] - m_new);
+        l_run = l_run * tr_ex2(m_run - m_new) + acc;
+        m_run = m_new;
+      }
       tc_fence_before();
       __syncthreads();  // every thread has read S(j) before the next S-type MMA overwrites it
     }
-    lse2 = m_run + __log2f(l_run);
-    if (row < L) p.lse[(size_t)bh * L + row] = lse2;
+    // combine the two column halves of the row (the other thread of the row is tid ^ 128)
+    sXch[(ch * 2 + 0) * 128 + rl] = m_run;
+    sXch[(ch * 2 + 1) * 128 + rl] = l_run;
+    __syncthreads();
+    {
+      const float m_o = sXch[((ch ^ 1) * 2 + 0) * 128 + rl], l_o = sXch[((ch ^ 1) * 2 + 1) * 128 + rl];
+      const float mm = fmaxf(m_run, m_o);  // finite: key 0 is always valid
+      const float a_me = (m_run == -INFINITY) ? 0.0f : l_run * tr_ex2(m_run - mm);
+      const float a_ot = (m_o == -INFINITY) ? 0.0f : l_o * tr_ex2(m_o - mm);
+      lse2 = mm + __log2f(a_me + a_ot);
+    }
+    if (row < L && ch == 0) p.lse[(size_t)bh * L + row] = lse2;
   } else if (MODE == TR_DQ) {
     if (row < L) {
       lse2 = p.lse[(size_t)bh * L + row];
@@ -299,31 +315,30 @@ __global__ void __launch_bounds__(128)
     tc_fence_after();
 
     // ---- TMEM -> registers -> probabilities / gradients (8 columns at a time)
-    float t0[64], t1[64];
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
+    float t0[32], t1[32];
+    {
       uint32_t v[32], w[32];
-      tmem_ld32(tS + half * 32, v);
-      if (MODE != TR_FWD) tmem_ld32(tP + half * 32, w);
+      tmem_ld32(tS, v);
+      if (MODE != TR_FWD) tmem_ld32(tP, w);
       tmem_ld_wait();
 #pragma unroll
       for (int c = 0; c < 32; ++c) {
-        const int cc = half * 32 + c;
+        const int cc = ch * 32 + c;
         const int o = j * TR_OTH + cc;  // other-side index: key (FWD / DQ) or query (DKV)
         if (MODE == TR_DKV) {
           const float x = fmaf(__uint_as_float(v[c]), p.scale_log2e, sLut[row - o + lut_off]);
           const float pr = own_valid ? tr_ex2(x - sLse[st * 64 + cc]) : 0.0f;
           const float keep = tr_keep(p, bh, o, row);
-          t0[cc] = pr * keep;
-          t1[cc] = pr * (__uint_as_float(w[c]) * keep - sDelta[st * 64 + cc]) * p.scale;
+          t0[c] = pr * keep;
+          t1[c] = pr * (__uint_as_float(w[c]) * keep - sDelta[st * 64 + cc]) * p.scale;
         } else {
           const float x = fmaf(__uint_as_float(v[c]), p.scale_log2e, sLut[o - row + lut_off]);
           const float pr = (o < len) ? tr_ex2(x - lse2) : 0.0f;
           const float keep = tr_keep(p, bh, row, o);
           if (MODE == TR_FWD)
-            t0[cc] = pr * keep;
+            t0[c] = pr * keep;
           else
-            t0[cc] = own_valid ? pr * (__uint_as_float(w[c]) * keep - dlt) * p.scale : 0.0f;
+            t0[c] = own_valid ? pr * (__uint_as_float(w[c]) * keep - dlt) * p.scale : 0.0f;
         }
       }
     }
@@ -335,15 +350,15 @@ __global__ void __launch_bounds__(128)
     }
     if (tid == 0 && j + 1 < n_oth) TR_LOAD_OTHER(j + 1, (ld_base + j + 1) & 1, true);
 #pragma unroll
-    for (int ch = 0; ch < 8; ++ch) {
+    for (int k = 0; k < 4; ++k) {  // this thread's 4 of the row's 8 sixteen-byte chunks
       float a[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) a[e] = t0[ch * 8 + e];
-      tr_store_chunk(sT0, tid, ch, a);
+      for (int e = 0; e < 8; ++e) a[e] = t0[k * 8 + e];
+      tr_store_chunk(sT0, rl, ch * 4 + k, a);
       if (MODE == TR_DKV) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) a[e] = t1[ch * 8 + e];
-        tr_store_chunk(sT1, tid, ch, a);
+        for (int e = 0; e < 8; ++e) a[e] = t1[k * 8 + e];
+        tr_store_chunk(sT1, rl, ch * 4 + k, a);
       }
     }
     fence_proxy_async_smem();
@@ -371,7 +386,7 @@ __global__ void __launch_bounds__(128)
   mbar_wait(bar_acc, n_acc & 1);
   tc_fence_after();
 
-  // ---- epilogue: accumulators -> global (thread <-> own row; 128 contiguous bytes per row and tensor)
+  // ---- epilogue: accumulators -> global (two threads per own row, 32 columns = 64 contiguous bytes each)
   {
     uint32_t v[32];
     const size_t base = (MODE == TR_FWD) ? ((size_t)row * B + b) * D + h * TR_HD
@@ -380,22 +395,19 @@ __global__ void __launch_bounds__(128)
     for (int acc = 0; acc < (MODE == TR_DKV ? 2 : 1); ++acc) {
       // DKV: accumulator 0 = dV -> column block 2D, accumulator 1 = dK -> column block D
       const size_t off = (MODE == TR_DKV) ? (acc == 0 ? 2 * (size_t)D : (size_t)D) : 0;
+      tmem_ld32(acc == 0 ? tA0 : tA1, v);
+      tmem_ld_wait();
+      if (row < L) {
+        const bool zero = (MODE == TR_DQ) && !own_valid;  // padded query rows: zero gradient
+        uint4* op = reinterpret_cast<uint4*>(p.out + base + off + ch * 32);
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        tmem_ld32((acc == 0 ? tA0 : tA1) + half * 32, v);
-        tmem_ld_wait();
-        if (row < L) {
-          const bool zero = (MODE == TR_DQ) && !own_valid;  // padded query rows: zero gradient
-          uint4* op = reinterpret_cast<uint4*>(p.out + base + off + half * 32);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int o = c * 8;
-            op[c] = zero ? make_uint4(0, 0, 0, 0)
-                         : make_uint4(pack_bf16x2(__uint_as_float(v[o]), __uint_as_float(v[o + 1])),
-                                      pack_bf16x2(__uint_as_float(v[o + 2]), __uint_as_float(v[o + 3])),
-                                      pack_bf16x2(__uint_as_float(v[o + 4]), __uint_as_float(v[o + 5])),
-                                      pack_bf16x2(__uint_as_float(v[o + 6]), __uint_as_float(v[o + 7])));
-          }
+        for (int c = 0; c < 4; ++c) {
+          const int o = c * 8;
+          op[c] = zero ? make_uint4(0, 0, 0, 0)
+                       : make_uint4(pack_bf16x2(__uint_as_float(v[o]), __uint_as_float(v[o + 1])),
+                                    pack_bf16x2(__uint_as_float(v[o + 2]), __uint_as_float(v[o + 3])),
+                                    pack_bf16x2(__uint_as_float(v[o + 4]), __uint_as_float(v[o + 5])),
+                                    pack_bf16x2(__uint_as_float(v[o + 6]), __uint_as_float(v[o + 7])));
         }
       }
     }
@@ -411,7 +423,7 @@ __global__ void __launch_bounds__(128)
 static inline int attn_train_smem(int L) {
   const int lut_off = ((L + 127) / 128) * 128;
   return 2 * TR_OWN_BYTES + 4 * TR_OTH_BYTES + 2 * TR_OWN_BYTES + 64 /*barriers*/ + 4 * 128 * 2 /*stats*/ +
-         4 * 2 * lut_off + 1024 /*align*/;
+         4 * 512 /*(m, l) exchange*/ + 4 * 2 * lut_off + 1024 /*align*/;
 }
 
 static uint32_t mix_key(uint64_t seed, int site) {
@@ -478,11 +490,11 @@ static int attn_train_launch(int mode, const void* qkv, const void* dO, void* ou
   }
   dim3 grid((L + TR_OWN - 1) / TR_OWN, B * H);
   if (mode == TR_FWD)
-    attn_train_kernel<TR_FWD><<<grid, 128, smem, st>>>(tm128, tm64, tmdo128, tmdo64, p);
+    attn_train_kernel<TR_FWD><<<grid, 256, smem, st>>>(tm128, tm64, tmdo128, tmdo64, p);
   else if (mode == TR_DQ)
-    attn_train_kernel<TR_DQ><<<grid, 128, smem, st>>>(tm128, tm64, tmdo128, tmdo64, p);
+    attn_train_kernel<TR_DQ><<<grid, 256, smem, st>>>(tm128, tm64, tmdo128, tmdo64, p);
   else
-    attn_train_kernel<TR_DKV><<<grid, 128, smem, st>>>(tm128, tm64, tmdo128, tmdo64, p);
+    attn_train_kernel<TR_DKV><<<grid, 256, smem, st>>>(tm128, tm64, tmdo128, tmdo64, p);
   FBKST_CHECK_CUDA(cudaGetLastError());
   return FBKST_OK;
 }
