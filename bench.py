@@ -834,10 +834,11 @@ def run_ragged(args, rank, world, local_rank):
     rng = random.Random(20210421)  # the same pool on every rank
     pool = []
     want = world * args.steps
-    while True:
-        pool += [rng.randint(200, 3000) for _ in range(64 * world)]
+    pool_for = max(world, 8) * args.steps  # the SAME pool at every world size <= 8: the length mix per rank
+    while True:                            # does not depend on N (weak scaling compares like with like)
+        pool += [rng.randint(200, 3000) for _ in range(512)]
         batches = sharding.bucket_by_length(pool, MAXF, pad_multiple=PAD)
-        if len(batches) >= want + 1:  # + 1: the last (shortest, partly filled) batch is dropped
+        if len(batches) >= pool_for + 1:  # + 1: the last (shortest, partly filled) batch is dropped
             break
     # `want` batches spread over the whole length range (every k-th of the sorted batch list)
     stride = (len(batches) - 1) // want
