@@ -907,6 +907,8 @@ def run_ragged(args, rank, world, local_rank):
     barrier()
     gc.enable()
     my_ms = ev0.elapsed_time(ev1)
+    last_lens = dev_batches[-1][1].tolist()
+    ratio_last = float(out.src_lengths.sum().item()) / sum(((n + 1) // 2 + 1) // 2 for n in last_lens)
     launches = (ops.LAUNCHES - launches0) // max(1, len(dev_batches))
     clocks = sampler.stop() if sampler else None
     stats = torch.tensor([my_ms, frames, padded], dtype=torch.float64, device=dev)
@@ -932,6 +934,7 @@ def run_ragged(args, rank, world, local_rank):
                     shapes_rank0=["%dx%d" % s for s in shapes[:4]] + ["..."] + ["%dx%d" % s for s in shapes[-2:]],
                     valid_frames_total=tot_frames, padded_frames_total=tot_padded,
                     padding_overhead=round(tot_padded / tot_frames - 1.0, 4),
+                    compression_ratio_last_batch_rank0=round(ratio_last, 3),
                     launch="eager" if args.no_graph else "CUDA graph replay, one graph per (shape, lane)",
                     parallelism="utterance-batch sharded x%d by fbkst_b200.sharding, no forward collective" % world,
                     cache="every batch is a different tensor (%.0f MB per rank in total)" % (padded * Fd * 4 / 1e6 / world)),

@@ -477,6 +477,11 @@ def make_encoder_class(base):
                     L = L2
             h["out_len_host"] = len_host
             xf = xf.view(L, B, D)
+            # `model.half()` (generate.py --fp16, fairseq_cli/generate.py:84-87): the decoder's weights are fp16,
+            # so the encoder hands over fp16 like the reference module would (a cast of the final result)
+            odt = self.layer_norm.weight.dtype
+            if odt != torch.float32:
+                xf = xf.to(odt)
             if h["return_all_hiddens"]:
                 states[-1] = xf
             out_lengths = torch.tensor(len_host, dtype=h["len_dtype"]).to(dev, non_blocking=True)
@@ -668,9 +673,17 @@ def make_encoder_class(base):
             (the new lengths) gives the exact output shape."""
             D = self.embed_dim
             want_prob = self.ctc_compress_strategy != "avg"
-            # fused epilogue: measured 303 us against 217 (GEMM) + 116 (arg-max pass) at cfg2 for `avg`; with the
-            # sum of exponentials (weighted / softmax) the 8 epilogue warps become the bottleneck (374 us against
-            # 217 + 127), so those strategies keep the separate pass (scripts/bench_ctc_fc.py, profiles/r02j)
+            bump = None
+            if self.ctc_logit_bump is not None:
+                bl, bm = self.ctc_logit_bump
+                if callable(bl):  # per-shape label plans (ragged streams): fn(L, B) -> [L, B] int32
+                    bl = bl(L, B)
+                if tuple(bl.shape) != (L, B) or bl.dtype != torch.int32 or not bl.is_contiguous():
+                    raise ValueError("fbkst_b200: ctc_logit_bump labels must be a contiguous [L, B] int32 tensor")
+                bump = (bl.view(L * B), float(bm))
+            # fused epilogue: measured 269 us against 217 (GEMM) + 116 (arg-max pass) at cfg2 for `avg`; with the
+            # sum of exponentials (weighted / softmax) the 8 epilogue warps become the bottleneck (342 us against
+            # 217 + 127: a tie), so those strategies keep the separate pass (scripts/bench_ctc_fc.py)
             fused = (not self.ctc_fc._forward_hooks and not self.ctc_fc._forward_pre_hooks
                      and self.ctc_fc.logits_dtype == torch.float32 and not want_prob
                      and os.environ.get("FBKST_CTC_FUSED", "1") != "0")
@@ -680,20 +693,15 @@ def make_encoder_class(base):
                 pre = getattr(self.ctc_fc, "_bf16_operand", None)
                 self.ctc_fc._bf16_operand = None
                 xb = pre[1] if pre is not None and pre[0] == x.data_ptr() else None
-                bump = None
-                if self.ctc_logit_bump is not None:
-                    bl, bm = self.ctc_logit_bump
-                    if callable(bl):  # per-shape label plans (ragged streams): fn(L, B) -> [L, B] int32
-                        bl = bl(L, B)
-                    if tuple(bl.shape) != (L, B) or bl.dtype != torch.int32 or not bl.is_contiguous():
-                        raise ValueError("fbkst_b200: ctc_logit_bump labels must be a contiguous [L, B] int32 tensor")
-                    bump = (bl.view(L * B), float(bm))
                 lg, labels, prob, _ = self.ctc_fc.project_argmax(x, xb, lengths, L, B, want_prob, bump)
                 V = lg.shape[1]
                 logits = lg.view(L, B, V)
             else:
                 logits = self.ctc_fc(x.view(L, B, D))  # module call: forward hooks apply
                 V = logits.shape[-1]
+                if bump is not None:  # test / benchmark logit injection on the unfused path (in place)
+                    logits.scatter_add_(2, bump[0].view(L, B, 1).long(),
+                                        torch.full((L, B, 1), bump[1], dtype=logits.dtype, device=logits.device))
                 try:
                     lg = logits.view(L * B, V)
                 except RuntimeError:

@@ -321,7 +321,11 @@ class EncoderTrainFn(torch.autograd.Function):
         dW1, G["cb1"] = ops.conv1_wgrad(dz1, S["x_in"])
         G["cw1"] = dW1.reshape(C, 1, 3, 3)
         ctx.S = None  # release the saved activations
-        return (None, None, None, None) + tuple(_assemble_grads(enc, G, d_ctc is not None))
+        grads = _assemble_grads(enc, G, d_ctc is not None)
+        # fp16 training (`--fp16`: model.half(), fp32 master copy in fairseq's FP16Optimizer): autograd wants
+        # every gradient in its parameter's dtype
+        grads = [g if g is None or g.dtype == p.dtype else g.to(p.dtype) for g, p in zip(grads, flat_parameters(enc))]
+        return (None, None, None, None) + tuple(grads)
 
 
 def _assemble_grads(enc, G, have_ctc):
@@ -361,6 +365,10 @@ def forward_train(enc, src_tokens, src_lengths, return_all_hiddens):
     ex = enc._train_extras
     enc._train_extras = None
     out = res[0]
+    odt = enc.layer_norm.weight.dtype
+    if odt != torch.float32:  # model.half(): hand fp16 activations to the fp16 decoder (differentiable casts)
+        res = tuple(r.to(odt) for r in res)
+        out = res[0]
     states = None
     if return_all_hiddens:
         states = [s.detach() for s in ex["states"][:-1]] + [out]
