@@ -16,6 +16,7 @@ except Exception as e:
     print("  no json", e)
 PY
 }
-run cfg3r --config cfg3r --steps 20 --warmup 3
-run cfg4 --config cfg4 --steps 10 --warmup 3
-run cfg2 --steps 20 --warmup 5 --no-cpu-baseline
+ONLY=${3:-all}
+if [ "$ONLY" = "all" ] || [ "$ONLY" = "cfg3r" ]; then run cfg3r --config cfg3r --steps 20 --warmup 3; fi
+if [ "$ONLY" = "all" ] || [ "$ONLY" = "cfg4" ]; then run cfg4 --config cfg4 --steps 10 --warmup 3; fi
+if [ "$ONLY" = "all" ] || [ "$ONLY" = "cfg2" ]; then run cfg2 --steps 20 --warmup 5 --no-cpu-baseline; fi
