@@ -26,17 +26,12 @@ constexpr int G2_BK = 64;
 constexpr int G2_A_BYTES = G2_BM * G2_BK * 2;        // 16 KB
 constexpr int G2_B_BYTES = (G2_BN / 2) * G2_BK * 2;  // 16 KB
 constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
-// Epilogue staging: 4 KB tiles (32 rows x 128 B), per epilogue warp.  The residual epilogue loads the fp32
-// residual into them by TMA, adds in place and stores from the same tile; with TWO tiles per warp only one
-// residual load was ever in flight per warp (32 KB per SM -> ~3.4 TB/s by Little's law: the out_proj / fc2
-// epilogue took ~6 x the K=512 main loop).  THREE tiles keep two loads in flight.
-constexpr int G2_RB = 3;
-constexpr int g2_epi_bytes(bool resid) { return 8 * (resid ? G2_RB : 2) * 4096; }
+constexpr int G2_EPI_BYTES = 8 * 2 * 4096;
 constexpr int G2_XB_BYTES = 8 * 4096;  // LNS: per-warp staging of the bf16 copy (32 rows x 64 columns)
-// The residual / LayerNorm-statistics variants trade operand stages for the staging tiles.
-constexpr int g2_stages(bool resid, bool lns) { return lns ? 3 : (resid ? 4 : 5); }
-constexpr int g2_smem(bool resid, bool lns) {
-  return g2_stages(resid, lns) * G2_STAGE_BYTES + g2_epi_bytes(resid) + (lns ? G2_XB_BYTES : 0) + 512 + 1024;
+// The LayerNorm-statistics variant trades one operand stage for the bf16 staging buffers.
+constexpr int g2_stages(bool lns) { return lns ? 4 : 5; }
+constexpr int g2_smem(bool lns) {
+  return g2_stages(lns) * G2_STAGE_BYTES + G2_EPI_BYTES + (lns ? G2_XB_BYTES : 0) + 512 + 1024;
 }
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -163,8 +158,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
                  const uint32_t idesc, const int splits, const int split_rows, const ArgmaxEpi am) {
   static_assert(!LNS || (OUT_F32 && RESID), "row statistics are produced by the residual epilogue");
   static_assert(!AM || (OUT_F32 && !RESID), "the arg-max epilogue rides on the plain fp32 store");
-  constexpr int G2_STAGES = g2_stages(RESID, LNS);
-  constexpr int G2_EPI_BYTES = g2_epi_bytes(RESID);
+  constexpr int G2_STAGES = g2_stages(LNS);
   constexpr uint32_t TMEM_COLS = 512;  // two 256-column accumulator stages
 
   extern __shared__ uint8_t smem_raw[];
@@ -176,8 +170,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
   uint64_t* empty_bar = full_bar + G2_STAGES;                                 // per CTA
   uint64_t* tfull_bar = empty_bar + G2_STAGES;                                // per CTA
   uint64_t* tempty_bar = tfull_bar + 2;                                       // used in the leader
-  uint64_t* res_bar = tempty_bar + 2;                                         // [8][G2_RB]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 8 * G2_RB);
+  uint64_t* res_bar = tempty_bar + 2;                                         // [8][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 16);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -202,7 +196,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], 16);  // 8 epilogue warps x 2 CTAs
     }
-    for (int s = 0; s < 8 * G2_RB; ++s) mbar_init(&res_bar[s], 1);
+    for (int s = 0; s < 16; ++s) mbar_init(&res_bar[s], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -297,9 +291,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
     const int ew = warp - 4;
     const int q = ew & 3;      // TMEM lane quarter == row block of 32
     const int half = ew >> 2;  // column half of the tile
-    uint8_t* stg = smem_epi + ew * (RESID ? G2_RB : 2) * 4096;
-    uint64_t* rbar = res_bar + ew * G2_RB;
-    uint32_t rphase[G2_RB] = {0, 0, 0};
+    uint8_t* stg = smem_epi + ew * 2 * 4096;
+    uint64_t* rbar = res_bar + ew * 2;
+    uint32_t rphase[2] = {0, 0};
     int acc = 0;
     uint32_t acc_phase = 0;
     const int swz = lane & 7;
@@ -331,15 +325,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         }
       }
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * G2_BN + half * 128;
-      if (RESID) {  // fp32 out, 4 units of 32 columns, residual prefetched TWO units ahead (3 tiles per warp)
+      if (RESID) {  // fp32 out, 4 units of 32 columns, residual prefetched one unit ahead
         if (lane == 0) {
           tma_store_wait_read<0>();
           mbar_arrive_expect_tx(&rbar[0], 4096);
           tma_load_2d(stg, &tmR, &rbar[0], n0, m0);
-          if (n0 + 32 < N) {  // unit 1 as well: neither depends on the accumulator
-            mbar_arrive_expect_tx(&rbar[1], 4096);
-            tma_load_2d(stg + 4096, &tmR, &rbar[1], n0 + 32, m0);
-          }
         }
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
@@ -353,15 +343,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         for (int u = 0; u < 4; ++u) {
           const int col0 = n0 + u * 32;
           if (col0 >= N) break;
-          const int bsel = u % G2_RB;  // staging tile of this unit
-          const int xsel = u & 1;      // half of the 64-column bf16 staging row (LNS)
-          if (u + 2 < 4 && col0 + 64 < N && lane == 0) {  // prefetch the residual of unit u + 2 ...
-            const int nb = (u + 2) % G2_RB;              // ... into the tile unit u - 1 used:
-            tma_store_wait_read<0>();                    // its store must have read it
-            mbar_arrive_expect_tx(&rbar[nb], 4096);
-            tma_load_2d(stg + nb * 4096, &tmR, &rbar[nb], col0 + 64, m0);
+          const int bsel = u & 1;
+          if (u + 1 < 4 && col0 + 32 < N && lane == 0) {  // prefetch the next residual unit
+            tma_store_wait_read<0>();                    // its buffer was read by store(u-1)
+            mbar_arrive_expect_tx(&rbar[bsel ^ 1], 4096);
+            tma_load_2d(stg + (bsel ^ 1) * 4096, &tmR, &rbar[bsel ^ 1], col0 + 32, m0);
           }
-          if (LNS && xsel == 0) {  // the bf16 staging buffer was read by the store issued at unit u-1
+          if (LNS && bsel == 0) {  // the bf16 staging buffer was read by the store issued at unit u-1
             if (lane == 0) tma_store_wait_read<0>();
             __syncwarp();
           }
@@ -399,7 +387,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
               ln_s2 = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, ln_s2))));
               // columns (u&1)*32 + 4g .. +3 of the 64-column staging row: 8 bytes at offset
               // (u&1)*64 + 8g, i.e. 16-byte chunk (u&1)*4 + g/2 (XOR-swizzled), half g&1
-              *reinterpret_cast<uint2*>(xrow + ((((xsel << 2) | (g >> 1)) ^ swz) << 4) + ((g & 1) << 3)) =
+              *reinterpret_cast<uint2*>(xrow + ((((bsel << 2) | (g >> 1)) ^ swz) << 4) + ((g & 1) << 3)) =
                   make_uint2(pack_bf16x2(r.x, r.y), pack_bf16x2(r.z, r.w));
             }
           }
@@ -407,7 +395,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
           __syncwarp();
           if (lane == 0) {
             tma_store_2d(&tmO, stg + bsel * 4096, col0, m0);
-            if (LNS && (xsel == 1 || col0 + 32 >= N))
+            if (LNS && (bsel == 1 || col0 + 32 >= N))
               tma_store_2d(&tmX, smem_xb + ew * 4096, n0 + (u >> 1) * 64, m0);
             tma_store_commit();
           }
@@ -565,7 +553,7 @@ static int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, 
                         int relu, const int* m_limit, int m_limit_mult, const LnStatsIn& ln_in,
                         void* out_bf16, int64_t ldob, float* stats_out, int ab_f16, int splits,
                         int split_rows, cudaStream_t stream, const ArgmaxEpi* am_in = nullptr) {
-  constexpr int SMEM = g2_smem(RESID, LNS);
+  constexpr int SMEM = g2_smem(LNS);
   static_assert(SMEM <= 232448, "shared memory budget exceeded");
   auto kern = gemm2_kernel<OUT_F32, RESID, LNS, AM>;
   ArgmaxEpi am{};
