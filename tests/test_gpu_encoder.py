@@ -322,3 +322,33 @@ def test_learned_positional_embeddings():
     finally:
         O.positional_embedding = orig
     check_against(out, ref, lens)
+
+
+@pytest.mark.parametrize("lens_in", [[5, 3, 1], [1], [9, 9], [130, 2]])
+def test_tiny_and_degenerate_batches(lens_in):
+    """Edge cases of the shape logic: utterances of 1-9 frames (L = 1-3 after the two stride-2 convs, single
+    partly filled tiles everywhere), B = 1, and a batch that mixes a 130-frame utterance with a 2-frame one."""
+    cfg = dict(embed_dim=128, ffn_dim=256, heads=2, layers=2, conv_channels=64, feat_dim=40, vocab=64,
+               distance_penalty="log", ctc_layer=1, ctc_strategy="weighted")
+    sd = O.init_state_dict(cfg, seed=31)
+    x, lens = O.synthetic_batch(lens_in, 40, seed=7)
+    L = ((max(lens_in) + 1) // 2 + 1) // 2
+    labels = O.synthetic_ctc_bump(L, len(lens_in), 64, seed=3)
+    hook = O.bump_hook(labels, 30.0)
+    ref = O.encoder_forward(sd, cfg, x, lens, ctc_logits_hook=hook)
+    enc = build_encoder(cfg, sd)
+    dev_hook = O.bump_hook(labels.cuda(), 30.0)
+    enc.ctc_fc.register_forward_hook(lambda m, i, o: dev_hook(o))
+    out = enc(x.cuda(), lens.cuda())
+    check_against(out, ref, lens)
+    enc.use_cuda_graph = True
+    out_g = enc(x.cuda(), lens)
+    assert torch.equal(out_g.encoder_out, out.encoder_out)
+    # and the differentiable chain on the same degenerate shapes
+    for p in enc.parameters():
+        p.requires_grad_(True)
+    enc.use_cuda_graph = False
+    o2 = enc(x.cuda(), lens.cuda(), return_all_hiddens=True)
+    assert o2.src_lengths.cpu().tolist() == ref["src_lengths"].tolist()
+    (o2.encoder_out.float().pow(2).sum() + o2.ctc_out.float().pow(2).sum() * 1e-3).backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in enc.parameters())
