@@ -81,6 +81,48 @@ class CtcLossFn(torch.autograd.Function):
         return dz.view(T, B, V), None, None, None, None
 
 
+class CtcProjLossFn(torch.autograd.Function):
+    """``CtcLossFn`` + the backward of the CTC projection (``ctc_fc``: conv_transformer.py:278-280) in ONE node.
+
+    Why: autograd runs nodes in reverse creation order, so the loss nodes run first, then the whole decoder
+    backward (bound by the host's launch rate, GPU nearly idle), and only then the encoder's node.  With the
+    projection's backward here -- d logits, d W_ctc = d logits^T x, d b_ctc, d x = d logits W_ctc, the largest
+    GEMMs of the step (V = 8005) -- that work executes on the GPU WHILE the host walks the decoder's backward
+    instead of on the GPU-bound stretch after it.  ``x`` is the tap the encoder's training forward hands out
+    (``ctc_out._fbkst_tap``); ``logits`` are the values (already computed by the encoder, hooks applied)."""
+
+    @staticmethod
+    def forward(ctx, logits, x, weight, bias, enc, in_lengths, targets, target_lengths, blank_idx):
+        rows, T, B, V = _time_major_rows(logits)
+        labels, lse, _ = ops.ctc_argmax_lse(rows, in_lengths, T, B, V)
+        nll, loss = ops.ctc_loss_fwd(rows, lse, in_lengths, targets, target_lengths, blank_idx, T, B, V)
+        ctx.save_for_backward(rows, lse, in_lengths, targets, target_lengths, x)
+        ctx.dims = (T, B, V, blank_idx)
+        ctx.enc = enc
+        ctx.mark_non_differentiable(labels, nll)
+        return loss.reshape(()), labels, nll
+
+    @staticmethod
+    def backward(ctx, grad_loss, _gl, _gn):
+        from .train import prepare_train_weights
+        rows, lse, il, tg, tl, x = ctx.saved_tensors
+        T, B, V, blank = ctx.dims
+        enc = ctx.enc
+        W = prepare_train_weights(enc)
+        D = x.shape[-1]
+        M, Vp = T * B, (V + 7) // 8 * 8
+        dz = ops.ctc_loss_bwd(rows, lse, il, tg, tl, blank, grad_loss, T, B, V)  # [M, V] fp32, pitch ceil8(V)
+        gb, gT, dbias = ops.grad_prep(dz, n_pad=Vp)
+        xb = ops.cast_bf16(x.reshape(M, D))
+        dW = ops.linear_wgrad(gT, ops.transpose_bf16(xb))
+        wcT = W["wcT"]
+        wcT_full = wcT if Vp == V else torch.as_strided(wcT, (D, Vp), (wcT.stride(0), 1))
+        dx = ops.linear(gb, wcT_full, None, out_dtype=torch.float32)
+        w, b = enc.ctc_fc.weight, enc.ctc_fc.bias
+        return (None, dx.view(x.shape), dW if dW.dtype == w.dtype else dW.to(w.dtype),
+                dbias if dbias.dtype == b.dtype else dbias.to(b.dtype), None, None, None, None, None)
+
+
 def ctc_loss_and_uer(ctc_out, ctc_padding_mask, targets, target_lengths, blank_idx, pad_idx=None):
     """What ``CTCCriterion.forward`` computes from the encoder output (CTC_loss.py:118-154):
 
@@ -122,6 +164,12 @@ def ctc_loss_train(ctc_out, ctc_padding_mask, targets, target_lengths, blank_idx
         il = (T - ctc_padding_mask.sum(dim=0 if mask_time_first else 1)).to(torch.int32)
     tl = _i32(target_lengths, dev)
     tg = torch.as_tensor(targets, device=dev).to(torch.int64).contiguous()
-    loss, labels, _ = CtcLossFn.apply(ctc_out, il, tg, tl, int(blank_idx))
+    tap = getattr(ctc_out, "_fbkst_tap", None)
+    if tap is not None and tap[0].requires_grad and tap[1].ctc_fc.weight.requires_grad:
+        x, enc = tap  # the encoder's own training forward produced these logits: projection backward done here
+        loss, labels, _ = CtcProjLossFn.apply(ctc_out.detach(), x, enc.ctc_fc.weight, enc.ctc_fc.bias, enc, il, tg,
+                                              tl, int(blank_idx))
+    else:
+        loss, labels, _ = CtcLossFn.apply(ctc_out, il, tg, tl, int(blank_idx))
     _, _, totals = ops.ctc_uer(labels, il, tg, tl, blank_idx, T, B)
     return loss, totals, il

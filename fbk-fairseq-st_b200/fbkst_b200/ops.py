@@ -14,7 +14,16 @@ def _count(n=1):
     LAUNCHES += n
 
 
+try:  # raw handle of the current stream of the current device: two C calls (~0.3 us) instead of the
+    # torch.cuda.current_stream() Python path (~5 us; 400+ launches per training step go through here)
+    _raw_stream, _cur_device = torch._C._cuda_getCurrentRawStream, torch._C._cuda_getDevice
+except AttributeError:  # pragma: no cover
+    _raw_stream = _cur_device = None
+
+
 def _stream():
+    if _raw_stream is not None:
+        return _raw_stream(_cur_device())
     return torch.cuda.current_stream().cuda_stream
 
 

@@ -136,6 +136,7 @@ class EncoderTrainFn(torch.autograd.Function):
     def forward(ctx, enc, src_tokens, len_host, seed, *params):
         dev = src_tokens.device
         train = enc.training
+        ctx.set_materialize_grads(False)  # an unused output (ctc_out or the tap) must arrive as None, not zeros
         W = prepare_train_weights(enc)
         B, T, Fd = src_tokens.shape
         C, D, H = enc.conv_channels, enc.embed_dim, enc.heads
@@ -210,7 +211,11 @@ class EncoderTrainFn(torch.autograd.Function):
                 if enc.ctc_logit_bump is not None:  # the inference path's built-in injection, same semantics
                     bl, bm = enc.ctc_logit_bump
                     bl = bl(cur_L, B) if callable(bl) else bl
-                    hooked = hooked.scatter_add(2, bl.long().unsqueeze(-1), torch.full_like(hooked[..., :1], float(bm)))
+                    bump = torch.full((cur_L, B, 1), float(bm), dtype=hooked.dtype, device=dev)
+                    if hooked is x_ctc:  # our own fresh buffer: in place (no 771 MB copy, rows stay 16-byte aligned)
+                        hooked.scatter_add_(2, bl.long().unsqueeze(-1), bump)
+                    else:
+                        hooked = hooked.scatter_add(2, bl.long().unsqueeze(-1), bump)
                 lg = hooked.reshape(M, V) if hooked.stride(-1) == 1 else hooked.contiguous().view(M, V)
                 want_prob = enc.ctc_compress_strategy != "avg"
                 labels, prob = ops.ctc_argmax(lg, cur_len, cur_L, B, V, want_prob)
@@ -220,7 +225,7 @@ class EncoderTrainFn(torch.autograd.Function):
                 new_host = new_len.cpu().tolist()  # the step's one shape synchronisation
                 L2 = max(new_host)
                 rec["ctc"] = dict(xb=xb, seg_id=seg_id, weight=weight, L2=L2, V=V)
-                ctc_ret = hooked
+                ctc_ret, ctc_tap = hooked, x2  # (x2: the projection's input, handed out as a gradient tap)
                 x2 = xc[: L2 * B]
                 cur_L, cur_len, cur_host = L2, new_len, new_host
                 mask = ops.lengths_to_mask(cur_len, cur_L)[0] if min(cur_host) < cur_L else None
@@ -232,6 +237,19 @@ class EncoderTrainFn(torch.autograd.Function):
             x = x2
         xf = ops.layernorm(x, W["gf"], W["bf"], out_dtype=torch.float32, eps=enc.layer_norm.eps)
         S.update(layers=saved, x_last=x, L_out=cur_L)
+        # The weight-gradient GEMMs contract over tokens and want token-contiguous operands.  The activation
+        # halves of those operands depend on the forward only, so their transposes are enqueued HERE, behind the
+        # last forward kernel: under fairseq's train_step the GPU is idle at this point (the decoder forward and
+        # backward are bound by the host's launch rate), while in the backward they would sit on the GPU-bound
+        # critical path (44 launches, ~1.5 ms per cfg4 step).  Cost: the transposed copies live until the backward.
+        if getattr(enc, "pretranspose_activations", True):
+            for rec in saved:
+                rec["T"] = dict(f=ops.transpose_bf16(rec["f"]), ln2=ops.transpose_bf16(rec["ln2"]),
+                                att=ops.transpose_bf16(rec["att"]), ln1=ops.transpose_bf16(rec["ln1"]))
+                if rec["ctc"] is not None:
+                    rec["ctc"]["xbT"] = ops.transpose_bf16(rec["ctc"]["xb"])
+            S["y2T"] = ops.transpose_bf16(y2.view(B * L, -1))
+            S["colT"] = ops.conv2_im2col_t(y1)
         ctx.S, ctx.enc = S, enc
         if getattr(enc, "keep_train_state", False):  # tests: the activation patterns of this forward
             enc.last_train_state = S
@@ -243,10 +261,13 @@ class EncoderTrainFn(torch.autograd.Function):
         enc._train_extras = extras
         if x_ctc is None:
             return (out,)
-        return out, ctc_ret
+        # third output: the CTC projection's INPUT.  A criterion that computes the projection's backward itself
+        # (criterion.CtcProjLossFn: early in the backward, while the decoder's backward keeps the host busy)
+        # sends d loss / d x back through it; with any other criterion the gradient arrives through ctc_ret
+        return out, ctc_ret, ctc_tap
 
     @staticmethod
-    def backward(ctx, d_out, d_ctc=None):
+    def backward(ctx, d_out, d_ctc=None, d_tap=None):
         S, enc = ctx.S, ctx.enc
         W = prepare_train_weights(enc)
         B, L, D, H, C = S["B"], S["L"], enc.embed_dim, enc.heads, enc.conv_channels
@@ -263,10 +284,16 @@ class EncoderTrainFn(torch.autograd.Function):
             cur_L, cur_len, sites = R["L"], R["lengths"], R["sites"]
             M = cur_L * B
             g = {}
+            RT = R.get("T") or {}
+
+            def tr(name):  # token-contiguous copy of a saved activation (made at the end of the forward)
+                return RT[name] if name in RT else ops.transpose_bf16(R[name])
             if R["ctc"] is not None:
                 ct = R["ctc"]
                 # dx holds the L2*B compressed rows; a frame's segment id is < its utterance's new length <= L2
                 dx = ops.ctc_compress_bwd(dx, ct["seg_id"], ct["weight"], cur_L, B)
+                if d_tap is not None:
+                    dx += d_tap.reshape(M, D)
                 if d_ctc is not None:
                     V = ct["V"]
                     Vp = (V + 7) // 8 * 8
@@ -274,33 +301,35 @@ class EncoderTrainFn(torch.autograd.Function):
                     if gc.dtype != torch.float32 or gc.stride(-1) != 1:
                         gc = gc.float().contiguous()
                     gb, gT, G["bc"] = ops.grad_prep(gc, n_pad=Vp)
-                    G["wc"] = ops.linear_wgrad(gT, ops.transpose_bf16(ct["xb"]))
+                    G["wc"] = ops.linear_wgrad(gT, ct.get("xbT") if ct.get("xbT") is not None
+                                               else ops.transpose_bf16(ct["xb"]))
                     wcT = W["wcT"]
                     wcT_full = wcT if Vp == V else torch.as_strided(wcT, (D, Vp), (wcT.stride(0), 1))
                     dx = ops.linear(gb, wcT_full, None, residual=dx, out_dtype=torch.float32)
             # ---- feed-forward block (transformer_layer.py:124-136)
             g2, g2T, g["b2"] = ops.grad_prep(dx, p=p, seed=seed, site=sites["ffn"], dp_cols=D)
-            g["w2"] = ops.linear_wgrad(g2T, ops.transpose_bf16(R["f"]))
+            g["w2"] = ops.linear_wgrad(g2T, tr("f"))
             df = ops.linear(g2, Wl["w2T"])
             dh, dhT, g["b1"] = ops.grad_prep(df, act=R["f"], act_scale=1.0 / (1.0 - p_act) if p_act > 0 else 1.0)
-            g["w1"] = ops.linear_wgrad(dhT, ops.transpose_bf16(R["ln2"]))
+            g["w1"] = ops.linear_wgrad(dhT, tr("ln2"))
             dln2 = ops.linear(dh, Wl["w1T"], out_dtype=torch.float32)
             dx, g["g2"], g["be2"] = ops.ln_bwd(dln2, R["x1"], Wl["g2"], dx=dx, eps=Wl["eps2"])
             # ---- self-attention block (:104-122)
             g1, g1T, g["bo"] = ops.grad_prep(dx, p=p, seed=seed, site=sites["out"], dp_cols=D)
-            g["wo"] = ops.linear_wgrad(g1T, ops.transpose_bf16(R["att"]))
+            g["wo"] = ops.linear_wgrad(g1T, tr("att"))
             dO = ops.linear(g1, Wl["woT"])
             dqkv = ops.attention_train_bwd(R["qkv"], R["att"], dO, R["lse"], cur_len, cur_L, B, H, enc.log_penalty,
                                            p_att, seed, sites["att"])
             _, dqkvT, g["bqkv"] = ops.grad_prep(dqkv, want_gb=False)
-            g["wqkv"] = ops.linear_wgrad(dqkvT, ops.transpose_bf16(R["ln1"]))
+            g["wqkv"] = ops.linear_wgrad(dqkvT, tr("ln1"))
             dln1 = ops.linear(dqkv, Wl["wqkvT"], out_dtype=torch.float32)
             dx, g["g1"], g["be1"] = ops.ln_bwd(dln1, R["x"], Wl["g1"], dx=dx, eps=Wl["eps1"])
             G[li] = g
         # ---- embedding dropout, positions (constant), fc3 + ReLU (conv_transformer.py:225-232)
         F2C = S["y2"].shape[2] * C
         dh3, dh3T, G["b3"] = ops.grad_prep(dx, act=S["h3b"], remap=(L, B), p=p, seed=seed, site=_SITE_EMB, dp_cols=D)
-        dW3p = ops.linear_wgrad(dh3T, ops.transpose_bf16(S["y2"].view(B * L, F2C)))  # [D, F2*C] (f, c) order
+        y2T = S["y2T"] if "y2T" in S else ops.transpose_bf16(S["y2"].view(B * L, F2C))
+        dW3p = ops.linear_wgrad(dh3T, y2T)  # [D, F2*C] (f, c) order
         G["w3"] = dW3p.view(D, enc.feat_out, C).permute(0, 2, 1).reshape(D, C * enc.feat_out)
         dy2 = ops.linear(dh3, W["w3T"])  # [B*L, F2*C] bf16 == [B, T2, F2, C]
         # ---- conv2 block
@@ -309,7 +338,7 @@ class EncoderTrainFn(torch.autograd.Function):
                                                       S["bn2"][0], S["bn2"][1], S["train"], p_conv, seed, _SITE_CONV2)
         P2 = dz2.numel() // C
         _, dz2T, G["cb2"] = ops.grad_prep(dz2.view(P2, C), want_gb=False)
-        dW2p = ops.linear_wgrad(dz2T, ops.conv2_im2col_t(S["y1"]))  # [Cout, (tap, ci)]
+        dW2p = ops.linear_wgrad(dz2T, S["colT"] if "colT" in S else ops.conv2_im2col_t(S["y1"]))  # [Cout, (tap, ci)]
         G["cw2"] = dW2p.view(C, 3, 3, C).permute(0, 3, 1, 2).contiguous()
         dcol = ops.linear(dz2.view(P2, C), W["w2d"])
         T1, F1 = S["y1"].shape[1], S["y1"].shape[2]
@@ -362,6 +391,8 @@ def forward_train(enc, src_tokens, src_lengths, return_all_hiddens):
     seed = int(torch.empty((), dtype=torch.int64).random_().item()) if enc.training else 0
     params = flat_parameters(enc)
     res = EncoderTrainFn.apply(enc, src_tokens, len_host, seed, *params)
+    tap = res[2] if len(res) > 2 else None
+    res = res[:2]
     ex = enc._train_extras
     enc._train_extras = None
     out = res[0]
@@ -369,6 +400,10 @@ def forward_train(enc, src_tokens, src_lengths, return_all_hiddens):
     if odt != torch.float32:  # model.half(): hand fp16 activations to the fp16 decoder (differentiable casts)
         res = tuple(r.to(odt) for r in res)
         out = res[0]
+    if tap is not None and getattr(enc, "ctc_grad_tap", True):
+        # read by criterion.ctc_loss_train (same tensor object, i.e. as long as nobody transforms ctc_out on the
+        # way to the criterion): (projection input with grad_fn, encoder)
+        res[1]._fbkst_tap = (tap, enc)
     states = None
     if return_all_hiddens:
         states = [s.detach() for s in ex["states"][:-1]] + [out]

@@ -187,3 +187,44 @@ def test_training_mode_optimises():
     with torch.no_grad():
         e1 = enc(x, lens).encoder_out
     assert torch.isfinite(e1).all()
+
+
+def test_ctc_projection_backward_in_the_criterion_node():
+    """``criterion.ctc_loss_train`` on the encoder's own ctc_out takes the projection's backward into the loss
+    node (CtcProjLossFn, via the ``_fbkst_tap`` the training forward attaches); every parameter gradient must be
+    what the plain route (d logits handed back through ctc_out) gives, and the pre-transposed activation copies
+    must not change anything either."""
+    from fbkst_b200 import criterion as C
+    cfg = dict(embed_dim=128, ffn_dim=256, heads=2, layers=3, conv_channels=64, feat_dim=40, vocab=61,
+               distance_penalty="log", ctc_layer=2, ctc_strategy="avg")
+    sd = O.init_state_dict(cfg, seed=21)
+    lens_in = [160, 131, 97, 160]
+    x, lens = O.synthetic_batch(lens_in, 40, seed=22)
+    L, B = 40, len(lens_in)
+    labels = O.synthetic_ctc_bump(L, B, cfg["vocab"], seed=23)
+    g = torch.Generator().manual_seed(24)
+    targets = torch.randint(1, cfg["vocab"] - 1, (B, 9), generator=g)
+    tgt_len = torch.tensor([9, 7, 5, 8])
+    blank = cfg["vocab"] - 1
+    grads, losses = [], []
+    for tap, pre in ((True, True), (False, False)):
+        enc = build_encoder(cfg, sd)
+        enc.ctc_grad_tap, enc.pretranspose_activations = tap, pre
+        enc.ctc_logit_bump = (labels.to(torch.int32).cuda().contiguous(), 30.0)
+        for p in enc.parameters():
+            p.requires_grad_(True)
+        out = enc(x.cuda(), lens.cuda(), return_all_hiddens=True)
+        assert hasattr(out.ctc_out, "_fbkst_tap") == tap
+        r = torch.randn(out.encoder_out.shape, generator=torch.Generator().manual_seed(25)).cuda()
+        loss_ctc, totals, il = C.ctc_loss_train(out.ctc_out, out.ctc_padding_mask.t() if out.ctc_padding_mask is not None
+                                                else None, targets.cuda(), tgt_len.cuda(), blank)
+        assert type(loss_ctc.grad_fn).__name__.startswith("CtcProjLossFn" if tap else "CtcLossFn")
+        loss = (out.encoder_out * r).sum() + 0.5 * loss_ctc
+        loss.backward()
+        losses.append(loss.item())
+        grads.append({n: p.grad.clone() for n, p in enc.named_parameters()})
+    assert abs(losses[0] - losses[1]) <= 1e-6 * abs(losses[1])
+    for n in grads[0]:
+        a, b = grads[0][n], grads[1][n]
+        assert (a - b).abs().max() <= 2e-3 * b.abs().max().clamp_min(1e-6), n
+    assert grads[0]["ctc_fc.weight"].abs().max() > 0
