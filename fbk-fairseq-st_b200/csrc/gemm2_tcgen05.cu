@@ -714,6 +714,23 @@ extern "C" int fbkst_linear_wgrad_bf16(const void* gT, int64_t ldg, const void* 
   return fbkst_reduce_sum(workspace, sp, (int64_t)split_rows * ldo, n_out, k_in, ldo, dW, lddw, 1.0f, stream);
 }
 
+extern "C" int fbkst_linear_wgrad_slices_bf16(const void* gT, int64_t ldg, const void* xT, int64_t ldx,
+                                              float* workspace, int n_out, int k_in, int tokens, int* splits,
+                                              fbkst_stream_t stream) {
+  using namespace fbkst;
+  FBKST_REQUIRE(gT && xT && workspace && splits, "fbkst_linear_wgrad_slices_bf16: null pointer");
+  FBKST_REQUIRE(n_out > 0 && k_in > 0 && tokens > 0, "fbkst_linear_wgrad_slices_bf16: empty problem");
+  FBKST_REQUIRE(ldg % 8 == 0 && ldx % 8 == 0 && ldg >= tokens && ldx >= tokens,
+                "fbkst_linear_wgrad_slices_bf16: operand pitches must be multiples of 8 and >= tokens");
+  int sp = wgrad_splits(n_out, k_in, tokens);
+  const int split_rows = (n_out + 31) / 32 * 32;
+  const int64_t ldo = ((int64_t)k_in + 7) / 8 * 8;
+  int rc = linear_pair_splitk(gT, ldg, xT, ldx, workspace, ldo, n_out, k_in, tokens, &sp, split_rows,
+                              reinterpret_cast<cudaStream_t>(stream));
+  *splits = sp;
+  return rc;
+}
+
 /* a9 + a10 step 1 fused: logits = A W^T + bias (fp32, pitch ldo) AND, per row, the arg-max partials of every
  * 128-column chunk (partial: [M, ceil(N/128)] float4), optionally after adding `bump` to column bump_cols[row].
  * Follow with fbkst_ctc_argmax_merge.  replaces conv_transformer.py:279 + :282-284 without re-reading the logits. */

@@ -226,13 +226,13 @@ struct GradPrepParams {
   int dp_cols;  // columns per row of the tensor the dropout mask was drawn for (counter pitch = dp_cols / 4)
 };
 
+// one 64 x 64 tile (tile column bx, tile row by) of the grad_prep pass
 template <int IN_T>  // 0: bf16, 1: fp32, 2: IEEE fp16 (the conv front end's activations)
-__global__ void __launch_bounds__(256) grad_prep_kernel(const GradPrepParams p) {
+__device__ __forceinline__ void grad_prep_tile(const GradPrepParams& p, const int bx, const int by,
+                                               __nv_bfloat16 (*tileT)[72], float (*cs)[65]) {
   constexpr int IN_F32 = IN_T == 1;
-  __shared__ __align__(16) __nv_bfloat16 tileT[64][72];  // [n][m], 144-byte rows
-  __shared__ float cs[16][65];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int m0 = by * 64, n0 = bx * 64;
   const int n = n0 + tx * 4;
   float csum[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(256) grad_prep_kernel(const GradPrepParams p) 
     float s = 0.f;
 #pragma unroll
     for (int k = 0; k < 16; ++k) s += cs[k][threadIdx.x];
-    if (n0 + (int)threadIdx.x < p.ld_cs) p.colsum[(size_t)blockIdx.y * p.ld_cs + n0 + threadIdx.x] = s;
+    if (n0 + (int)threadIdx.x < p.ld_cs) p.colsum[(size_t)by * p.ld_cs + n0 + threadIdx.x] = s;
   }
   if (p.gT != nullptr) {
     const int nr = threadIdx.x >> 2, seg = (threadIdx.x & 3) * 16;  // output row n0+nr, columns m0+seg..+15
@@ -325,6 +325,116 @@ __global__ void __launch_bounds__(256) grad_prep_kernel(const GradPrepParams p) 
           if (m0 + seg + j < p.M) op[j] = tileT[nr][seg + j];
       }
     }
+  }
+}
+
+template <int IN_T>
+__global__ void __launch_bounds__(256) grad_prep_kernel(const GradPrepParams p) {
+  __shared__ __align__(16) __nv_bfloat16 tileT[64][72];  // [n][m], 144-byte rows
+  __shared__ float cs[16][65];
+  grad_prep_tile<IN_T>(p, blockIdx.x, blockIdx.y, tileT, cs);
+}
+
+// ---- many (cast, transpose) jobs in ONE launch.  A training step derives ~70 bf16 operand copies (+ their
+// transposes) from the fp32 master weights, and ~45 token-contiguous activation copies for the weight-gradient
+// GEMMs; one launch per matrix made those stretches of the step bound by the HOST's launch rate.  The job
+// table travels in the kernel parameters (no staging copy); a block finds its job by a scan of the tile-offset
+// prefix.
+constexpr int PREP_BATCH_MAX = 48;
+struct PrepBatch {
+  fbkst_prep_desc_t d[PREP_BATCH_MAX];
+  int tile0[PREP_BATCH_MAX + 1];
+  int n;
+};
+__global__ void __launch_bounds__(256) prep_batch_kernel(const __grid_constant__ PrepBatch tb) {
+  __shared__ __align__(16) __nv_bfloat16 tileT[64][72];
+  __shared__ float cs[16][65];
+  int di = 0;
+  while (di + 1 < tb.n && (int)blockIdx.x >= tb.tile0[di + 1]) ++di;
+  const fbkst_prep_desc_t& d = tb.d[di];
+  const int t = blockIdx.x - tb.tile0[di];
+  const int tiles_x = (d.cols + 63) / 64;
+  GradPrepParams q;
+  q.g = d.src;
+  q.ldg = d.ld_src;
+  q.act = nullptr;
+  q.lda = 0;
+  q.act_scale = 1.f;
+  q.remap_inner = q.remap_outer = 0;
+  q.gb = reinterpret_cast<__nv_bfloat16*>(d.copy);
+  q.ldb = d.ld_copy;
+  q.n_pad = d.cols;
+  q.gT = reinterpret_cast<__nv_bfloat16*>(d.transposed);
+  q.ldt = d.ld_transposed;
+  q.colsum = nullptr;
+  q.ld_cs = 0;
+  q.M = d.rows;
+  q.N = d.cols;
+  q.vec_ok = d.reserved;  // (set by the host: source rows aligned for vector loads)
+  q.dp.p = 0.f;
+  q.dp.scale = 1.f;
+  q.dp.threshold = q.dp.seed_lo = q.dp.seed_hi = q.dp.site = 0u;
+  q.dp_cols = 4;
+  const int bx = t % tiles_x, by = t / tiles_x;
+  if (d.src_type == 1)
+    grad_prep_tile<1>(q, bx, by, tileT, cs);
+  else if (d.src_type == 2)
+    grad_prep_tile<2>(q, bx, by, tileT, cs);
+  else
+    grad_prep_tile<0>(q, bx, by, tileT, cs);
+}
+
+// ---- many fixed-order reductions in ONE launch (bias gradients, split-K slices of the weight-gradient GEMMs,
+// LayerNorm parameter gradients: ~120 per training step, each a few microseconds of a nearly empty GPU)
+constexpr int REDUCE_BATCH_MAX = 56;
+struct ReduceBatch {
+  fbkst_reduce_desc_t d[REDUCE_BATCH_MAX];
+  int blk0[REDUCE_BATCH_MAX + 1];
+  int n;
+};
+__global__ void __launch_bounds__(256) reduce_sum_batch_kernel(const __grid_constant__ ReduceBatch tb) {
+  __shared__ float red[32][9];
+  int di = 0;
+  while (di + 1 < tb.n && (int)blockIdx.x >= tb.blk0[di + 1]) ++di;
+  const fbkst_reduce_desc_t& d = tb.d[di];
+  const int blk = blockIdx.x - tb.blk0[di], nblk = tb.blk0[di + 1] - tb.blk0[di];
+  const long long total = (long long)d.rows * d.cols;
+  if (d.G <= 16) {  // few slices, many outputs: thread per output element
+    for (long long i = (long long)blk * 256 + threadIdx.x; i < total; i += (long long)nblk * 256) {
+      const int r = (int)(i / d.cols), c = (int)(i - (long long)r * d.cols);
+      const float* ip = d.in + (long long)r * d.ldi + c;
+      float s = 0.f;
+      for (int g = 0; g < d.G; ++g) s += ip[(long long)g * d.g_stride];
+      d.out[(long long)r * d.ldo + c] = s * d.scale;
+    }
+    return;
+  }
+  const int e = threadIdx.x & 7, gl = threadIdx.x >> 3;  // many slices: 32 lanes split the slices of 8 outputs
+  for (long long i0 = (long long)blk * 8; i0 < total; i0 += (long long)nblk * 8) {
+    const long long i = i0 + e;
+    float s = 0.f;
+    if (i < total) {
+      const int r = (int)(i / d.cols), c = (int)(i - (long long)r * d.cols);
+      const float* ip = d.in + (long long)r * d.ldi + c;
+      float s0 = 0.f, s1 = 0.f;
+      int g = gl;
+      for (; g + 32 < d.G; g += 64) {
+        s0 += ip[(long long)g * d.g_stride];
+        s1 += ip[(long long)(g + 32) * d.g_stride];
+      }
+      if (g < d.G) s0 += ip[(long long)g * d.g_stride];
+      s = s0 + s1;
+    }
+    red[gl][e] = s;
+    __syncthreads();
+    if (gl == 0 && i < total) {
+      float t = 0.f;
+#pragma unroll
+      for (int l = 0; l < 32; ++l) t += red[l][e];
+      const int r = (int)(i / d.cols), c = (int)(i - (long long)r * d.cols);
+      d.out[(long long)r * d.ldo + c] = t * d.scale;
+    }
+    __syncthreads();
   }
 }
 
@@ -560,6 +670,63 @@ extern "C" int fbkst_reduce_sum(const float* in, int G, int64_t g_stride, int ro
     reduce_sum_kernel<<<(int)grid, 256, 0, st>>>(in, G, g_stride, rows, cols, ldi, out, ldo, scale);
   }
   FBKST_CHECK_CUDA(cudaGetLastError());
+  return FBKST_OK;
+}
+
+extern "C" int fbkst_prep_batch(const fbkst_prep_desc_t* descs, int n, fbkst_stream_t stream) {
+  using namespace fbkst;
+  FBKST_REQUIRE(descs && n > 0, "fbkst_prep_batch: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  for (int i0 = 0; i0 < n; i0 += PREP_BATCH_MAX) {
+    PrepBatch tb;
+    tb.n = n - i0 < PREP_BATCH_MAX ? n - i0 : PREP_BATCH_MAX;
+    long long tiles = 0;
+    for (int i = 0; i < tb.n; ++i) {
+      fbkst_prep_desc_t d = descs[i0 + i];
+      FBKST_REQUIRE(d.src && (d.copy || d.transposed) && d.rows > 0 && d.cols > 0 && d.src_type >= 0 &&
+                        d.src_type <= 2 && d.ld_src >= d.cols,
+                    "fbkst_prep_batch: bad job %d", i0 + i);
+      FBKST_REQUIRE(d.copy == nullptr || d.ld_copy >= d.cols, "fbkst_prep_batch: job %d: bad copy pitch", i0 + i);
+      FBKST_REQUIRE(d.transposed == nullptr || d.ld_transposed >= d.rows,
+                    "fbkst_prep_batch: job %d: bad transposed pitch", i0 + i);
+      const size_t esz = d.src_type == 1 ? 4 : 2;
+      d.reserved = ((reinterpret_cast<uintptr_t>(d.src) % (4 * esz)) == 0 && d.ld_src % 4 == 0) ? 1 : 0;
+      tb.d[i] = d;
+      tb.tile0[i] = (int)tiles;
+      tiles += (long long)((d.cols + 63) / 64) * ((d.rows + 63) / 64);
+      FBKST_REQUIRE(tiles < (1ll << 30), "fbkst_prep_batch: too many tiles");
+    }
+    tb.tile0[tb.n] = (int)tiles;
+    prep_batch_kernel<<<(int)tiles, 256, 0, st>>>(tb);
+    FBKST_CHECK_CUDA(cudaGetLastError());
+  }
+  return FBKST_OK;
+}
+
+extern "C" int fbkst_reduce_sum_batch(const fbkst_reduce_desc_t* descs, int n, fbkst_stream_t stream) {
+  using namespace fbkst;
+  FBKST_REQUIRE(descs && n > 0, "fbkst_reduce_sum_batch: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  for (int i0 = 0; i0 < n; i0 += REDUCE_BATCH_MAX) {
+    ReduceBatch tb;
+    tb.n = n - i0 < REDUCE_BATCH_MAX ? n - i0 : REDUCE_BATCH_MAX;
+    int blocks = 0;
+    for (int i = 0; i < tb.n; ++i) {
+      const fbkst_reduce_desc_t& d = descs[i0 + i];
+      FBKST_REQUIRE(d.in && d.out && d.G > 0 && d.rows > 0 && d.cols > 0, "fbkst_reduce_sum_batch: bad job %d",
+                    i0 + i);
+      tb.d[i] = d;
+      tb.blk0[i] = blocks;
+      const long long total = (long long)d.rows * d.cols;
+      long long nb = d.G <= 16 ? (total + 255) / 256 : (total + 7) / 8;
+      const long long cap = d.G <= 16 ? 2 * num_sms() : 4 * num_sms();
+      if (nb > cap) nb = cap;
+      blocks += (int)nb;
+    }
+    tb.blk0[tb.n] = blocks;
+    reduce_sum_batch_kernel<<<blocks, 256, 0, st>>>(tb);
+    FBKST_CHECK_CUDA(cudaGetLastError());
+  }
   return FBKST_OK;
 }
 

@@ -104,10 +104,14 @@ class CtcProjLossFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_loss, _gl, _gn):
-        from .train import prepare_train_weights
+        from .train import prepare_train_weights, pretranspose
         rows, lse, il, tg, tl, x = ctx.saved_tensors
         T, B, V, blank = ctx.dims
         enc = ctx.enc
+        # this node runs FIRST in the backward: enqueue the encoder's activation transposes now, so that they
+        # execute while the host walks the decoder's backward
+        pretranspose(getattr(enc, "_train_pending", None))
+        enc._train_pending = None
         W = prepare_train_weights(enc)
         D = x.shape[-1]
         M, Vp = T * B, (V + 7) // 8 * 8

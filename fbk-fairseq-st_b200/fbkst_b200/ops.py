@@ -576,6 +576,96 @@ def prep_bn_affine(gamma, beta, mean, var, eps=1e-5):
 
 
 # ------------------------------------------------------------------------------------- training side
+# Batched launches: the job tables of fbkst_reduce_sum_batch / fbkst_prep_batch are packed HOST arrays of the
+# structs declared in include/fbkst_b200.h (fbkst_reduce_desc_t: 56 bytes, fbkst_prep_desc_t: 64 bytes).
+import ctypes as _ct  # noqa: E402
+import struct as _struct  # noqa: E402
+
+_REDUCE_FMT, _PREP_FMT = "<QQqqqiiif", "<QQQqqqiiii"
+assert _struct.calcsize(_REDUCE_FMT) == 56 and _struct.calcsize(_PREP_FMT) == 64
+_SRC_TYPE = {torch.bfloat16: 0, torch.float32: 1, torch.float16: 2}
+
+
+class _ReduceQueue:
+    """Fixed-order reductions whose results are only needed later (bias / weight / LayerNorm parameter
+    gradients): collected while ``deferred_reductions()`` is active, launched together by ``flush``."""
+
+    def __init__(self):
+        self.buf, self.keep, self.n = bytearray(), [], 0
+
+    def add(self, src, G, g_stride, rows, cols, ldi, out, ldo, scale):
+        self.buf += _struct.pack(_REDUCE_FMT, src.data_ptr(), out.data_ptr(), g_stride, ldi, ldo, G, rows, cols, scale)
+        self.keep.append((src, out))  # the partial sums must outlive the launch
+        self.n += 1
+
+    def flush(self):
+        if self.n:
+            lib = _lib.require_device()
+            raw = (_ct.c_char * len(self.buf)).from_buffer(self.buf)
+            check(lib.fbkst_reduce_sum_batch(_ct.addressof(raw), self.n, _stream()))
+            _count((self.n + 55) // 56)
+            del raw
+        self.buf, self.keep, self.n = bytearray(), [], 0
+
+
+_DEFER = None
+
+
+class deferred_reductions:
+    """``with ops.deferred_reductions():`` -- ``reduce_sum`` calls made inside (directly or by grad_prep / ln_bwd /
+    linear_wgrad) are queued and run as one batched launch on exit.  Their outputs must not be read inside."""
+
+    def __enter__(self):
+        global _DEFER
+        self.prev, _DEFER = _DEFER, _ReduceQueue()
+        return _DEFER
+
+    def __exit__(self, *exc):
+        global _DEFER
+        q, _DEFER = _DEFER, self.prev
+        if exc[0] is None:
+            q.flush()
+        return False
+
+
+def reduce_sum(src, G, g_stride, rows, cols, ldi, out, ldo, scale=1.0):
+    """out[r, c] = scale * sum_g src[g * g_stride + r * ldi + c] (fixed order); queued when deferral is active."""
+    if _DEFER is not None:
+        _DEFER.add(src, G, g_stride, rows, cols, ldi, out, ldo, scale)
+        return
+    lib = _lib.require_device()
+    check(lib.fbkst_reduce_sum(src.data_ptr(), G, g_stride, rows, cols, ldi, out.data_ptr(), ldo, scale, _stream()))
+    _count()
+
+
+def prep_batch(jobs):
+    """jobs: iterable of (src [rows, cols] bf16/fp32/fp16 with unit column stride, copy or None, transposed or
+    None); copy [rows, cols] bf16 / transposed [cols, rows] bf16 are 2-D tensors or views with unit column stride
+    (pitches taken from their strides).  One launch per 48 jobs."""
+    lib = _lib.require_device()
+    buf, n = bytearray(), 0
+    for src, copy, tr in jobs:
+        if src.dim() != 2 or src.stride(1) != 1 or src.dtype not in _SRC_TYPE or not src.is_cuda:
+            raise ValueError("fbkst_b200.prep_batch: src must be a 2-D CUDA bf16/fp32/fp16 tensor, unit column stride")
+        rows, cols = src.shape
+        for t, shp, name in ((copy, (rows, cols), "copy"), (tr, (cols, rows), "transposed")):
+            if t is not None and (t.dtype != torch.bfloat16 or tuple(t.shape) != shp or t.stride(1) != 1):
+                raise ValueError("fbkst_b200.prep_batch: bad %s tensor" % name)
+        buf += _struct.pack(_PREP_FMT, src.data_ptr(), _ptr(copy), _ptr(tr), src.stride(0),
+                            copy.stride(0) if copy is not None else 0, tr.stride(0) if tr is not None else 0,
+                            rows, cols, _SRC_TYPE[src.dtype], 0)
+        n += 1
+    if n:
+        raw = (_ct.c_char * len(buf)).from_buffer(buf)
+        check(lib.fbkst_prep_batch(_ct.addressof(raw), n, _stream()))
+        _count((n + 47) // 48)
+
+
+def transposed_buffer(rows, cols, device):
+    """An empty [cols, rows] bf16 view of a [cols, ceil8(rows)] buffer (the wgrad GEMM wants pitches % 8 == 0)."""
+    return torch.empty(cols, (rows + 7) // 8 * 8, dtype=torch.bfloat16, device=device)[:, :rows]
+
+
 def dropout_add_ln(y, residual=None, gamma=None, beta=None, eps=1e-5, p=0.0, seed=0, site=0, want_x=True):
     """x1 = residual + dropout(y); ln = LayerNorm(x1) in bf16 (when gamma is given).  -> (x1, ln)."""
     lib = _lib.require_device()
@@ -606,8 +696,8 @@ def ln_bwd(dy, x, gamma, dx=None, eps=1e-5):
     check(lib.fbkst_ln_bwd(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), dx.data_ptr(), acc, partial.data_ptr(),
                            float(eps), M, D, _stream()))
     dgb = torch.empty(2, D, dtype=torch.float32, device=x.device)
-    check(lib.fbkst_reduce_sum(partial.data_ptr(), G, 2 * D, 1, 2 * D, 2 * D, dgb.data_ptr(), 2 * D, 1.0, _stream()))
-    _count(2)
+    _count()
+    reduce_sum(partial, G, 2 * D, 1, 2 * D, 2 * D, dgb, 2 * D)
     return dx, dgb[0], dgb[1]
 
 
@@ -638,9 +728,7 @@ def grad_prep(g, act=None, act_scale=1.0, remap=None, want_gb=True, want_gT=True
     colsum = None
     if want_colsum:
         colsum = torch.empty(n_pad, dtype=torch.float32, device=dev)
-        check(lib.fbkst_reduce_sum(cs.data_ptr(), tiles, n_pad, 1, n_pad, n_pad, colsum.data_ptr(), n_pad, 1.0,
-                                   _stream()))
-        _count()
+        reduce_sum(cs, tiles, n_pad, 1, n_pad, n_pad, colsum, n_pad)
         colsum = colsum[:N]
     return gb, (gT[:, :M] if gT is not None else None), colsum
 
@@ -662,6 +750,8 @@ def linear_wgrad(gT, xT):
         raise ValueError("fbkst_b200.linear_wgrad: token counts differ")
     ws = torch.empty(lib.fbkst_linear_wgrad_workspace(n_out, k_in, tokens), dtype=torch.float32, device=gT.device)
     dW = torch.empty(n_out, k_in, dtype=torch.float32, device=gT.device)
+    # (the reduction of the split-K slices is NOT deferred: run right behind the GEMM it reads the slices from
+    # L2; batched at the end of the backward it read 1.9 GB from HBM -- 0.9 ms against 0.45 ms per cfg4 step)
     check(lib.fbkst_linear_wgrad_bf16(gT.data_ptr(), gT.stride(0), xT.data_ptr(), xT.stride(0), ws.data_ptr(),
                                       dW.data_ptr(), k_in, n_out, k_in, tokens, _stream()))
     _count(2)

@@ -23,6 +23,8 @@ Operand precision: bf16 GEMM operands / fp16 conv-front-end activations, fp32 ac
 stream and fp32 parameter gradients in the reference's parameter layout (so fairseq's optimizers, gradient
 clipping and the legacy DDP all-reduce see exactly what they expect).
 """
+import os
+
 import torch
 
 from . import ops
@@ -35,17 +37,6 @@ def _layer_sites(li):
     return dict(att=base, out=base + 1, act=base + 2, ffn=base + 3)
 
 
-def _zeros_transpose(w):
-    """[N, K] bf16/fp32/fp16 -> [K, N] bf16 as a view of a ZERO-padded [K, ceil8(N)] buffer: the B operand of
-    a dgrad GEMM whose contraction length is the padded N (pad columns must be finite zeros)."""
-    t = ops.transpose_bf16(w)
-    if t.stride(0) != t.shape[1]:
-        base = torch.zeros(t.shape[0], t.stride(0), dtype=torch.bfloat16, device=t.device)
-        base[:, : t.shape[1]].copy_(t)
-        t = base[:, : t.shape[1]]
-    return t
-
-
 def prepare_train_weights(enc):
     """bf16 / fp16 operand copies of the master parameters for one training step (re-derived whenever a
     parameter's version counter changes, i.e. after every optimizer step)."""
@@ -55,6 +46,7 @@ def prepare_train_weights(enc):
         return enc._train_prep
     with torch.no_grad():
         C = enc.conv_channels
+        dev = params[0].device
         W = {}
         W["w1"] = enc.convolutions[0].weight.detach().reshape(C, 9).float().contiguous()
         W["b1"] = enc.convolutions[0].bias.detach().float().contiguous()
@@ -65,30 +57,64 @@ def prepare_train_weights(enc):
         W["w2d"] = ops.cast_bf16(w2.permute(2, 3, 1, 0).reshape(9 * C, C).contiguous())
         W["w3"] = ops.prep_fc3_weight(enc.fc3.weight.detach().float(), C, enc.feat_out)  # [D, F2*C] fp16
         W["b3"] = enc.fc3.bias.detach().float().contiguous()
-        W["w3T"] = ops.transpose_bf16(W["w3"])  # [F2*C, D] bf16
+        # bf16 operand copies + transposed copies of every nn.Linear weight: ONE batched launch per 48 matrices
+        # into buffers that persist across steps (~130 cat / cast / transpose launches per step before)
+        bufs = getattr(enc, "_train_bufs", None)
+        if bufs is None or bufs["device"] != dev:
+            bufs = enc._train_bufs = dict(device=dev)
+        jobs = []
+
+        def buf(name, rows, cols, zero_pad=False):
+            t = bufs.get(name)
+            if t is None:
+                pitch = (cols + 7) // 8 * 8
+                t = (torch.zeros if zero_pad else torch.empty)(rows, pitch, dtype=torch.bfloat16, device=dev)
+                bufs[name] = t
+            return t[:, :cols]
+
+        def linear_weight(name, blocks, want_copy=True, zero_pad=False):
+            """blocks: row blocks [n_i, k] of one logical weight [sum n_i, k] -> (copy [N, k], transposed [k, N])."""
+            N, K = sum(w.shape[0] for w in blocks), blocks[0].shape[1]
+            cp = buf(name, N, K) if want_copy else None
+            tr = buf(name + "T", K, N, zero_pad)
+            r = 0
+            for w in blocks:
+                w = w.detach()
+                n = w.shape[0]
+                jobs.append((w if w.stride(1) == 1 else w.contiguous(), cp[r:r + n] if cp is not None else None,
+                             tr[:, r:r + n]))
+                r += n
+            return cp, tr
+        _, W["w3T"] = linear_weight("w3", [W["w3"]], want_copy=False)  # [F2*C, D] bf16 from the fp16 fc3 operand
         layers = []
-        for lyr in enc.layers:
-            w, b = lyr.self_attn.qkv()
-            d = dict(wqkv=ops.cast_bf16(w.detach().float().contiguous()), bqkv=b.detach().float().contiguous(),
-                     wo=ops.cast_bf16(lyr.self_attn.out_proj.weight.detach().float()),
-                     bo=lyr.self_attn.out_proj.bias.detach().float().contiguous(),
-                     w1=ops.cast_bf16(lyr.fc1.weight.detach().float()), b1=lyr.fc1.bias.detach().float().contiguous(),
-                     w2=ops.cast_bf16(lyr.fc2.weight.detach().float()), b2=lyr.fc2.bias.detach().float().contiguous(),
+        for li, lyr in enumerate(enc.layers):
+            sa = lyr.self_attn
+            if hasattr(sa, "in_proj_weight"):
+                qkv_blocks, bqkv = [sa.in_proj_weight], sa.in_proj_bias.detach().float().contiguous()
+            else:
+                qkv_blocks = [sa.q_proj.weight, sa.k_proj.weight, sa.v_proj.weight]
+                bqkv = torch.cat([sa.q_proj.bias, sa.k_proj.bias, sa.v_proj.bias], 0).detach().float()
+            d = dict(bqkv=bqkv, bo=sa.out_proj.bias.detach().float().contiguous(),
+                     b1=lyr.fc1.bias.detach().float().contiguous(), b2=lyr.fc2.bias.detach().float().contiguous(),
                      g1=lyr.self_attn_layer_norm.weight.detach().float().contiguous(),
                      be1=lyr.self_attn_layer_norm.bias.detach().float().contiguous(),
                      g2=lyr.final_layer_norm.weight.detach().float().contiguous(),
                      be2=lyr.final_layer_norm.bias.detach().float().contiguous(),
                      eps1=lyr.self_attn_layer_norm.eps, eps2=lyr.final_layer_norm.eps)
-            for n in ("wqkv", "wo", "w1", "w2"):
-                d[n + "T"] = ops.transpose_bf16(d[n])
+            d["wqkv"], d["wqkvT"] = linear_weight("l%d.wqkv" % li, qkv_blocks)
+            d["wo"], d["woT"] = linear_weight("l%d.wo" % li, [sa.out_proj.weight])
+            d["w1"], d["w1T"] = linear_weight("l%d.w1" % li, [lyr.fc1.weight])
+            d["w2"], d["w2T"] = linear_weight("l%d.w2" % li, [lyr.fc2.weight])
             layers.append(d)
         W["layers"] = layers
         W["gf"] = enc.layer_norm.weight.detach().float().contiguous()
         W["bf"] = enc.layer_norm.bias.detach().float().contiguous()
         if enc.ctc_compress_out:
-            W["wc"] = ops.cast_bf16(enc.ctc_fc.weight.detach().float())
+            # wcT: [D, V] view of a [D, ceil8(V)] buffer whose pad columns stay zero (the dgrad GEMM contracts
+            # over the padded V)
+            W["wc"], W["wcT"] = linear_weight("wc", [enc.ctc_fc.weight], zero_pad=True)
             W["bc"] = enc.ctc_fc.bias.detach().float().contiguous()
-            W["wcT"] = _zeros_transpose(W["wc"])  # [D, V] view of [D, ceil8(V)], zero padded
+        ops.prep_batch(jobs)
     enc._train_prep, enc._train_prep_key = W, key
     return W
 
@@ -129,6 +155,28 @@ def _bn_state(enc, i, y_relu, train):
     mean = bn.running_mean.float().contiguous()
     rstd = (bn.running_var.float() + bn.eps).rsqrt().contiguous()  # [C]: parameter-sized, not activations
     return mean, rstd, sc, sh
+
+
+def pretranspose(S):
+    """Token-contiguous (transposed) bf16 copies of the activations the weight-gradient GEMMs read, for the saved
+    state ``S`` of one training forward: one batched launch (+ conv2's im2col).  Idempotent."""
+    if S is None or S.get("pretransposed"):
+        return
+    S["pretransposed"] = True
+    x_in = S["x_in"]
+    dev = x_in.device
+    jobs = []
+
+    def tjob(t):
+        out = ops.transposed_buffer(t.shape[0], t.shape[1], dev)
+        jobs.append((t, None, out))
+        return out
+    for rec in S["layers"]:
+        rec["T"] = dict(f=tjob(rec["f"]), ln2=tjob(rec["ln2"]), att=tjob(rec["att"]), ln1=tjob(rec["ln1"]))
+    y2 = S["y2"]
+    S["y2T"] = tjob(y2.view(y2.shape[0] * y2.shape[1], -1))
+    ops.prep_batch(jobs)
+    S["colT"] = ops.conv2_im2col_t(S["y1"])
 
 
 class EncoderTrainFn(torch.autograd.Function):
@@ -237,19 +285,16 @@ class EncoderTrainFn(torch.autograd.Function):
             x = x2
         xf = ops.layernorm(x, W["gf"], W["bf"], out_dtype=torch.float32, eps=enc.layer_norm.eps)
         S.update(layers=saved, x_last=x, L_out=cur_L)
-        # The weight-gradient GEMMs contract over tokens and want token-contiguous operands.  The activation
-        # halves of those operands depend on the forward only, so their transposes are enqueued HERE, behind the
-        # last forward kernel: under fairseq's train_step the GPU is idle at this point (the decoder forward and
-        # backward are bound by the host's launch rate), while in the backward they would sit on the GPU-bound
-        # critical path (44 launches, ~1.5 ms per cfg4 step).  Cost: the transposed copies live until the backward.
-        if getattr(enc, "pretranspose_activations", True):
-            for rec in saved:
-                rec["T"] = dict(f=ops.transpose_bf16(rec["f"]), ln2=ops.transpose_bf16(rec["ln2"]),
-                                att=ops.transpose_bf16(rec["att"]), ln1=ops.transpose_bf16(rec["ln1"]))
-                if rec["ctc"] is not None:
-                    rec["ctc"]["xbT"] = ops.transpose_bf16(rec["ctc"]["xb"])
-            S["y2T"] = ops.transpose_bf16(y2.view(B * L, -1))
-            S["colT"] = ops.conv2_im2col_t(y1)
+        # The weight-gradient GEMMs contract over tokens and want token-contiguous operands; the activation halves
+        # of those operands depend on the forward only.  `pretranspose(S)` makes them in one batched launch; it is
+        # called by whoever runs first in the backward (criterion.CtcProjLossFn: before the decoder's backward,
+        # which is bound by the host's launch rate and leaves the GPU idle) -- inside this node's backward they
+        # sit on the GPU-bound critical path (44 launches, ~1.3 ms per cfg4 step).
+        mode = getattr(enc, "pretranspose_activations", True)
+        mode = os.environ.get("FBKST_PRETRANSPOSE", "bwd" if mode is True else ("off" if not mode else mode))
+        enc._train_pending = S if mode == "bwd" else None
+        if mode == "fwd":
+            pretranspose(S)
         ctx.S, ctx.enc = S, enc
         if getattr(enc, "keep_train_state", False):  # tests: the activation patterns of this forward
             enc.last_train_state = S
@@ -269,86 +314,94 @@ class EncoderTrainFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_out, d_ctc=None, d_tap=None):
         S, enc = ctx.S, ctx.enc
+        if getattr(enc, "_train_pending", None) is S:  # no criterion node did it earlier: one batched launch here
+            enc._train_pending = None
+            pretranspose(S)
+        elif not S.get("pretransposed") and getattr(enc, "pretranspose_activations", True) and \
+                os.environ.get("FBKST_PRETRANSPOSE", "") != "off":
+            pretranspose(S)
         W = prepare_train_weights(enc)
         B, L, D, H, C = S["B"], S["L"], enc.embed_dim, enc.heads, enc.conv_channels
         seed, p, p_act, p_att, p_conv = S["seed"], S["p"], S["p_act"], S["p_att"], S["p_conv"]
-        G = {}
-        M_out = S["L_out"] * B
-        if d_out is None:
-            dx = torch.zeros(M_out, D, dtype=torch.float32, device=S["x_in"].device)
-        else:
-            dy = d_out.reshape(M_out, D).float().contiguous()
-            dx, G["gf"], G["bf"] = ops.ln_bwd(dy, S["x_last"], W["gf"], eps=enc.layer_norm.eps)
-        for li in range(len(S["layers"]) - 1, -1, -1):
-            R, Wl = S["layers"][li], W["layers"][li]
-            cur_L, cur_len, sites = R["L"], R["lengths"], R["sites"]
-            M = cur_L * B
-            g = {}
-            RT = R.get("T") or {}
+        # every reduction whose result is only read when the backward returns (bias gradients, split-K slices of
+        # the weight gradients, LayerNorm parameter gradients: ~120 per step) is queued and launched as ONE batch
+        with ops.deferred_reductions():
+            G = {}
+            M_out = S["L_out"] * B
+            if d_out is None:
+                dx = torch.zeros(M_out, D, dtype=torch.float32, device=S["x_in"].device)
+            else:
+                dy = d_out.reshape(M_out, D).float().contiguous()
+                dx, G["gf"], G["bf"] = ops.ln_bwd(dy, S["x_last"], W["gf"], eps=enc.layer_norm.eps)
+            for li in range(len(S["layers"]) - 1, -1, -1):
+                R, Wl = S["layers"][li], W["layers"][li]
+                cur_L, cur_len, sites = R["L"], R["lengths"], R["sites"]
+                M = cur_L * B
+                g = {}
+                RT = R.get("T") or {}
 
-            def tr(name):  # token-contiguous copy of a saved activation (made at the end of the forward)
-                return RT[name] if name in RT else ops.transpose_bf16(R[name])
-            if R["ctc"] is not None:
-                ct = R["ctc"]
-                # dx holds the L2*B compressed rows; a frame's segment id is < its utterance's new length <= L2
-                dx = ops.ctc_compress_bwd(dx, ct["seg_id"], ct["weight"], cur_L, B)
-                if d_tap is not None:
-                    dx += d_tap.reshape(M, D)
-                if d_ctc is not None:
-                    V = ct["V"]
-                    Vp = (V + 7) // 8 * 8
-                    gc = d_ctc.reshape(M, V)
-                    if gc.dtype != torch.float32 or gc.stride(-1) != 1:
-                        gc = gc.float().contiguous()
-                    gb, gT, G["bc"] = ops.grad_prep(gc, n_pad=Vp)
-                    G["wc"] = ops.linear_wgrad(gT, ct.get("xbT") if ct.get("xbT") is not None
-                                               else ops.transpose_bf16(ct["xb"]))
-                    wcT = W["wcT"]
-                    wcT_full = wcT if Vp == V else torch.as_strided(wcT, (D, Vp), (wcT.stride(0), 1))
-                    dx = ops.linear(gb, wcT_full, None, residual=dx, out_dtype=torch.float32)
-            # ---- feed-forward block (transformer_layer.py:124-136)
-            g2, g2T, g["b2"] = ops.grad_prep(dx, p=p, seed=seed, site=sites["ffn"], dp_cols=D)
-            g["w2"] = ops.linear_wgrad(g2T, tr("f"))
-            df = ops.linear(g2, Wl["w2T"])
-            dh, dhT, g["b1"] = ops.grad_prep(df, act=R["f"], act_scale=1.0 / (1.0 - p_act) if p_act > 0 else 1.0)
-            g["w1"] = ops.linear_wgrad(dhT, tr("ln2"))
-            dln2 = ops.linear(dh, Wl["w1T"], out_dtype=torch.float32)
-            dx, g["g2"], g["be2"] = ops.ln_bwd(dln2, R["x1"], Wl["g2"], dx=dx, eps=Wl["eps2"])
-            # ---- self-attention block (:104-122)
-            g1, g1T, g["bo"] = ops.grad_prep(dx, p=p, seed=seed, site=sites["out"], dp_cols=D)
-            g["wo"] = ops.linear_wgrad(g1T, tr("att"))
-            dO = ops.linear(g1, Wl["woT"])
-            dqkv = ops.attention_train_bwd(R["qkv"], R["att"], dO, R["lse"], cur_len, cur_L, B, H, enc.log_penalty,
-                                           p_att, seed, sites["att"])
-            _, dqkvT, g["bqkv"] = ops.grad_prep(dqkv, want_gb=False)
-            g["wqkv"] = ops.linear_wgrad(dqkvT, tr("ln1"))
-            dln1 = ops.linear(dqkv, Wl["wqkvT"], out_dtype=torch.float32)
-            dx, g["g1"], g["be1"] = ops.ln_bwd(dln1, R["x"], Wl["g1"], dx=dx, eps=Wl["eps1"])
-            G[li] = g
-        # ---- embedding dropout, positions (constant), fc3 + ReLU (conv_transformer.py:225-232)
-        F2C = S["y2"].shape[2] * C
-        dh3, dh3T, G["b3"] = ops.grad_prep(dx, act=S["h3b"], remap=(L, B), p=p, seed=seed, site=_SITE_EMB, dp_cols=D)
-        y2T = S["y2T"] if "y2T" in S else ops.transpose_bf16(S["y2"].view(B * L, F2C))
-        dW3p = ops.linear_wgrad(dh3T, y2T)  # [D, F2*C] (f, c) order
+                def tr(name):  # token-contiguous copy of a saved activation (made at the end of the forward)
+                    return RT[name] if name in RT else ops.transpose_bf16(R[name])
+                if R["ctc"] is not None:
+                    ct = R["ctc"]
+                    # dx holds the L2*B compressed rows; a frame's segment id is < its utterance's new length <= L2
+                    dx = ops.ctc_compress_bwd(dx, ct["seg_id"], ct["weight"], cur_L, B)
+                    if d_tap is not None:
+                        dx += d_tap.reshape(M, D)
+                    if d_ctc is not None:
+                        V = ct["V"]
+                        Vp = (V + 7) // 8 * 8
+                        gc = d_ctc.reshape(M, V)
+                        if gc.dtype != torch.float32 or gc.stride(-1) != 1:
+                            gc = gc.float().contiguous()
+                        gb, gT, G["bc"] = ops.grad_prep(gc, n_pad=Vp)
+                        G["wc"] = ops.linear_wgrad(gT, ops.transpose_bf16(ct["xb"]))
+                        wcT = W["wcT"]
+                        wcT_full = wcT if Vp == V else torch.as_strided(wcT, (D, Vp), (wcT.stride(0), 1))
+                        dx = ops.linear(gb, wcT_full, None, residual=dx, out_dtype=torch.float32)
+                # ---- feed-forward block (transformer_layer.py:124-136)
+                g2, g2T, g["b2"] = ops.grad_prep(dx, p=p, seed=seed, site=sites["ffn"], dp_cols=D)
+                g["w2"] = ops.linear_wgrad(g2T, tr("f"))
+                df = ops.linear(g2, Wl["w2T"])
+                dh, dhT, g["b1"] = ops.grad_prep(df, act=R["f"], act_scale=1.0 / (1.0 - p_act) if p_act > 0 else 1.0)
+                g["w1"] = ops.linear_wgrad(dhT, tr("ln2"))
+                dln2 = ops.linear(dh, Wl["w1T"], out_dtype=torch.float32)
+                dx, g["g2"], g["be2"] = ops.ln_bwd(dln2, R["x1"], Wl["g2"], dx=dx, eps=Wl["eps2"])
+                # ---- self-attention block (:104-122)
+                g1, g1T, g["bo"] = ops.grad_prep(dx, p=p, seed=seed, site=sites["out"], dp_cols=D)
+                g["wo"] = ops.linear_wgrad(g1T, tr("att"))
+                dO = ops.linear(g1, Wl["woT"])
+                dqkv = ops.attention_train_bwd(R["qkv"], R["att"], dO, R["lse"], cur_len, cur_L, B, H, enc.log_penalty,
+                                               p_att, seed, sites["att"])
+                _, dqkvT, g["bqkv"] = ops.grad_prep(dqkv, want_gb=False)
+                g["wqkv"] = ops.linear_wgrad(dqkvT, tr("ln1"))
+                dln1 = ops.linear(dqkv, Wl["wqkvT"], out_dtype=torch.float32)
+                dx, g["g1"], g["be1"] = ops.ln_bwd(dln1, R["x"], Wl["g1"], dx=dx, eps=Wl["eps1"])
+                G[li] = g
+            # ---- embedding dropout, positions (constant), fc3 + ReLU (conv_transformer.py:225-232)
+            F2C = S["y2"].shape[2] * C
+            dh3, dh3T, G["b3"] = ops.grad_prep(dx, act=S["h3b"], remap=(L, B), p=p, seed=seed, site=_SITE_EMB, dp_cols=D)
+            y2T = S["y2T"] if "y2T" in S else ops.transpose_bf16(S["y2"].view(B * L, F2C))
+            dW3p = ops.linear_wgrad(dh3T, y2T)  # [D, F2*C] (f, c) order
+            dy2 = ops.linear(dh3, W["w3T"])  # [B*L, F2*C] bf16 == [B, T2, F2, C]
+            # ---- conv2 block
+            bn = enc.bn[1]
+            dz2, G["bn1_b"], G["bn1_w"] = ops.bn_relu_bwd(dy2.view(S["y2"].shape), S["y2r"], bn.weight.detach().float(),
+                                                          S["bn2"][0], S["bn2"][1], S["train"], p_conv, seed, _SITE_CONV2)
+            P2 = dz2.numel() // C
+            _, dz2T, G["cb2"] = ops.grad_prep(dz2.view(P2, C), want_gb=False)
+            dW2p = ops.linear_wgrad(dz2T, S["colT"] if "colT" in S else ops.conv2_im2col_t(S["y1"]))  # [Cout, (tap, ci)]
+            dcol = ops.linear(dz2.view(P2, C), W["w2d"])
+            T1, F1 = S["y1"].shape[1], S["y1"].shape[2]
+            dy1 = ops.conv2_col2im(dcol, B, T1, F1, C)
+            # ---- conv1 block
+            bn = enc.bn[0]
+            dz1, G["bn0_b"], G["bn0_w"] = ops.bn_relu_bwd(dy1, S["y1r"], bn.weight.detach().float(), S["bn1"][0],
+                                                          S["bn1"][1], S["train"], p_conv, seed, _SITE_CONV1)
+            dW1, G["cb1"] = ops.conv1_wgrad(dz1, S["x_in"])
+            G["cw1"] = dW1.reshape(C, 1, 3, 3)
         G["w3"] = dW3p.view(D, enc.feat_out, C).permute(0, 2, 1).reshape(D, C * enc.feat_out)
-        dy2 = ops.linear(dh3, W["w3T"])  # [B*L, F2*C] bf16 == [B, T2, F2, C]
-        # ---- conv2 block
-        bn = enc.bn[1]
-        dz2, G["bn1_b"], G["bn1_w"] = ops.bn_relu_bwd(dy2.view(S["y2"].shape), S["y2r"], bn.weight.detach().float(),
-                                                      S["bn2"][0], S["bn2"][1], S["train"], p_conv, seed, _SITE_CONV2)
-        P2 = dz2.numel() // C
-        _, dz2T, G["cb2"] = ops.grad_prep(dz2.view(P2, C), want_gb=False)
-        dW2p = ops.linear_wgrad(dz2T, S["colT"] if "colT" in S else ops.conv2_im2col_t(S["y1"]))  # [Cout, (tap, ci)]
         G["cw2"] = dW2p.view(C, 3, 3, C).permute(0, 3, 1, 2).contiguous()
-        dcol = ops.linear(dz2.view(P2, C), W["w2d"])
-        T1, F1 = S["y1"].shape[1], S["y1"].shape[2]
-        dy1 = ops.conv2_col2im(dcol, B, T1, F1, C)
-        # ---- conv1 block
-        bn = enc.bn[0]
-        dz1, G["bn0_b"], G["bn0_w"] = ops.bn_relu_bwd(dy1, S["y1r"], bn.weight.detach().float(), S["bn1"][0],
-                                                      S["bn1"][1], S["train"], p_conv, seed, _SITE_CONV1)
-        dW1, G["cb1"] = ops.conv1_wgrad(dz1, S["x_in"])
-        G["cw1"] = dW1.reshape(C, 1, 3, 3)
         ctx.S = None  # release the saved activations
         grads = _assemble_grads(enc, G, d_ctc is not None)
         # fp16 training (`--fp16`: model.half(), fp32 master copy in fairseq's FP16Optimizer): autograd wants

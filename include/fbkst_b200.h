@@ -370,11 +370,43 @@ int fbkst_grad_prep(const void* g, int g_is_f32, int64_t ldg, const void* act_bf
 int fbkst_reduce_sum(const float* in, int G, int64_t g_stride, int rows, int cols, int64_t ldi, float* out,
                      int64_t ldo, float scale, fbkst_stream_t stream);
 
+/* The same for many independent reductions in ONE launch (a training step has ~120 of them: bias gradients,
+ * split-K slices of the weight-gradient GEMMs, LayerNorm parameter gradients -- all consumed only when the
+ * backward returns).  `descs` is a HOST array; it is copied into the kernel parameters, so it may be reused
+ * as soon as the call returns. */
+typedef struct {
+  const float* in;
+  float* out;
+  int64_t g_stride, ldi, ldo;
+  int32_t G, rows, cols;
+  float scale;
+} fbkst_reduce_desc_t;
+int fbkst_reduce_sum_batch(const fbkst_reduce_desc_t* descs, int n, fbkst_stream_t stream);
+
+/* Many (bf16 copy, transposed bf16 copy) jobs in ONE launch: job i reads src [rows, cols] (src_type 0 bf16,
+ * 1 fp32, 2 IEEE fp16; pitch ld_src elements) and writes copy [rows, cols] bf16 (pitch ld_copy; optional) and
+ * transposed [cols, rows] bf16 (pitch ld_transposed; optional).  Used for the per-step operand copies of the
+ * fp32 master weights (what autocast / `.half()` does per nn.Linear in the reference's fp16 training) and for
+ * the token-contiguous activation copies of the weight-gradient GEMMs.  `descs` is a HOST array (see above);
+ * `reserved` is ignored on input. */
+typedef struct {
+  const void* src;
+  void* copy;
+  void* transposed;
+  int64_t ld_src, ld_copy, ld_transposed;
+  int32_t rows, cols, src_type, reserved;
+} fbkst_prep_desc_t;
+int fbkst_prep_batch(const fbkst_prep_desc_t* descs, int n, fbkst_stream_t stream);
+
 /* Weight gradient of a linear layer: dW[n, k] = sum_m gT[n, m] xT[k, m] (fp32), split-K over the tokens on
  * the CTA-pair tcgen05 kernel + fixed-order reduction.  workspace: fbkst_linear_wgrad_workspace() floats. */
 long long fbkst_linear_wgrad_workspace(int n_out, int k_in, int tokens);
 int fbkst_linear_wgrad_bf16(const void* gT, int64_t ldg, const void* xT, int64_t ldx, float* workspace, float* dW,
                             int64_t lddw, int n_out, int k_in, int tokens, fbkst_stream_t stream);
+/* Only the split-K GEMM of the call above: the slices stay in `workspace` as [*splits][ceil32(n_out)][ceil8(k_in)]
+ * fp32 and the caller reduces them (fbkst_reduce_sum / fbkst_reduce_sum_batch) when it needs dW. */
+int fbkst_linear_wgrad_slices_bf16(const void* gT, int64_t ldg, const void* xT, int64_t ldx, float* workspace,
+                                   int n_out, int k_in, int tokens, int* splits, fbkst_stream_t stream);
 
 /* Self-attention for training (local_attention.py:115-139 incl. F.dropout on the probabilities, :136):
  * qkv [L*B, 3*H*64] bf16 UNSCALED (the kernel applies head_dim^-0.5, :98); out [L*B, H*64] bf16;

@@ -309,3 +309,75 @@ def test_conv1_wgrad():
     dW1, db1 = ops.conv1_wgrad(dz1, x)
     assert rel_err(dW1.reshape(C, 1, 3, 3), w.grad) < 1e-4
     assert rel_err(db1, b.grad) < 1e-4
+
+
+def test_prep_batch_many_jobs():
+    """fbkst_prep_batch: > 48 (copy, transposed) jobs of mixed source types and ragged shapes in one call,
+    including row-block jobs that fill one destination (the q / k / v layout) and a zero-padded transposed pitch."""
+    from fbkst_b200 import ops as O
+    torch.manual_seed(3)
+    g = torch.Generator(device="cuda").manual_seed(4)
+    jobs, checks = [], []
+    shapes = [(64, 64), (130, 72), (512, 1536), (77, 8), (1, 200), (300, 1), (2048, 512)]
+    for i in range(55):
+        r, c = shapes[i % len(shapes)]
+        dt = (torch.float32, torch.bfloat16, torch.float16)[i % 3]
+        src = (torch.randn(r, c, device="cuda", generator=g) * 3).to(dt)
+        cp = torch.empty(r, (c + 7) // 8 * 8, dtype=torch.bfloat16, device="cuda")[:, :c] if i % 4 != 3 else None
+        tr = O.transposed_buffer(r, c, "cuda") if i % 5 != 4 or cp is None else None
+        jobs.append((src, cp, tr))
+        checks.append((src, cp, tr))
+    # three row blocks into one destination pair
+    D = 96
+    blocks = [torch.randn(D, 40, device="cuda", generator=g) for _ in range(3)]
+    full = torch.empty(3 * D, 40, dtype=torch.bfloat16, device="cuda")
+    fullT = torch.zeros(40, 3 * D + 8, dtype=torch.bfloat16, device="cuda")
+    for k, w in enumerate(blocks):
+        jobs.append((w, full[k * D:(k + 1) * D], fullT[:, k * D:(k + 1) * D]))
+    O.prep_batch(jobs)
+    torch.cuda.synchronize()
+    for src, cp, tr in checks:
+        ref = src.float().to(torch.bfloat16)
+        if cp is not None:
+            assert torch.equal(cp, ref)
+        if tr is not None:
+            assert torch.equal(tr, ref.t())
+    ref = torch.cat(blocks, 0).to(torch.bfloat16)
+    assert torch.equal(full, ref) and torch.equal(fullT[:, :3 * D], ref.t())
+    assert (fullT[:, 3 * D:] == 0).all()  # pad columns untouched
+
+
+def test_deferred_reductions_match_immediate():
+    """ops.deferred_reductions(): > 56 queued reductions (both kernels: few / many slices) == immediate ones."""
+    from fbkst_b200 import ops as O
+    g = torch.Generator(device="cuda").manual_seed(5)
+    cases = []
+    for i in range(70):
+        G, rows, cols = [(3, 40, 24), (375, 1, 512), (10, 512, 512), (40, 2, 1024), (17, 1, 7)][i % 5]
+        ldi = cols + (8 if i % 2 else 0)
+        src = torch.randn(G, rows, ldi, device="cuda", generator=g)
+        cases.append((src, G, rows * ldi, rows, cols, ldi))
+    outs_now = []
+    for src, G, gs, rows, cols, ldi in cases:
+        o = torch.empty(rows, cols, device="cuda")
+        O.reduce_sum(src, G, gs, rows, cols, ldi, o, cols, 0.5)
+        outs_now.append(o)
+    outs_q = []
+    with O.deferred_reductions():
+        for src, G, gs, rows, cols, ldi in cases:
+            o = torch.full((rows, cols), float("nan"), device="cuda")
+            O.reduce_sum(src, G, gs, rows, cols, ldi, o, cols, 0.5)
+            outs_q.append(o)
+    torch.cuda.synchronize()
+    for (src, G, gs, rows, cols, ldi), a, b in zip(cases, outs_now, outs_q):
+        assert torch.equal(a, b)  # same fixed summation order
+        ref = 0.5 * src[:, :, :cols].double().sum(0)
+        assert (a.double() - ref).abs().max() <= 1e-4 * max(1.0, ref.abs().max().item())
+    # wgrad through the queue == wgrad without
+    gT = torch.randn(256, 4096, device="cuda", generator=g).to(torch.bfloat16)
+    xT = torch.randn(192, 4096, device="cuda", generator=g).to(torch.bfloat16)
+    a = O.linear_wgrad(gT, xT)
+    with O.deferred_reductions():
+        b = O.linear_wgrad(gT, xT)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
