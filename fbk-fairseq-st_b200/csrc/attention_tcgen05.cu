@@ -57,7 +57,12 @@ static inline int attention_lut_floats(int L) {
 static inline int attention_smem_bytes(int L) { return AT_SMEM_FIXED + 4 * attention_lut_floats(L); }
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
-
+// Decoupled kernel, one-pass softmax (default; 0 = max pass + exp pass, two TMEM reads of S): log2 units by
+// which a row's raw scores may exceed the running reference before it is raised.
+#ifndef FBKST_ATTN_ONEPASS
+#define FBKST_ATTN_ONEPASS 1
+#endif
+constexpr float kGrowThreshold = 24.0f;
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -81,6 +86,27 @@ __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// maximum of 32 raw scores held in two 16-register TMEM load groups
+__device__ __forceinline__ float raw_max32(const uint32_t (&a)[16], const uint32_t (&b)[16]) {
+  float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+  for (int cc = 0; cc < 16; ++cc) {
+    m4[cc & 3] = fmaxf(m4[cc & 3], __uint_as_float(a[cc]));
+    m4[(cc + 2) & 3] = fmaxf(m4[(cc + 2) & 3], __uint_as_float(b[cc]));
+  }
+  return fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+}
+// the same over the first nv columns only (a = columns 0..15, b = 16..31 of the half); -inf when nv <= 0
+__device__ __forceinline__ float raw_max32_masked(const uint32_t (&a)[16], const uint32_t (&b)[16], int nv) {
+  float m = -INFINITY;
+#pragma unroll
+  for (int cc = 0; cc < 16; ++cc) {
+    if (cc < nv) m = fmaxf(m, __uint_as_float(a[cc]));
+    if (16 + cc < nv) m = fmaxf(m, __uint_as_float(b[cc]));
+  }
+  return m;
 }
 
 // 2^x on the FMA/ALU pipes for part of every row (Cody-Waite range reduction + degree-3 minimax
@@ -622,9 +648,20 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
 //       event loop over non-blocking mbarrier.test_wait probes that issues K/Q loads, V loads and PV
 //       MMAs as their barriers complete: S-wait 170-250 cycles, 59.5 vs 61.4 us at L=375, ragged cfg3
 //       attention 0.644 vs 0.662 ms/step, nothing slower.
-// What still bounds it: a group's tile period is ~3500 cycles of which the exp pass is ~2500 with four
-// groups sharing one MUFU pipe (floor 2048) and ~0.55 IPC per scheduler; the next step is fewer issue
-// slots per element (S row kept in registers, one TMEM read), not more overlap.
+//   v3  (round 2) one-pass softmax (ONE TMEM read of S: the row maximum is only an overflow guard because P is
+//       bf16 and l / O are fp32, see the tile loop), P and V handed over in two 32-key halves with their own
+//       barriers, PV and V streams of the two groups independent of each other: parity green, SAME time
+//       (61.4 us) -- and so is the kernel with the LUT loads, the exponentials and the P stores all knocked out
+//       (59.4 us).  The softmax arithmetic is not what bounds this kernel.
+// What bounds it (scripts/probes/umma_probe.cu, profiles/r02w_umma_probe.txt): one tcgen05.mma with M = 128 takes
+// ~186 cycles of the tensor pipe WHATEVER its N (64, 128 and 256 alike: N = 256 is the math rate behind the measured
+// 1.6 PFLOP/s bf16 peak), two issuing warps overlap to one per ~93 cycles, four issuing warps (or one thread
+// alternating between accumulators) fall to one per 220-320.  With head_dim 64 every instruction here has N = 64:
+// a 128 x 64 key tile costs 4 (QK) + 4 (PV) instructions, 32 per tile period of the four groups on an SM = ~3000
+// cycles at the best observed rate, against the ~3500 measured.  The kernel sits at its INSTRUCTION-count roof on
+// the tensor pipe (a quarter of the FLOP roof); wider S tiles (N = 128 halves the QK count) do not fit the 256 TMEM
+// columns a CTA has next to O, and PV's N is the head dimension.  An L2 prefetch of the next item's boxes and a TMA
+// store of the output tile were measured slower (66.6 / 63.5 us).
 constexpr int ATD_SMEM_FIXED = 2 * AT_QB + AT_KST * AT_KB + 2 * AT_KB + 2 * AT_QB /*P x2*/ +
                                256 /*barriers*/ + 64 * 16 /*item table*/ + 1024 /*align*/;
 static inline int attention_dec_smem_bytes(int L) { return ATD_SMEM_FIXED + 4 * attention_lut_floats(L); }
@@ -657,7 +694,7 @@ struct GrpCursor {
 template <int LOGPEN>
 __global__ void __launch_bounds__(AT_THREADS, 2)
     attention_fwd_dec_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-                             __nv_bfloat16* __restrict__ out, const int* __restrict__ lengths, int L, int B,
+                             const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, const int* __restrict__ lengths, int L, int B,
                              int H, const int* __restrict__ q_limit) {
   const int D = H * AT_HD;
   const int nq = (L + AT_BM - 1) / AT_BM;
@@ -680,17 +717,26 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
   uint64_t* q_empty = bars + 2;   // [2]
   uint64_t* k_full = bars + 4;    // [3]
   uint64_t* k_empty = bars + 7;   // [3]
-  uint64_t* v_full = bars + 10;   // [2]
-  uint64_t* v_empty = bars + 12;  // [2]
+  // V is loaded in the same two 32-key halves the PV product consumes (boxes of tmV), each half free again as
+  // soon as ITS PV half has completed (pv_lo / pv_hi): the next tile's V is on its way half a tile before it is
+  // needed, although V is single-buffered
+  uint64_t* v_lo = bars + 10;     // [2]
+  uint64_t* v_hi = bars + 12;     // [2]
   uint64_t* s_full = bars + 14;   // [2]
-  uint64_t* p_full = bars + 16;   // [2]
-  uint64_t* pv_done = bars + 18;  // [2]
+  // P is handed to the tensor pipe in two 32-key halves (same 16 KB tile, k-steps 0-1 / 2-3 of the PV product),
+  // each with its own full / done barrier: the first half of the NEXT tile's P only waits for the PV half that
+  // was issued half a tile earlier, so the one-pass softmax never sits on the latency of the PV it just requested
+  uint64_t* p_lo = bars + 16;     // [2]
+  uint64_t* pv_lo = bars + 18;    // [2]
   uint64_t* s_free = bars + 20;   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+  uint64_t* p_hi = bars + 22;     // [2]
+  uint64_t* pv_hi = bars + 24;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmKV);
+    tma_prefetch_desc(&tmV);
     for (int s = 0; s < AT_KST; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&k_empty[s], 1);
@@ -698,11 +744,13 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
     for (int s = 0; s < 2; ++s) {
       mbar_init(&q_full[s], 1);
       mbar_init(&q_empty[s], 1);
-      mbar_init(&v_full[s], 1);
-      mbar_init(&v_empty[s], 1);
+      mbar_init(&v_lo[s], 1);
+      mbar_init(&v_hi[s], 1);
       mbar_init(&s_full[s], 1);
-      mbar_init(&p_full[s], 128);
-      mbar_init(&pv_done[s], 1);
+      mbar_init(&p_lo[s], 128);
+      mbar_init(&p_hi[s], 128);
+      mbar_init(&pv_lo[s], 1);
+      mbar_init(&pv_hi[s], 1);
       mbar_init(&s_free[s], 128);
     }
     fence_barrier_init();
@@ -741,7 +789,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
     GrpCursor kc0, kc1, vc0, vc1, pc0, pc1;
     kc0.init(items, 0); kc1.init(items, 1); vc0.init(items, 0); vc1.init(items, 1);
     pc0.init(items, 0); pc1.init(items, 1);
-    int kturn = 0, vturn = 0, pturn = 0;
+    int kturn = 0;
     uint32_t gk = 0;
     auto try_k = [&](GrpCursor& c, int g) -> bool {
       const uint32_t ks = gk % AT_KST;
@@ -761,32 +809,45 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
       c.advance(items);
       return true;
     };
+    int v_half[2] = {0, 0};  // which half of the group's current V tile is loaded next
     auto try_v = [&](GrpCursor& c, int g) -> bool {
-      if (!mbar_test_wait(&v_empty[g], (c.c & 1) ^ 1)) return false;
+      const int hf = v_half[g];
+      // the half-buffer was read by the matching PV half of the group's previous tile
+      if (c.c >= 1 && !mbar_test_wait(hf ? &pv_hi[g] : &pv_lo[g], (c.c - 1) & 1)) return false;
       const int cv = 2 * D + c.it.h * AT_HD;
       if (elect_one()) {
-        mbar_arrive_expect_tx(&v_full[g], AT_KB);
-        tma_load_3d(sV + g * AT_KB, &tmKV, &v_full[g], cv, c.it.b, c.j * AT_BN);
+        uint64_t* bar = hf ? &v_hi[g] : &v_lo[g];
+        mbar_arrive_expect_tx(bar, AT_KB / 2);
+        tma_load_3d(sV + g * AT_KB + hf * (AT_KB / 2), &tmV, bar, cv, c.it.b, c.j * AT_BN + hf * (AT_BN / 2));
       }
       __syncwarp();
-      c.advance(items);
+      v_half[g] = hf ^ 1;
+      if (hf == 1) c.advance(items);
       return true;
     };
+    int pv_half[2] = {0, 0};  // which half of the group's current tile is issued next
     auto try_pv = [&](GrpCursor& c, int g) -> bool {
       const uint32_t ph = c.c & 1;
-      if (!mbar_test_wait(&p_full[g], ph) || !mbar_test_wait(&v_full[g], ph)) return false;
+      const int hf = pv_half[g];
+      if (hf == 0) {
+        if (!mbar_test_wait(&p_lo[g], ph) || !mbar_test_wait(&v_lo[g], ph)) return false;
+      } else {
+        if (!mbar_test_wait(&p_hi[g], ph) || !mbar_test_wait(&v_hi[g], ph)) return false;
+      }
       tc_fence_after();
       const uint32_t pa = smem_u32(sP + g * AT_QB), va = smem_u32(sV + g * AT_KB);
       if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < AT_BN / 16; ++kk)
+        for (int k2 = 0; k2 < 2; ++k2) {
+          const int kk = hf * 2 + k2;
           umma_bf16_ss(tmem_O + g * AT_HD, desc_kmajor_sw128(pa) + 2 * kk,
                        desc_mnmajor_sw128(va + kk * 2048, AT_KB), IDESC_PV, (c.j > 0) || kk != 0);
-        umma_commit(&pv_done[g]);
-        umma_commit(&v_empty[g]);
+        }
+        umma_commit(hf ? &pv_hi[g] : &pv_lo[g]);
       }
       __syncwarp();
-      c.advance(items);
+      pv_half[g] = hf ^ 1;
+      if (hf == 1) c.advance(items);
       return true;
     };
     uint32_t idle = 0;
@@ -796,22 +857,22 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
       const bool p_left = pc0.valid(n_items) || pc1.valid(n_items);
       if (!k_left && !v_left && !p_left) break;
       bool progressed = false;
-      if (p_left) {  // PV first: it is what the softmax groups wait for
-        const bool ok = (ATD_PICK(pc0, pc1, pturn) == 0) ? try_pv(pc0, 0) : try_pv(pc1, 1);
-        if (ok) { pturn ^= 1; progressed = true; }
+      if (p_left) {  // PV first: it is what the softmax groups wait for; the groups' PV streams are independent
+        if (pc0.valid(n_items) && try_pv(pc0, 0)) progressed = true;
+        if (pc1.valid(n_items) && try_pv(pc1, 1)) progressed = true;
       }
       if (k_left) {
         const bool ok = (ATD_PICK(kc0, kc1, kturn) == 0) ? try_k(kc0, 0) : try_k(kc1, 1);
         if (ok) { kturn ^= 1; progressed = true; }
       }
-      if (v_left) {
-        const bool ok = (ATD_PICK(vc0, vc1, vturn) == 0) ? try_v(vc0, 0) : try_v(vc1, 1);
-        if (ok) { vturn ^= 1; progressed = true; }
+      if (v_left) {  // per-group buffers: the groups' V streams are independent as well
+        if (vc0.valid(n_items) && try_v(vc0, 0)) progressed = true;
+        if (vc1.valid(n_items) && try_v(vc1, 1)) progressed = true;
       }
       if (!progressed) __nanosleep(32);  // do not take issue slots from the softmax warps of this SMSP
 #if FBKST_WATCHDOG
       idle = progressed ? 0 : idle + 1;
-      if (idle > (1u << 25)) {
+      if (idle > (1u << 27)) {
         printf("fbkst: attention event loop watchdog block=%d\n", blockIdx.x);
         __trap();
       }
@@ -862,8 +923,10 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
     const uint32_t tO = tmem_O + lane_addr + grp * AT_HD;
     const int swz = q & 7;
     uint64_t* my_s_full = &s_full[grp];
-    uint64_t* my_p_full = &p_full[grp];
-    uint64_t* my_pv_done = &pv_done[grp];
+    uint64_t* my_p_lo = &p_lo[grp];
+    uint64_t* my_p_hi = &p_hi[grp];
+    uint64_t* my_pv_lo = &pv_lo[grp];
+    uint64_t* my_pv_hi = &pv_hi[grp];
     uint64_t* my_s_free = &s_free[grp];
     uint8_t* myP = sP + grp * AT_QB + q * 128;
     const int lut_off = nq * AT_BM;
@@ -899,6 +962,124 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
         mbar_wait(my_s_full, ph);
         if (warp == 2 || warp == 6) AT_TRACE(2 * c + grp, 3);
         tc_fence_after();
+#if FBKST_ATTN_ONEPASS
+        // ONE pass over S (one TMEM read): the row maximum is only an overflow guard here -- P is bf16 and
+        // l / O are fp32, all with the fp32 exponent range, so any reference m_used within 2^kGrowThreshold
+        // of the row's scores gives the same softmax.  The raw maximum of each 32-column half is taken from
+        // the registers the half was loaded into, BEFORE S is handed back: the first half may raise the
+        // reference (always at an item's first tile), a second half that exceeds it restarts the tile
+        // (S is still in TMEM) -- rare: scores 16.6 nats above everything the row has seen so far.
+        const uint32_t lut_addr = smem_u32(sLut + (lut_off - i) + k0);
+        const float2 l2e2 = make_float2(kLog2e, kLog2e);
+        float2 sm2[2];
+        float m_restart = -INFINITY;  // reference demanded by a second half that overflowed (restart)
+        for (;;) {
+          uint32_t sa[16], sb[16];
+          float pn[8];
+          bool redo = false;
+          tmem_ld16(tS, sa);
+          tmem_ld16(tS + 16, sb);
+          if (LOGPEN) {
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) pn[cc] = lds32(lut_addr + cc * 4);
+          }
+          sm2[0] = make_float2(0.f, 0.f);
+          sm2[1] = make_float2(0.f, 0.f);
+          tmem_ld_wait();
+          if (warp == 2 || warp == 6) AT_TRACE(2 * c + grp, 8);
+          {
+            const float m_half =
+                fmaxf((nvalid == AT_BN ? raw_max32(sa, sb) : raw_max32_masked(sa, sb, nvalid)) * kLog2e, m_restart);
+            const bool grow = m_half > m_used + kGrowThreshold;
+            if (__any_sync(0xffffffffu, grow)) {
+              const float m_next = grow ? m_half : m_used;
+              if (j > 0) {
+                mbar_wait(my_pv_hi, ph ^ 1);  // O[grp] quiescent: every PV of the previous tile has completed
+                const float alpha = ex2(m_used - m_next);
+                tc_fence_after();
+                // rare path: rolled, 8 columns at a time, so that it costs the hot path no registers
+#pragma unroll 1
+                for (int cb = 0; cb < AT_HD; cb += 8) {
+                  uint32_t o0[8];
+                  tmem_ld8(tO + cb, o0);
+                  tmem_ld_wait();
+#pragma unroll
+                  for (int cc = 0; cc < 8; ++cc) o0[cc] = __float_as_uint(__uint_as_float(o0[cc]) * alpha);
+                  tmem_st8(tO + cb, o0);
+                }
+                tmem_st_wait();
+                l *= alpha;
+              }
+              m_used = m_next;
+            }
+          }
+          if (warp == 2 || warp == 6) AT_TRACE(2 * c + grp, 4);
+          const float2 negm2 = make_float2(-m_used, -m_used);
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            uint32_t(&s0)[16] = (ch & 2) ? sb : sa;
+            const int o = (ch & 1) * 8;
+            float2 t[4];
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+              float2 add = negm2;
+              if (LOGPEN) add = fadd2(negm2, make_float2(pn[2 * cc], pn[2 * cc + 1]));
+              t[cc] = ffma2(make_float2(__uint_as_float(s0[o + 2 * cc]), __uint_as_float(s0[o + 2 * cc + 1])),
+                            l2e2, add);
+            }
+            if (ch == 1 || ch == 3) tmem_ld16(tS + (ch + 3) * 8, s0);
+            if (LOGPEN && ch < 7) {
+#pragma unroll
+              for (int cc = 0; cc < 8; ++cc) pn[cc] = lds32(lut_addr + ((ch + 1) * 8 + cc) * 4);
+            }
+            if (ch == 3) {  // the second half is in registers: check it, then hand the accumulator back
+              tmem_ld_wait();
+              if (warp == 2 || warp == 6) AT_TRACE(2 * c + grp, 9);
+              const float m_half =
+                  (nvalid == AT_BN ? raw_max32(sa, sb) : raw_max32_masked(sa, sb, nvalid - 32)) * kLog2e;
+              const bool grow = m_half > m_used + kGrowThreshold;
+              if (__any_sync(0xffffffffu, grow)) {
+                // restart the tile against the raised reference (the first-half path rescales O / l)
+                redo = true;
+                m_restart = grow ? m_half : -INFINITY;
+                break;
+              }
+              tc_fence_before();
+              mbar_arrive(my_s_free);
+              if (warp == 2 || warp == 6) AT_TRACE(2 * c + grp, 10);
+            }
+            if (nvalid != AT_BN) {
+#pragma unroll
+              for (int cc = 0; cc < 4; ++cc) {
+                if (ch * 8 + 2 * cc >= nvalid) t[cc].x = -INFINITY;
+                if (ch * 8 + 2 * cc + 1 >= nvalid) t[cc].y = -INFINITY;
+              }
+            }
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+              t[cc].x = ex2(t[cc].x);
+              t[cc].y = ex2(t[cc].y);
+            }
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) sm2[cc & 1] = fadd2(sm2[cc & 1], t[cc]);
+            // the half of P[grp] about to be overwritten was read by the matching PV half of the previous tile
+            if (ch == 0 && c >= 1) mbar_wait(my_pv_lo, ph ^ 1);
+            if (ch == 4 && c >= 1) mbar_wait(my_pv_hi, ph ^ 1);
+            if (ch == 4 && (warp == 2 || warp == 6)) AT_TRACE(2 * c + grp, 12);
+            if (ch == 0 && (warp == 2 || warp == 6)) AT_TRACE(2 * c + grp, 5);
+            reinterpret_cast<uint4*>(myP)[ch ^ swz] =
+                make_uint4(pack_bf16x2(t[0].x, t[0].y), pack_bf16x2(t[1].x, t[1].y),
+                           pack_bf16x2(t[2].x, t[2].y), pack_bf16x2(t[3].x, t[3].y));
+            if (ch == 3) {
+              tc_fence_before();  // (orders the O reads of the previous item's epilogue / a rescale before PV)
+              fence_proxy_async_smem();
+              mbar_arrive(my_p_lo);
+              if (warp == 2 || warp == 6) AT_TRACE(2 * c + grp, 11);
+            }
+          }
+          if (!redo) break;
+        }
+#else
         // pass 1: row maximum (S is read again in pass 2: registers are the scarce resource)
         float mx = -INFINITY;
         {
@@ -922,7 +1103,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
         const float m_new = fmaxf(m_used, mx * kLog2e);
         if (warp == 2 || warp == 6) AT_TRACE(2 * c + grp, 4);
         // P[grp] / O[grp] were last used by this group's previous tile
-        if (c >= 1) mbar_wait(my_pv_done, ph ^ 1);
+        if (c >= 1) mbar_wait(my_pv_hi, ph ^ 1);
         if (warp == 2 || warp == 6) AT_TRACE(2 * c + grp, 5);
         const bool grow = m_new > m_used + kRescaleThreshold;
         if (__any_sync(0xffffffffu, grow)) {
@@ -1000,14 +1181,21 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
                            pack_bf16x2(t[2].x, t[2].y), pack_bf16x2(t[3].x, t[3].y));
           }
         }
+#endif
         l += (sm2[0].x + sm2[0].y) + (sm2[1].x + sm2[1].y);
+        if (warp == 2 || warp == 6) AT_TRACE(2 * c + grp, 0);
         tc_fence_before();
         fence_proxy_async_smem();
-        mbar_arrive(my_p_full);
+#if !FBKST_ATTN_ONEPASS
+        mbar_arrive(my_p_lo);
+#endif
+        mbar_arrive(my_p_hi);
         if (warp == 2 || warp == 6) AT_TRACE(2 * c + grp, 6);
       }
-      // ---- item epilogue (this group only): O / l -> bf16, 128 B per query row
-      mbar_wait(my_pv_done, (c - 1) & 1);  // O[grp] final
+      // ---- item epilogue (this group only): O / l -> bf16, 128 B per query row.  (Staging the tile in P[grp]
+      // and storing it with one TMA box was measured slower: 63.5 vs 62.1 us at cfg2 -- the item boundary is
+      // bound by the completion of the last PV, not by these stores.)
+      mbar_wait(my_pv_hi, (c - 1) & 1);  // O[grp] final
       tc_fence_after();
       const float inv = 1.0f / l;
 #pragma unroll
@@ -1029,7 +1217,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
         }
       }
       // O[grp] is overwritten by the PV of the group's next tile, which waits for this group's next
-      // p_full arrival (ordered after the TMEM reads above by the fence before that arrive)
+      // p_lo arrival (ordered after the TMEM reads above by the fence before that arrive)
       if (warp == 2 || warp == 6) AT_TRACE(2 * (c - 1) + grp, 7);
     }
   }
@@ -1058,7 +1246,7 @@ static int attention_entry(const void* qkv, void* out, const int32_t* lengths, i
   FBKST_REQUIRE(L > 0 && B > 0 && H > 0, "fbkst_attention_fwd: bad shape L=%d B=%d H=%d", L, B, H);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int D = H * AT_HD;
-  CUtensorMap tmQ, tmKV;
+  CUtensorMap tmQ, tmKV, tmV;
   uint64_t dims[3] = {(uint64_t)3 * D, (uint64_t)B, (uint64_t)L};
   uint64_t strides[2] = {(uint64_t)3 * D * 2, (uint64_t)B * 3 * D * 2};
   uint32_t boxq[3] = {AT_HD, 1, AT_BM};
@@ -1067,6 +1255,9 @@ static int attention_entry(const void* qkv, void* out, const int32_t* lengths, i
                            nullptr);
   if (rc) return rc;
   rc = make_tensor_map(&tmKV, qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3, dims, strides, boxk, nullptr);
+  if (rc) return rc;
+  uint32_t boxv[3] = {AT_HD, 1, AT_BN / 2};  // V halves of the decoupled kernel
+  rc = make_tensor_map(&tmV, qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3, dims, strides, boxv, nullptr);
   if (rc) return rc;
   static PerDeviceFlag configured;
   if (!configured) {
@@ -1091,10 +1282,10 @@ static int attention_entry(const void* qkv, void* out, const int32_t* lengths, i
     if (grid > n_items_all) grid = (int)n_items_all;
     if (log_penalty)
       FBKST_CHECK_CUDA(launch_pdl(attention_fwd_dec_kernel<1>, dim3(grid), dim3(AT_THREADS), smem_dec, st,
-                                  tmQ, tmKV, (__nv_bfloat16*)out, lengths, L, B, H, q_limit));
+                                  tmQ, tmKV, tmV, (__nv_bfloat16*)out, lengths, L, B, H, q_limit));
     else
       FBKST_CHECK_CUDA(launch_pdl(attention_fwd_dec_kernel<0>, dim3(grid), dim3(AT_THREADS), smem_dec, st,
-                                  tmQ, tmKV, (__nv_bfloat16*)out, lengths, L, B, H, q_limit));
+                                  tmQ, tmKV, tmV, (__nv_bfloat16*)out, lengths, L, B, H, q_limit));
     return FBKST_OK;
   }
   const int smem = attention_smem_bytes(log_penalty ? L : 0);

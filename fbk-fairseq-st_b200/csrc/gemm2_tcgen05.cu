@@ -148,7 +148,11 @@ struct ArgmaxEpi {
   int chunks;
 };
 
-template <bool OUT_F32, bool RESID, bool LNS, bool AM = false>
+// MNM: both operands are MN-major ("TN" weight-gradient product dW[n, k] = sum_t g[t, n] x[t, k], operands
+// in their natural token-major layouts): tmA / tmB are maps of the [tokens, n_out] / [tokens, k_in] matrices
+// with {64 (MN), 64 (tokens)} boxes; a CTA's 128 MN rows are two such boxes 8 KB apart (descriptor LBO), a
+// 16-token k-step advances the start address by 16 rows x 128 B.
+template <bool OUT_F32, bool RESID, bool LNS, bool AM = false, bool MNM = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
     gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
@@ -242,8 +246,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
           if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);
           const uint32_t leader_full = map_to_cta(smem_u32(&full_bar[stage]), 0);
           uint8_t* sa = smem + stage * G2_STAGE_BYTES;
-          tma_load_2d_cg2(sa, &tmA, leader_full, kb * G2_BK, row_a);
-          tma_load_2d_cg2(sa + G2_A_BYTES, &tmB, leader_full, kb * G2_BK, row_b);
+          if (MNM) {
+            tma_load_2d_cg2(sa, &tmA, leader_full, row_a, kb * G2_BK);
+            tma_load_2d_cg2(sa + G2_A_BYTES / 2, &tmA, leader_full, row_a + 64, kb * G2_BK);
+            tma_load_2d_cg2(sa + G2_A_BYTES, &tmB, leader_full, row_b, kb * G2_BK);
+            tma_load_2d_cg2(sa + G2_A_BYTES + G2_B_BYTES / 2, &tmB, leader_full, row_b + 64, kb * G2_BK);
+          } else {
+            tma_load_2d_cg2(sa, &tmA, leader_full, kb * G2_BK, row_a);
+            tma_load_2d_cg2(sa + G2_A_BYTES, &tmB, leader_full, kb * G2_BK, row_b);
+          }
         }
         __syncwarp();
         if (++stage == G2_STAGES) {
@@ -268,12 +279,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * G2_STAGE_BYTES);
-          const uint64_t adesc = desc_kmajor_sw128(sa);
-          const uint64_t bdesc = desc_kmajor_sw128(sa + G2_A_BYTES);
+          const uint64_t adesc = MNM ? desc_mnmajor_sw128(sa, G2_A_BYTES / 2) : desc_kmajor_sw128(sa);
+          const uint64_t bdesc =
+              MNM ? desc_mnmajor_sw128(sa + G2_A_BYTES, G2_B_BYTES / 2) : desc_kmajor_sw128(sa + G2_A_BYTES);
+          constexpr int KSTEP = MNM ? (16 * 128) >> 4 : 2;  // descriptor units (16 B) per 16-element k-step
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < G2_BK / 16; ++k)
-              umma_bf16_ss_cg2(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, ((kb - kb0) | k) != 0);
+              umma_bf16_ss_cg2(d_tmem, adesc + KSTEP * k, bdesc + KSTEP * k, idesc, ((kb - kb0) | k) != 0);
             umma_commit_cg2_mc(&empty_bar[stage], 0x3);
             if (kb == kb1 - 1) umma_commit_cg2_mc(&tfull_bar[acc], 0x3);
           }
@@ -547,7 +560,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
   }
 }
 
-template <bool OUT_F32, bool RESID, bool LNS, bool AM = false>
+template <bool OUT_F32, bool RESID, bool LNS, bool AM = false, bool MNM = false>
 static int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
                         const float* resid, int64_t ldr, void* out, int64_t ldo, int M, int N, int K,
                         int relu, const int* m_limit, int m_limit_mult, const LnStatsIn& ln_in,
@@ -555,7 +568,7 @@ static int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, 
                         int split_rows, cudaStream_t stream, const ArgmaxEpi* am_in = nullptr) {
   constexpr int SMEM = g2_smem(LNS);
   static_assert(SMEM <= 232448, "shared memory budget exceeded");
-  auto kern = gemm2_kernel<OUT_F32, RESID, LNS, AM>;
+  auto kern = gemm2_kernel<OUT_F32, RESID, LNS, AM, MNM>;
   ArgmaxEpi am{};
   if (am_in != nullptr) am = *am_in;
   static PerDeviceFlag configured;
@@ -564,9 +577,12 @@ static int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, 
     configured = true;
   }
   CUtensorMap tmA, tmB, tmO, tmR, tmX;
-  int rc = make_tensor_map_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, G2_BM, G2_BK);
+  // MNM: A is [K, M] (tokens x n_out), W is [K, N] (tokens x k_in); boxes of 64 tokens x 64 MN columns
+  int rc = MNM ? make_tensor_map_2d_bf16(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 64, 64)
+               : make_tensor_map_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, G2_BM, G2_BK);
   if (rc) return rc;
-  rc = make_tensor_map_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, G2_BN / 2, G2_BK);
+  rc = MNM ? make_tensor_map_2d_bf16(&tmB, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, 64, 64)
+           : make_tensor_map_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, G2_BN / 2, G2_BK);
   if (rc) return rc;
   {
     uint64_t dims[2] = {(uint64_t)N, splits > 1 ? (uint64_t)splits * split_rows : (uint64_t)M};
@@ -599,7 +615,8 @@ static int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, 
   FBKST_CHECK_CUDA(launch_pdl(kern, dim3(2 * clusters), dim3(384), SMEM, stream, tmA, tmB, tmO, tmR, tmX,
                               M, N, K, bias, relu, dbg, m_limit, m_limit_mult, ln_in,
                               reinterpret_cast<float2*>(stats_out),
-                              ab_f16 ? idesc_f16_f32(256, G2_BN, 0, 0) : idesc_bf16_f32(256, G2_BN, 0, 0),
+                              MNM ? idesc_bf16_f32(256, G2_BN, 1, 1)
+                                  : (ab_f16 ? idesc_f16_f32(256, G2_BN, 0, 0) : idesc_bf16_f32(256, G2_BN, 0, 0)),
                               splits, split_rows, am));
   return FBKST_OK;
 }
@@ -670,6 +687,27 @@ int linear_pair_splitk(const void* A, int64_t lda, const void* W, int64_t ldw, f
                                           0, ln_in, nullptr, 0, nullptr, 0, sp, split_rows, stream);
 }
 
+// The same with both operands in their natural token-major layout (no transposed copies): partial[s, n, k] =
+// sum over the s-th slice of tokens of g[t, n] x[t, k].  g [tokens, n_out] bf16, x [tokens, k_in] bf16 / fp16.
+int linear_pair_splitk_nt(const void* g, int64_t ldg, const void* x, int64_t ldx, int x_f16, float* partial,
+                          int64_t ldo, int n_out, int k_in, int tokens, int* splits, int split_rows,
+                          cudaStream_t stream) {
+  const int num_kb = (tokens + G2_BK - 1) / G2_BK;
+  int sp = *splits < 1 ? 1 : *splits;
+  if (sp > num_kb) sp = num_kb;
+  const int kb_per = (num_kb + sp - 1) / sp;
+  sp = (num_kb + kb_per - 1) / kb_per;  // no empty slice
+  *splits = sp;
+  LnStatsIn ln_in;
+  ln_in.stats = nullptr;
+  ln_in.parts = 0;
+  ln_in.dim = tokens;
+  ln_in.eps = 0.f;
+  return launch_gemm2<true, false, false, false, true>(g, ldg, x, ldx, nullptr, nullptr, 0, partial, ldo, n_out, k_in,
+                                                       tokens, 0, nullptr, 0, ln_in, nullptr, 0, nullptr, x_f16, sp,
+                                                       split_rows, stream);
+}
+
 // splits for a wgrad GEMM with `tiles_mn` output tiles over K = tokens: fill the CTA pairs about twice,
 // keep >= 8 k-blocks (512 tokens) per slice
 static int wgrad_splits(int M, int N, int K) {
@@ -710,6 +748,27 @@ extern "C" int fbkst_linear_wgrad_bf16(const void* gT, int64_t ldg, const void* 
   const int split_rows = (n_out + 31) / 32 * 32;
   const int64_t ldo = ((int64_t)k_in + 7) / 8 * 8;
   int rc = linear_pair_splitk(gT, ldg, xT, ldx, workspace, ldo, n_out, k_in, tokens, &sp, split_rows, st);
+  if (rc) return rc;
+  return fbkst_reduce_sum(workspace, sp, (int64_t)split_rows * ldo, n_out, k_in, ldo, dW, lddw, 1.0f, stream);
+}
+
+extern "C" int fbkst_linear_wgrad_nt(const void* g, int64_t ldg, const void* x, int64_t ldx, int x_is_f16,
+                                     float* workspace, float* dW, int64_t lddw, int n_out, int k_in, int tokens,
+                                     fbkst_stream_t stream) {
+  using namespace fbkst;
+  FBKST_REQUIRE(g && x && workspace && dW, "fbkst_linear_wgrad_nt: null pointer");
+  FBKST_REQUIRE(n_out > 0 && k_in > 0 && tokens > 0, "fbkst_linear_wgrad_nt: empty problem");
+  // (one tcgen05.mma takes both operands in the SAME 16-bit format: a bf16 x fp16 product is an illegal instruction)
+  FBKST_REQUIRE(!x_is_f16, "fbkst_linear_wgrad_nt: fp16 activations are not supported (use fbkst_linear_wgrad_bf16)");
+  FBKST_REQUIRE(ldg % 8 == 0 && ldx % 8 == 0 && ldg >= n_out && ldx >= k_in,
+                "fbkst_linear_wgrad_nt: operand pitches must be multiples of 8 and >= the row length");
+  FBKST_REQUIRE((reinterpret_cast<uintptr_t>(g) & 15) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0,
+                "fbkst_linear_wgrad_nt: operands must be 16-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int sp = wgrad_splits(n_out, k_in, tokens);
+  const int split_rows = (n_out + 31) / 32 * 32;
+  const int64_t ldo = ((int64_t)k_in + 7) / 8 * 8;
+  int rc = linear_pair_splitk_nt(g, ldg, x, ldx, x_is_f16, workspace, ldo, n_out, k_in, tokens, &sp, split_rows, st);
   if (rc) return rc;
   return fbkst_reduce_sum(workspace, sp, (int64_t)split_rows * ldo, n_out, k_in, ldo, dW, lddw, 1.0f, stream);
 }

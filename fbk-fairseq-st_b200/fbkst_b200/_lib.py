@@ -55,6 +55,7 @@ SIGNATURES = {
     "fbkst_grad_prep": [P, I, I64, P, I64, F, I, I, P, I64, I, P, I64, P, I, I, I, F, U64, I, I, P],
     "fbkst_reduce_sum": [P, I, I64, I, I, I64, P, I64, F, P],
     "fbkst_linear_wgrad_bf16": [P, I64, P, I64, P, P, I64, I, I, I, P],
+    "fbkst_linear_wgrad_nt": [P, I64, P, I64, I, P, P, I64, I, I, I, P],
     "fbkst_linear_wgrad_slices_bf16": [P, I64, P, I64, P, I, I, I, P, P],
     "fbkst_reduce_sum_batch": [P, I, P],
     "fbkst_prep_batch": [P, I, P],

@@ -758,6 +758,23 @@ def linear_wgrad(gT, xT):
     return dW
 
 
+def linear_wgrad_nt(g, x):
+    """dW [n_out, k_in] fp32 = g^T x from the natural layouts: g [tokens, n_out] bf16, x [tokens, k_in] bf16
+    (unit column strides, pitches % 8 == 0): no transposed copies."""
+    lib = _lib.require_device()
+    if g.dtype != torch.bfloat16 or x.dtype != torch.bfloat16 or g.stride(1) != 1 or x.stride(1) != 1 or \
+            g.shape[0] != x.shape[0]:
+        raise ValueError("fbkst_b200.linear_wgrad_nt: g [tokens, n] bf16 and x [tokens, k] bf16 expected")
+    tokens, n_out = g.shape
+    k_in = x.shape[1]
+    ws = torch.empty(lib.fbkst_linear_wgrad_workspace(n_out, k_in, tokens), dtype=torch.float32, device=g.device)
+    dW = torch.empty(n_out, k_in, dtype=torch.float32, device=g.device)
+    check(lib.fbkst_linear_wgrad_nt(g.data_ptr(), g.stride(0), x.data_ptr(), x.stride(0), 0, ws.data_ptr(),
+                                    dW.data_ptr(), k_in, n_out, k_in, tokens, _stream()))
+    _count(2)
+    return dW
+
+
 def attention_train_fwd(qkv, lengths, L, B, H, log_penalty=True, p=0.0, seed=0, site=0):
     """Training attention: qkv [L*B, 3*H*64] bf16 UNSCALED -> (out [L*B, H*64] bf16, lse [B*H, L] fp32)."""
     lib = _lib.require_device()

@@ -403,7 +403,13 @@ int fbkst_prep_batch(const fbkst_prep_desc_t* descs, int n, fbkst_stream_t strea
 long long fbkst_linear_wgrad_workspace(int n_out, int k_in, int tokens);
 int fbkst_linear_wgrad_bf16(const void* gT, int64_t ldg, const void* xT, int64_t ldx, float* workspace, float* dW,
                             int64_t lddw, int n_out, int k_in, int tokens, fbkst_stream_t stream);
-/* Only the split-K GEMM of the call above: the slices stay in `workspace` as [*splits][ceil32(n_out)][ceil8(k_in)]
+/* The same product from the operands' NATURAL layouts (no transposed copies): g [tokens, n_out] bf16 (pitch
+ * ldg), x [tokens, k_in] bf16 (pitch ldx; x_is_f16 must be 0: one MMA takes both operands in one format); both
+ * 16-byte aligned with pitches % 8 == 0.
+ * The tensor cores read both operands MN-major straight from their TMA tiles. */
+int fbkst_linear_wgrad_nt(const void* g, int64_t ldg, const void* x, int64_t ldx, int x_is_f16, float* workspace,
+                          float* dW, int64_t lddw, int n_out, int k_in, int tokens, fbkst_stream_t stream);
+/* Only the split-K GEMM of fbkst_linear_wgrad_bf16: the slices stay in `workspace` as [*splits][ceil32(n_out)][ceil8(k_in)]
  * fp32 and the caller reduces them (fbkst_reduce_sum / fbkst_reduce_sum_batch) when it needs dW. */
 int fbkst_linear_wgrad_slices_bf16(const void* gT, int64_t ldg, const void* xT, int64_t ldx, float* workspace,
                                    int n_out, int k_in, int tokens, int* splits, fbkst_stream_t stream);

@@ -24,6 +24,14 @@ torch.cuda.synchronize()
 lib.fbkst_debug_set_attention_trace(None)
 t = buf.view(64, 16).cpu()[:, :13]
 t0 = int(t[t > 0].min())
+if os.environ.get("FBKST_TRACE_SOFTMAX"):
+    # decoupled one-pass kernel, softmax warp of each group (rows: even = group 0, odd = group 1), in time order
+    order = [(3, "s_full"), (8, "ld_a"), (4, "max_a"), (5, "pv_lo_ok"), (9, "ld_b"), (10, "s_free"), (11, "p_lo"),
+             (12, "pv_hi_ok"), (0, "ch7"), (6, "p_hi"), (7, "epilogue")]
+    print("tile " + " ".join("%9s" % n for _, n in order))
+    for i in range(40):
+        print("%4d " % i + " ".join("%9d" % (int(t[i][k]) - t0 if t[i][k] > 0 else -1) for k, _ in order))
+    sys.exit(0)
 names = ["mma:p_full", "mma:PV", "mma:QK+2", "sm:s_full", "sm:pass1", "sm:PO_free", "sm:arrive", "epilogue",
          "mma:s_free", "mma:k_full", "tma:K", "tma:V", "mma:v_full"]
 print("tile " + " ".join("%11s" % n for n in names))

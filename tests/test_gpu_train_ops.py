@@ -120,6 +120,29 @@ def test_linear_wgrad(n_out, k_in, tokens):
     assert torch.equal(dW, dW2)  # fixed summation order
 
 
+@pytest.mark.parametrize("n_out,k_in,tokens,x_f16", [(512, 512, 1000, False), (1536, 512, 24000, False),
+                                                      (2048, 512, 4099, False), (8005, 512, 3000, False),
+                                                      (64, 576, 30000, False), (512, 640, 777, False),
+                                                      (512, 2048, 24000, False), (200, 72, 130, False)])
+def test_linear_wgrad_nt(n_out, k_in, tokens, x_f16):
+    """dW = g^T x with both operands read MN-major from their natural layouts (fbkst_linear_wgrad_nt), pitch-padded
+    operands included; must equal the transposed-copy route bit for bit (same tiles, same split-K order)."""
+    from fbkst_b200 import ops
+    g = torch.Generator().manual_seed(n_out + tokens)
+    ldg, ldx = (n_out + 7) // 8 * 8, (k_in + 7) // 8 * 8
+    dy = torch.zeros(tokens, ldg, dtype=torch.bfloat16, device=dev())[:, :n_out]
+    dy.copy_(bf(torch.randn(tokens, n_out, generator=g)))
+    x = torch.zeros(tokens, ldx, dtype=torch.float16 if x_f16 else torch.bfloat16, device=dev())[:, :k_in]
+    x.copy_(torch.randn(tokens, k_in, generator=g))
+    dW = ops.linear_wgrad_nt(dy, x)
+    ref = dy.float().t() @ x.float()
+    assert dW.shape == (n_out, k_in)
+    assert rel_err(dW, ref) < 1e-4
+    if not x_f16:
+        dW2 = ops.linear_wgrad(ops.transpose_bf16(dy), ops.transpose_bf16(x))
+        assert torch.equal(dW, dW2)
+
+
 # ----------------------------------------------------------------------- attention (training)
 def attn_train_ref(qkv, lengths, L, B, H, log_penalty, keep=None):
     """local_attention.py:98-139 in fp32, differentiable; keep [B*H, L, L] = dropout keep-scale."""
