@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     ctc_argmax_merge_kernel(const float4* __restrict__ partial, int chunks, const int* __restrict__ lengths,
                             int* __restrict__ labels, float* __restrict__ top_prob, float* __restrict__ lse,
-                            int rows, int B) {
+                            int rows, int B, const float* __restrict__ logits, long long ldv, int V) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -302,16 +302,36 @@ __global__ void __launch_bounds__(256)
   const bool want_sum = top_prob != nullptr || lse != nullptr;
   ArgMax a{-INFINITY, 0x7fffffff, 0.0f};
   const float4* p = partial + (size_t)row * chunks;
+  bool rescan = false;
   for (int c = lane; c < chunks; c += 32) {
     const float4 v = __ldg(p + c);
+    rescan = v.w != 0.0f;  // (uniform over the row: set by the lean epilogue)
     argmax_merge(a, v.x, __float_as_int(v.y), v.z, want_sum);
   }
+  rescan = __any_sync(0xffffffffu, rescan);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const float v = __shfl_xor_sync(0xffffffffu, a.v, o);
     const int i = __shfl_xor_sync(0xffffffffu, a.i, o);
     const float s2 = __shfl_xor_sync(0xffffffffu, a.s, o);
     argmax_merge(a, v, i, s2, want_sum);
+  }
+  if (rescan) {
+    // lean partials: a.i is the first column of the winning 128-column chunk (the lowest one among equal maxima);
+    // the arg-max is the first stored logit of that chunk equal to the maximum (lane <-> 4 consecutive columns;
+    // rows are 16-byte aligned and the chunk starts at a multiple of 128 columns)
+    const int c0 = a.i + 4 * lane;
+    int first = 0x7fffffff;
+    if (c0 < V) {
+      const float4 x = __ldg(reinterpret_cast<const float4*>(logits + (size_t)row * ldv + c0));
+      if (c0 + 3 < V && x.w == a.v) first = c0 + 3;
+      if (c0 + 2 < V && x.z == a.v) first = c0 + 2;
+      if (c0 + 1 < V && x.y == a.v) first = c0 + 1;
+      if (x.x == a.v) first = c0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+    a.i = first;
   }
   if (lane == 0) {
     labels[row] = a.i;
@@ -631,13 +651,16 @@ extern "C" int fbkst_ctc_compress(const float* x, const int32_t* seg_id, const i
   return FBKST_OK;
 }
 
-extern "C" int fbkst_ctc_argmax_merge(const float* partial, int chunks, const int32_t* lengths, int32_t* labels,
-                                      float* top_prob, float* lse, int L, int B, fbkst_stream_t stream) {
+extern "C" int fbkst_ctc_argmax_merge(const float* partial, int chunks, const float* logits, int64_t ldv, int V,
+                                      const int32_t* lengths, int32_t* labels, float* top_prob, float* lse, int L,
+                                      int B, fbkst_stream_t stream) {
   FBKST_REQUIRE(partial && lengths && labels && chunks > 0 && L > 0 && B > 0, "fbkst_ctc_argmax_merge: bad arguments");
+  FBKST_REQUIRE(logits && V > 0 && ldv >= V && ldv % 4 == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0,
+                "fbkst_ctc_argmax_merge: the logits of fbkst_linear_argmax_f32 (16-byte aligned rows) are required");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int rows = L * B;
   ctc_argmax_merge_kernel<<<(rows + 7) / 8, 256, 0, st>>>(reinterpret_cast<const float4*>(partial), chunks,
-                                                             lengths, labels, top_prob, lse, rows, B);
+                                                             lengths, labels, top_prob, lse, rows, B, logits, ldv, V);
   FBKST_CHECK_CUDA(cudaGetLastError());
   return FBKST_OK;
 }

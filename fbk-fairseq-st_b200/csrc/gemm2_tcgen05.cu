@@ -468,8 +468,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
                 a2 = fmaxf(a2, 0.f);
                 a3 = fmaxf(a3, 0.f);
               }
-              if (AM) {
-                // running (max, first arg-max[, sum exp]) of this row over the warp's columns.  ~1.5 instructions
+              if (AM && !am.want_sum) {
+                // LEAN form (no sum exp wanted): only the row maximum of the chunk, two FMNMX3 per four logits.
+                // The arg-max column is recovered by the merge kernel from the ONE winning chunk of the row
+                // (128 logits re-read per row: 12 MB of the 771 MB at cfg2); the bumped logit is folded in
+                // after the loop from the staging row.
+                const int c = col0 + 4 * g;
+                float x0 = a0, x1 = a1, x2 = a2, x3 = a3;
+                if (am_tail) {  // tile-uniform: only the last column tile
+                  x0 = (c < N) ? a0 : -INFINITY;
+                  x1 = (c + 1 < N) ? a1 : -INFINITY;
+                  x2 = (c + 2 < N) ? a2 : -INFINITY;
+                  x3 = (c + 3 < N) ? a3 : -INFINITY;
+                }
+                am_best = fmaxf(fmaxf(am_best, x0), fmaxf(fmaxf(x1, x2), x3));
+              } else if (AM) {
+                // running (max, first arg-max, sum exp) of this row over the warp's columns.  ~1.5 instructions
                 // per element: the max changes O(log n) times per row, so the update branch is rare.  The logit
                 // bump and the columns >= N of the last tile are handled outside this loop.
                 const int c = col0 + 4 * g;
@@ -519,6 +533,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
           if (AM && am_bump >= col0 && am_bump < col0 + UCOLS) {  // the stored logit carries the bump as well
             const int j = am_bump - col0;
             float* e = reinterpret_cast<float*>(rowp + (((j >> 2) ^ swz) << 4)) + (j & 3);
+            if (!am.want_sum) am_bump_val = *e;  // (lean form: the un-bumped logit was not tracked in the loop)
             *e += am.bump;
           }
           fence_proxy_async_smem();
@@ -538,13 +553,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
               am_sum = am_sum * exp2f((am_best - mx) * 1.4426950408889634f) -
                        exp2f((am_bump_val - mx) * 1.4426950408889634f) + exp2f((v - mx) * 1.4426950408889634f);
             }
-            if (v > am_best || (v == am_best && am_bump < am_idx)) {
+            if (v > am_best || (am.want_sum && v == am_best && am_bump < am_idx)) {
               am_best = v;
               am_idx = am_bump;
             }
           }
+          // lean form: .y = first column of the chunk (ties between chunks resolve to the lowest), .w = 1 asks the
+          // merge kernel to recover the column inside the winning chunk from the stored logits
           am.partial[(size_t)(m0 + lane) * am.chunks + (n0 >> 7)] =
-              make_float4(am_best, __int_as_float(am_idx), am_sum, 0.f);
+              am.want_sum ? make_float4(am_best, __int_as_float(am_idx), am_sum, 0.f)
+                          : make_float4(am_best, __int_as_float(n0), 0.f, 1.f);
         }
       }
       acc ^= 1;
@@ -802,6 +820,8 @@ extern "C" int fbkst_linear_argmax_f32(const void* A, int64_t lda, const void* W
   FBKST_REQUIRE(M > 0 && N > 0 && K > 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldo % 4 == 0 && ldo >= N,
                 "fbkst_linear_argmax_f32: bad shape / pitch");
   FBKST_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "fbkst_linear_argmax_f32: out must be 16-byte aligned");
+  // (the un-bumped logit of the bump column stays in the running maximum: exact only for a non-negative bump)
+  FBKST_REQUIRE(bump_cols == nullptr || bump >= 0.f, "fbkst_linear_argmax_f32: the logit bump must be >= 0");
   return linear_pair_argmax(A, lda, W, ldw, bias, out, ldo, M, N, K, bump_cols, bump, want_sum, partial, m_limit,
                             m_limit_mult, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -34,7 +34,7 @@ SIGNATURES = {
     "fbkst_lengths_to_mask": [P, P, P, I, I, P],
     "fbkst_subsample_lengths": [P, I, P, I, I, P],
     "fbkst_linear_argmax_f32": [P, I64, P, I64, P, P, I64, I, I, I, P, F, I, P, P, I, P],
-    "fbkst_ctc_argmax_merge": [P, I, P, P, P, P, I, I, P],
+    "fbkst_ctc_argmax_merge": [P, I, P, I64, I, P, P, P, P, I, I, P],
     "fbkst_ctc_argmax": [P, I, I64, P, P, P, I, I, I, P],
     "fbkst_ctc_argmax_lse": [P, I, I64, P, P, P, P, I, I, I, P],
     "fbkst_ctc_uer": [P, P, P, I64, P, I, P, P, P, I, I, I, P],

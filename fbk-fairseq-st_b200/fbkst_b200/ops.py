@@ -396,8 +396,8 @@ def linear_argmax(a, w, bias, lengths, L, B, want_prob=True, want_lse=False, bum
     labels = torch.empty(M, dtype=torch.int32, device=dev)
     prob = torch.empty(M, dtype=torch.float32, device=dev) if want_prob else None
     lse = torch.empty(M, dtype=torch.float32, device=dev) if want_lse else None
-    check(lib.fbkst_ctc_argmax_merge(partial.data_ptr(), chunks, lengths.data_ptr(), labels.data_ptr(), _ptr(prob),
-                                     _ptr(lse), L, B, _stream()))
+    check(lib.fbkst_ctc_argmax_merge(partial.data_ptr(), chunks, out.data_ptr(), ldo, V, lengths.data_ptr(),
+                                     labels.data_ptr(), _ptr(prob), _ptr(lse), L, B, _stream()))
     _count(2)
     return out[:, :V], labels, prob, lse
 

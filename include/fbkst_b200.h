@@ -201,13 +201,17 @@ int fbkst_subsample_lengths(const void* lengths, int lengths_are_i64, int32_t* o
  * partial [M, ceil(N/128)] x (max, arg-max, sum exp) per 128-column chunk, so that the logits are never re-read
  * (conv_transformer.py:279 + :282-284).  bump_cols [M] int32 (optional): `bump` is added to that column of each
  * row before the store and the arg-max (benchmark / test logit injection, equivalent to a forward hook).
- * want_sum: also accumulate sum exp (weighted / softmax pooling need the top probability).
- * fbkst_ctc_argmax_merge folds the partials: labels [L*B] int32 (-1 for padded frames), top_prob / lse optional. */
+ * (bump >= 0.)  want_sum: also accumulate sum exp and the arg-max column (weighted / softmax pooling need the top
+ * probability); without it the epilogue only tracks the chunk maximum.
+ * fbkst_ctc_argmax_merge folds the partials: labels [L*B] int32 (-1 for padded frames), top_prob / lse optional;
+ * it takes the logits written by the call above (pitch ldv, V columns) to recover the arg-max column inside the
+ * row's winning chunk when the partials carry maxima only (128 logits re-read per row). */
 int fbkst_linear_argmax_f32(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, float* out,
                             int64_t ldo, int M, int N, int K, const int32_t* bump_cols, float bump, int want_sum,
                             float* partial, const int32_t* m_limit, int m_limit_mult, fbkst_stream_t stream);
-int fbkst_ctc_argmax_merge(const float* partial, int chunks, const int32_t* lengths, int32_t* labels,
-                           float* top_prob, float* lse, int L, int B, fbkst_stream_t stream);
+int fbkst_ctc_argmax_merge(const float* partial, int chunks, const float* logits, int64_t ldv, int V,
+                           const int32_t* lengths, int32_t* labels, float* top_prob, float* lse, int L, int B,
+                           fbkst_stream_t stream);
 
 /* ---- a10 step 1: CTC argmax (+ probability of the arg-max label) --------------------------
  * replaces conv_transformer.py:282-284 (softmax + per-utterance argmax().tolist()).

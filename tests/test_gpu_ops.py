@@ -555,16 +555,22 @@ def test_linear_argmax_fused_epilogue(L, B, V, K, want_prob):
     if want_prob:
         ref_p = torch.softmax(lg.double(), -1).max(-1).values.float()
         assert ((prob[valid] - ref_p[valid]).abs() / ref_p[valid]).max() < 1e-3
-    # ties -> lowest index: duplicate the winning weight row under a lower AND a higher index
-    w2 = w.clone()
-    bias2 = bias.clone()
+    # the lean epilogue (maxima only; the merge kernel recovers the column from the winning chunk)
+    lg3, lab3, _, _ = ops.linear_argmax(a, w, bias, lens, L, B, want_prob=False)
+    assert torch.equal(lg3, plain)
+    assert torch.equal(lab3[valid], ref_lab[valid]) and (lab3[~valid] == -1).all()
+    # ties -> lowest index: duplicate the winning weight row under a lower AND a higher index, in the same
+    # 128-column chunk and in other chunks
     top = int(ref_lab[0])
-    lo, hi = (top - 3) % V, (top + 5) % V
-    for j in (lo, hi):
-        w2[j] = w2[top]
-        bias2[j] = bias2[top]
-    _, lab2, _, _ = ops.linear_argmax(a, w2, bias2, lens, L, B, want_prob=False)
-    assert int(lab2[0]) == min(top, lo, hi)
+    for lo, hi in (((top - 3) % V, (top + 5) % V), ((top - 131) % V, (top + 259) % V)):
+        w2 = w.clone()
+        bias2 = bias.clone()
+        for j in (lo, hi):
+            w2[j] = w2[top]
+            bias2[j] = bias2[top]
+        for wp in (False, True):
+            _, lab2, _, _ = ops.linear_argmax(a, w2, bias2, lens, L, B, want_prob=wp)
+            assert int(lab2[0]) == min(top, lo, hi)
     # built-in bump == hook semantics
     plan = torch.randint(0, V, (L * B,), generator=g).to(torch.int32).to(dev())
     lgb, labb, _, _ = ops.linear_argmax(a, w, bias, lens, L, B, want_prob=False, bump=(plan, 30.0))
