@@ -23,7 +23,7 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
 
 // mode: 0 SS back to back | 1 TS back to back | 2 SS with a commit after every 4 | 3 SS from two warps (own D each)
 // 4 / 5 / 6: SS from one thread, round-robin over 2 / 4 / 3 independent accumulators (D columns i * (512 / n))
-template <int N>
+template <int N, int MM = 128>
 __global__ void __launch_bounds__(128, 1) probe(long long* out, int reps, int mode) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(128, 1) probe(long long* out, int reps, int mo
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *slot;
-  const uint32_t idesc = idesc_bf16_f32(128, N, 0, 0);
+  const uint32_t idesc = idesc_bf16_f32(MM, N, 0, 0);
   const uint64_t adesc = desc_kmajor_sw128(smem_u32(sA)), bdesc = desc_kmajor_sw128(smem_u32(sB));
   const int issuers = (mode == 3) ? 2 : (mode == 7 ? 4 : 1);
   if (warp < issuers) {
@@ -99,20 +99,20 @@ __global__ void __launch_bounds__(128, 1) probe(long long* out, int reps, int mo
   }
 }
 
-template <int N>
+template <int N, int MM = 128>
 static void run(const char* what, int mode, int reps) {
   long long* d;
   cudaMalloc(&d, 128);
   cudaMemset(d, 0, 128);
   const int smem = 16384 + 32768 + 1024 + 256;
-  cudaFuncSetAttribute(probe<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  probe<N><<<148, 128, smem>>>(d, reps, mode);
+  cudaFuncSetAttribute(probe<N, MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  probe<N, MM><<<148, 128, smem>>>(d, reps, mode);
   cudaError_t e = cudaDeviceSynchronize();
   long long h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   cudaMemcpy(h, d, 64, cudaMemcpyDeviceToHost);
   const double n = 4.0 * reps * (mode == 4 ? 2 : mode == 5 ? 4 : mode == 6 ? 3 : 1);
-  printf("%-34s N=%3d  issue %7.1f clk/UMMA  complete %7.1f clk/UMMA  (math at full rate %5.1f)%s", what, N,
-         h[0] / n, h[1] / n, 128.0 * N * 16 * 2 / 8192.0, mode == 3 ? "" : "\n");
+  printf("%-34s M=%3d N=%3d  issue %7.1f clk/UMMA  complete %7.1f clk/UMMA  (math at full rate %5.1f)%s", what, MM, N,
+         h[0] / n, h[1] / n, (double)MM * N * 16 * 2 / 8192.0, mode == 3 ? "" : "\n");
   if (mode == 3) printf("  | warp 1: issue %7.1f complete %7.1f\n", h[2] / n, h[3] / n);
   if (mode == 7) printf("four issuing warps N=%d: complete %7.1f %7.1f %7.1f %7.1f clk/UMMA each\n", N, h[1] / n, h[3] / n, h[5] / n, h[7] / n);
   if (e != cudaSuccess) printf("  CUDA error: %s\n", cudaGetErrorString(e));
@@ -124,6 +124,11 @@ int main() {
   run<64>("SS back to back", 0, reps);
   run<128>("SS back to back", 0, reps);
   run<256>("SS back to back", 0, reps);
+  run<64, 64>("SS back to back, M = 64", 0, reps);
+  run<128, 64>("SS back to back, M = 64", 0, reps);
+  run<256, 64>("SS back to back, M = 64", 0, reps);
+  run<128, 64>("SS, two issuing warps, M = 64", 3, reps);
+  run<256>("SS, two issuing warps", 3, reps);
   run<64>("SS, commit + wait after every 4", 2, reps);
   run<128>("SS, commit + wait after every 4", 2, reps);
   run<64>("SS, two issuing warps", 3, reps);
