@@ -362,6 +362,43 @@ def test_attention(L, B, H, lens, pen):
     assert torch.isfinite(out).all()
 
 
+@pytest.mark.parametrize("pattern", ["ramp", "late_spike", "second_half"])
+@pytest.mark.parametrize("pen", [True, False])
+def test_attention_growing_scores(pattern, pen):
+    """The one-pass softmax takes its running reference from the first 32 columns of the first key tile and raises it
+    only when a later half-tile exceeds it by 2^24: scores that GROW along the key axis drive both rare paths (the
+    first-half raise with the rescale of O / l, and the restart of a tile whose second half overflows)."""
+    from fbkst_b200 import ops
+    L, B, H = 375, 2, 2
+    lens = [375, 230]
+    g = torch.Generator().manual_seed(11)
+    qkv = torch.randn(L, B, 3, H, 64, generator=g) * 0.3
+    u = torch.randn(64, generator=g)
+    u = u / u.norm()
+    j = torch.arange(L, dtype=torch.float32)
+    if pattern == "ramp":            # +0.75 nats per key: every 32-column half is 24 nats above the previous one
+        amp = 0.75 * j
+    elif pattern == "late_spike":    # flat, then a few keys 60-90 nats above everything seen so far
+        amp = torch.zeros(L)
+        amp[150] = 60.0
+        amp[151] = 59.0
+        amp[300] = 150.0
+    else:                            # only the SECOND half of the third tile jumps (restart path, no earlier hint)
+        amp = torch.zeros(L)
+        amp[64 * 2 + 40: 64 * 2 + 64] = 45.0
+    qkv[:, :, 0] = qkv[:, :, 0] * 0.1 + u          # q ~ u (norm ~1)
+    qkv[:, :, 1] = qkv[:, :, 1] * 0.1 + amp[:, None, None, None] * u
+    qkv = bf(qkv.reshape(L * B, 3 * H * 64)).to(dev())
+    lengths = torch.tensor(lens, dtype=torch.int32, device=dev())
+    out = ops.attention(qkv, lengths, L, B, H, pen).float().view(L, B, H * 64)
+    torch.cuda.synchronize()
+    ref = attn_ref(qkv, lengths, L, B, H, pen).view(L, B, H * 64)
+    assert torch.isfinite(out).all()
+    for b, n in enumerate(lens):
+        e = rel_err(out[:n, b], ref[:n, b])
+        assert e < 2e-2, (pattern, b, n, e)
+
+
 # ------------------------------------------------------------------------------------- CTC
 def run_ctc(x, logits, lengths, strategy):
     from fbkst_b200 import ops
