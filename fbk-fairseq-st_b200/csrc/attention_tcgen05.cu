@@ -653,15 +653,13 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
 //       barriers, PV and V streams of the two groups independent of each other: parity green, SAME time
 //       (61.4 us) -- and so is the kernel with the LUT loads, the exponentials and the P stores all knocked out
 //       (59.4 us).  The softmax arithmetic is not what bounds this kernel.
-// What bounds it (scripts/probes/umma_probe.cu, profiles/r02w_umma_probe.txt): one tcgen05.mma with M = 128 takes
-// ~186 cycles of the tensor pipe WHATEVER its N (64, 128 and 256 alike: N = 256 is the math rate behind the measured
-// 1.6 PFLOP/s bf16 peak), two issuing warps overlap to one per ~93 cycles, four issuing warps (or one thread
-// alternating between accumulators) fall to one per 220-320.  With head_dim 64 every instruction here has N = 64:
-// a 128 x 64 key tile costs 4 (QK) + 4 (PV) instructions, 32 per tile period of the four groups on an SM = ~3000
-// cycles at the best observed rate, against the ~3500 measured.  The kernel sits at its INSTRUCTION-count roof on
-// the tensor pipe (a quarter of the FLOP roof); wider S tiles (N = 128 halves the QK count) do not fit the 256 TMEM
-// columns a CTA has next to O, and PV's N is the head dimension.  An L2 prefetch of the next item's boxes and a TMA
-// store of the output tile were measured slower (66.6 / 63.5 us).
+// What bounds it (profiles/r02y_ncu_attention.txt, r02w_attention_timeline.txt, r02y_umma_probe.txt): 13 % of the
+// warp-time sits at the final barrier (1536 items over 592 groups = 2.59 each: one group of most CTAs idles for an
+// item), 12 % in the softmax warps' mbarrier waits (next S, the PV halves, the last PV of an item), and the exp pass
+// itself issues one instruction per ~10 cycles and warp (short-scoreboard / fixed-latency stalls; 96 registers leave
+// no room to pipeline two chunks).  The tensor pipe is not the limiter: an N = 64 tcgen05.mma takes 133 cycles in a
+// chain but independent chains overlap to ~53 cycles aggregate, 1700 of the ~3500 cycles of a tile period.  An L2
+// prefetch of the next item's boxes and a TMA store of the output tile were measured slower (66.6 / 63.5 us).
 constexpr int ATD_SMEM_FIXED = 2 * AT_QB + AT_KST * AT_KB + 2 * AT_KB + 2 * AT_QB /*P x2*/ +
                                256 /*barriers*/ + 64 * 16 /*item table*/ + 1024 /*align*/;
 static inline int attention_dec_smem_bytes(int L) { return ATD_SMEM_FIXED + 4 * attention_lut_floats(L); }

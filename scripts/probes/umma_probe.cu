@@ -55,36 +55,51 @@ __global__ void __launch_bounds__(128, 1) probe(long long* out, int reps, int mo
   if (warp < issuers) {
     const uint32_t d = tmem + warp * (mode == 7 ? 128 : 256);  // D: N <= 256 (128 with four issuers) columns per issuer
     const uint32_t a_t = tmem + 448;               // TS: A (128 x 16 bf16 = 8 columns per k-step) in the last columns
+    // Warp-uniform control flow with ONE elected lane issuing, as the production kernels do: `if (lane == 0)` makes
+    // ptxas wrap every UTCHMMA in an ELECT / BRA.U.ANY waterfall that costs ~190 cycles per instruction by itself
+    // (build with -DPROBE_LANE0 to see that).
     long long t0 = 0, t1 = 0, t2 = 0;
+#ifdef PROBE_LANE0
     if (lane == 0) {
+#else
+    {
+#endif
       t0 = clock64();
       uint32_t ph = 0;
       for (int r = 0; r < reps; ++r) {
+#ifndef PROBE_LANE0
+        if (elect_one()) {
+#else
+        {
+#endif
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (mode == 1) {
-            umma_bf16_ts(d, a_t + 8 * k, bdesc + 2 * k, idesc, 1);
-          } else if (mode >= 4) {
-            const int nacc = mode == 4 ? 2 : (mode == 5 ? 4 : 3);
-            for (int a = 0; a < nacc; ++a)
-              umma_bf16_ss(tmem + a * (mode == 6 ? 128 : 512 / nacc), adesc + 2 * k, bdesc + 2 * k, idesc, 1);
-          } else {
-            umma_bf16_ss(d, adesc + 2 * k, bdesc + 2 * k, idesc, 1);
+          for (int k = 0; k < 4; ++k) {
+            if (mode == 1) {
+              umma_bf16_ts(d, a_t + 8 * k, bdesc + 2 * k, idesc, 1);
+            } else if (mode >= 4 && mode <= 6) {
+              const int nacc = mode == 4 ? 2 : (mode == 5 ? 4 : 3);
+              for (int a = 0; a < nacc; ++a)
+                umma_bf16_ss(tmem + a * (mode == 6 ? 128 : 512 / nacc), adesc + 2 * k, bdesc + 2 * k, idesc, 1);
+            } else {
+              umma_bf16_ss(d, adesc + 2 * k, bdesc + 2 * k, idesc, 1);
+            }
           }
+          if (mode == 2) umma_commit(&bars[warp]);
         }
+        __syncwarp();
         if (mode == 2) {
-          umma_commit(&bars[warp]);
           mbar_wait(&bars[warp], ph);
           ph ^= 1;
         }
       }
       t1 = clock64();
       if (mode != 2) {
-        umma_commit(&bars[warp]);
+        if (elect_one()) umma_commit(&bars[warp]);
+        __syncwarp();
         mbar_wait(&bars[warp], 0);
       }
       t2 = clock64();
-      if (blockIdx.x == 0) {
+      if (blockIdx.x == 0 && lane == 0) {
         out[warp * 2 + 0] = t1 - t0;  // issue loop
         out[warp * 2 + 1] = t2 - t0;  // until everything has completed
       }
