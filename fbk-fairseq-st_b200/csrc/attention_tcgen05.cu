@@ -1238,12 +1238,24 @@ extern "C" int fbkst_debug_set_attention_trace(long long* buf) {
 
 using namespace fbkst;
 
+namespace fbkst {
+// attention_wide.cu: one CTA per SM, 128-key tiles; returns 1 when the shape is not served
+int attention_wide_launch(const void* qkv, void* out, const int32_t* lengths, int L, int B, int H, int log_penalty,
+                          const int32_t* q_limit, cudaStream_t st);
+}  // namespace fbkst
+
 static int attention_entry(const void* qkv, void* out, const int32_t* lengths, int L, int B, int H,
                            int log_penalty, const int32_t* q_limit, fbkst_stream_t stream) {
   FBKST_REQUIRE(qkv && out && lengths, "fbkst_attention_fwd: null pointer");
   FBKST_REQUIRE(L > 0 && B > 0 && H > 0, "fbkst_attention_fwd: bad shape L=%d B=%d H=%d", L, B, H);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int D = H * AT_HD;
+  // FBKST_ATTN_WIDE=1: the wide kernel (A/B switch)
+  static const bool wide_enabled = getenv("FBKST_ATTN_WIDE") && atoi(getenv("FBKST_ATTN_WIDE")) != 0;
+  if (wide_enabled) {
+    const int rc = attention_wide_launch(qkv, out, lengths, L, B, H, log_penalty, q_limit, st);
+    if (rc != 1) return rc;
+  }
   CUtensorMap tmQ, tmKV, tmV;
   uint64_t dims[3] = {(uint64_t)3 * D, (uint64_t)B, (uint64_t)L};
   uint64_t strides[2] = {(uint64_t)3 * D * 2, (uint64_t)B * 3 * D * 2};

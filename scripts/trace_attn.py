@@ -18,6 +18,22 @@ lengths = torch.full((B,), L, dtype=torch.int32, device=d)
 for _ in range(3):
     ops.attention(qkv, lengths, L, B, H, True)
 buf = torch.zeros(64 * 16, dtype=torch.int64, device=d)
+if os.environ.get("FBKST_ATTN_WIDE"):
+    # wide kernel (attention_wide.cu): its own hook and column set
+    lib.fbkst_debug_set_attention_wide_trace.argtypes = [ctypes.c_void_p]
+    assert lib.fbkst_debug_set_attention_wide_trace(buf.data_ptr()) == 0
+    ops.attention(qkv, lengths, L, B, H, True)
+    torch.cuda.synchronize()
+    lib.fbkst_debug_set_attention_wide_trace(None)
+    t = buf.view(64, 16).cpu()
+    t0 = int(t[t > 0].min())
+    order = [(14, "tma:K"), (11, "mma:QK"), (0, "s_full"), (1, "S_regs"), (2, "guard"), (3, "lo_done"), (4, "lo_free"),
+             (5, "p_lo"), (12, "mma:PVlo"), (6, "hi_done"), (7, "hi_free"), (8, "p_hi"), (13, "mma:PVhi"),
+             (9, "last_pv"), (10, "stored")]
+    print("tile " + " ".join("%9s" % n for _, n in order))
+    for i in range(40):
+        print("%4d " % i + " ".join("%9d" % (int(t[i][k]) - t0 if t[i][k] > 0 else -1) for k, _ in order))
+    sys.exit(0)
 assert lib.fbkst_debug_set_attention_trace(buf.data_ptr()) == 0
 ops.attention(qkv, lengths, L, B, H, True)
 torch.cuda.synchronize()
