@@ -77,6 +77,12 @@ __device__ __forceinline__ float ex2(float x) {
 #ifndef FBKST_AW_STAGGER_ITEM
 #define FBKST_AW_STAGGER_ITEM 1
 #endif
+// P handed to the PV product through tensor memory (A operand of tcgen05.mma from TMEM) instead of two
+// swizzled shared-memory sub-tiles: no 64 KB store + 64 KB operand fetch per tile pair on the 128 B/clk
+// shared-memory path, no generic -> async proxy fence.  0 = shared memory (A/B switch).
+#ifndef FBKST_AW_PTMEM
+#define FBKST_AW_PTMEM 1
+#endif
 #ifndef FBKST_AW_NPOLY
 #define FBKST_AW_NPOLY 0
 #endif
@@ -104,6 +110,14 @@ __device__ __forceinline__ void aw_exp4(float2 (&t)[4]) {
       t[cc].y = ex2(t[cc].y);
     }
   }
+}
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 // TMEM load without a memory clobber (it touches no memory: ordered against the barrier waits / fences /
 // tcgen05.wait around it by `volatile`, against its consumers by the register outputs), so that the
@@ -171,7 +185,7 @@ __device__ __forceinline__ void aw_chunk(const uint32_t* __restrict__ s8, const 
 template <int LOGPEN>
 __device__ __forceinline__ void aw_half(const uint32_t (&s0)[16], const uint32_t (&s1)[16], const uint32_t (&s2)[16],
                                         const uint32_t (&s3)[16], const float4* __restrict__ lp, float2 negm2,
-                                        float2 (&sm2)[4], uint32_t (&pk)[32]) {
+                                        float2 (&sm2)[4], uint32_t* __restrict__ pk) {
 #pragma unroll
   for (int ch = 0; ch < 8; ++ch) {
     const uint32_t* sq = (ch >> 1) == 0 ? s0 : ((ch >> 1) == 1 ? s1 : ((ch >> 1) == 2 ? s2 : s3));
@@ -185,40 +199,10 @@ __device__ __forceinline__ void aw_half(const uint32_t (&s0)[16], const uint32_t
     }
   }
 }
-// 16 keys of a tile's last, partial half: nv (warp-uniform) of them are valid
-template <int LOGPEN>
-__device__ __forceinline__ void aw_quarter_masked(const uint32_t (&sq)[16], const float4* __restrict__ lp, float2 negm2,
-                                                  int nv, float2 (&sm2)[4], uint32_t (&pk8)[8]) {
-  if (nv <= 0) {
-#pragma unroll
-    for (int cc = 0; cc < 8; ++cc) pk8[cc] = 0u;
-    return;
-  }
-#pragma unroll
-  for (int ch = 0; ch < 2; ++ch) {
-    float2 t[4];
-    aw_chunk<LOGPEN>(sq + ch * 8, lp + 2 * ch, negm2, t);
-    if (nv < 16) {
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        if (ch * 8 + 2 * cc >= nv) t[cc].x = -INFINITY;
-        if (ch * 8 + 2 * cc + 1 >= nv) t[cc].y = -INFINITY;
-      }
-    }
-    aw_exp4(t);
-#pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
-      sm2[cc] = fadd2(sm2[cc], t[cc]);
-      pk8[4 * ch + cc] = pack_bf16x2(t[cc].x, t[cc].y);
-    }
-  }
-}
-
 // Optional timeline of CTA 0 (compiled in only with -DFBKST_ATTN_TRACE, scripts/trace_attn.py): 16 x int64 per
 // key tile of the CTA's stream, row = 2 * (tile count of the group) + group:  [0] S seen  [1] S in registers
-// [2] guard done  [3] first half computed  [4] its P buffer free  [5] first half handed over  [6] second half
-// computed  [7] its P buffer free  [8] second half handed over  [9] last PV of the item seen  [10] item stored
-// [11] QK issued  [12] / [13] PV halves issued  [14] K load issued
+// [2] guard done  [3] P computed  [4] P buffer free  [5] P handed over  [9] last PV of the item seen
+// [10] item stored  [11] QK issued  [12] PV issued  [14] K load issued
 __device__ long long* g_aw_trace = nullptr;
 #ifdef FBKST_ATTN_TRACE
 #define AW_TRACE(tile, slot)                                                        \
@@ -284,7 +268,7 @@ struct WCursor {
 
 template <int LOGPEN>
 __global__ void __launch_bounds__(AW_THREADS, 1)
-    attention_fwd_wide_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tm64,
+    attention_fwd_wide_kernel(const __grid_constant__ CUtensorMap tm128,
                               __nv_bfloat16* __restrict__ out, const int* __restrict__ lengths, int L, int B, int H,
                               const int* __restrict__ q_limit) {
   const int D = H * AW_HD;
@@ -308,19 +292,15 @@ __global__ void __launch_bounds__(AW_THREADS, 1)
   uint64_t* q_empty = bars + 2;   // [2]
   uint64_t* k_full = bars + 4;    // [3]
   uint64_t* k_empty = bars + 7;   // [3]
-  uint64_t* v_lo = bars + 10;     // [2]
-  uint64_t* v_hi = bars + 12;     // [2]
-  uint64_t* s_full = bars + 14;   // [2]
-  uint64_t* p_lo = bars + 16;     // [2]
-  uint64_t* pv_lo = bars + 18;    // [2]
-  uint64_t* s_free = bars + 20;   // [2]
-  uint64_t* p_hi = bars + 22;     // [2]
-  uint64_t* pv_hi = bars + 24;    // [2]
+  uint64_t* v_full = bars + 10;   // [2]
+  uint64_t* s_full = bars + 12;   // [2]
+  uint64_t* p_full = bars + 14;   // [2]  P[g] written (128 arrivals)
+  uint64_t* pv_done = bars + 16;  // [2]  the PV product of the group's tile has completed: P[g] / V[g] free, O[g] updated
+  uint64_t* s_free = bars + 18;   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm128);
-    tma_prefetch_desc(&tm64);
     for (int s = 0; s < AW_KST; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&k_empty[s], 1);
@@ -328,13 +308,10 @@ __global__ void __launch_bounds__(AW_THREADS, 1)
     for (int s = 0; s < 2; ++s) {
       mbar_init(&q_full[s], 1);
       mbar_init(&q_empty[s], 1);
-      mbar_init(&v_lo[s], 1);
-      mbar_init(&v_hi[s], 1);
+      mbar_init(&v_full[s], 1);
       mbar_init(&s_full[s], 1);
-      mbar_init(&p_lo[s], 128);
-      mbar_init(&p_hi[s], 128);
-      mbar_init(&pv_lo[s], 1);
-      mbar_init(&pv_hi[s], 1);
+      mbar_init(&p_full[s], 128);
+      mbar_init(&pv_done[s], 1);
       mbar_init(&s_free[s], 128);
     }
     fence_barrier_init();
@@ -354,7 +331,8 @@ __global__ void __launch_bounds__(AW_THREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_O = tmem_base + 2 * AW_BN;  // S[0] +0, S[1] +128, O[0] +256, O[1] +320
+  const uint32_t tmem_O = tmem_base + 2 * AW_BN;  // S[0] +0, S[1] +128, O[0] +256, O[1] +320, P[0] +384, P[1] +448
+  const uint32_t tmem_P = tmem_O + 2 * AW_HD;     // P[g]: 128 bf16 keys = 64 columns per row
 
   // Fixed interleaved order of the two groups' tile streams on the shared K ring (identical in the load
   // warp and the QK warp): the group whose turn it is, or the other one when that stream is exhausted.
@@ -388,20 +366,16 @@ __global__ void __launch_bounds__(AW_THREADS, 1)
         c.advance(items);
         return true;
       };
-      int v_half[2] = {0, 0};  // which half of the group's current V tile is loaded next
       auto try_v = [&](WCursor& c, int g) -> bool {
-        const int hf = v_half[g];
-        // the half-buffer was read by the matching PV half of the group's previous tile
-        if (c.c >= 1 && !mbar_test_wait(hf ? &pv_hi[g] : &pv_lo[g], (c.c - 1) & 1)) return false;
+        // V[g] was read by the PV product of the group's previous tile
+        if (c.c >= 1 && !mbar_test_wait(&pv_done[g], (c.c - 1) & 1)) return false;
         const int cv = 2 * D + c.it.h * AW_HD;
         if (elect_one()) {
-          uint64_t* bar = hf ? &v_hi[g] : &v_lo[g];
-          mbar_arrive_expect_tx(bar, AW_KB / 2);
-          tma_load_3d(sV + g * AW_KB + hf * (AW_KB / 2), &tm64, bar, cv, c.it.b, c.j * AW_BN + hf * (AW_BN / 2));
+          mbar_arrive_expect_tx(&v_full[g], AW_KB);
+          tma_load_3d(sV + g * AW_KB, &tm128, &v_full[g], cv, c.it.b, c.j * AW_BN);
         }
         __syncwarp();
-        v_half[g] = hf ^ 1;
-        if (hf == 1) c.advance(items);
+        c.advance(items);
         return true;
       };
       uint32_t idle = 0;
@@ -467,26 +441,31 @@ __global__ void __launch_bounds__(AW_THREADS, 1)
       const int g = warp - 2;
       WCursor pc;
       pc.init(items, g);
-      const uint32_t pa = smem_u32(sP + g * AW_PB), va = smem_u32(sV + g * AW_KB);
+      const uint32_t va = smem_u32(sV + g * AW_KB);
+#if !FBKST_AW_PTMEM
+      const uint32_t pa = smem_u32(sP + g * AW_PB);
+#endif
       while (pc.valid(n_items)) {
         const uint32_t ph = pc.c & 1;
+        mbar_wait(&p_full[g], ph);
+        mbar_wait(&v_full[g], ph);
+        tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          mbar_wait(hf ? &p_hi[g] : &p_lo[g], ph);
-          mbar_wait(hf ? &v_hi[g] : &v_lo[g], ph);
-          tc_fence_after();
-          if (elect_one()) {
-#pragma unroll
-            for (int k2 = 0; k2 < 4; ++k2) {
-              const int kk = hf * 4 + k2;
-              umma_bf16_ss(tmem_O + g * AW_HD, desc_kmajor_sw128(pa + hf * (AW_PB / 2)) + 2 * k2,
-                           desc_mnmajor_sw128(va + kk * 2048, AW_KB), IDESC_PV, (pc.j > 0) || kk != 0);
-            }
-            umma_commit(hf ? &pv_hi[g] : &pv_lo[g]);
-            AW_TRACE(2 * pc.c + g, 12 + hf);
+          for (int kk = 0; kk < 8; ++kk) {
+#if FBKST_AW_PTMEM
+            // A = P[g] from tensor memory: 128 lanes (query rows) x 8 columns (16 bf16 keys) per k-step
+            umma_bf16_ts(tmem_O + g * AW_HD, tmem_P + g * (AW_BN / 2) + 8 * kk,
+                         desc_mnmajor_sw128(va + kk * 2048, AW_KB), IDESC_PV, (pc.j > 0) || kk != 0);
+#else
+            umma_bf16_ss(tmem_O + g * AW_HD, desc_kmajor_sw128(pa + (kk >> 2) * (AW_PB / 2)) + 2 * (kk & 3),
+                         desc_mnmajor_sw128(va + kk * 2048, AW_KB), IDESC_PV, (pc.j > 0) || kk != 0);
+#endif
           }
-          __syncwarp();
+          umma_commit(&pv_done[g]);
+          AW_TRACE(2 * pc.c + g, 12);
         }
+        __syncwarp();
         pc.advance(items);
       }
     }
@@ -499,11 +478,10 @@ __global__ void __launch_bounds__(AW_THREADS, 1)
     const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const uint32_t tS = tmem_base + lane_addr + grp * AW_BN;
     const uint32_t tO = tmem_O + lane_addr + grp * AW_HD;
+    const uint32_t tP = tmem_P + lane_addr + grp * (AW_BN / 2);
     uint64_t* my_s_full = &s_full[grp];
-    uint64_t* my_p_lo = &p_lo[grp];
-    uint64_t* my_p_hi = &p_hi[grp];
-    uint64_t* my_pv_lo = &pv_lo[grp];
-    uint64_t* my_pv_hi = &pv_hi[grp];
+    uint64_t* my_p_full = &p_full[grp];
+    uint64_t* my_pv_done = &pv_done[grp];
     uint64_t* my_s_free = &s_free[grp];
     // the row's eight 16-byte chunks inside a 128B-swizzled sub-tile
     // (the row starts on a 128-byte boundary: chunk c8 sits at p_row ^ (c8 << 4), one LOP3 per store)
@@ -559,7 +537,7 @@ __global__ void __launch_bounds__(AW_THREADS, 1)
         const int nvalid = min(AW_BN, it.len - k0);
         const float4* lp = lut_row + (k0 >> 2);
         float2 sm2[4];
-        uint32_t s[8][16], pk[32];
+        uint32_t s[8][16], pk[64];
 #if FBKST_AW_STAGGER
         // the two groups share one MUFU pipe per scheduler: started together they run their exponentials at the
         // same time and wait at the same time (timeline r02z); group 1 drops half a tile behind after the
@@ -584,21 +562,30 @@ __global__ void __launch_bounds__(AW_THREADS, 1)
         AW_TRACE(2 * c + grp, 1);
         tc_fence_before();
         mbar_arrive(my_s_free);
+        if (nvalid != AW_BN) {
+          // last tile of the utterance: scores of keys at or beyond the length become -inf in the registers
+          // (warp-uniform per 16-score group: untouched / 16 selects / 16 moves), so that the guard and the
+          // exponentials below have ONE straight-line form for every tile
+#pragma unroll
+          for (int a = 0; a < 8; ++a) {
+            const int nv = nvalid - 16 * a;
+            if (nv < 16) {
+#pragma unroll
+              for (int cc = 0; cc < 16; ++cc)
+                if (cc >= nv) s[a][cc] = 0xff800000u;
+            }
+          }
+        }
         {
           float mx = -INFINITY;
-          if (nvalid == AW_BN) {
 #pragma unroll
-            for (int a = 0; a < 8; ++a) mx = fmaxf(mx, max16(s[a], 16));
-          } else {
-#pragma unroll
-            for (int a = 0; a < 8; ++a) mx = fmaxf(mx, max16(s[a], nvalid - 16 * a));
-          }
+          for (int a = 0; a < 8; ++a) mx = fmaxf(mx, max16(s[a], 16));
           const float m_row = mx * kLog2e;
           const bool grow = m_row > m_used + kGrow;
           if (__any_sync(0xffffffffu, grow)) {
             const float m_next = grow ? m_row : m_used;
             if (j > 0) {
-              mbar_wait(my_pv_hi, ph ^ 1);  // O[grp] quiescent: every PV of the previous tile has completed
+              mbar_wait(my_pv_done, ph ^ 1);  // O[grp] quiescent: the PV product of the previous tile has completed
               const float alpha = ex2(m_used - m_next);
               tc_fence_after();
               // rare path: rolled, 8 columns at a time
@@ -619,39 +606,40 @@ __global__ void __launch_bounds__(AW_THREADS, 1)
         }
         const float2 negm2 = make_float2(-m_used, -m_used);
         AW_TRACE(2 * c + grp, 2);
+        // all 16 chunks of 8 scores in ONE basic block, P packed into registers (they replace the score
+        // registers as those die) ...
+        aw_half<LOGPEN>(s[0], s[1], s[2], s[3], lp, negm2, sm2, pk);
+        aw_half<LOGPEN>(s[4], s[5], s[6], s[7], lp + 16, negm2, sm2, pk + 32);
+        AW_TRACE(2 * c + grp, 3);
+        // ... and stored once the PV product of the previous tile, which read this buffer, has completed
+        if (c >= 1) mbar_wait(my_pv_done, ph ^ 1);
+        AW_TRACE(2 * c + grp, 4);
+#if FBKST_AW_PTMEM
+        tc_fence_after();
+        tmem_st32(tP, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
+        tmem_st32(tP + 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[32]));
+        l += (sm2[0].x + sm2[0].y) + (sm2[1].x + sm2[1].y) + (sm2[2].x + sm2[2].y) + (sm2[3].x + sm2[3].y);
+        tmem_st_wait();
+        tc_fence_before();  // (also orders the O reads of the previous item's epilogue / a rescale before PV)
+        mbar_arrive(my_p_full);
+#else
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          // 8 chunks of 8 scores in ONE basic block, P packed into registers ...
-          const int nvh = nvalid - 64 * hf;
-          if (nvh >= 64) {
-            aw_half<LOGPEN>(s[4 * hf], s[4 * hf + 1], s[4 * hf + 2], s[4 * hf + 3], lp + 16 * hf, negm2, sm2, pk);
-          } else {
-#pragma unroll
-            for (int qt = 0; qt < 4; ++qt)
-              aw_quarter_masked<LOGPEN>(s[4 * hf + qt], lp + 16 * hf + 4 * qt, negm2, nvh - 16 * qt, sm2,
-                                        *reinterpret_cast<uint32_t(*)[8]>(&pk[8 * qt]));
-          }
-          // ... and stored once the PV half of the previous tile that read this buffer has completed
-          AW_TRACE(2 * c + grp, 3 + 3 * hf);
-          if (c >= 1) mbar_wait(hf ? my_pv_hi : my_pv_lo, ph ^ 1);
-          AW_TRACE(2 * c + grp, 4 + 3 * hf);
-#pragma unroll
-          for (int ch = 0; ch < 8; ++ch)
-            sts128((p_row ^ (uint32_t)(ch << 4)) + hf * (AW_PB / 2), pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
-          if (hf == 1)
-            l += (sm2[0].x + sm2[0].y) + (sm2[1].x + sm2[1].y) + (sm2[2].x + sm2[2].y) + (sm2[3].x + sm2[3].y);
-          tc_fence_before();  // (also orders the O reads of the previous item's epilogue / a rescale before PV)
-          fence_proxy_async_smem();
-          mbar_arrive(hf ? my_p_hi : my_p_lo);
-          AW_TRACE(2 * c + grp, 5 + 3 * hf);
-        }
+        for (int ch = 0; ch < 16; ++ch)
+          sts128((p_row ^ (uint32_t)((ch & 7) << 4)) + (ch >> 3) * (AW_PB / 2), pk[4 * ch], pk[4 * ch + 1],
+                 pk[4 * ch + 2], pk[4 * ch + 3]);
+        l += (sm2[0].x + sm2[0].y) + (sm2[1].x + sm2[1].y) + (sm2[2].x + sm2[2].y) + (sm2[3].x + sm2[3].y);
+        tc_fence_before();  // (also orders the O reads of the previous item's epilogue / a rescale before PV)
+        fence_proxy_async_smem();
+        mbar_arrive(my_p_full);
+#endif
+        AW_TRACE(2 * c + grp, 5);
       }
       // ---- item epilogue (this group only): O / l -> bf16.  A thread owns a query row (128 B); stored
       // straight from there every STG.128 touches 32 rows (32 sectors per instruction: 2250 cycles per item
       // in the timeline, and the next item's first shared-memory loads queue behind them).  Each warp stages
       // its 32 rows in its own rows of P[grp] (free: every PV product of the item has completed; swizzled, so
       // both directions are conflict-free) and writes them back out 4 full rows per instruction.
-      mbar_wait(my_pv_hi, (c - 1) & 1);  // O[grp] final
+      mbar_wait(my_pv_done, (c - 1) & 1);  // O[grp] final
       AW_TRACE(2 * (c - 1) + grp, 9);
       tc_fence_after();
       const float inv = 1.0f / l;
@@ -684,7 +672,7 @@ __global__ void __launch_bounds__(AW_THREADS, 1)
         __syncwarp();  // the staging rows are this warp's P rows of the next tile
       }
       // O[grp] is overwritten by the PV of the group's next tile, which waits for this group's next
-      // p_lo arrival (ordered after the TMEM reads above by the fence before that arrive)
+      // p_full arrival (ordered after the TMEM reads above by the fence before that arrive)
       AW_TRACE(2 * (c - 1) + grp, 10);
     }
   }
@@ -714,14 +702,11 @@ int attention_wide_launch(const void* qkv, void* out, const int32_t* lengths, in
   const int smem = aw_smem_bytes(L, log_penalty);
   if (smem > 227 * 1024) return 1;
   const int D = H * AW_HD;
-  CUtensorMap tm128, tm64;
+  CUtensorMap tm128;
   uint64_t dims[3] = {(uint64_t)3 * D, (uint64_t)B, (uint64_t)L};
   uint64_t strides[2] = {(uint64_t)3 * D * 2, (uint64_t)B * 3 * D * 2};
   uint32_t box128[3] = {AW_HD, 1, 128};
-  uint32_t box64[3] = {AW_HD, 1, 64};
   int rc = make_tensor_map(&tm128, qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3, dims, strides, box128, nullptr);
-  if (rc) return rc;
-  rc = make_tensor_map(&tm64, qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3, dims, strides, box64, nullptr);
   if (rc) return rc;
   static PerDeviceFlag configured;
   if (!configured) {
@@ -736,10 +721,10 @@ int attention_wide_launch(const void* qkv, void* out, const int32_t* lengths, in
   int grid = num_sms();
   if (2 * (long long)grid > n_items) grid = (int)((n_items + 1) / 2);
   if (log_penalty)
-    FBKST_CHECK_CUDA(launch_pdl(attention_fwd_wide_kernel<1>, dim3(grid), dim3(AW_THREADS), smem, st, tm128, tm64,
+    FBKST_CHECK_CUDA(launch_pdl(attention_fwd_wide_kernel<1>, dim3(grid), dim3(AW_THREADS), smem, st, tm128,
                                 (__nv_bfloat16*)out, lengths, L, B, H, q_limit));
   else
-    FBKST_CHECK_CUDA(launch_pdl(attention_fwd_wide_kernel<0>, dim3(grid), dim3(AW_THREADS), smem, st, tm128, tm64,
+    FBKST_CHECK_CUDA(launch_pdl(attention_fwd_wide_kernel<0>, dim3(grid), dim3(AW_THREADS), smem, st, tm128,
                                 (__nv_bfloat16*)out, lengths, L, B, H, q_limit));
   return FBKST_OK;
 }

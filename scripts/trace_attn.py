@@ -27,9 +27,8 @@ if os.environ.get("FBKST_ATTN_WIDE"):
     lib.fbkst_debug_set_attention_wide_trace(None)
     t = buf.view(64, 16).cpu()
     t0 = int(t[t > 0].min())
-    order = [(14, "tma:K"), (11, "mma:QK"), (0, "s_full"), (1, "S_regs"), (2, "guard"), (3, "lo_done"), (4, "lo_free"),
-             (5, "p_lo"), (12, "mma:PVlo"), (6, "hi_done"), (7, "hi_free"), (8, "p_hi"), (13, "mma:PVhi"),
-             (9, "last_pv"), (10, "stored")]
+    order = [(14, "tma:K"), (11, "mma:QK"), (0, "s_full"), (1, "S_regs"), (2, "guard"), (3, "P_done"), (4, "P_free"),
+             (5, "p_full"), (12, "mma:PV"), (9, "last_pv"), (10, "stored")]
     print("tile " + " ".join("%9s" % n for _, n in order))
     for i in range(40):
         print("%4d " % i + " ".join("%9d" % (int(t[i][k]) - t0 if t[i][k] > 0 else -1) for k, _ in order))
