@@ -137,7 +137,7 @@ __device__ __forceinline__ void tmem_ld_wait16(uint32_t (&v)[16]) {
                  "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]),
                  "+r"(v[15]));
 }
-__device__ __forceinline__ uint4 lds128u(uint32_t addr) {
+__device__ __forceinline__ uint4 lds128u_unused(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
   return v;
@@ -268,7 +268,7 @@ struct WCursor {
 
 template <int LOGPEN>
 __global__ void __launch_bounds__(AW_THREADS, 1)
-    attention_fwd_wide_kernel(const __grid_constant__ CUtensorMap tm128,
+    attention_fwd_wide_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tmO,
                               __nv_bfloat16* __restrict__ out, const int* __restrict__ lengths, int L, int B, int H,
                               const int* __restrict__ q_limit) {
   const int D = H * AW_HD;
@@ -301,6 +301,7 @@ __global__ void __launch_bounds__(AW_THREADS, 1)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm128);
+    tma_prefetch_desc(&tmO);
     for (int s = 0; s < AW_KST; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&k_empty[s], 1);
@@ -486,7 +487,7 @@ __global__ void __launch_bounds__(AW_THREADS, 1)
     // the row's eight 16-byte chunks inside a 128B-swizzled sub-tile
     // (the row starts on a 128-byte boundary: chunk c8 sits at p_row ^ (c8 << 4), one LOP3 per store)
     const uint32_t p_row = smem_u32(sP + grp * AW_PB + q * 128) + ((uint32_t)(q & 7) << 4);
-    const uint32_t stage_warp = smem_u32(sP + grp * AW_PB) + (uint32_t)(warp & 3) * 4096u;  // epilogue staging
+    uint8_t* stage_warp = sP + grp * AW_PB + (warp & 3) * 4096;  // epilogue staging: 32 rows x 128 B
     const int lut_off = nq * AW_BM;
     const int lut_n = aw_lut_floats(L);
     if (LOGPEN) {
@@ -636,9 +637,9 @@ __global__ void __launch_bounds__(AW_THREADS, 1)
       }
       // ---- item epilogue (this group only): O / l -> bf16.  A thread owns a query row (128 B); stored
       // straight from there every STG.128 touches 32 rows (32 sectors per instruction: 2250 cycles per item
-      // in the timeline, and the next item's first shared-memory loads queue behind them).  Each warp stages
-      // its 32 rows in its own rows of P[grp] (free: every PV product of the item has completed; swizzled, so
-      // both directions are conflict-free) and writes them back out 4 full rows per instruction.
+      // in the first timeline, and the next item's shared-memory loads queued behind them).  Each warp stages
+      // its 32 rows (4 KB, 128B-swizzled) in shared memory and ONE lane hands them to the TMA unit as a
+      // {64 columns, 1 utterance, 32 rows} box of the [L, B, D] output (rows at or beyond L are clipped).
       mbar_wait(my_pv_done, (c - 1) & 1);  // O[grp] final
       AW_TRACE(2 * (c - 1) + grp, 9);
       tc_fence_after();
@@ -647,8 +648,11 @@ __global__ void __launch_bounds__(AW_THREADS, 1)
         uint32_t o0[32], o1[32];
         tmem_ld32(tO, o0);
         tmem_ld32(tO + 32, o1);
+        // the staging rows are free once the previous item's store has read them
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
         tmem_ld_wait();
-        const uint32_t my_row = stage_warp + (uint32_t)lane * 128u;
+        const uint32_t my_row = smem_u32(stage_warp) + (uint32_t)lane * 128u;
 #pragma unroll
         for (int gq4 = 0; gq4 < 8; ++gq4) {
           const uint32_t* ov = (gq4 < 4) ? &o0[gq4 * 8] : &o1[(gq4 - 4) * 8];
@@ -658,23 +662,24 @@ __global__ void __launch_bounds__(AW_THREADS, 1)
                  pack_bf16x2(__uint_as_float(ov[4]) * inv, __uint_as_float(ov[5]) * inv),
                  pack_bf16x2(__uint_as_float(ov[6]) * inv, __uint_as_float(ov[7]) * inv));
         }
+        fence_proxy_async_smem();
         __syncwarp();
-        // lane <-> (row it * 4 + lane / 8, 16-byte chunk lane % 8)
-        const int r0 = lane >> 3, ck = lane & 7;
-        const int row_first = it.q0 + (warp & 3) * 32;  // query index of the warp's first row
-        __nv_bfloat16* obase = out + ((size_t)row_first * B + it.b) * D + it.h * AW_HD + ck * 8;
-#pragma unroll
-        for (int itr = 0; itr < 8; ++itr) {
-          const int r = itr * 4 + r0;
-          const uint4 v = lds128u(stage_warp + (uint32_t)r * 128u + (((uint32_t)ck ^ (uint32_t)(r & 7)) << 4));
-          if (row_first + r < L) *reinterpret_cast<uint4*>(obase + (size_t)r * B * D) = v;
+        if (lane == 0) {
+          tma_store_3d(&tmO, stage_warp, it.h * AW_HD, it.b, it.q0 + (warp & 3) * 32);
+          tma_store_commit();
+#if !FBKST_AW_PTMEM
+          tma_store_wait_read<0>();  // the staging rows are this warp's P rows of the next tile
+#endif
         }
-        __syncwarp();  // the staging rows are this warp's P rows of the next tile
+#if !FBKST_AW_PTMEM
+        __syncwarp();
+#endif
       }
       // O[grp] is overwritten by the PV of the group's next tile, which waits for this group's next
       // p_full arrival (ordered after the TMEM reads above by the fence before that arrive)
       AW_TRACE(2 * (c - 1) + grp, 10);
     }
+    if (lane == 0) tma_store_wait<0>();  // output stores complete (and staging rows read) before the CTA retires
   }
 #undef AW_PICK
   tc_fence_before();
@@ -708,6 +713,14 @@ int attention_wide_launch(const void* qkv, void* out, const int32_t* lengths, in
   uint32_t box128[3] = {AW_HD, 1, 128};
   int rc = make_tensor_map(&tm128, qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3, dims, strides, box128, nullptr);
   if (rc) return rc;
+  CUtensorMap tmO;
+  {
+    uint64_t odims[3] = {(uint64_t)D, (uint64_t)B, (uint64_t)L};
+    uint64_t ostrides[2] = {(uint64_t)D * 2, (uint64_t)B * D * 2};
+    uint32_t obox[3] = {AW_HD, 1, 32};
+    rc = make_tensor_map(&tmO, out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3, odims, ostrides, obox, nullptr);
+    if (rc) return rc;
+  }
   static PerDeviceFlag configured;
   if (!configured) {
     FBKST_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_wide_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -721,10 +734,10 @@ int attention_wide_launch(const void* qkv, void* out, const int32_t* lengths, in
   int grid = num_sms();
   if (2 * (long long)grid > n_items) grid = (int)((n_items + 1) / 2);
   if (log_penalty)
-    FBKST_CHECK_CUDA(launch_pdl(attention_fwd_wide_kernel<1>, dim3(grid), dim3(AW_THREADS), smem, st, tm128,
+    FBKST_CHECK_CUDA(launch_pdl(attention_fwd_wide_kernel<1>, dim3(grid), dim3(AW_THREADS), smem, st, tm128, tmO,
                                 (__nv_bfloat16*)out, lengths, L, B, H, q_limit));
   else
-    FBKST_CHECK_CUDA(launch_pdl(attention_fwd_wide_kernel<0>, dim3(grid), dim3(AW_THREADS), smem, st, tm128,
+    FBKST_CHECK_CUDA(launch_pdl(attention_fwd_wide_kernel<0>, dim3(grid), dim3(AW_THREADS), smem, st, tm128, tmO,
                                 (__nv_bfloat16*)out, lengths, L, B, H, q_limit));
   return FBKST_OK;
 }
