@@ -71,8 +71,10 @@ __device__ __forceinline__ float ex2(float x) {
 // 2^x on the FMA pipe for FBKST_AW_NPOLY of every 4 register pairs (Cody-Waite range reduction + degree-3
 // minimax polynomial, max rel. error 7.5e-5, far below the bf16 rounding of P; x clamped at -126): the MUFU
 // pipe runs 16 ex2 per clock and SM = 1024 clocks for each 128 x 128 tile of each group.
+// Cycles by which group 1 falls behind group 0 at the start of its item FBKST_AW_STAGGER_ITEM: 51.2 -> 47.1 us
+// at cfg2 L = 375 (0 = off).
 #ifndef FBKST_AW_STAGGER
-#define FBKST_AW_STAGGER 0
+#define FBKST_AW_STAGGER 1200
 #endif
 #ifndef FBKST_AW_STAGGER_ITEM
 #define FBKST_AW_STAGGER_ITEM 1
@@ -136,11 +138,6 @@ __device__ __forceinline__ void tmem_ld_wait16(uint32_t (&v)[16]) {
                : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
                  "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]),
                  "+r"(v[15]));
-}
-__device__ __forceinline__ uint4 lds128u_unused(uint32_t addr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-  return v;
 }
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d));
@@ -540,9 +537,11 @@ __global__ void __launch_bounds__(AW_THREADS, 1)
         float2 sm2[4];
         uint32_t s[8][16], pk[64];
 #if FBKST_AW_STAGGER
-        // the two groups share one MUFU pipe per scheduler: started together they run their exponentials at the
-        // same time and wait at the same time (timeline r02z); group 1 drops half a tile behind after the
-        // (instruction-cache-cold) first tile
+        // The two groups share one MUFU pipe per scheduler.  Started together they stay in lockstep: both run
+        // their exponentials at the same time (2400 cycles for the pair, the pipe's floor being 2048) and both
+        // sit in their guard / hand-over / TMEM-load phases at the same time (~1100 cycles per tile in which
+        // the pipe idles: timeline in profiles/r02z_attention_wide.txt).  Group 1 therefore drops a third of a
+        // tile behind, once, after the instruction-cache-cold first item (which re-aligns the groups)
         if (grp == 1 && j == 0 && k == 1 + 2 * FBKST_AW_STAGGER_ITEM) {
           const long long t_go = clock64() + FBKST_AW_STAGGER;
           while (clock64() < t_go) {

@@ -362,7 +362,7 @@ def test_attention(L, B, H, lens, pen):
     assert torch.isfinite(out).all()
 
 
-@pytest.mark.parametrize("pattern", ["ramp", "late_spike", "second_half"])
+@pytest.mark.parametrize("pattern", ["ramp", "late_spike", "second_half", "second_tile_128"])
 @pytest.mark.parametrize("pen", [True, False])
 def test_attention_growing_scores(pattern, pen):
     """The one-pass softmax takes its running reference from the first 32 columns of the first key tile and raises it
@@ -383,6 +383,9 @@ def test_attention_growing_scores(pattern, pen):
         amp[150] = 60.0
         amp[151] = 59.0
         amp[300] = 150.0
+    elif pattern == "second_tile_128":  # keys 198..237 of the second 128-key tile jump (raise + rescale of O / l
+        amp = torch.zeros(L)            # in the wide kernel, whose tiles are 128 keys)
+        amp[128 + 70: 128 + 110] = 45.0
     else:                            # only the SECOND half of the third tile jumps (restart path, no earlier hint)
         amp = torch.zeros(L)
         amp[64 * 2 + 40: 64 * 2 + 64] = 45.0
