@@ -966,13 +966,19 @@ def parity_numbers(ours, ref, lengths):
     """Both readings of the north_star's 2e-2 (bf16) over the valid positions of T x B x D outputs:
     max|a-b|/max|ref| and max over elements of |a-b| / (|ref| + rms(ref)), per utterance, worst case."""
     worst_max = worst_el = 0.0
+    bad_ours = bad_ref = 0
     for b, n in enumerate(lengths):
         a, r = ours[:n, b].double(), ref[:n, b].double()
         d = (a - r).abs()
+        if not bool(torch.isfinite(d).all()):  # (max() would silently drop a NaN)
+            worst_max = worst_el = float("inf")
+            bad_ours += int((~torch.isfinite(a)).sum())
+            bad_ref += int((~torch.isfinite(r)).sum())
+            continue
         worst_max = max(worst_max, (d.max() / r.abs().max().clamp_min(1e-12)).item())
         worst_el = max(worst_el, (d / (r.abs() + r.pow(2).mean().sqrt().clamp_min(1e-12))).max().item())
     return dict(max_rel=round(worst_max, 5), elementwise=round(worst_el, 5), tolerance=2e-2,
-                utterances=len(lengths),
+                utterances=len(lengths), nonfinite_ours=bad_ours, nonfinite_reference=bad_ref,
                 criteria="max_rel = max|a-b|/max|ref|; elementwise = max(|a-b|/(|ref|+rms(ref))); both per "
                          "utterance over valid positions, worst utterance; lengths compared exactly")
 

@@ -418,8 +418,8 @@ __global__ void __launch_bounds__(128)
                                 const float* __restrict__ weight, const int* __restrict__ lengths,
                                 const int* __restrict__ new_lengths,
                                 const int* __restrict__ max_new_len, float* __restrict__ out, int L,
-                                int B, int D) {
-  const int rows = min(__ldg(max_new_len), L) * B;
+                                int B, int D, int guard) {
+  const int rows = min(__ldg(max_new_len) + guard, L) * B;  // (guard rows: see fbkst_ctc_compress)
   const int nvec = D >> 2;
   for (int row = blockIdx.x; row < rows; row += gridDim.x) {
     const int s = row / B, b = row - s * B;
@@ -460,7 +460,7 @@ __global__ void __launch_bounds__(128)
 //     loop: warps drift out of phase, so frame loads stream continuously instead of in waves
 //     (the one-task-per-warp version ran 2.6 waves of issue -> wait -> fold: 46 % of HBM peak,
 //     profiles/r01e_ncu_ctc.txt; one task per OUTPUT row was worse still: profiles/r01b).
-// The task of chunk c also zero-fills the padding rows new_len[b] <= s < max_new_len, s in chunk c.
+// The task of chunk c also zero-fills the padding rows new_len[b] <= s < max_new_len + guard, s in chunk c.
 constexpr int CTC_CH = 16;
 
 __device__ __forceinline__ int ctc_window_sid(const int* __restrict__ seg_id, int task, int ncg, int B,
@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(256)
                         const int* __restrict__ seg_start, const float* __restrict__ weight,
                         const int* __restrict__ lengths, const int* __restrict__ new_lengths,
                         const int* __restrict__ max_new_len, float* __restrict__ out, int L, int B, int D,
-                        int tasks) {
+                        int tasks, int guard) {
   constexpr int FR = CTC_CH;
   const int ncg = D >> 7;  // 128-column groups per row
   const int lane = threadIdx.x & 31;
@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(256)
   int task = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (task >= tasks) return;
   const size_t fstride = (size_t)B * (D >> 2);  // float4 elements between consecutive frames
-  const int mx = min(__ldg(max_new_len), L);
+  const int mx = min(__ldg(max_new_len) + guard, L);  // zero fill incl. the guard rows (fbkst_ctc_compress)
   int sidw = ctc_window_sid(seg_id, task, ncg, B, L, lane);
   for (; task < tasks; task += nwarps) {
     const int cg = task % ncg, b = (task / ncg) % B, c = task / (ncg * B);
@@ -626,12 +626,20 @@ extern "C" int fbkst_ctc_compress(const float* x, const int32_t* seg_id, const i
                 "fbkst_ctc_compress: null pointer");
   FBKST_REQUIRE(L > 0 && B > 0 && D > 0 && D % 4 == 0, "fbkst_ctc_compress: bad shape (D %% 4)");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // Guard rows: the layers after compression run on worst-case grids with a device-side row limit
+  // (max_new_len * B rows) that their GEMM tiles round up to 256 rows, so up to 255 rows past the limit are
+  // read-modify-written (x += f(x)) by every residual epilogue.  Left untouched here they carry their values
+  // from one forward to the next in a persistent workspace, grow geometrically (x1.4 per step measured) and
+  // reach inf after ~70 forwards -- and attention then reads them as V rows of a partially valid key tile
+  // (0 * inf = NaN in every row of the utterance).  Zeroing them with the other padding rows restarts them
+  // at every forward.
+  const int guard = (512 + B - 1) / B + 1;
   if (D % 128 != 0 || D > 1024) {
     int g = L * B;
     const int gcap = num_sms() * 16;
     if (g > gcap) g = gcap;
     ctc_compress_generic_kernel<<<g, 128, 0, st>>>(x, seg_start, weight, lengths, new_lengths,
-                                                   max_new_len, out, L, B, D);
+                                                   max_new_len, out, L, B, D, guard);
     FBKST_CHECK_CUDA(cudaGetLastError());
     return FBKST_OK;
   }
@@ -646,7 +654,7 @@ extern "C" int fbkst_ctc_compress(const float* x, const int32_t* seg_id, const i
   long long grid = (tasks + 7) / 8;
   if (grid > (long long)num_sms() * ctas_per_sm) grid = (long long)num_sms() * ctas_per_sm;
   ctc_compress_kernel<<<(int)grid, 256, 0, st>>>(x, seg_id, seg_start, weight, lengths, new_lengths,
-                                                 max_new_len, out, L, B, D, (int)tasks);
+                                                 max_new_len, out, L, B, D, (int)tasks, guard);
   FBKST_CHECK_CUDA(cudaGetLastError());
   return FBKST_OK;
 }

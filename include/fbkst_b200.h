@@ -242,8 +242,9 @@ int fbkst_ctc_segment(const int32_t* labels, const float* top_prob, const int32_
 
 /* ---- a10 step 3: segmented weighted reduction (the reference's dense bmm) ------------------
  * replaces conv_transformer.py:290-291.  x [L*B, D] fp32 -> out [L*B, D] fp32 (rows
- * s*B+b; rows with new_lengths[b] <= s < max_new_len are written as 0; rows >= max_new_len
- * are untouched).  seg_id, seg_start, weight as produced by fbkst_ctc_segment.  D % 4 == 0
+ * s*B+b; rows with new_lengths[b] <= s < max_new_len + G are written as 0, G = ceil(512/B) + 1
+ * guard rows that cover the tile rounding of the row-limited GEMMs run on `out` afterwards; rows
+ * beyond are untouched).  seg_id, seg_start, weight as produced by fbkst_ctc_segment.  D % 4 == 0
  * (D % 128 == 0 takes the input-stationary streaming kernel).  Every output row has one writer
  * and a fixed summation order (ascending t): results are run-to-run identical. */
 int fbkst_ctc_compress(const float* x, const int32_t* seg_id, const int32_t* seg_start,

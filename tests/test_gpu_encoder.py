@@ -352,3 +352,38 @@ def test_tiny_and_degenerate_batches(lens_in):
     assert o2.src_lengths.cpu().tolist() == ref["src_lengths"].tolist()
     (o2.encoder_out.float().pow(2).sum() + o2.ctc_out.float().pow(2).sum() * 1e-3).backward()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in enc.parameters())
+
+
+def test_sustained_ragged_inference_stays_finite_and_identical():
+    """Regression (round 2): after CTC compression the remaining layers run on worst-case grids with a
+    device-side row limit in a PERSISTENT workspace; the rows between that limit and the end of the last
+    256-row GEMM tile are read-modify-written by every residual epilogue.  They used to survive from one
+    forward to the next, grew ~1.4x per forward and reached inf after ~70 forwards of a ragged batch, after
+    which attention read them as V rows of partially valid key tiles (0 * inf = NaN).  fbkst_ctc_compress
+    now zeroes them with the other padding rows: 150 forwards of the same ragged batch stay finite and
+    bit-identical to the first one, launch by launch and under graph replay."""
+    cfg = dict(embed_dim=256, ffn_dim=768, heads=4, layers=6, conv_channels=64, feat_dim=40,
+               vocab=105, distance_penalty=None, ctc_layer=4, ctc_strategy="avg")
+    sd = O.init_state_dict(cfg, seed=0)
+    x, lens = O.synthetic_batch([1000, 950, 900, 800, 700, 600, 500, 400], 40, seed=1234)
+    labels = O.synthetic_ctc_bump(250, 8, 105, seed=7)
+    hook = O.bump_hook(labels, 30.0)
+    for graph in (False, True):
+        enc = build_encoder(cfg, sd)
+        enc.ctc_fc.register_forward_hook(lambda m, i, o: hook(o))
+        enc.use_cuda_graph = graph
+        xd = x.cuda()
+        first = enc(xd, lens)
+        torch.cuda.synchronize()
+        first_out, first_len = first.encoder_out.clone(), first.src_lengths.clone()
+        assert torch.isfinite(first_out).all()
+        for _ in range(150):
+            out = enc(xd, lens)
+        torch.cuda.synchronize()
+        assert torch.equal(out.src_lengths, first_len)
+        assert torch.isfinite(out.encoder_out).all(), "graph=%s" % graph
+        assert torch.equal(out.encoder_out, first_out), "graph=%s" % graph
+        if not graph:  # the workspace itself stays bounded (it reached 1e10 before the fix)
+            for name, t in enc._ws[0][1].items():
+                assert torch.isfinite(t.float()).all(), name
+                assert float(t.float().abs().max()) < 1e4, name
