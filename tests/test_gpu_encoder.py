@@ -367,10 +367,9 @@ def test_sustained_ragged_inference_stays_finite_and_identical():
     sd = O.init_state_dict(cfg, seed=0)
     x, lens = O.synthetic_batch([1000, 950, 900, 800, 700, 600, 500, 400], 40, seed=1234)
     labels = O.synthetic_ctc_bump(250, 8, 105, seed=7)
-    hook = O.bump_hook(labels, 30.0)
     for graph in (False, True):
         enc = build_encoder(cfg, sd)
-        enc.ctc_fc.register_forward_hook(lambda m, i, o: hook(o))
+        enc.ctc_logit_bump = (labels.to(torch.int32).cuda().contiguous(), 30.0)  # (capturable, unlike a hook)
         enc.use_cuda_graph = graph
         xd = x.cuda()
         first = enc(xd, lens)
