@@ -18,7 +18,7 @@ lengths = torch.full((B,), L, dtype=torch.int32, device=d)
 for _ in range(3):
     ops.attention(qkv, lengths, L, B, H, True)
 buf = torch.zeros(64 * 16, dtype=torch.int64, device=d)
-if os.environ.get("FBKST_ATTN_WIDE"):
+if os.environ.get("FBKST_ATTN_WIDE", "1") != "0":
     # wide kernel (attention_wide.cu): its own hook and column set
     lib.fbkst_debug_set_attention_wide_trace.argtypes = [ctypes.c_void_p]
     assert lib.fbkst_debug_set_attention_wide_trace(buf.data_ptr()) == 0
