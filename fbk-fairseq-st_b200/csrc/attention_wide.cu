@@ -1,27 +1,38 @@
-// Self-attention core, "wide" layout (reference: local_attention.py:115-139 with LogPenalty
-// conv_transformer_layer.py:22-27).  Same arithmetic and the same pipeline roles as
-// attention_fwd_dec_kernel (attention_tcgen05.cu), re-cut for what that kernel's profile showed
-// (profiles/r02y_ncu_attention.txt, r02z_attention_wide.txt): its softmax warps ran at 7.3 issued
-// instructions per score and ~0.1 IPC each (96 registers: one 8-score chunk in flight per warp), and its
-// tensor-pipe stream was 16 M128 x N64 instructions per 128 x 128 scores at 133 cycles apiece.
+// Self-attention core, "wide" layout: the default kernel for L <~ 1450 (reference: local_attention.py:115-139
+// with LogPenalty conv_transformer_layer.py:22-27).  Same arithmetic and the same pipeline roles as
+// attention_fwd_dec_kernel (attention_tcgen05.cu, the round-1 kernel, still selected by FBKST_ATTN_WIDE=0 and
+// for longer inputs), re-cut for what that kernel's profile showed (profiles/r02y_ncu_attention.txt): softmax
+// warps at 7.3 issued instructions per score and ~0.1 IPC each (96 registers: one 8-score chunk in flight),
+// 64 KB of P written to and read back from shared memory per 128 x 128 scores next to 64 KB of penalty loads
+// on a 128 B/clk path, and 16 M128 x N64 tensor instructions per 128 x 128 scores at 133 cycles apiece.
 //
 //   * ONE CTA per SM, 384 threads: a producer warpgroup that shrinks to 56 registers (warp 0 TMA loads,
-//     warp 1 QK issue, warps 2/3 PV issue of group 0/1 [FBKST_AW_EPI: they also own the item epilogue])
-//     and two softmax warpgroups that grow to 224 registers, each working on its OWN work item
-//     (128-query tile, utterance, head) as in the decoupled kernel;
-//   * 128-key tiles: S = Q K^T is ONE chain of four M128 x N128 x K16 instructions per 128 keys (half the
-//     QK instructions), S[g] = 128 TMEM columns, O[g] = 64;  TMEM: S0 | S1 | O0 | O1 = 384 of 512 columns;
-//   * the softmax thread (one query row) holds 64 scores in registers and refills them from TMEM while it
-//     consumes them; all 16 chunks of a tile are unrolled in one basic block with no memory clobbers in
-//     between, so ptxas overlaps the LDS -> FFMA2 -> MUFU -> FADD2 -> F2FP -> STS chains of several chunks;
-//   * penalty LUT in four copies shifted by one float each: every thread reads its 128 consecutive
-//     penalties with aligned LDS.128 (8 per 64 scores instead of 64 scalar loads);
-//   * P (bf16) goes to two 128B-swizzled 16 KB sub-tiles (keys 0-63 / 64-127) and is handed to the PV
-//     product in those two halves, V arrives in the same halves, exactly as in the decoupled kernel.
+//     warp 1 QK issue, warps 2 / 3 PV issue of group 0 / 1) and two softmax warpgroups that grow to 224,
+//     each working on its OWN work item (128-query tile, utterance, head);
+//   * 128-key tiles: S = Q K^T is ONE chain of four M128 x N128 x K16 instructions per 128 keys;
+//     TMEM: S0 | S1 (128 columns each) | O0 | O1 (64) | P0 | P1 (64) = all 512 columns;
+//   * the softmax thread (one query row) pulls its whole 128-score row into registers and hands S[g] back at
+//     once, so the next QK product runs under this tile's exponentials; key padding is written into the
+//     score registers (-inf), after which every tile runs ONE straight-line block of 16 chunks with no
+//     shared-memory store inside it (ptxas does not move a chunk's LUT loads above an earlier store), in
+//     which the LDS -> FADD2 -> FFMA2 -> MUFU -> FADD2 -> F2FP chains of several chunks overlap: measured
+//     2400 cycles for the two groups' tiles together against the MUFU pipe's floor of 2048
+//     (profiles/r02z_attention_timeline.txt, r02z_pipe_probe.txt);
+//   * penalty LUT in four copies shifted by one float each and padded by 0 / 12 / 20 / 28 floats: every
+//     thread reads its 128 consecutive penalties with aligned, bank-conflict-free LDS.128;
+//   * P (bf16) is handed to the PV product THROUGH TENSOR MEMORY (tcgen05.st, then tcgen05.mma with the A
+//     operand in TMEM): one hand-over per tile, no generic -> async proxy fence, half the shared-memory
+//     traffic of the tile (61.4 -> 53.2 us together with the straight-line block);
+//   * the item's output goes through a per-warp swizzled staging tile and one TMA store (a thread owns a
+//     128-byte row: stored directly, every STG.128 touched 32 rows);
+//   * group 1 drops a third of a tile behind group 0 once, after the first item: the two groups share one
+//     MUFU pipe per scheduler and otherwise run -- and wait -- in lockstep (51.2 -> 47.1 us).
+// Measured at cfg2 (L = 375, B = 64, H = 8): 47.1 us against 61.4 us; L = 1500, B = 8, H = 16: 142 us
+// against 172 us (profiles/r02z_attention_ab.txt).  Development log: profiles/r02z_attention_wide.txt.
 //
 // One-pass softmax: the running reference m is an overflow guard only (P is bf16, l / O are fp32 -- all
-// with the fp32 exponent range), raised when a half's raw maximum exceeds it by 2^24; see the comments in
-// attention_fwd_dec_kernel for the restart protocol, which is kept verbatim.
+// with the fp32 exponent range), raised (with a rescale of O and l) when a row's raw maximum exceeds it by
+// 2^24.  The whole row is in registers before any exponential, so there is no tile restart here.
 #include <math.h>
 #include <stdlib.h>
 
