@@ -924,11 +924,16 @@ def run_ragged(args, rank, world, local_rank):
     barrier()
     gc.enable()
     my_ms = ev0.elapsed_time(ev1)
+    # untimed: every output of one more pass over the rank's batches must be finite (a ragged stream in persistent
+    # workspaces is where stale rows beyond a device-side limit would show: DESIGN.md 4e)
+    bad = torch.zeros((), dtype=torch.int64, device=dev)
+    for o in pipe.run_device(iter(dev_batches)):
+        bad += (~torch.isfinite(o.encoder_out)).sum()
     last_lens = dev_batches[-1][1].tolist()
     ratio_last = float(out.src_lengths.sum().item()) / sum(((n + 1) // 2 + 1) // 2 for n in last_lens)
     launches = (ops.LAUNCHES - launches0) // max(1, len(dev_batches))
     clocks = sampler.stop() if sampler else None
-    stats = torch.tensor([my_ms, frames, padded], dtype=torch.float64, device=dev)
+    stats = torch.tensor([my_ms, frames, padded, float(bad.item())], dtype=torch.float64, device=dev)
     allr = [torch.zeros_like(stats) for _ in range(world)]
     if world > 1:
         torch.distributed.all_gather(allr, stats)
@@ -957,6 +962,7 @@ def run_ragged(args, rank, world, local_rank):
                     cache="every batch is a different tensor (%.0f MB per rank in total)" % (padded * Fd * 4 / 1e6 / world)),
         rank_time_ms=dict(min=round(min(ms), 3), max=round(worst, 3), mean=round(sum(ms) / len(ms), 3),
                           spread=round(worst / min(ms), 4), per_rank=[round(m, 3) for m in ms]),
+        nonfinite_outputs=int(sum(float(t[3]) for t in allr)),
         step_imbalance_padded_frames=round(imbalance, 4),
         e2e=None, gpu_launches=launches, clocks=clocks, impl="ours", roofline=None, cpu_baseline=None)
 

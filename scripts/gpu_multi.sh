@@ -10,7 +10,7 @@ run() { # name, args
 import json
 try:
     r = json.load(open("gpurun_out/${TAG}_${name}_${N}gpu.json"))
-    print("  value %.3fM  ms/step %.4f" % (r["value"]/1e6, r["ms_per_step"]), {k: r.get(k) for k in ("rank_time_ms", "step_imbalance_padded_frames", "train_step_split", "allreduce") if r.get(k)})
+    print("  value %.3fM  ms/step %.4f" % (r["value"]/1e6, r["ms_per_step"]), {k: r.get(k) for k in ("rank_time_ms", "step_imbalance_padded_frames", "nonfinite_outputs", "train_step_split", "allreduce") if r.get(k)})
     if r.get("e2e"): print("  e2e %.3fM" % (r["e2e"]["value"]/1e6))
 except Exception as e:
     print("  no json", e)
