@@ -1,4 +1,6 @@
 """Shared helpers for the GPU parity tests (test infrastructure)."""
+import torch
+
 from fbkst_b200.config import DictStub, build_encoder, make_args  # noqa: F401
 
 # BASELINE.json north_star: floating-point encoder outputs within 2e-2 under bf16.  Two readings
@@ -10,7 +12,11 @@ TOL_BF16 = 2e-2
 
 
 def rel_err(a, b):
+    """max|a-b| / max|ref|; inf when either side holds a non-finite value (a NaN must never compare as small:
+    Python's max(x, nan) keeps x and torch's max() propagates NaN only by luck of the call site)."""
     a, b = a.double().cpu(), b.double().cpu()
+    if not (bool(torch.isfinite(a).all()) and bool(torch.isfinite(b).all())):
+        return float("inf")
     return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
 
 
@@ -18,6 +24,8 @@ def elementwise_err(a, b):
     """max over elements of |a-b| / (|ref| + rms(ref)): the element-wise criterion holds iff the
     returned value is <= TOL."""
     a, b = a.double().cpu(), b.double().cpu()
+    if not (bool(torch.isfinite(a).all()) and bool(torch.isfinite(b).all())):
+        return float("inf")
     rms = b.pow(2).mean().sqrt().clamp_min(1e-12)
     return ((a - b).abs() / (b.abs() + rms)).max().item()
 
