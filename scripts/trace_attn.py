@@ -15,6 +15,13 @@ d = torch.device("cuda:0")
 L, B, H = 375, 64, 8
 qkv = (torch.randn(L * B, 3 * H * 64, device=d) * 0.7).bfloat16()
 lengths = torch.full((B,), L, dtype=torch.int32, device=d)
+q_limit = None
+if os.environ.get("FBKST_TRACE_POST"):  # the in-step shape after CTC compression: worst-case grid, short utterances
+    lens = [120 + (i * 7) % 13 for i in range(B)]
+    lengths = torch.tensor(lens, dtype=torch.int32, device=d)
+    q_limit = torch.tensor([max(lens)], dtype=torch.int32, device=d)
+_attention = ops.attention
+ops.attention = lambda *a, **k: _attention(*a, q_limit=q_limit, **k)
 for _ in range(3):
     ops.attention(qkv, lengths, L, B, H, True)
 buf = torch.zeros(64 * 16, dtype=torch.int64, device=d)
