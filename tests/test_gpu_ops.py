@@ -618,3 +618,32 @@ def test_linear_argmax_fused_epilogue(L, B, V, K, want_prob):
     hooked.scatter_add_(1, plan.long().unsqueeze(-1), torch.full((L * B, 1), 30.0, device=dev()))
     assert torch.allclose(lgb, hooked, atol=1e-5)
     assert torch.equal(labb[valid], plan[valid])
+
+
+@pytest.mark.parametrize("env", [{"FBKST_ATTN_WIDE": "0"}, {"FBKST_ATTN_WIDE": "0", "FBKST_ATTN_DEC": "0"}])
+def test_attention_round1_kernels_still_match(env):
+    """The kernel selection is read once per process, so the A/B paths (round-1 decoupled kernel, split-KV kernel)
+    are exercised in a child process: same shapes, same fp32 reference, same tolerance as the default kernel."""
+    import subprocess
+    import sys
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import sys, torch
+sys.path.insert(0, %r); sys.path.insert(0, %r); sys.path.insert(0, %r)
+from fbkst_b200 import ops
+from test_gpu_ops import attn_ref, bf, rel_err
+for L, B, H, lens, pen in [(375, 3, 4, [375, 201, 64], True), (300, 2, 4, [300, 129], False), (1600, 1, 2, [1600], True)]:
+    g = torch.Generator().manual_seed(L + B)
+    qkv = bf(torch.randn(L * B, 3 * H * 64, generator=g) * 0.7).cuda()
+    lengths = torch.tensor(lens, dtype=torch.int32, device="cuda")
+    out = ops.attention(qkv, lengths, L, B, H, pen).float().view(L, B, H * 64)
+    ref = attn_ref(qkv, lengths, L, B, H, pen).view(L, B, H * 64)
+    assert torch.isfinite(out).all()
+    for b, n in enumerate(lens):
+        e = rel_err(out[:n, b], ref[:n, b])
+        assert e < 2e-2, (L, b, n, e)
+print("ok")
+''' % (os.path.join(ROOT, "fbk-fairseq-st_b200"), os.path.join(ROOT, "tests"), ROOT)
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
