@@ -83,7 +83,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   // try_wait suspends the thread in hardware for a bounded time per attempt, so the loop body is
   // only a counter (no clock reads: the spinning TMA/MMA warps share issue slots with the math warps)
   for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
-    if (spins > (1u << 26)) {  // seconds: never legitimate
+    if (spins > (1u << 26)) {  // ~133 s (a failing try_wait returns after ~2 us: scripts/probes/trywait_probe.cu)
       printf("fbkst: mbarrier watchdog block=(%d,%d) thread=%d bar=%u parity=%u\n", blockIdx.x,
              blockIdx.y, threadIdx.x, smem_u32(bar), parity);
       __trap();
