@@ -1251,7 +1251,7 @@ static int attention_entry(const void* qkv, void* out, const int32_t* lengths, i
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int D = H * AT_HD;
   // wide kernel (attention_wide.cu: one CTA per SM, 128-key tiles, P through tensor memory) whenever its shared
-  // memory fits (L <~ 1450 with the penalty LUT); FBKST_ATTN_WIDE=0 selects the round-1 kernels below (A/B switch)
+  // memory fits (L <~ 2500 with the penalty LUT); FBKST_ATTN_WIDE=0 selects the round-1 kernels below (A/B switch)
   static const bool wide_enabled = !(getenv("FBKST_ATTN_WIDE") && atoi(getenv("FBKST_ATTN_WIDE")) == 0);
   if (wide_enabled) {
     const int rc = attention_wide_launch(qkv, out, lengths, L, B, H, log_penalty, q_limit, st);

@@ -1,4 +1,4 @@
-// Self-attention core, "wide" layout: the default kernel for L <~ 1450 (reference: local_attention.py:115-139
+// Self-attention core, "wide" layout: the default kernel for L <~ 2500 (reference: local_attention.py:115-139
 // with LogPenalty conv_transformer_layer.py:22-27).  Same arithmetic and the same pipeline roles as
 // attention_fwd_dec_kernel (attention_tcgen05.cu, the round-1 kernel, still selected by FBKST_ATTN_WIDE=0 and
 // for longer inputs), re-cut for what that kernel's profile showed (profiles/r02y_ncu_attention.txt): softmax
@@ -10,7 +10,9 @@
 //     warp 1 QK issue, warps 2 / 3 PV issue of group 0 / 1) and two softmax warpgroups that grow to 224,
 //     each working on its OWN work item (128-query tile, utterance, head);
 //   * 128-key tiles: S = Q K^T is ONE chain of four M128 x N128 x K16 instructions per 128 keys;
-//     TMEM: S0 | S1 (128 columns each) | O0 | O1 (64) | P0 | P1 (64) = all 512 columns;
+//     TMEM: S0 | S1 (128 columns each) | O0 | O1 (64) | P0 | P1 (64) = all 512 columns; shared memory:
+//     Q x2, K x3, V x2 tiles of 16 KB + 2 x 16 KB of output staging + the LUT = 167 KB + 16 B per LUT entry
+//     (L <~ 2400 with the penalty);
 //   * the softmax thread (one query row) pulls its whole 128-score row into registers and hands S[g] back at
 //     once, so the next QK product runs under this tile's exponentials; key padding is written into the
 //     score registers (-inf), after which every tile runs ONE straight-line block of 16 chunks with no
@@ -47,7 +49,16 @@ constexpr int AW_BN = 128;  // keys per tile
 constexpr int AW_HD = 64;
 constexpr int AW_QB = AW_BM * AW_HD * 2;  // 16 KB
 constexpr int AW_KB = AW_BN * AW_HD * 2;  // 16 KB (K tile; V tile = two 8 KB halves)
-constexpr int AW_PB = AW_BM * AW_BN * 2;  // 32 KB
+// P handed to the PV product through tensor memory (A operand of tcgen05.mma from TMEM) instead of two
+// swizzled shared-memory sub-tiles: no 64 KB store + 64 KB operand fetch per tile pair on the 128 B/clk
+// shared-memory path, no generic -> async proxy fence.  0 = shared memory (A/B switch).
+#ifndef FBKST_AW_PTMEM
+#define FBKST_AW_PTMEM 1
+#endif
+// per-group shared-memory tile behind sP: the output staging rows (4 warps x 32 rows x 128 B) and, without
+// FBKST_AW_PTMEM, the whole 128 x 128 bf16 P tile
+constexpr int AW_PB = FBKST_AW_PTMEM ? AW_BM * AW_HD * 2 : AW_BM * AW_BN * 2;  // 16 KB / 32 KB
+constexpr int AW_PSUB = AW_BM * AW_HD * 2;  // one 64-key sub-tile of P (FBKST_AW_PTMEM=0)
 constexpr int AW_KST = 3;
 constexpr int AW_THREADS = 384;
 constexpr int AW_TABLE = 64;
@@ -89,12 +100,6 @@ __device__ __forceinline__ float ex2(float x) {
 #endif
 #ifndef FBKST_AW_STAGGER_ITEM
 #define FBKST_AW_STAGGER_ITEM 1
-#endif
-// P handed to the PV product through tensor memory (A operand of tcgen05.mma from TMEM) instead of two
-// swizzled shared-memory sub-tiles: no 64 KB store + 64 KB operand fetch per tile pair on the 128 B/clk
-// shared-memory path, no generic -> async proxy fence.  0 = shared memory (A/B switch).
-#ifndef FBKST_AW_PTMEM
-#define FBKST_AW_PTMEM 1
 #endif
 #ifndef FBKST_AW_NPOLY
 #define FBKST_AW_NPOLY 0
@@ -467,7 +472,7 @@ __global__ void __launch_bounds__(AW_THREADS, 1)
             umma_bf16_ts(tmem_O + g * AW_HD, tmem_P + g * (AW_BN / 2) + 8 * kk,
                          desc_mnmajor_sw128(va + kk * 2048, AW_KB), IDESC_PV, (pc.j > 0) || kk != 0);
 #else
-            umma_bf16_ss(tmem_O + g * AW_HD, desc_kmajor_sw128(pa + (kk >> 2) * (AW_PB / 2)) + 2 * (kk & 3),
+            umma_bf16_ss(tmem_O + g * AW_HD, desc_kmajor_sw128(pa + (kk >> 2) * AW_PSUB) + 2 * (kk & 3),
                          desc_mnmajor_sw128(va + kk * 2048, AW_KB), IDESC_PV, (pc.j > 0) || kk != 0);
 #endif
           }
@@ -636,7 +641,7 @@ __global__ void __launch_bounds__(AW_THREADS, 1)
 #else
 #pragma unroll
         for (int ch = 0; ch < 16; ++ch)
-          sts128((p_row ^ (uint32_t)((ch & 7) << 4)) + (ch >> 3) * (AW_PB / 2), pk[4 * ch], pk[4 * ch + 1],
+          sts128((p_row ^ (uint32_t)((ch & 7) << 4)) + (ch >> 3) * AW_PSUB, pk[4 * ch], pk[4 * ch + 1],
                  pk[4 * ch + 2], pk[4 * ch + 3]);
         l += (sm2[0].x + sm2[0].y) + (sm2[1].x + sm2[1].y) + (sm2[2].x + sm2[2].y) + (sm2[3].x + sm2[3].y);
         tc_fence_before();  // (also orders the O reads of the previous item's epilogue / a rescale before PV)

@@ -344,6 +344,7 @@ def attn_ref(qkv, lengths, L, B, H, log_penalty):
 @pytest.mark.parametrize("L,B,H,lens,pen", [
     (128, 2, 2, [128, 128], True), (100, 3, 2, [100, 64, 5], True), (375, 2, 8, [375, 201], True),
     (300, 2, 4, [300, 129], False), (700, 1, 2, [700], True),
+    (1700, 1, 2, [1700], True), (2100, 2, 1, [2100, 1300], False),  # long inputs on the default kernel (L <~ 2500)
     # more work items than persistent CTAs (several items per CTA, item boundaries inside the
     # flattened key-tile stream), ragged lengths incl. tiles of padded queries
     (375, 24, 8, [375] * 6 + [300] * 6 + [190] * 6 + [64, 65, 127, 128, 129, 1], True),
@@ -632,7 +633,7 @@ import sys, torch
 sys.path.insert(0, %r); sys.path.insert(0, %r); sys.path.insert(0, %r)
 from fbkst_b200 import ops
 from test_gpu_ops import attn_ref, bf, rel_err
-for L, B, H, lens, pen in [(375, 3, 4, [375, 201, 64], True), (300, 2, 4, [300, 129], False), (1600, 1, 2, [1600], True)]:
+for L, B, H, lens, pen in [(375, 3, 4, [375, 201, 64], True), (300, 2, 4, [300, 129], False), (2600, 1, 2, [2600], True)]:
     g = torch.Generator().manual_seed(L + B)
     qkv = bf(torch.randn(L * B, 3 * H * 64, generator=g) * 0.7).cuda()
     lengths = torch.tensor(lens, dtype=torch.int32, device="cuda")
