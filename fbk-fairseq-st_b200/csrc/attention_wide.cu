@@ -296,8 +296,8 @@ __global__ void __launch_bounds__(AW_THREADS, 1)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;                 // 2 x 16 KB: one per group
   uint8_t* sK = sQ + 2 * AW_QB;       // AW_KST stages, shared by both groups (fixed interleaved order)
-  uint8_t* sV = sK + AW_KST * AW_KB;  // one 16 KB tile per group, loaded / consumed in two 64-key halves
-  uint8_t* sP = sV + 2 * AW_KB;       // one 32 KB tile per group: sub-tiles of keys 0-63 / 64-127
+  uint8_t* sV = sK + AW_KST * AW_KB;  // one 16 KB tile (128 keys) per group
+  uint8_t* sP = sV + 2 * AW_KB;       // per group: the output staging rows (and the P tile without FBKST_AW_PTMEM)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * AW_PB);
   int4* sItems = reinterpret_cast<int4*>(bars + 32);
   float* sLut = reinterpret_cast<float*>(sItems + AW_TABLE);
