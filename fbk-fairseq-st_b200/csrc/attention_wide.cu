@@ -104,6 +104,11 @@ __device__ __forceinline__ float ex2(float x) {
 #ifndef FBKST_AW_NPOLY
 #define FBKST_AW_NPOLY 0
 #endif
+// Experimental: strict alternation of the two groups' exponential phases (a token passed through two mbarriers),
+// so that one group's guard / hand-over / TMEM-load phases always run under the other group's exponentials.
+#ifndef FBKST_AW_PINGPONG
+#define FBKST_AW_PINGPONG 0
+#endif
 __device__ __forceinline__ float2 aw_ex2_poly2(float2 x) {
   const float kMagic = 12582912.0f;  // 1.5 * 2^23: the integer part of x lands in the low mantissa bits
   x.x = fmaxf(x.x, -126.0f);
@@ -311,6 +316,10 @@ __global__ void __launch_bounds__(AW_THREADS, 1)
   uint64_t* pv_done = bars + 16;  // [2]  the PV product of the group's tile has completed: P[g] / V[g] free, O[g] updated
   uint64_t* s_free = bars + 18;   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+#if FBKST_AW_PINGPONG
+  uint64_t* turn = bars + 20;  // [2] token: group g may run its exponentials
+  volatile uint32_t* grp_done = reinterpret_cast<volatile uint32_t*>(bars + 22);  // [2] group g has no tiles left
+#endif
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm128);
@@ -327,6 +336,10 @@ __global__ void __launch_bounds__(AW_THREADS, 1)
       mbar_init(&p_full[s], 128);
       mbar_init(&pv_done[s], 1);
       mbar_init(&s_free[s], 128);
+#if FBKST_AW_PINGPONG
+      mbar_init(&turn[s], 128);
+      grp_done[s] = 0u;
+#endif
     }
     fence_barrier_init();
   }
@@ -514,6 +527,9 @@ __global__ void __launch_bounds__(AW_THREADS, 1)
     // first LUT index of row i for key k0 is lut_off - i + k0 = r (mod 4) with r = (-q) & 3
     const int lut_r = (4 - (q & 3)) & 3;
     uint32_t c = 0;  // key tiles of this group before the current one
+#if FBKST_AW_PINGPONG
+    bool partner_done = false;
+#endif
     const int q_lim = q_limit ? __ldg(q_limit) : L;  // (after pdl_wait: written by the previous kernel)
     WItem it;
     // (item index, stride and count pinned in registers: ptxas otherwise rebuilds them from the kernel
@@ -552,7 +568,7 @@ __global__ void __launch_bounds__(AW_THREADS, 1)
         const float4* lp = lut_row + (k0 >> 2);
         float2 sm2[4];
         uint32_t s[8][16], pk[64];
-#if FBKST_AW_STAGGER
+#if FBKST_AW_STAGGER && !FBKST_AW_PINGPONG
         // The two groups share one MUFU pipe per scheduler.  Started together they stay in lockstep: both run
         // their exponentials at the same time (2400 cycles for the pair, the pipe's floor being 2048) and both
         // sit in their guard / hand-over / TMEM-load phases at the same time (~1100 cycles per tile in which
@@ -622,10 +638,30 @@ __global__ void __launch_bounds__(AW_THREADS, 1)
         }
         const float2 negm2 = make_float2(-m_used, -m_used);
         AW_TRACE(2 * c + grp, 2);
+#if FBKST_AW_PINGPONG
+        // group 0's first phase needs no token; afterwards the token alternates (the partner's flag releases a
+        // group whose partner has run out of tiles)
+        if (!partner_done && (grp == 1 || c >= 1)) {
+          const uint32_t par = (grp == 0 ? (c - 1) : c) & 1u;
+          for (uint32_t spins = 0; !mbar_try_wait(&turn[grp], par); ++spins) {
+            if (grp_done[grp ^ 1]) {
+              partner_done = true;
+              break;
+            }
+            if (spins > (1u << 24)) {  // ~30 s: never legitimate
+              printf("fbkst: wide attention ping-pong watchdog block=%d group=%d tile=%u\n", blockIdx.x, grp, c);
+              __trap();
+            }
+          }
+        }
+#endif
         // all 16 chunks of 8 scores in ONE basic block, P packed into registers (they replace the score
         // registers as those die) ...
         aw_half<LOGPEN>(s[0], s[1], s[2], s[3], lp, negm2, sm2, pk);
         aw_half<LOGPEN>(s[4], s[5], s[6], s[7], lp + 16, negm2, sm2, pk + 32);
+#if FBKST_AW_PINGPONG
+        mbar_arrive(&turn[grp ^ 1]);
+#endif
         AW_TRACE(2 * c + grp, 3);
         // ... and stored once the PV product of the previous tile, which read this buffer, has completed
         if (c >= 1) mbar_wait(my_pv_done, ph ^ 1);
@@ -694,6 +730,10 @@ __global__ void __launch_bounds__(AW_THREADS, 1)
       // p_full arrival (ordered after the TMEM reads above by the fence before that arrive)
       AW_TRACE(2 * (c - 1) + grp, 10);
     }
+#if FBKST_AW_PINGPONG
+    grp_done[grp] = 1u;
+    __threadfence_block();
+#endif
     if (lane == 0) tma_store_wait<0>();  // output stores complete (and staging rows read) before the CTA retires
   }
 #undef AW_PICK
