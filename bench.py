@@ -1135,6 +1135,10 @@ def run_reference(args, rank, world):
 
 
 def main():
+    # A run that is still going after 25 minutes is stuck (the default line takes ~1 minute, the reference arm is
+    # budgeted at 4): dump every thread's Python stack and exit non-zero instead of hanging without a trace.
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("FBKST_BENCH_DEADLINE_S", "1500")), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
