@@ -59,7 +59,11 @@ constexpr int AW_KB = AW_BN * AW_HD * 2;  // 16 KB (K tile; V tile = two 8 KB ha
 // FBKST_AW_PTMEM, the whole 128 x 128 bf16 P tile
 constexpr int AW_PB = FBKST_AW_PTMEM ? AW_BM * AW_HD * 2 : AW_BM * AW_BN * 2;  // 16 KB / 32 KB
 constexpr int AW_PSUB = AW_BM * AW_HD * 2;  // one 64-key sub-tile of P (FBKST_AW_PTMEM=0)
-constexpr int AW_KST = 3;
+#ifndef FBKST_AW_KST
+#define FBKST_AW_KST 3
+#endif
+static_assert(FBKST_AW_KST >= 2 && FBKST_AW_KST <= 4, "K ring: 2..4 stages");
+constexpr int AW_KST = FBKST_AW_KST;  // K ring stages (4 measured the same: r02z_attention_wide.txt)
 constexpr int AW_THREADS = 384;
 constexpr int AW_TABLE = 64;
 constexpr int AW_SMEM_FIXED = 2 * AW_QB + AW_KST * AW_KB + 2 * AW_KB + 2 * AW_PB + 256 /*barriers*/ +
@@ -103,6 +107,9 @@ __device__ __forceinline__ float ex2(float x) {
 #endif
 #ifndef FBKST_AW_NPOLY
 #define FBKST_AW_NPOLY 0
+#endif
+#ifndef FBKST_AW_IDLE_NS
+#define FBKST_AW_IDLE_NS 64  // back-off of the idle load loop
 #endif
 // Experimental: strict alternation of the two groups' exponential phases (a token passed through two mbarriers),
 // so that one group's guard / hand-over / TMEM-load phases always run under the other group's exponentials.
@@ -308,17 +315,17 @@ __global__ void __launch_bounds__(AW_THREADS, 1)
   float* sLut = reinterpret_cast<float*>(sItems + AW_TABLE);
   uint64_t* q_full = bars + 0;    // [2]
   uint64_t* q_empty = bars + 2;   // [2]
-  uint64_t* k_full = bars + 4;    // [3]
-  uint64_t* k_empty = bars + 7;   // [3]
-  uint64_t* v_full = bars + 10;   // [2]
-  uint64_t* s_full = bars + 12;   // [2]
-  uint64_t* p_full = bars + 14;   // [2]  P[g] written (128 arrivals)
-  uint64_t* pv_done = bars + 16;  // [2]  the PV product of the group's tile has completed: P[g] / V[g] free, O[g] updated
-  uint64_t* s_free = bars + 18;   // [2]
+  uint64_t* k_full = bars + 4;    // [AW_KST <= 4]
+  uint64_t* k_empty = bars + 8;   // [AW_KST <= 4]
+  uint64_t* v_full = bars + 12;   // [2]
+  uint64_t* s_full = bars + 14;   // [2]
+  uint64_t* p_full = bars + 16;   // [2]  P[g] written (128 arrivals)
+  uint64_t* pv_done = bars + 18;  // [2]  the PV product of the group's tile has completed: P[g] / V[g] free, O[g] updated
+  uint64_t* s_free = bars + 20;   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
 #if FBKST_AW_PINGPONG
-  uint64_t* turn = bars + 20;  // [2] token: group g may run its exponentials
-  volatile uint32_t* grp_done = reinterpret_cast<volatile uint32_t*>(bars + 22);  // [2] group g has no tiles left
+  uint64_t* turn = bars + 22;  // [2] token: group g may run its exponentials
+  volatile uint32_t* grp_done = reinterpret_cast<volatile uint32_t*>(bars + 24);  // [2] group g has no tiles left
 #endif
 
   if (warp == 0 && lane == 0) {
@@ -419,7 +426,7 @@ __global__ void __launch_bounds__(AW_THREADS, 1)
           const bool ok = (AW_PICK(kc0, kc1, kturn) == 0) ? try_k(kc0, 0) : try_k(kc1, 1);
           if (ok) { kturn ^= 1; progressed = true; }
         }
-        if (!progressed) __nanosleep(64);
+        if (!progressed) __nanosleep(FBKST_AW_IDLE_NS);
 #if FBKST_WATCHDOG
         idle = progressed ? 0 : idle + 1;
         if (idle > (1u << 26)) {
