@@ -108,6 +108,14 @@ __device__ __forceinline__ float ex2(float x) {
 #ifndef FBKST_AW_NPOLY
 #define FBKST_AW_NPOLY 0
 #endif
+// registers per thread after the split: 128 producer threads + 256 softmax threads <= 384 x 168 at launch
+#ifndef FBKST_AW_REGS_PRODUCER
+#define FBKST_AW_REGS_PRODUCER 56
+#endif
+#ifndef FBKST_AW_REGS_SOFTMAX
+#define FBKST_AW_REGS_SOFTMAX 224
+#endif
+static_assert(128 * FBKST_AW_REGS_PRODUCER + 256 * FBKST_AW_REGS_SOFTMAX <= 384 * 168, "register split");
 #ifndef FBKST_AW_IDLE_NS
 #define FBKST_AW_IDLE_NS 64  // back-off of the idle load loop
 #endif
@@ -373,7 +381,7 @@ __global__ void __launch_bounds__(AW_THREADS, 1)
 #define AW_PICK(c0, c1, turn) (((turn) == 0) ? ((c0).valid(n_items) ? 0 : 1) : ((c1).valid(n_items) ? 1 : 0))
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FBKST_AW_REGS_PRODUCER));
     if (warp == 0) {
       // ------------------------------------------------ TMA loads (Q, K, V halves): event loop over
       // non-blocking mbarrier.test_wait probes, so no load queues behind a wait that belongs to the other group
@@ -504,7 +512,7 @@ __global__ void __launch_bounds__(AW_THREADS, 1)
       }
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FBKST_AW_REGS_SOFTMAX));
     // ---- softmax / correction / output: thread <-> (query row of the group's own item)
     const int grp = (warp - 4) >> 2;
     const int q = (warp & 3) * 32 + lane;  // row in the tile == TMEM lane
